@@ -1,0 +1,215 @@
+"""Generate tests/golden/*.npz from the unmodified reference (run in the build container).
+
+Each fixture holds one grid (the arrays of pp.Grid the hot path reads), one set of
+parameters (permeability / stiffness / boundary condition / coupling tensors) and
+the matrices the reference's ``Mpfa/Mpsa/Biot.discretize`` wrote to
+``data[pp.DISCRETIZATION_MATRICES][kw]``.  The GPU box never sees /root/reference;
+tests read only these files.
+
+    python tools/make_golden.py
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sps
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from ref_loader import load_porepy  # noqa: E402
+
+pp = load_porepy()
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def grid_arrays(g) -> dict:
+    fn = sps.csc_matrix(g.face_nodes)
+    cf = sps.csc_matrix(g.cell_faces)
+    cf.sort_indices()
+    return dict(
+        dim=np.int64(g.dim), name=np.array(str(g.name)), nodes=g.nodes,
+        fn_indptr=fn.indptr.astype(np.int32), fn_indices=fn.indices.astype(np.int32),
+        cf_indptr=cf.indptr.astype(np.int32), cf_indices=cf.indices.astype(np.int32),
+        cf_data=cf.data.astype(np.int8), face_normals=g.face_normals,
+        face_centers=g.face_centers, face_areas=g.face_areas,
+        cell_centers=g.cell_centers, cell_volumes=g.cell_volumes,
+        fracture_faces=np.asarray(g.tags["fracture_faces"], bool),
+    )
+
+
+def put_matrix(d: dict, key: str, m) -> None:
+    m = sps.csr_matrix(m)
+    m.sum_duplicates()
+    d[f"M__{key}__data"] = m.data
+    d[f"M__{key}__indices"] = m.indices.astype(np.int32)
+    d[f"M__{key}__indptr"] = m.indptr.astype(np.int32)
+    d[f"M__{key}__shape"] = np.array(m.shape, dtype=np.int64)
+
+
+def perturb(g, rng, amp=0.2):
+    g.compute_geometry()
+    h = np.min(g.cell_volumes) ** (1.0 / g.dim)
+    bn = np.zeros(g.num_nodes, bool)
+    bf = g.get_all_boundary_faces()
+    fn = sps.csc_matrix(g.face_nodes)
+    for f in bf:
+        bn[fn.indices[fn.indptr[f]:fn.indptr[f + 1]]] = True
+    pert = amp * h * (0.5 - rng.random((g.dim, g.num_nodes)))
+    pert[:, bn] = 0
+    g.nodes[:g.dim] += pert
+    g.compute_geometry()
+
+
+def make_grid(kind, rng):
+    if kind == "cart3d":
+        g = pp.CartGrid([4, 3, 3], [1.0, 1.0, 1.0])
+    elif kind == "cart3d_pert":
+        g = pp.CartGrid([4, 4, 3], [1.0, 1.0, 1.0])
+        perturb(g, rng)
+        return g
+    elif kind == "tet3d":
+        g = pp.StructuredTetrahedralGrid([2, 2, 2], [1.0, 1.0, 1.0])
+    elif kind == "tet3d_delaunay":
+        pts = rng.random((3, 22))
+        corners = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [0, 0, 1], [1, 0, 1],
+                            [0, 1, 1], [1, 1, 1]], float).T
+        g = pp.TetrahedralGrid(np.hstack((corners, pts)))
+    elif kind == "cart2d":
+        g = pp.CartGrid([5, 4], [1.0, 1.0])
+    elif kind == "tri2d":
+        g = pp.StructuredTriangleGrid([3, 3], [1.0, 1.0])
+    else:
+        raise ValueError(kind)
+    g.compute_geometry()
+    return g
+
+
+def scalar_bc(g, rng, robin):
+    bf = g.get_all_boundary_faces()
+    xf = g.face_centers[:, bf]
+    labels = np.array(["neu"] * bf.size, dtype=object)
+    labels[xf[0] < 1e-10] = "dir"
+    labels[xf[0] > 1 - 1e-10] = "dir"
+    if robin:
+        labels[(xf[1] < 1e-10) & (xf[0] > 1e-10) & (xf[0] < 1 - 1e-10)] = "rob"
+    bc = pp.BoundaryCondition(g, bf, list(labels))
+    if robin:
+        bc.robin_weight = 0.5 + rng.random(g.num_faces)
+    return bc
+
+
+def vector_bc(g, rng, robin):
+    bf = g.get_all_boundary_faces()
+    xf = g.face_centers[:, bf]
+    bc = pp.BoundaryConditionVectorial(g)
+    d0 = bf[xf[0] < 1e-10]
+    bc.is_dir[:, d0] = True
+    bc.is_neu[:, d0] = False
+    r0 = bf[(xf[1] < 1e-10) & (xf[0] > 1e-10)]  # roller: Dirichlet in y only
+    bc.is_dir[1, r0] = True
+    bc.is_neu[1, r0] = False
+    if robin:
+        t0 = bf[(xf[1] > 1 - 1e-10) & (xf[0] > 1e-10)]
+        bc.is_rob[:, t0] = True
+        bc.is_neu[:, t0] = False
+        bc.robin_weight = bc.robin_weight * (0.5 + rng.random(g.num_faces))
+    return bc
+
+
+def case_mpfa(name, kind, robin, seed, contrast=False):
+    rng = np.random.default_rng(seed)
+    g = make_grid(kind, rng)
+    nc = g.num_cells
+    if contrast:  # heterogeneous isotropic kappa = 1e+-6 (test_mpfa.py:140-251 pattern)
+        kk = np.where(rng.random(nc) < 0.5, 1e-6, 1e6)
+        k = pp.SecondOrderTensor(kk)
+    else:
+        k = pp.SecondOrderTensor(1 + rng.random(nc), 1 + rng.random(nc), 1 + rng.random(nc),
+                                 0.3 * rng.random(nc), 0.3 * rng.random(nc), 0.3 * rng.random(nc))
+    bc = scalar_bc(g, rng, robin)
+    data = pp.initialize_data({}, "flow", {"second_order_tensor": k, "bc": bc,
+                                            "mpfa_inverter": "python"})
+    discr = pp.Mpfa("flow")
+    discr.discretize(g, data)
+    M = data[pp.DISCRETIZATION_MATRICES]["flow"]
+    d = grid_arrays(g)
+    d.update(kind=np.array("mpfa"), K=k.values, bc_is_dir=bc.is_dir, bc_is_neu=bc.is_neu,
+             bc_is_rob=bc.is_rob, bc_is_internal=bc.is_internal,
+             bc_robin_weight=np.asarray(bc.robin_weight, float),
+             eta=np.float64(pp.numerics.fv._fvutils.determine_eta(g)))
+    for key in ("flux", "bound_flux", "bound_pressure_cell", "bound_pressure_face",
+                "vector_source", "bound_pressure_vector_source"):
+        put_matrix(d, key, M[key])
+    # a solved problem: A p = b with unit Dirichlet data on x=0 (fv_elliptic.py:67-112)
+    bv = np.zeros(g.num_faces)
+    bf = g.get_all_boundary_faces()
+    bv[bf[g.face_centers[0, bf] < 1e-10]] = 1.0
+    data[pp.PARAMETERS]["flow"]["bc_values"] = bv
+    A, b = discr.assemble_matrix_rhs(g, data)
+    d["bc_values"] = bv
+    d["solution"] = sps.linalg.spsolve(sps.csc_matrix(A), b)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "nc", nc, "nf", g.num_faces)
+
+
+def case_mpsa(name, kind, robin, seed, biot=False):
+    rng = np.random.default_rng(seed)
+    g = make_grid(kind, rng)
+    nc = g.num_cells
+    mu = np.exp(0.5 * rng.standard_normal(nc))
+    lam = np.exp(0.5 * rng.standard_normal(nc))
+    C = pp.FourthOrderTensor(mu, lam)
+    bc = vector_bc(g, rng, robin)
+    params = {"fourth_order_tensor": C, "bc": bc, "inverter": "python"}
+    d = grid_arrays(g)
+    if biot:
+        at = pp.SecondOrderTensor(1 + rng.random(nc), 1 + rng.random(nc), 1 + rng.random(nc),
+                                  0.2 * rng.random(nc), 0.2 * rng.random(nc), 0.2 * rng.random(nc))
+        params["scalar_vector_mappings"] = {"flow": at, "temp": 0.5}
+        d["alpha__flow"] = at.values
+        d["alpha__temp"] = np.float64(0.5)
+    data = pp.initialize_data({}, "mech", params)
+    discr = pp.Biot("mech") if biot else pp.Mpsa("mech")
+    discr.discretize(g, data)
+    M = data[pp.DISCRETIZATION_MATRICES]["mech"]
+    d.update(kind=np.array("biot" if biot else "mpsa"), C=C.values, mu=mu, lmbda=lam,
+             bc_is_dir=bc.is_dir, bc_is_neu=bc.is_neu, bc_is_rob=bc.is_rob,
+             bc_is_internal=bc.is_internal, bc_robin_weight=np.asarray(bc.robin_weight, float),
+             bc_basis=np.asarray(bc.basis, float), eta=np.float64(pp.numerics.fv._fvutils.determine_eta(g)))
+    for key in ("stress", "bound_stress", "bound_displacement_cell", "bound_displacement_face"):
+        put_matrix(d, key, M[key])
+    if biot:
+        for key in ("displacement_divergence", "boundary_displacement_divergence",
+                    "scalar_gradient", "mpsa_consistency", "bound_displacement_pressure"):
+            for ak in ("flow", "temp"):
+                put_matrix(d, f"{key}:{ak}", M[key][ak])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "nc", nc, "nf", g.num_faces)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    case_mpfa("mpfa_cart3d", "cart3d", False, 1)
+    case_mpfa("mpfa_cart3d_robin", "cart3d", True, 2)
+    case_mpfa("mpfa_cart3d_pert", "cart3d_pert", False, 3)
+    case_mpfa("mpfa_cart3d_contrast", "cart3d", False, 4, contrast=True)
+    case_mpfa("mpfa_tet3d_robin", "tet3d", True, 5)
+    case_mpfa("mpfa_tet3d_delaunay", "tet3d_delaunay", False, 6)
+    case_mpfa("mpfa_cart2d", "cart2d", True, 7)
+    case_mpfa("mpfa_tri2d", "tri2d", False, 8)
+    case_mpsa("mpsa_cart3d", "cart3d", False, 11)
+    case_mpsa("mpsa_cart3d_robin", "cart3d", True, 12)
+    case_mpsa("mpsa_cart3d_pert", "cart3d_pert", False, 13)
+    case_mpsa("mpsa_tet3d", "tet3d", False, 14)
+    case_mpsa("mpsa_tet3d_delaunay", "tet3d_delaunay", False, 15)
+    case_mpsa("mpsa_cart2d_robin", "cart2d", True, 16)
+    case_mpsa("mpsa_tri2d", "tri2d", False, 17)
+    case_mpsa("biot_cart3d", "cart3d", False, 21, biot=True)
+    case_mpsa("biot_tet3d_robin", "tet3d", True, 22, biot=True)
+    case_mpsa("biot_cart2d", "cart2d", False, 23, biot=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,158 @@
+/* poreb200.h -- C ABI of libporeb200.so: B200 (sm_100a) MPFA / MPSA / Biot
+ * interaction-region assembly and CSR SpMV behind PorePy's discretization API.
+ *
+ * Plain pointers and sizes only; no torch / numpy types.  The Python host side
+ * (porepy_b200/_lib.py) binds these with ctypes.  Every entry point names the
+ * reference interface (pmgbergen/porepy v1.11.0) it replaces.
+ *
+ * Ownership: the caller owns every host buffer passed in or out.  The library
+ * owns the device memory inside a plan handle.  Handles are not thread-safe;
+ * use one host thread (one process under torchrun) per GPU.
+ *
+ * Return codes (all functions returning int):
+ *   PB_OK 0
+ *   PB_EINVAL 1     invalid argument
+ *   PB_ESINGULAR 2  singular local system; the node id is in pb_last_error_node()
+ *                   -> Python raises ValueError("Error in inversion of local linear
+ *                   systems"), parity with numerics/linalg/matrix_operations.py:1487-1490
+ *   PB_ECELLTYPE 3  a cell vertex does not have exactly nd faces of the cell meeting
+ *                   in it (pyramids ...) -> AssertionError, parity with
+ *                   numerics/fv/_fvutils.py:735 and mpsa.py:1569
+ *   PB_ECUDA 4      CUDA runtime error (text in pb_last_error())
+ *   PB_ENOTIMPL 5   feature of the reference not covered by this build
+ */
+#ifndef POREB200_H
+#define POREB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_OK 0
+#define PB_EINVAL 1
+#define PB_ESINGULAR 2
+#define PB_ECELLTYPE 3
+#define PB_ECUDA 4
+#define PB_ENOTIMPL 5
+
+/* boundary-condition codes per face (scalar) / per component and face (vector) */
+#define PB_BC_INTERIOR 0
+#define PB_BC_DIR 1
+#define PB_BC_NEU 2
+#define PB_BC_ROB 3
+
+/* sparsity patterns shared by the output matrices (scalar "base" patterns) */
+#define PB_PAT_FACE_CELL 0  /* nf x nc : flux, bound_pressure_cell; x nd columns: vector_source;
+                               nd x nd blocks: stress, bound_displacement_cell; ...          */
+#define PB_PAT_FACE_BFACE 1 /* nf x nf : bound_flux, bound_pressure_face, bound_stress, ...   */
+#define PB_PAT_CELL_CELL 2  /* nc x nc : mpsa_consistency, displacement_divergence (x nd)     */
+#define PB_PAT_CELL_BFACE 3 /* nc x nf : boundary_displacement_divergence (x nd)              */
+
+typedef struct pb_plan pb_plan; /* opaque */
+
+/* ---- library state ------------------------------------------------------------------ */
+const char *pb_last_error(void);
+int64_t pb_last_error_node(void);
+/* number of CUDA devices visible, or -1 (no driver / no device).  Never falls back to CPU. */
+int pb_device_count(void);
+/* cudaSetDevice for this process (one process per GPU). */
+int pb_set_device(int device);
+/* kernels launched by this library since load (bench.py's gpu_launches evidence). */
+int64_t pb_launch_count(void);
+
+/* ---- plan: sub-cell topology + output patterns --------------------------------------- */
+/* Replaces _fvutils.SubcellTopology.__init__ (numerics/fv/_fvutils.py:51-172), the
+ * sub-face pairing (:163-172, pair_over_subfaces :183-216), cell_node_blocks /
+ * sub_cell_index of scalar_tensor_vector_prod (:697-762), Mpfa._block_diagonal_structure
+ * (numerics/fv/mpfa.py:1357-1412) and the implicit sparsity patterns of the scipy SpGEMM
+ * chains (mpfa.py:1080-1147, mpsa.py:735-781, biot.py:776-866).
+ *   nd: grid dimension (2 or 3).  cell_faces: nf x nc CSC with +-1 data (pp.Grid.cell_faces),
+ *   face_nodes: nn x nf CSC (pp.Grid.face_nodes).  Row indices need not be sorted. */
+int pb_plan_create(int nd, int64_t nc, int64_t nf, int64_t nn,
+                   const int32_t *cf_indptr, const int32_t *cf_indices, const int8_t *cf_data,
+                   const int32_t *fn_indptr, const int32_t *fn_indices,
+                   pb_plan **out);
+void pb_plan_destroy(pb_plan *p);
+
+/* sizes: sub-cells, unique sub-faces, sub-half-faces, largest local system (sub-faces at a node) */
+int pb_plan_sizes(const pb_plan *p, int64_t *num_subcells, int64_t *num_subfaces,
+                  int64_t *num_subhalffaces, int32_t *max_subfaces_per_node,
+                  int32_t *max_subcells_per_node);
+/* base pattern `which` (PB_PAT_*): nrows and nnz; then copy indptr (nrows+1) / indices (nnz). */
+int pb_plan_pattern_size(const pb_plan *p, int which, int64_t *nrows, int64_t *nnz);
+int pb_plan_pattern_get(const pb_plan *p, int which, int32_t *indptr, int32_t *indices);
+
+/* Geometry the path reads from pp.Grid (grids/grid.py:32): nodes (3 x nn), face_normals /
+ * face_centers (3 x nf), cell_centers (3 x nc) row-major as numpy stores them; face_areas (nf),
+ * cell_volumes (nc).  Copied to the device inside the plan. */
+int pb_plan_set_geometry(pb_plan *p, const double *nodes, const double *face_normals,
+                         const double *face_centers, const double *face_areas,
+                         const double *cell_centers, const double *cell_volumes);
+
+/* ---- MPFA ----------------------------------------------------------------------------- */
+/* Replaces Mpfa._flux_discretization (numerics/fv/mpfa.py:592-1156) incl. _create_bound_rhs
+ * (:1414-1578), _discretize_vector_source (:1158-1307), reconstruct_presssure (:1628-1690),
+ * _fvutils.scalar_tensor_vector_prod / compute_dist_face_cell / ExcludeBoundaries and
+ * matrix_operations.invert_diagonal_blocks (numerics/linalg/matrix_operations.py:1175).
+ *   perm:  SecondOrderTensor.values, (3,3,nc) row-major (params/tensor.py:157)
+ *   bc:    nf codes PB_BC_* (internal/fracture faces already mapped to PB_BC_NEU, mpfa.py:1452)
+ *   robin_weight: nf doubles (may be NULL when no Robin face)
+ *   eta:   continuity point parameter (mpfa_eta)
+ * Outputs: CSR `data` arrays on the base patterns; NULL = not wanted.
+ *   flux, bound_pressure_cell: nnz(FACE_CELL);  vector_source, bound_pressure_vector_source:
+ *   nd*nnz(FACE_CELL) (entry p expands to p*nd+j);  bound_flux, bound_pressure_face:
+ *   nnz(FACE_BFACE). */
+int pb_mpfa_upload(pb_plan *p, const double *perm, const uint8_t *bc, const double *robin_weight,
+                   double eta);
+/* device-resident assembly of the uploaded problem; want_* select outputs. ms = device time. */
+int pb_mpfa_assemble(pb_plan *p, int want_flux_terms, int want_trace_terms,
+                     int want_vector_source, float *ms);
+int pb_mpfa_download(pb_plan *p, double *flux, double *bound_flux, double *bound_pressure_cell,
+                     double *bound_pressure_face, double *vector_source,
+                     double *bound_pressure_vector_source);
+
+/* ---- MPSA / Biot ------------------------------------------------------------------------ */
+/* Replaces Mpsa._stress_discretization (numerics/fv/mpsa.py:531-781),
+ * _create_inverse_gradient_matrix (:784-930), _tensor_vector_prod (:1520-1675),
+ * _eliminate_ncasym (:1932-2000), _create_bound_rhs (:984-1185), _reconstruct_displacement
+ * (:1187-1275) and, with n_alpha > 0, Biot._local_discretization (numerics/fv/biot.py:714-878).
+ *   stiffness: FourthOrderTensor.values (9,9,nc) row-major (params/tensor.py:348)
+ *   bc:        (nd, nf) codes PB_BC_* row-major (BoundaryConditionVectorial.is_dir/is_neu/is_rob)
+ *   robin_weight: (nd,nd,nf) row-major or NULL
+ *   alpha:     n_alpha coupling tensors, each (3,3,nc) row-major (scalar_vector_mappings)
+ * Outputs: data arrays; block expansion of the base patterns, row f*nd+i, column c*nd+j:
+ *   stress, bound_displacement_cell: nd*nd*nnz(FACE_CELL); bound_stress,
+ *   bound_displacement_face: nd*nd*nnz(FACE_BFACE); per coupling tensor:
+ *   displacement_divergence nd*nnz(CELL_CELL), boundary_displacement_divergence
+ *   nd*nnz(CELL_BFACE), scalar_gradient / bound_displacement_pressure nd*nnz(FACE_CELL),
+ *   mpsa_consistency nnz(CELL_CELL). */
+int pb_mpsa_upload(pb_plan *p, const double *stiffness, const uint8_t *bc,
+                   const double *robin_weight, double eta, int n_alpha, const double *alpha);
+int pb_mpsa_assemble(pb_plan *p, float *ms);
+int pb_mpsa_download(pb_plan *p, double *stress, double *bound_stress,
+                     double *bound_displacement_cell, double *bound_displacement_face);
+int pb_biot_download(pb_plan *p, int which_alpha, double *displacement_divergence,
+                     double *boundary_displacement_divergence, double *scalar_gradient,
+                     double *mpsa_consistency, double *bound_displacement_pressure);
+
+/* ---- CSR SpMV ---------------------------------------------------------------------------- */
+/* Replaces the scipy `M @ val` of AdArray.__rmatmul__ (numerics/ad/forward_mode.py:565-595)
+ * and the residual chain of EquationSystem.assemble(evaluate_jacobian=False)
+ * (numerics/ad/equation_system.py:1579-1713).  y = A x (+ beta*y).  */
+typedef struct pb_csr pb_csr; /* device-resident CSR matrix */
+int pb_csr_create(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t *indptr,
+                  const int32_t *indices, const double *data, pb_csr **out);
+void pb_csr_destroy(pb_csr *a);
+/* host vectors in/out (H2D + kernel + D2H) */
+int pb_csr_spmv(pb_csr *a, const double *x, double *y);
+/* device pointers (e.g. torch tensors' data_ptr()); stream = cudaStream_t as integer (0 = default) */
+int pb_csr_spmv_dev(pb_csr *a, const double *x_dev, double *y_dev, uint64_t stream);
+/* time `reps` device SpMVs with CUDA events on the launching stream; returns mean ms */
+int pb_csr_spmv_bench(pb_csr *a, int reps, float *mean_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POREB200_H */

@@ -1,0 +1,429 @@
+// mpsa_node.cuh -- per-interaction-region MPSA-W (+ Biot coupling) assembly routine.
+//
+// Reference formulation (numerics/fv/mpsa.py:784-930): unknowns are the sub-cell displacement
+// gradients G_K (order nd^2 * #subcells).  As for MPFA, displacement continuity at the
+// continuity points, d_{K,f}.G_K[a,:] + u_{K,a} = ubar_{f,a}, holds exactly and each sub-cell has
+// nd sub-faces at the node, so G_K[a,:] = D_K^{-1}(ubar_{F_K,a} - u_{K,a} 1): the unknowns that
+// remain are the continuity-point displacements ubar_{f,a} (order nd * #subfaces: 36 instead
+// of 72 on interior Cartesian nodes, 108 instead of 216 on 24-cell tetrahedral nodes).
+//
+//   traction functional of sub-cell K on sub-face f, component i (mpsa.py:1520-1675):
+//     Tsym_{K,i}(n)  = sum_r n_r (C_K o S)[(i,r),:] vec(G_K)              own sub-cell
+//     Tasym_i(n)     = sum_r n_r  SigmaA[(i,r)],
+//     SigmaA[p]      = sum_{K'} w_{K'} (C_{K'} o !S)[p,:] vec(G_{K'})     node-volume average
+//   rows: interior stress continuity (sym parts only, mpsa.py:884-892), Neumann / Robin
+//   boundary rows incl. the asymmetric part unless eliminated (_eliminate_ncasym,
+//   mpsa.py:1932-2000), Dirichlet rows ubar = u_b; right-hand sides: cell displacements,
+//   boundary values (mpsa.py:984-1185) and, for Biot, the pressure jump n^T alpha
+//   (biot.py:969-1019).  Outputs: hook (traction from the unique side, mpsa.py:1782-1832),
+//   displacement trace (mpsa.py:760-781), and Biot's cell-row terms (biot.py:1054-1135).
+#pragma once
+#include "node_kernels.cuh"
+
+namespace pb {
+
+PB_HD int64_t mpsa_smem_doubles(int nd, int nsf, int nsc, int nb, int nalpha) {
+    const int64_t nd2 = nd * nd, n = (int64_t)nsf * nd;
+    const int64_t nrhs = (int64_t)nsc * nd + (int64_t)nb * nd + (int64_t)nalpha * nsc;
+    const int64_t W = (n + nrhs) | 1;
+    int64_t d = n * W;                          // A
+    d += (int64_t)nsc * nd2 * nd2;              // PS
+    d += (int64_t)nsc * nd2;                    // E
+    d += nd2 * (n + (int64_t)nsc * nd);         // SA | SAc
+    d += nd2 * nrhs;                            // Z
+    d += nsf;                                   // invmf
+    d += n;                                     // ipiv
+    d += (int64_t)nsf * nd;                     // nrm
+    d += 2 * (int64_t)nsc;                      // wk, volk
+    d += (int64_t)nalpha * nsc * nd2 * 2;       // NA, AE
+    int64_t ints = nsc + 3 * (int64_t)nsf + (int64_t)nsf * nd + n + (int64_t)nsc * nd + 2 * nd;
+    return d + (ints + 1) / 2 + 2;
+}
+
+// 9-index of the stored (9,9,nc) stiffness for the local (i,r) pair (2-D: rows/cols
+// 2,5,6,7,8 deleted, mpsa.py:1475-1480)
+template <int ND>
+PB_HD int c9(int i, int r) { return 3 * i + r; }
+
+// symmetric-part mask S of _split_stiffness_matrix (mpsa.py:1461-1518) in local indices
+template <int ND>
+PB_HD bool sym_mask(int p, int q) {
+    if (p == q) return true;
+    // p = (i,i), q = (a,a), i != a  <->  (0,4),(0,8),(4,0),(4,8),(8,0),(8,4) in 3-D; (0,3),(3,0) in 2-D
+    return (p % (ND + 1) == 0) && (q % (ND + 1) == 0);
+}
+
+template <int ND, class Team>
+PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaParams &prm,
+                     const MpsaOut &o, int64_t s, double *smd, int *err) {
+    constexpr int ND2 = ND * ND;
+    const int sc0 = P.node_sc_ptr[s], nsc = P.node_sc_ptr[s + 1] - sc0;
+    const int sf0 = P.node_sf_ptr[s], nsf = P.node_sf_ptr[s + 1] - sf0;
+    const int nb = P.node_nb[s];
+    if (nsf == 0) return;
+    const int nal = prm.n_alpha;
+    const int n = nsf * ND;
+    const int ncc = nsc * ND;        // cell-displacement columns
+    const int nbc = nb * ND;         // boundary-value columns
+    const int nrhs = ncc + nbc + nal * nsc;
+    const int W = (n + nrhs) | 1;
+    const int64_t nf = P.nf, nc = P.nc, nn = P.nn;
+
+    double *A = smd;
+    double *PS = A + (int64_t)n * W;            // [k][p][a][m]
+    double *E = PS + nsc * ND2 * ND2;           // [k][kappa][m]
+    double *SA = E + nsc * ND2;                 // [p][x], x < n
+    double *SAc = SA + ND2 * n;                 // [p][k*ND+a]
+    double *Z = SAc + ND2 * ncc;                // [p][c], c < nrhs
+    double *invmf = Z + ND2 * nrhs;
+    double *ipiv = invmf + nsf;
+    double *nrm = ipiv + n;                     // [u][r]  n_f / m_f
+    double *wk = nrm + nsf * ND;
+    double *volk = wk + nsc;
+    double *NA = volk + nsc;                    // [q][k][m][i]  (n_{u(k,m)}^T alpha_k)_i
+    double *AE = NA + nal * nsc * ND2;          // [q][k][a][m]  sum_kappa alpha_k[a][kappa] E_k[kappa][m]
+    int *cell = (int *)(AE + nal * nsc * ND2);
+    int *face = cell + nsc;
+    int *sides = face + nsf;
+    int *bloc = sides + nsf;
+    int *bcu = bloc + nsf;                      // [u][i]
+    int *rowidx = bcu + nsf * ND;
+    int *slot = rowidx + n;
+    int *elim = slot + nsc * ND;                // [i] neumann, [ND+i] robin
+
+    // ---- phase 1: lists
+    for (int k = t.tid(); k < nsc; k += t.size()) cell[k] = P.sc_cell[sc0 + k];
+    for (int i = t.tid(); i < nsc * ND; i += t.size()) slot[i] = P.slot_sf[(int64_t)sc0 * ND + i];
+    for (int u = t.tid(); u < nsf; u += t.size()) {
+        const int64_t f = P.sf_face[sf0 + u];
+        face[u] = (int)f;
+        sides[u] = (int)P.sf_sides[sf0 + u];
+        const int bl = P.sf_bloc[sf0 + u];
+        bloc[u] = (bl == 0xFFFF) ? -1 : bl;
+        const double im = 1.0 / (double)(P.fn_indptr[f + 1] - P.fn_indptr[f]);
+        invmf[u] = im;
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+            int code = 0;
+            if (bl != 0xFFFF) {
+                code = prm.bc[i * nf + f];
+                if (code == 0) code = 2;
+            }
+            bcu[u * ND + i] = code;
+            nrm[u * ND + i] = G.fnorm[i * nf + f] * im;
+        }
+    }
+    for (int x = t.tid(); x < n; x += t.size()) rowidx[x] = x;
+    for (int i = t.tid(); i < n * W; i += t.size()) A[i] = 0.0;
+    for (int i = t.tid(); i < ND2 * (n + ncc); i += t.size()) SA[i] = 0.0;
+    t.sync();
+
+    // ---- phase 2: per sub-cell  E = D^{-1}, weights, Biot helper products
+    for (int k = t.tid(); k < nsc; k += t.size()) {
+        const int64_t c = cell[k];
+        double xc[ND], xs[ND], D[ND][ND], Ei[ND][ND];
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+            xc[i] = G.ccent[i * nc + c];
+            xs[i] = G.nodes[i * nn + s];
+        }
+#pragma unroll
+        for (int m = 0; m < ND; ++m) {
+            const int u = slot[k * ND + m] >> 1;
+            const int64_t f = face[u];
+            const double e = (bloc[u] >= 0) ? 0.0 : prm.eta;
+#pragma unroll
+            for (int i = 0; i < ND; ++i) {
+                const double xf = G.fcent[i * nf + f];
+                D[m][i] = xf + e * (xs[i] - xf) - xc[i];
+            }
+        }
+        if (!invert_small<ND>(D, Ei)) flag_singular(err, s);
+#pragma unroll
+        for (int q = 0; q < ND; ++q)
+#pragma unroll
+            for (int m = 0; m < ND; ++m) E[k * ND2 + q * ND + m] = Ei[q][m];
+        volk[k] = G.cvol[c] / (double)P.sc_ncn[c];
+        for (int q = 0; q < nal; ++q) {
+            const double *al = prm.alpha + (int64_t)q * 9 * nc;
+            double a2[ND][ND];
+#pragma unroll
+            for (int a = 0; a < ND; ++a)
+#pragma unroll
+                for (int b = 0; b < ND; ++b) a2[a][b] = al[(3 * a + b) * nc + c];
+#pragma unroll
+            for (int m = 0; m < ND; ++m) {
+                const int u = slot[k * ND + m] >> 1;
+#pragma unroll
+                for (int i = 0; i < ND; ++i) {
+                    double v = 0.0, w = 0.0;
+#pragma unroll
+                    for (int r = 0; r < ND; ++r) {
+                        v += nrm[u * ND + r] * a2[r][i];   // (n^T alpha)_i
+                        w += a2[i][r] * Ei[r][m];          // AE[a=i][m]
+                    }
+                    NA[((q * nsc + k) * ND + m) * ND + i] = v;
+                    AE[((q * nsc + k) * ND + i) * ND + m] = w;
+                }
+            }
+        }
+    }
+    t.sync();
+    // node-volume weights w_K (mpsa.py:1619-1640) and the elimination flags
+    if (t.tid() == 0) {
+        double tot = 0.0;
+        for (int k = 0; k < nsc; ++k) tot += volk[k];
+        for (int k = 0; k < nsc; ++k) wk[k] = volk[k] / tot;
+        for (int i = 0; i < ND; ++i) {
+            int cn = 0, cr = 0;
+            for (int u = 0; u < nsf; ++u) {
+                cn += bcu[u * ND + i] == 2;
+                cr += bcu[u * ND + i] == 3;
+            }
+            elim[i] = nsc < cn;
+            elim[ND + i] = nsc < cr;
+        }
+    }
+    t.sync();
+
+    // ---- phase 3: PS[k][p][a][m] = sum_kappa (C o S)[p,(a,kappa)] E[kappa][m];
+    //               SA[p][(u,a)]  += w_k sum_kappa (C o !S)[p,(a,kappa)] E[kappa][m]
+    for (int it = t.tid(); it < nsc * ND2; it += t.size()) {
+        const int k = it / ND2, p = it - k * ND2;
+        const int64_t c = cell[k];
+        const int pi = p / ND, pr = p - pi * ND;
+        const double *Crow = prm.stiff + (int64_t)c9<ND>(pi, pr) * 9 * nc + c;  // C[p9][q9][c]
+#pragma unroll
+        for (int a = 0; a < ND; ++a) {
+            double cs[ND];
+#pragma unroll
+            for (int q = 0; q < ND; ++q)
+                cs[q] = sym_mask<ND>(p, a * ND + q) ? Crow[(int64_t)c9<ND>(a, q) * nc] : 0.0;
+#pragma unroll
+            for (int m = 0; m < ND; ++m) {
+                double v = 0.0;
+#pragma unroll
+                for (int q = 0; q < ND; ++q) v += cs[q] * E[k * ND2 + q * ND + m];
+                PS[((k * ND2 + p) * ND + a) * ND + m] = v;
+            }
+        }
+    }
+    for (int it = t.tid(); it < ND2 * ND; it += t.size()) {
+        const int p = it / ND, a = it - p * ND;
+        const int pi = p / ND, pr = p - pi * ND;
+        for (int k = 0; k < nsc; ++k) {
+            const int64_t c = cell[k];
+            const double *Crow = prm.stiff + (int64_t)c9<ND>(pi, pr) * 9 * nc + c;
+            double ca[ND];
+#pragma unroll
+            for (int q = 0; q < ND; ++q)
+                ca[q] = sym_mask<ND>(p, a * ND + q) ? 0.0 : wk[k] * Crow[(int64_t)c9<ND>(a, q) * nc];
+            double sum = 0.0;
+#pragma unroll
+            for (int m = 0; m < ND; ++m) {
+                double v = 0.0;
+#pragma unroll
+                for (int q = 0; q < ND; ++q) v += ca[q] * E[k * ND2 + q * ND + m];
+                SA[p * n + (slot[k * ND + m] >> 1) * ND + a] += v;
+                sum += v;
+            }
+            SAc[p * ncc + k * ND + a] = -sum;
+        }
+    }
+    t.sync();
+
+    // ---- phase 4: one row per (sub-face, component)
+    for (int x = t.tid(); x < n; x += t.size()) {
+        const int u = x / ND, i = x - u * ND;
+        double *row = A + (int64_t)x * W;
+        const int code = bcu[x];
+        if (code == 1) {  // Dirichlet component: ubar_{u,i} = u_b
+            row[x] = 1.0;
+            row[n + ncc + bloc[u] * ND + i] = 1.0;
+            continue;
+        }
+        const double *nu = nrm + u * ND;
+        for (int sd = 0; sd < 2; ++sd) {
+            const int side = sd == 0 ? (sides[u] & 0xFFFF) : ((sides[u] >> 16) & 0xFFFF);
+            if (side == 0xFFFF) continue;
+            const int k = side / ND;
+            const double sg = (slot[side] & 1) ? -1.0 : 1.0;
+            const double *ps = PS + (k * ND2 + i * ND) * ND2;  // [r][a][m]
+#pragma unroll
+            for (int a = 0; a < ND; ++a) {
+                double csum = 0.0;
+#pragma unroll
+                for (int m = 0; m < ND; ++m) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int r = 0; r < ND; ++r) v += nu[r] * ps[(r * ND + a) * ND + m];
+                    v *= sg;
+                    row[(slot[k * ND + m] >> 1) * ND + a] += v;
+                    csum += v;
+                }
+                row[n + k * ND + a] += csum;
+            }
+            for (int q = 0; q < nal; ++q)  // Biot pressure jump (biot.py:969-1019)
+                row[n + ncc + nbc + q * nsc + k] += sg * NA[((q * nsc + k) * ND + (side - k * ND)) * ND + i];
+            if (code != 0) {  // boundary Neumann / Robin row: asymmetric part (single side)
+                const bool el = code == 2 ? elim[i] : elim[ND + i];
+                if (!el) {
+                    for (int c = 0; c < n; ++c) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int r = 0; r < ND; ++r) v += nu[r] * SA[(i * ND + r) * n + c];
+                        row[c] += sg * v;
+                    }
+                    for (int c = 0; c < ncc; ++c) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int r = 0; r < ND; ++r) v += nu[r] * SAc[(i * ND + r) * ncc + c];
+                        row[n + c] -= sg * v;
+                    }
+                }
+            }
+        }
+        if (code == 2 || code == 3) row[n + ncc + bloc[u] * ND + i] = invmf[u];  // mpsa.py:1123-1137
+        if (code == 3) {  // Robin: + (A_f/m_f) sum_j w[i][j] ubar_{u,j}  (mpsa.py:1381-1459)
+            const int64_t f = face[u];
+            const double as = G.farea[f] * invmf[u];
+#pragma unroll
+            for (int j = 0; j < ND; ++j) {
+                const double w = prm.robw ? prm.robw[(int64_t)(i * ND + j) * nf + f] : (i == j ? 1.0 : 0.0);
+                row[u * ND + j] += as * w;
+            }
+        }
+        double sum = 0.0;
+        for (int c = 0; c < n; ++c) sum += fabs(row[c]);
+        if (!(sum > 0.0)) { flag_singular(err, s); continue; }
+        const double is = 1.0 / sum;
+        for (int c = 0; c < n + nrhs; ++c) row[c] *= is;
+    }
+    t.sync();
+
+    // ---- phase 5: solve
+    if (!gauss_jordan(t, A, n, W, nrhs, rowidx, ipiv)) {
+        if (t.tid() == 0) flag_singular(err, s);
+        t.sync();
+        return;
+    }
+
+    // ---- phase 6: Z[p][c] = SigmaA[p] applied to the solution (+ direct cell-displacement term)
+    for (int it = t.tid(); it < ND2 * nrhs; it += t.size()) {
+        const int p = it / nrhs, c = it - p * nrhs;
+        double v = (c < ncc) ? SAc[p * ncc + c] : 0.0;
+        for (int x = 0; x < n; ++x) v += SA[p * n + x] * A[(int64_t)rowidx[x] * W + n + c];
+        Z[it] = v;
+    }
+    t.sync();
+
+    // ---- phase 7: face rows (traction from the unique side, displacement trace)
+    const int32_t *pfc = P.pos_fc + P.posfc_ptr[s];
+    const int32_t *pfb = P.pos_fb + P.posfb_ptr[s];
+    for (int x = t.warp(); x < n; x += t.nwarps()) {
+        const int u = x / ND, i = x - u * ND;
+        const int side1 = sides[u] & 0xFFFF;
+        const int k1 = side1 / ND, m1 = side1 - k1 * ND;
+        const double *nu = nrm + u * ND;
+        const double *ps = PS + (k1 * ND2 + i * ND) * ND2;
+        double hs[ND][ND];  // [a][m] coefficient of ubar_{u(k1,m),a}
+        const double *xr[ND][ND];
+#pragma unroll
+        for (int a = 0; a < ND; ++a)
+#pragma unroll
+            for (int m = 0; m < ND; ++m) {
+                double v = 0.0;
+#pragma unroll
+                for (int r = 0; r < ND; ++r) v += nu[r] * ps[(r * ND + a) * ND + m];
+                hs[a][m] = v;
+                xr[a][m] = A + (int64_t)rowidx[(slot[k1 * ND + m] >> 1) * ND + a] * W + n;
+            }
+        const int code = bcu[x];
+        const bool use_asym = !((code == 2 && elim[i]) || (code == 3 && elim[ND + i]));
+        const double *xu = A + (int64_t)rowidx[x] * W + n;
+        const double im = invmf[u];
+        const int64_t f = face[u];
+        const int64_t fc0 = P.fc_indptr[f], fcl = P.fc_indptr[f + 1] - fc0;
+        const int64_t fb0 = P.fb_indptr[f], fbl = P.fb_indptr[f + 1] - fb0;
+        for (int c = t.lane(); c < nrhs; c += t.lanes()) {
+            double hk = 0.0;
+#pragma unroll
+            for (int a = 0; a < ND; ++a)
+#pragma unroll
+                for (int m = 0; m < ND; ++m) hk += hs[a][m] * xr[a][m][c];
+            if (use_asym) {
+#pragma unroll
+                for (int r = 0; r < ND; ++r) hk += nu[r] * Z[(i * ND + r) * nrhs + c];
+            }
+            const double tr = xu[c] * im;
+            if (c < ncc) {
+                const int k = c / ND, j = c - k * ND;
+                if (k == k1) {  // direct dependence of the own sub-cell's gradient on u_{k1,j}
+#pragma unroll
+                    for (int m = 0; m < ND; ++m) hk -= hs[j][m];
+                }
+                const int64_t pb = pfc[u * nsc + k];
+                const int64_t pos = ND2 * fc0 + (int64_t)i * ND * fcl + (pb - fc0) * ND + j;
+                if (o.stress) red_add(o.stress + pos, hk);
+                if (o.bdc) red_add(o.bdc + pos, tr);
+            } else if (c < ncc + nbc) {
+                const int cb = c - ncc;
+                const int b = cb / ND, j = cb - b * ND;
+                const int64_t pb = pfb[u * nb + b];
+                const int64_t pos = ND2 * fb0 + (int64_t)i * ND * fbl + (pb - fb0) * ND + j;
+                if (o.bstress) red_add(o.bstress + pos, hk);
+                if (o.bdf) red_add(o.bdf + pos, tr);
+            } else {
+                const int cq = c - ncc - nbc;
+                const int q = cq / nsc, k = cq - q * nsc;
+                if (k == k1) hk -= NA[((q * nsc + k1) * ND + m1) * ND + i];  // biot.py:853-855
+                const int64_t pb = pfc[u * nsc + k];
+                const int64_t pos = ND * fc0 + (int64_t)i * fcl + (pb - fc0);
+                if (o.sg[q]) red_add(o.sg[q] + pos, hk);
+                if (o.bdp[q]) red_add(o.bdp[q] + pos, tr);
+            }
+        }
+    }
+    // ---- phase 8 (Biot): cell rows  dv_K . G_K  (biot.py:1054-1135)
+    if (nal > 0) {
+        const int32_t *pcc = P.pos_cc + P.poscc_ptr[s];
+        const int32_t *pcb = P.pos_cb + P.poscb_ptr[s];
+        for (int it = t.warp(); it < nal * nsc; it += t.nwarps()) {
+            const int q = it / nsc, k = it - q * nsc;
+            const double *ae = AE + (q * nsc + k) * ND2;  // [a][m]
+            const double vol = volk[k];
+            const double *xr[ND][ND];
+#pragma unroll
+            for (int a = 0; a < ND; ++a)
+#pragma unroll
+                for (int m = 0; m < ND; ++m)
+                    xr[a][m] = A + (int64_t)rowidx[(slot[k * ND + m] >> 1) * ND + a] * W + n;
+            for (int c = t.lane(); c < nrhs; c += t.lanes()) {
+                double v = 0.0;
+#pragma unroll
+                for (int a = 0; a < ND; ++a)
+#pragma unroll
+                    for (int m = 0; m < ND; ++m) v += ae[a * ND + m] * xr[a][m][c];
+                if (c < ncc) {
+                    const int k2 = c / ND, j = c - k2 * ND;
+                    if (k2 == k) {
+#pragma unroll
+                        for (int m = 0; m < ND; ++m) v -= ae[j * ND + m];
+                    }
+                    if (o.dd[q]) red_add(o.dd[q] + (int64_t)pcc[k * nsc + k2] * ND + j, vol * v);
+                } else if (c < ncc + nbc) {
+                    const int cb = c - ncc;
+                    const int b = cb / ND, j = cb - b * ND;
+                    if (o.bdd[q]) red_add(o.bdd[q] + (int64_t)pcb[k * nb + b] * ND + j, vol * v);
+                } else {
+                    const int cq = c - ncc - nbc;
+                    const int q2 = cq / nsc, k2 = cq - q2 * nsc;
+                    if (q2 == q && o.cons[q]) red_add(o.cons[q] + (int64_t)pcc[k * nsc + k2], vol * v);
+                }
+            }
+        }
+    }
+    t.sync();
+}
+
+}  // namespace pb

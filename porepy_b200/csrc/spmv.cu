@@ -1,0 +1,152 @@
+// spmv.cu -- CSR SpMV / residual kernel on device-resident matrices (HBM-bandwidth bound).
+//
+// Replaces the scipy `M @ val` of AdArray.__rmatmul__ (numerics/ad/forward_mode.py:565-595)
+// and the SpMV chain of a residual-only EquationSystem.assemble
+// (numerics/ad/equation_system.py:1579-1713).  fp64 values, int32 column indices, as scipy
+// stores the reference's matrices.
+//
+// Algorithmic traffic per SpMV: 12 B per non-zero (value + column index)
+// + 20 B per row (row pointer 4, y write 8, x read 8).  A group of TPR lanes (power of two,
+// chosen from the mean row length) owns one row: the lanes read consecutive (value, index)
+// pairs (coalesced 64/128-byte segments), gather x through the read-only path, and reduce
+// with shuffles.  Grid-stride over rows, grid sized to a multiple of the 148 SMs.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/poreb200.h"
+
+extern "C" int64_t pb_launch_count(void);
+int pb_fail_(int code, const std::string &msg);   // api.cu
+void pb_count_launch_();                           // api.cu
+
+#define CUDA_TRY(x)                                                                         \
+    do {                                                                                    \
+        cudaError_t e_ = (x);                                                               \
+        if (e_ != cudaSuccess)                                                              \
+            return pb_fail_(PB_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+
+struct pb_csr {
+    int64_t nrows = 0, ncols = 0, nnz = 0;
+    int32_t *indptr = nullptr, *indices = nullptr;
+    double *data = nullptr, *x = nullptr, *y = nullptr;
+    int tpr = 8;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+template <int TPR>
+__global__ void __launch_bounds__(256)
+    csr_spmv_kernel(int64_t nrows, const int32_t *__restrict__ indptr,
+                    const int32_t *__restrict__ indices, const double *__restrict__ data,
+                    const double *__restrict__ x, double *__restrict__ y) {
+    const int lane = threadIdx.x & (TPR - 1);
+    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / TPR;
+    const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / TPR;
+    for (int64_t r = group; r < nrows; r += ngroups) {
+        const int b = __ldg(indptr + r), e = __ldg(indptr + r + 1);
+        double acc = 0.0;
+        for (int q = b + lane; q < e; q += TPR) acc += __ldg(data + q) * __ldg(x + __ldg(indices + q));
+#pragma unroll
+        for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, TPR);
+        if (lane == 0) y[r] = acc;
+    }
+}
+
+static int launch_spmv(pb_csr *a, const double *x, double *y, cudaStream_t st) {
+    const int block = 256;
+    const int64_t groups_per_block = block / a->tpr;
+    int64_t need = (a->nrows + groups_per_block - 1) / groups_per_block;
+    int64_t cap = 148LL * 8 * 4;  // 8 resident CTAs of 256 threads per SM, 4 waves
+    int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+    switch (a->tpr) {
+        case 2: csr_spmv_kernel<2><<<grid, block, 0, st>>>(a->nrows, a->indptr, a->indices, a->data, x, y); break;
+        case 4: csr_spmv_kernel<4><<<grid, block, 0, st>>>(a->nrows, a->indptr, a->indices, a->data, x, y); break;
+        case 8: csr_spmv_kernel<8><<<grid, block, 0, st>>>(a->nrows, a->indptr, a->indices, a->data, x, y); break;
+        case 16: csr_spmv_kernel<16><<<grid, block, 0, st>>>(a->nrows, a->indptr, a->indices, a->data, x, y); break;
+        default: csr_spmv_kernel<32><<<grid, block, 0, st>>>(a->nrows, a->indptr, a->indices, a->data, x, y); break;
+    }
+    pb_count_launch_();
+    CUDA_TRY(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" void pb_csr_destroy(pb_csr *a) {
+    if (!a) return;
+    cudaFree(a->indptr); cudaFree(a->indices); cudaFree(a->data); cudaFree(a->x); cudaFree(a->y);
+    if (a->e0) cudaEventDestroy(a->e0);
+    if (a->e1) cudaEventDestroy(a->e1);
+    if (a->stream) cudaStreamDestroy(a->stream);
+    delete a;
+}
+
+extern "C" int pb_csr_create(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t *indptr,
+                             const int32_t *indices, const double *data, pb_csr **out) {
+    if (!out || !indptr || (nnz > 0 && (!indices || !data)) || nrows < 0 || ncols < 0)
+        return pb_fail_(PB_EINVAL, "bad CSR arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return pb_fail_(PB_ECUDA, "no CUDA device: libporeb200 has no CPU path");
+    pb_csr *a = new pb_csr;
+    a->nrows = nrows; a->ncols = ncols; a->nnz = nnz;
+    auto bail = [&](cudaError_t e) {
+        std::string m = cudaGetErrorString(e);
+        pb_csr_destroy(a);
+        return pb_fail_(PB_ECUDA, m);
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreate(&a->e0)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreate(&a->e1)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&a->indptr, (nrows + 1) * sizeof(int32_t))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&a->indices, (nnz ? nnz : 1) * sizeof(int32_t))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&a->data, (nnz ? nnz : 1) * sizeof(double))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&a->x, (ncols ? ncols : 1) * sizeof(double))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&a->y, (nrows ? nrows : 1) * sizeof(double))) != cudaSuccess) return bail(e);
+    if ((e = cudaMemcpy(a->indptr, indptr, (nrows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
+    if (nnz) {
+        if ((e = cudaMemcpy(a->indices, indices, nnz * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
+        if ((e = cudaMemcpy(a->data, data, nnz * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
+    }
+    double mean = nrows ? (double)nnz / (double)nrows : 0.0;
+    a->tpr = mean <= 3 ? 2 : mean <= 6 ? 4 : mean <= 24 ? 8 : mean <= 48 ? 16 : 32;
+    *out = a;
+    return PB_OK;
+}
+
+extern "C" int pb_csr_spmv(pb_csr *a, const double *x, double *y) {
+    if (!a || !x || !y) return pb_fail_(PB_EINVAL, "null pointer");
+    CUDA_TRY(cudaMemcpyAsync(a->x, x, a->ncols * sizeof(double), cudaMemcpyHostToDevice, a->stream));
+    int rc = launch_spmv(a, a->x, a->y, a->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(y, a->y, a->nrows * sizeof(double), cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    return PB_OK;
+}
+
+extern "C" int pb_csr_spmv_dev(pb_csr *a, const double *x_dev, double *y_dev, uint64_t stream) {
+    if (!a || !x_dev || !y_dev) return pb_fail_(PB_EINVAL, "null pointer");
+    return launch_spmv(a, x_dev, y_dev, (cudaStream_t)stream);
+}
+
+extern "C" int pb_csr_spmv_bench(pb_csr *a, int reps, float *mean_ms) {
+    if (!a || reps < 1 || !mean_ms) return pb_fail_(PB_EINVAL, "bad arguments");
+    CUDA_TRY(cudaMemsetAsync(a->x, 0, a->ncols * sizeof(double), a->stream));
+    for (int i = 0; i < 3; ++i) {
+        int rc = launch_spmv(a, a->x, a->y, a->stream);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(a->e0, a->stream));
+    for (int i = 0; i < reps; ++i) {
+        int rc = launch_spmv(a, a->x, a->y, a->stream);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(a->e1, a->stream));
+    CUDA_TRY(cudaEventSynchronize(a->e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, a->e0, a->e1));
+    *mean_ms = ms / reps;
+    return PB_OK;
+}

@@ -1,0 +1,62 @@
+// views.hpp -- plain-pointer views of the plan / geometry / parameters that the node routines
+// index.  The same structs are filled with device pointers (api.cu) or, in the test-only kernel
+// emulation harness (tests/emu), with host pointers.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define PB_HD __host__ __device__ __forceinline__
+#else
+#define PB_HD inline
+#endif
+
+namespace pb {
+
+struct PlanView {
+    int nd;
+    int64_t nc, nf, nn;
+    const int32_t *fn_indptr;
+    const int32_t *node_sc_ptr, *sc_cell;
+    const int32_t *node_sf_ptr, *sf_face;
+    const uint32_t *sf_sides;
+    const uint16_t *sf_bloc, *slot_sf;
+    const int32_t *node_nb;
+    const int32_t *sc_ncn;
+    const int64_t *posfc_ptr, *posfb_ptr, *poscc_ptr, *poscb_ptr;
+    const int32_t *pos_fc, *pos_fb, *pos_cc, *pos_cb;
+    const int32_t *fc_indptr, *fb_indptr, *cc_indptr, *cb_indptr;
+};
+
+// geometry as pp.Grid stores it: (3, n) row-major -> component i of entity e at [i*n + e]
+struct GeoView {
+    const double *nodes, *fnorm, *fcent, *farea, *ccent, *cvol;
+};
+
+struct MpfaParams {
+    const double *perm;   // (3,3,nc)
+    const uint8_t *bc;    // nf
+    const double *robw;   // nf or null
+    double eta;
+};
+
+struct MpfaOut {
+    double *flux, *bflux, *bpc, *bpf, *vs, *bpvs;  // any may be null
+};
+
+struct MpsaParams {
+    const double *stiff;  // (9,9,nc)
+    const uint8_t *bc;    // (nd,nf)
+    const double *robw;   // (nd,nd,nf) or null
+    double eta;
+    int n_alpha;
+    const double *alpha;  // n_alpha x (3,3,nc)
+};
+
+#define PB_MAX_ALPHA 4
+struct MpsaOut {
+    double *stress, *bstress, *bdc, *bdf;
+    double *dd[PB_MAX_ALPHA], *bdd[PB_MAX_ALPHA], *sg[PB_MAX_ALPHA], *cons[PB_MAX_ALPHA],
+        *bdp[PB_MAX_ALPHA];
+};
+
+}  // namespace pb

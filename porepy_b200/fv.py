@@ -1,0 +1,478 @@
+"""Finite-volume discretizations behind PorePy's ``Discretization`` operator API, executed
+by the sm_100a kernels of libporeb200.so.
+
+Mirrors (same constructor, attribute names, matrix-dictionary keys, parameter keys and
+exceptions) of
+
+* ``pp.Mpfa``   reference src/porepy/numerics/fv/mpfa.py:29  (``discretize`` :65) with the
+  ``FVElliptic`` base (numerics/fv/fv_elliptic.py:16, ``assemble_matrix_rhs`` :67-112),
+* ``pp.Mpsa``   reference src/porepy/numerics/fv/mpsa.py:38  (``discretize`` :121,
+  ``assemble_matrix_rhs`` :486-529),
+* ``pp.Biot``   reference src/porepy/numerics/fv/biot.py:40  (``discretize`` :247).
+
+Inputs come from ``data["parameters"][keyword]``, outputs (scipy CSR) go to
+``data["discretization_matrices"][keyword][<key>]`` exactly as in the reference, so the classes
+drop into ``EquationSystem.discretize`` / the model mixins (see porepy_b200/porepy_plugin.py
+for the ``pp.ad.MpfaAd`` subclasses used when the reference is importable).
+
+There is no CPU path: without the built CUDA library or without a GPU every ``discretize``
+raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+import scipy.sparse as sps
+
+from . import _lib
+from .params import DISCRETIZATION_MATRICES, PARAMETERS
+
+
+def determine_eta(sd) -> float:
+    """numerics/fv/_fvutils.py:280-305: 1/3 on simplex grids, 0 otherwise."""
+    name = getattr(sd, "name", "")
+    if not isinstance(name, str):
+        name = " ".join(str(n) for n in name)
+    return 1.0 / 3.0 if ("TriangleGrid" in name or "TetrahedralGrid" in name) else 0.0
+
+
+def block_expand(ip: np.ndarray, ix: np.ndarray, br: int, bc: int):
+    """Expand a base pattern into br x bc blocks (row r*br+i, column c*bc+j).  The value of
+    block entry (i, j) of base entry p in base row r is stored at
+    ``br*bc*ip[r] + i*bc*len_r + (p-ip[r])*bc + j`` -- the layout the kernels scatter into."""
+    ip = ip.astype(np.int64)
+    lens = np.diff(ip)
+    new_ip = np.zeros(lens.size * br + 1, dtype=np.int64)
+    np.cumsum(np.repeat(lens * bc, br), out=new_ip[1:])
+    cols = ix.astype(np.int64)
+    if bc > 1:
+        cols = (cols[:, None] * bc + np.arange(bc, dtype=np.int64)).reshape(-1)
+    if br == 1:
+        return new_ip, cols
+    out = np.empty(new_ip[-1], dtype=np.int64)
+    rep = lens * bc
+    row_of = np.repeat(np.arange(lens.size, dtype=np.int64), rep)
+    off = np.arange(cols.size, dtype=np.int64) - np.repeat(ip[:-1] * bc, rep)
+    for i in range(br):
+        out[new_ip[row_of * br + i] + off] = cols
+    return new_ip, out
+
+
+def _index_dtype(nnz: int, ncols: int):
+    return np.int32 if max(nnz, ncols) < 2**31 - 1 else np.int64
+
+
+class DevicePlan:
+    """Device-resident sub-cell topology + output patterns of one grid (``pb_plan``).
+
+    Built once per grid topology and cached on the grid object; MPFA, MPSA and Biot share it.
+    """
+
+    def __init__(self, sd):
+        lib = _lib.load()
+        _lib.require_gpu()
+        self.lib = lib
+        if hasattr(sd, "periodic_face_map"):
+            raise NotImplementedError("periodic faces are not supported by porepy_b200")
+        if sd.dim not in (2, 3):
+            raise NotImplementedError(
+                f"porepy_b200 discretizes 2-D and 3-D grids; dim={sd.dim} (TPFA fallback of "
+                "mpfa.py:690-712) is not part of this build")
+        cf = sps.csc_matrix(sd.cell_faces)
+        fn = sps.csc_matrix(sd.face_nodes)
+        self.nd, self.nc, self.nf, self.nn = int(sd.dim), sd.num_cells, sd.num_faces, sd.num_nodes
+        cfp, cfi = cf.indptr.astype(np.int32), cf.indices.astype(np.int32)
+        cfd = np.asarray(cf.data).astype(np.int8)
+        fnp, fni = fn.indptr.astype(np.int32), fn.indices.astype(np.int32)
+        h = C.c_void_p()
+        t0 = time.perf_counter()
+        _lib.check(lib.pb_plan_create(self.nd, self.nc, self.nf, self.nn,
+                                      _lib.ptr(cfp, _lib._i32p), _lib.ptr(cfi, _lib._i32p),
+                                      _lib.ptr(cfd, _lib._i8p), _lib.ptr(fnp, _lib._i32p),
+                                      _lib.ptr(fni, _lib._i32p), C.byref(h)))
+        self.plan_seconds = time.perf_counter() - t0
+        self.h = h
+        self.fingerprint = (self.nd, self.nc, self.nf, self.nn, int(cf.nnz), int(fn.nnz))
+        self._base = {}
+        self._expanded = {}
+
+    def __del__(self):
+        h = getattr(self, "h", None)
+        if h is not None and h.value:
+            try:
+                self.lib.pb_plan_destroy(h)
+            except Exception:
+                pass
+            self.h = None
+
+    @classmethod
+    def for_grid(cls, sd) -> "DevicePlan":
+        cf, fn = sd.cell_faces, sd.face_nodes
+        fp = (int(sd.dim), sd.num_cells, sd.num_faces, sd.num_nodes, int(cf.nnz), int(fn.nnz))
+        plan = getattr(sd, "_b200_plan", None)
+        if plan is None or plan.fingerprint != fp:
+            plan = cls(sd)
+            try:
+                sd._b200_plan = plan
+            except AttributeError:
+                pass
+        plan.set_geometry(sd)
+        return plan
+
+    def set_geometry(self, sd) -> None:
+        if self.nd == 2:
+            z = np.asarray(sd.nodes)[2]
+            if np.ptp(z) > 1e-12 * max(1.0, np.abs(sd.nodes).max()):
+                raise NotImplementedError(
+                    "2-D grids must lie in the xy-plane (the rotation of mpfa.py:733-754 is "
+                    "not part of this build)")
+        arrs = [_lib.f64(a) for a in (sd.nodes, sd.face_normals, sd.face_centers, sd.face_areas,
+                                      sd.cell_centers, sd.cell_volumes)]
+        _lib.check(self.lib.pb_plan_set_geometry(self.h, *[_lib.ptr(a, _lib._f64p) for a in arrs]))
+
+    # ---- patterns
+    def base_pattern(self, which: int):
+        if which not in self._base:
+            nr, nz = C.c_int64(), C.c_int64()
+            _lib.check(self.lib.pb_plan_pattern_size(self.h, which, C.byref(nr), C.byref(nz)))
+            ip = np.zeros(nr.value + 1, np.int32)
+            ix = np.zeros(max(nz.value, 1), np.int32)
+            _lib.check(self.lib.pb_plan_pattern_get(self.h, which, _lib.ptr(ip, _lib._i32p),
+                                                    _lib.ptr(ix, _lib._i32p)))
+            self._base[which] = (ip, ix[:nz.value])
+        return self._base[which]
+
+    def nnz(self, which: int) -> int:
+        return int(self.base_pattern(which)[1].size)
+
+    def pattern(self, which: int, br: int, bc: int):
+        key = (which, br, bc)
+        if key not in self._expanded:
+            ip, ix = self.base_pattern(which)
+            if br == 1 and bc == 1:
+                self._expanded[key] = (ip, ix)
+            else:
+                nip, nix = block_expand(ip, ix, br, bc)
+                ncols = {0: self.nc, 1: self.nf, 2: self.nc, 3: self.nf}[which] * bc
+                dt = _index_dtype(int(nip[-1]), ncols)
+                self._expanded[key] = (nip.astype(dt), nix.astype(dt))
+        return self._expanded[key]
+
+    def matrix(self, which: int, br: int, bc: int, data: np.ndarray) -> sps.csr_matrix:
+        ip, ix = self.pattern(which, br, bc)
+        nrows = (ip.size - 1)
+        ncols = {0: self.nc, 1: self.nf, 2: self.nc, 3: self.nf}[which] * bc
+        m = sps.csr_matrix((data, ix, ip), shape=(nrows, ncols), copy=False)
+        m.has_sorted_indices = True
+        return m
+
+    def sizes(self) -> dict:
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        d, e = C.c_int32(), C.c_int32()
+        _lib.check(self.lib.pb_plan_sizes(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d),
+                                          C.byref(e)))
+        return dict(subcells=a.value, subfaces=b.value, subhalffaces=c.value,
+                    max_subfaces_per_node=d.value, max_subcells_per_node=e.value)
+
+    # ---- MPFA
+    def mpfa_upload(self, perm, codes, robw, eta) -> None:
+        perm = _lib.f64(perm)
+        if perm.shape != (3, 3, self.nc):
+            raise ValueError("second_order_tensor.values must have shape (3, 3, num_cells)")
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        robw = None if robw is None else _lib.f64(robw)
+        _lib.check(self.lib.pb_mpfa_upload(self.h, _lib.ptr(perm, _lib._f64p),
+                                           _lib.ptr(codes, _lib._u8p), _lib.ptr(robw, _lib._f64p),
+                                           float(eta)))
+
+    def mpfa_assemble(self, flux=True, trace=True, vector_source=True) -> float:
+        ms = C.c_float()
+        _lib.check(self.lib.pb_mpfa_assemble(self.h, int(flux), int(trace), int(vector_source),
+                                             C.byref(ms)))
+        return float(ms.value)
+
+    def mpfa_download(self, flux=True, trace=True, vector_source=True) -> dict:
+        nd = self.nd
+        nfc, nfb = self.nnz(0), self.nnz(1)
+        bufs = {
+            "flux": np.empty(nfc) if flux else None,
+            "bound_flux": np.empty(nfb) if flux else None,
+            "bound_pressure_cell": np.empty(nfc) if trace else None,
+            "bound_pressure_face": np.empty(nfb) if trace else None,
+            "vector_source": np.empty(nfc * nd) if (flux and vector_source) else None,
+            "bound_pressure_vector_source": np.empty(nfc * nd) if (trace and vector_source) else None,
+        }
+        _lib.check(self.lib.pb_mpfa_download(self.h, *[_lib.ptr(b, _lib._f64p) for b in bufs.values()]))
+        shape = {"flux": (0, 1, 1), "bound_flux": (1, 1, 1), "bound_pressure_cell": (0, 1, 1),
+                 "bound_pressure_face": (1, 1, 1), "vector_source": (0, 1, nd),
+                 "bound_pressure_vector_source": (0, 1, nd)}
+        return {k: self.matrix(*shape[k], v) for k, v in bufs.items() if v is not None}
+
+    # ---- MPSA / Biot
+    def mpsa_upload(self, stiff, codes, robw, eta, alphas=()) -> None:
+        stiff = _lib.f64(stiff)
+        if stiff.shape != (9, 9, self.nc):
+            raise ValueError("fourth_order_tensor.values must have shape (9, 9, num_cells)")
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        robw = None if robw is None else _lib.f64(robw)
+        nal = len(alphas)
+        al = None
+        if nal:
+            al = np.zeros((nal, 3, 3, self.nc))
+            for q, a in enumerate(alphas):
+                al[q] = a
+        _lib.check(self.lib.pb_mpsa_upload(self.h, _lib.ptr(stiff, _lib._f64p),
+                                           _lib.ptr(codes, _lib._u8p), _lib.ptr(robw, _lib._f64p),
+                                           float(eta), nal, _lib.ptr(al, _lib._f64p)))
+        self._nal = nal
+
+    def mpsa_assemble(self) -> float:
+        ms = C.c_float()
+        _lib.check(self.lib.pb_mpsa_assemble(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def mpsa_download(self) -> dict:
+        nd = self.nd
+        nd2 = nd * nd
+        nfc, nfb = self.nnz(0), self.nnz(1)
+        bufs = [np.empty(nfc * nd2), np.empty(nfb * nd2), np.empty(nfc * nd2), np.empty(nfb * nd2)]
+        _lib.check(self.lib.pb_mpsa_download(self.h, *[_lib.ptr(b, _lib._f64p) for b in bufs]))
+        return {
+            "stress": self.matrix(0, nd, nd, bufs[0]),
+            "bound_stress": self.matrix(1, nd, nd, bufs[1]),
+            "bound_displacement_cell": self.matrix(0, nd, nd, bufs[2]),
+            "bound_displacement_face": self.matrix(1, nd, nd, bufs[3]),
+        }
+
+    def biot_download(self, q: int) -> dict:
+        nd = self.nd
+        nfc, ncc, ncb = self.nnz(0), self.nnz(2), self.nnz(3)
+        bufs = [np.empty(ncc * nd), np.empty(ncb * nd), np.empty(nfc * nd), np.empty(ncc),
+                np.empty(nfc * nd)]
+        _lib.check(self.lib.pb_biot_download(self.h, q, *[_lib.ptr(b, _lib._f64p) for b in bufs]))
+        return {
+            "displacement_divergence": self.matrix(2, 1, nd, bufs[0]),
+            "boundary_displacement_divergence": self.matrix(3, 1, nd, bufs[1]),
+            "scalar_gradient": self.matrix(0, nd, 1, bufs[2]),
+            "mpsa_consistency": self.matrix(2, 1, 1, bufs[3]),
+            "bound_displacement_pressure": self.matrix(0, nd, 1, bufs[4]),
+        }
+
+
+# ------------------------------------------------------------------------------------------
+# boundary-condition encoding
+# ------------------------------------------------------------------------------------------
+
+
+def scalar_bc_codes(bc, nf: int) -> np.ndarray:
+    """Face codes for MPFA.  Internal (fracture) faces are Neumann (mpfa.py:1452-1454)."""
+    internal = np.asarray(getattr(bc, "is_internal", np.zeros(nf, bool)), bool)
+    codes = np.zeros(nf, np.uint8)
+    codes[np.asarray(bc.is_neu, bool) | internal] = _lib.BC_NEU
+    codes[np.asarray(bc.is_dir, bool) & ~internal] = _lib.BC_DIR
+    codes[np.asarray(bc.is_rob, bool) & ~internal] = _lib.BC_ROB
+    return codes
+
+
+def vector_bc_codes(bc, nd: int, nf: int):
+    if getattr(bc, "bc_type", "vectorial") != "vectorial":
+        raise AttributeError("MPSA must be given a vectorial boundary condition")  # mpsa.py:823
+    codes = np.zeros((nd, nf), np.uint8)
+    codes[np.asarray(bc.is_neu, bool)[:nd]] = _lib.BC_NEU
+    codes[np.asarray(bc.is_dir, bool)[:nd]] = _lib.BC_DIR
+    codes[np.asarray(bc.is_rob, bool)[:nd]] = _lib.BC_ROB
+    basis = getattr(bc, "basis", None)
+    if basis is not None:
+        b = np.asarray(basis, float)
+        if b.ndim == 3 and not np.allclose(b[:nd, :nd], np.eye(nd)[:, :, None]):
+            raise NotImplementedError("rotated boundary bases (bc.basis) are not supported yet")
+    robw = None
+    if np.any(codes == _lib.BC_ROB):
+        rw = np.asarray(bc.robin_weight, float)
+        robw = np.ascontiguousarray(rw[:nd, :nd])
+    return codes, robw
+
+
+# ------------------------------------------------------------------------------------------
+# discretization classes
+# ------------------------------------------------------------------------------------------
+
+
+class _Base:
+    """numerics/discretization.py:12-121."""
+
+    def __init__(self, keyword: str) -> None:
+        self.keyword = keyword
+        self.last_timing: dict = {}
+
+    def _key(self) -> str:
+        return self.keyword + "_"
+
+    def update_discretization(self, sd, data: dict) -> None:
+        """numerics/discretization.py:54.  The reference re-discretizes only around
+        ``specified_cells/faces/nodes``; a full pass on the GPU is cheaper than the bookkeeping,
+        and gives the same matrices."""
+        self.discretize(sd, data)
+
+    def _check_unsupported(self, params: dict) -> None:
+        pa = params.get("partition_arguments")
+        # partition_arguments bound the reference's working set; the kernels stream over nodes
+        # and never materialise the global block-diagonal inverse, so the key is accepted and ignored.
+        del pa
+
+
+class Mpfa(_Base):
+    """MPFA-O flux discretization; see module docstring.  Matrix keys as fv_elliptic.py:29-53."""
+
+    def __init__(self, keyword: str) -> None:
+        super().__init__(keyword)
+        self.flux_matrix_key = "flux"
+        self.bound_flux_matrix_key = "bound_flux"
+        self.bound_pressure_cell_matrix_key = "bound_pressure_cell"
+        self.bound_pressure_face_matrix_key = "bound_pressure_face"
+        self.vector_source_matrix_key = "vector_source"
+        self.bound_pressure_vector_source_matrix_key = "bound_pressure_vector_source"
+
+    def ndof(self, sd) -> int:
+        return sd.num_cells
+
+    def discretize(self, sd, data: dict) -> None:
+        """mpfa.py:65.  Reads ``second_order_tensor``, ``bc``, optional ``mpfa_eta`` and
+        ``ambient_dimension``; writes the six matrices of mpfa.py:496-508."""
+        params = data[PARAMETERS][self.keyword]
+        mats = data.setdefault(DISCRETIZATION_MATRICES, {}).setdefault(self.keyword, {})
+        k = params["second_order_tensor"]
+        bc = params["bc"]
+        eta = params.get("mpfa_eta", None)
+        if eta is None:
+            eta = determine_eta(sd)
+        if np.asarray(eta).size != 1:
+            raise NotImplementedError("sub-face valued mpfa_eta is not supported")
+        amb = params.get("ambient_dimension", sd.dim)
+        if amb != sd.dim:
+            raise NotImplementedError("ambient_dimension != sd.dim is not supported")
+        if np.asarray(bc.is_dir).shape[-1] != sd.num_faces:
+            raise NotImplementedError("sub-face boundary conditions are not supported")
+        self._check_unsupported(params)
+        t0 = time.perf_counter()
+        plan = DevicePlan.for_grid(sd)
+        codes = scalar_bc_codes(bc, sd.num_faces)
+        robw = np.asarray(bc.robin_weight, float) if np.any(codes == _lib.BC_ROB) else None
+        t1 = time.perf_counter()
+        plan.mpfa_upload(k.values, codes, robw, float(np.asarray(eta).ravel()[0]))
+        t2 = time.perf_counter()
+        ms = plan.mpfa_assemble()
+        t3 = time.perf_counter()
+        out = plan.mpfa_download()
+        t4 = time.perf_counter()
+        mats.update(out)
+        self.last_timing = dict(plan_s=t1 - t0, upload_s=t2 - t1, kernel_ms=ms,
+                                assemble_s=t3 - t2, download_s=t4 - t3)
+
+    def assemble_matrix_rhs(self, sd, data: dict):
+        """fv_elliptic.py:67-112: A = div @ flux, b = -div @ bound_flux @ bc_values
+        (- div @ vector_source_discr @ vector_source)."""
+        mats = data[DISCRETIZATION_MATRICES][self.keyword]
+        params = data[PARAMETERS][self.keyword]
+        div = sd.divergence(dim=1)
+        matrix = div @ mats[self.flux_matrix_key]
+        rhs = -div @ (mats[self.bound_flux_matrix_key] @ params["bc_values"])
+        if "vector_source" in params:
+            rhs -= div @ (mats[self.vector_source_matrix_key] @ params["vector_source"])
+        return matrix, rhs
+
+
+class Mpsa(_Base):
+    """MPSA-W stress discretization; see module docstring.  Matrix keys as mpsa.py:82-95."""
+
+    def __init__(self, keyword: str) -> None:
+        super().__init__(keyword)
+        self.stress_matrix_key = "stress"
+        self.bound_stress_matrix_key = "bound_stress"
+        self.bound_displacement_cell_matrix_key = "bound_displacement_cell"
+        self.bound_displacement_face_matrix_key = "bound_displacement_face"
+
+    def ndof(self, sd) -> int:
+        return sd.dim * sd.num_cells
+
+    def _alphas(self, sd, params):
+        return {}
+
+    def discretize(self, sd, data: dict) -> None:
+        """mpsa.py:121 (and biot.py:247 through ``_alphas``).  Reads ``fourth_order_tensor``,
+        ``bc`` (vectorial), optional ``mpsa_eta``."""
+        params = data[PARAMETERS][self.keyword]
+        mats = data.setdefault(DISCRETIZATION_MATRICES, {}).setdefault(self.keyword, {})
+        constit = params["fourth_order_tensor"]
+        bc = params["bc"]
+        eta = params.get("mpsa_eta", None)
+        if eta is None:
+            eta = determine_eta(sd)
+        hf_eta = params.get("reconstruction_eta", None)
+        if hf_eta is not None and hf_eta != eta:
+            raise NotImplementedError("reconstruction_eta != mpsa_eta is not supported")
+        if np.asarray(bc.is_dir).shape[-1] != sd.num_faces:
+            raise NotImplementedError("sub-face boundary conditions are not supported")
+        self._check_unsupported(params)
+        alphas = self._alphas(sd, params)
+        t0 = time.perf_counter()
+        plan = DevicePlan.for_grid(sd)
+        codes, robw = vector_bc_codes(bc, sd.dim, sd.num_faces)
+        t1 = time.perf_counter()
+        plan.mpsa_upload(constit.values, codes, robw, float(eta), list(alphas.values()))
+        t2 = time.perf_counter()
+        ms = plan.mpsa_assemble()
+        t3 = time.perf_counter()
+        out = plan.mpsa_download()
+        if alphas:
+            coupled = {k: {} for k in ("displacement_divergence", "boundary_displacement_divergence",
+                                       "scalar_gradient", "mpsa_consistency",
+                                       "bound_displacement_pressure")}
+            for q, key in enumerate(alphas):
+                for name, m in plan.biot_download(q).items():
+                    coupled[name][key] = m
+            out.update(coupled)
+        t4 = time.perf_counter()
+        mats.update(out)
+        self.last_timing = dict(plan_s=t1 - t0, upload_s=t2 - t1, kernel_ms=ms,
+                                assemble_s=t3 - t2, download_s=t4 - t3)
+
+    def assemble_matrix_rhs(self, sd, data: dict):
+        """mpsa.py:486-529."""
+        mats = data[DISCRETIZATION_MATRICES][self.keyword]
+        params = data[PARAMETERS][self.keyword]
+        div = sd.divergence(dim=sd.dim)
+        matrix = div @ mats["stress"]
+        rhs = -div @ (mats["bound_stress"] @ params["bc_values"]) + params["source"]
+        return matrix, rhs
+
+
+class Biot(Mpsa):
+    """MPSA + Biot coupling terms (biot.py:40; keys :94-111, dict-valued per coupling keyword)."""
+
+    def __init__(self, keyword: str = "mechanics") -> None:
+        super().__init__(keyword)
+        self.displacement_divergence_matrix_key = "displacement_divergence"
+        self.bound_displacement_divergence_matrix_key = "boundary_displacement_divergence"
+        self.scalar_gradient_matrix_key = "scalar_gradient"
+        self.consistency_matrix_key = "mpsa_consistency"
+        self.bound_pressure_matrix_key = "bound_displacement_pressure"
+
+    def _alphas(self, sd, params):
+        out = {}
+        for key, a in params["scalar_vector_mappings"].items():
+            if isinstance(a, (float, int, np.floating, np.integer)):
+                v = np.zeros((3, 3, sd.num_cells))
+                v[0, 0] = v[1, 1] = v[2, 2] = float(a)  # biot.py:312-321
+            else:
+                v = np.asarray(a.values, float)
+            out[key] = v
+        if len(out) > 4:
+            raise NotImplementedError("at most 4 coupling tensors per Biot discretization")
+        return out
+
+    def assemble_matrix_rhs(self, sd, data: dict):
+        """biot.py:125-149."""
+        raise NotImplementedError("This class cannot be used for assembly.\nUse the ad version instead")

@@ -1,0 +1,63 @@
+"""Device-resident CSR matrix with the SpMV the Newton residual / Krylov loop needs.
+
+Replaces the scipy ``M @ val`` of ``AdArray.__rmatmul__`` (reference
+src/porepy/numerics/ad/forward_mode.py:565-595) for matrices kept in HBM."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sps
+
+from . import _lib
+
+
+class DeviceCsr:
+    def __init__(self, a):
+        lib = _lib.load()
+        _lib.require_gpu()
+        a = sps.csr_matrix(a)
+        a.sort_indices()
+        if a.nnz >= 2**31:
+            raise ValueError("matrix too large for int32 indices")
+        self.shape = a.shape
+        self.nnz = int(a.nnz)
+        ip = a.indptr.astype(np.int32)
+        ix = a.indices.astype(np.int32)
+        da = np.ascontiguousarray(a.data, np.float64)
+        h = C.c_void_p()
+        _lib.check(lib.pb_csr_create(a.shape[0], a.shape[1], a.nnz, _lib.ptr(ip, _lib._i32p),
+                                     _lib.ptr(ix, _lib._i32p), _lib.ptr(da, _lib._f64p), C.byref(h)))
+        self.h = h
+        self.lib = lib
+
+    def __del__(self):
+        h = getattr(self, "h", None)
+        if h is not None and h.value:
+            try:
+                self.lib.pb_csr_destroy(h)
+            except Exception:
+                pass
+            self.h = None
+
+    def __matmul__(self, x):
+        x = _lib.f64(x)
+        if x.shape != (self.shape[1],):
+            raise ValueError("dimension mismatch")
+        y = np.empty(self.shape[0])
+        _lib.check(self.lib.pb_csr_spmv(self.h, _lib.ptr(x, _lib._f64p), _lib.ptr(y, _lib._f64p)))
+        return y
+
+    def spmv_device(self, x_ptr: int, y_ptr: int, stream: int = 0) -> None:
+        """y = A x on raw device pointers (e.g. ``torch.Tensor.data_ptr()``)."""
+        _lib.check(self.lib.pb_csr_spmv_dev(self.h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), stream))
+
+    def bench(self, reps: int = 50) -> float:
+        """Mean device milliseconds per SpMV (CUDA events on the launching stream)."""
+        ms = C.c_float()
+        _lib.check(self.lib.pb_csr_spmv_bench(self.h, reps, C.byref(ms)))
+        return float(ms.value)
+
+    def algorithmic_bytes(self) -> int:
+        """12 B per non-zero + 20 B per row."""
+        return 12 * self.nnz + 20 * self.shape[0]

@@ -1,0 +1,124 @@
+// emu.cpp -- TEST INFRASTRUCTURE ONLY: runs the *same* per-node routines the CUDA kernels
+// run (porepy_b200/csrc/node_kernels.cuh) on the host with a 1-thread team, so the arithmetic
+// and the plan indexing can be checked against the oracle / golden fixtures on a box without a
+// GPU.  Built by tests/emu_binding.py with g++ into tests/emu/_emu.so; the product
+// (porepy_b200, libporeb200.so) never builds, links or loads it.
+#include <climits>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../porepy_b200/csrc/node_kernels.cuh"
+#include "../../porepy_b200/csrc/plan_host.hpp"
+#if __has_include("../../porepy_b200/csrc/mpsa_node.cuh")
+#include "../../porepy_b200/csrc/mpsa_node.cuh"
+#define HAVE_MPSA 1
+#endif
+
+using namespace pb;
+
+struct Emu {
+    HostPlan P;
+    std::string err;
+};
+
+static PlanView view_of(const HostPlan &P) {
+    PlanView v;
+    v.nd = P.nd; v.nc = P.nc; v.nf = P.nf; v.nn = P.nn;
+    v.fn_indptr = P.fn_indptr.data();
+    v.node_sc_ptr = P.node_sc_ptr.data(); v.sc_cell = P.sc_cell.data();
+    v.node_sf_ptr = P.node_sf_ptr.data(); v.sf_face = P.sf_face.data();
+    v.sf_sides = P.sf_sides.data(); v.sf_bloc = P.sf_bloc.data(); v.slot_sf = P.slot_sf.data();
+    v.node_nb = P.node_nb.data(); v.sc_ncn = P.sc_ncn.data();
+    v.posfc_ptr = P.posfc_ptr.data(); v.posfb_ptr = P.posfb_ptr.data();
+    v.poscc_ptr = P.poscc_ptr.data(); v.poscb_ptr = P.poscb_ptr.data();
+    v.pos_fc = P.pos_fc.data(); v.pos_fb = P.pos_fb.data();
+    v.pos_cc = P.pos_cc.data(); v.pos_cb = P.pos_cb.data();
+    v.fc_indptr = P.pat[0].indptr.data(); v.fb_indptr = P.pat[1].indptr.data();
+    v.cc_indptr = P.pat[2].indptr.data(); v.cb_indptr = P.pat[3].indptr.data();
+    return v;
+}
+
+extern "C" {
+
+int emu_create(int nd, int64_t nc, int64_t nf, int64_t nn, const int32_t *cf_indptr,
+               const int32_t *cf_indices, const int8_t *cf_data, const int32_t *fn_indptr,
+               const int32_t *fn_indices, void **out) {
+    Emu *e = new Emu;
+    int rc = build_host_plan(nd, nc, nf, nn, cf_indptr, cf_indices, cf_data, fn_indptr, fn_indices,
+                             e->P, e->err);
+    if (rc) { fprintf(stderr, "emu_create: %s\n", e->err.c_str()); delete e; return rc; }
+    *out = e;
+    return 0;
+}
+void emu_destroy(void *h) { delete (Emu *)h; }
+
+int emu_pattern_size(void *h, int which, int64_t *nrows, int64_t *nnz) {
+    Emu *e = (Emu *)h;
+    *nrows = e->P.pat[which].nrows;
+    *nnz = e->P.pat[which].nnz();
+    return 0;
+}
+int emu_pattern_get(void *h, int which, int32_t *indptr, int32_t *indices) {
+    Emu *e = (Emu *)h;
+    const Csr &c = e->P.pat[which];
+    std::copy(c.indptr.begin(), c.indptr.end(), indptr);
+    std::copy(c.indices.begin(), c.indices.end(), indices);
+    return 0;
+}
+
+int emu_mpfa(void *h, const double *nodes, const double *fnorm, const double *fcent,
+             const double *farea, const double *ccent, const double *cvol, const double *perm,
+             const uint8_t *bc, const double *robw, double eta, double *flux, double *bflux,
+             double *bpc, double *bpf, double *vs, double *bpvs) {
+    Emu *e = (Emu *)h;
+    PlanView P = view_of(e->P);
+    GeoView G{nodes, fnorm, fcent, farea, ccent, cvol};
+    MpfaParams prm{perm, bc, robw, eta};
+    MpfaOut o{flux, bflux, bpc, bpf, vs, bpvs};
+    int err = INT_MAX;
+    int64_t need = 0;
+    for (int64_t s = 0; s < P.nn; ++s) {
+        int nsc = P.node_sc_ptr[s + 1] - P.node_sc_ptr[s], nsf = P.node_sf_ptr[s + 1] - P.node_sf_ptr[s];
+        need = std::max(need, mpfa_smem_doubles(P.nd, nsf, nsc, P.node_nb[s]));
+    }
+    std::vector<double> sm(need + 8);
+    CpuTeam t;
+    for (int64_t s = 0; s < P.nn; ++s) {
+        if (P.nd == 3) mpfa_node<3>(t, P, G, prm, o, s, sm.data(), &err);
+        else mpfa_node<2>(t, P, G, prm, o, s, sm.data(), &err);
+    }
+    return err == INT_MAX ? 0 : 2;
+}
+
+#ifdef HAVE_MPSA
+int emu_mpsa(void *h, const double *nodes, const double *fnorm, const double *fcent,
+             const double *farea, const double *ccent, const double *cvol, const double *stiff,
+             const uint8_t *bc, const double *robw, double eta, int n_alpha, const double *alpha,
+             double *stress, double *bstress, double *bdc, double *bdf, double **dd, double **bdd,
+             double **sg, double **cons, double **bdp) {
+    Emu *e = (Emu *)h;
+    PlanView P = view_of(e->P);
+    GeoView G{nodes, fnorm, fcent, farea, ccent, cvol};
+    MpsaParams prm{stiff, bc, robw, eta, n_alpha, alpha};
+    MpsaOut o{};
+    o.stress = stress; o.bstress = bstress; o.bdc = bdc; o.bdf = bdf;
+    for (int a = 0; a < n_alpha; ++a) {
+        o.dd[a] = dd[a]; o.bdd[a] = bdd[a]; o.sg[a] = sg[a]; o.cons[a] = cons[a]; o.bdp[a] = bdp[a];
+    }
+    int err = INT_MAX;
+    int64_t need = 0;
+    for (int64_t s = 0; s < P.nn; ++s) {
+        int nsc = P.node_sc_ptr[s + 1] - P.node_sc_ptr[s], nsf = P.node_sf_ptr[s + 1] - P.node_sf_ptr[s];
+        need = std::max(need, mpsa_smem_doubles(P.nd, nsf, nsc, P.node_nb[s], n_alpha));
+    }
+    std::vector<double> sm(need + 8);
+    CpuTeam t;
+    for (int64_t s = 0; s < P.nn; ++s) {
+        if (P.nd == 3) mpsa_node<3>(t, P, G, prm, o, s, sm.data(), &err);
+        else mpsa_node<2>(t, P, G, prm, o, s, sm.data(), &err);
+    }
+    return err == INT_MAX ? 0 : 2;
+}
+#endif
+}

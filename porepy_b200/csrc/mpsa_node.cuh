@@ -322,22 +322,48 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
     const int32_t *pfb = P.pos_fb + P.posfb_ptr[s];
     for (int x = t.warp(); x < n; x += t.nwarps()) {
         const int u = x / ND, i = x - u * ND;
-        const int side1 = sides[u] & 0xFFFF;
-        const int k1 = side1 / ND, m1 = side1 - k1 * ND;
+        // The reference takes the traction from the side with the smaller cell index
+        // (mpsa.py:1782-1832).  Traction continuity makes both sides agree; evaluate from the
+        // softer side, which is the well-conditioned one in the continuity-point formulation
+        // (see the MPFA routine).
         const double *nu = nrm + u * ND;
-        const double *ps = PS + (k1 * ND2 + i * ND) * ND2;
+        int side1 = sides[u] & 0xFFFF;
         double hs[ND][ND];  // [a][m] coefficient of ubar_{u(k1,m),a}
+        {
+            const int side2 = (sides[u] >> 16) & 0xFFFF;
+            double nrm1 = 0.0, nrm2 = 0.0, h2[ND][ND];
+            const double *ps1 = PS + ((side1 / ND) * ND2 + i * ND) * ND2;
+            const double *ps2 = PS + ((side2 == 0xFFFF ? 0 : side2 / ND) * ND2 + i * ND) * ND2;
+#pragma unroll
+            for (int a = 0; a < ND; ++a)
+#pragma unroll
+                for (int m = 0; m < ND; ++m) {
+                    double v = 0.0, w = 0.0;
+#pragma unroll
+                    for (int r = 0; r < ND; ++r) {
+                        v += nu[r] * ps1[(r * ND + a) * ND + m];
+                        w += nu[r] * ps2[(r * ND + a) * ND + m];
+                    }
+                    hs[a][m] = v;
+                    h2[a][m] = w;
+                    nrm1 += fabs(v);
+                    nrm2 += fabs(w);
+                }
+            if (side2 != 0xFFFF && nrm2 < nrm1) {
+                side1 = side2;
+#pragma unroll
+                for (int a = 0; a < ND; ++a)
+#pragma unroll
+                    for (int m = 0; m < ND; ++m) hs[a][m] = h2[a][m];
+            }
+        }
+        const int k1 = side1 / ND, m1 = side1 - k1 * ND;
         const double *xr[ND][ND];
 #pragma unroll
         for (int a = 0; a < ND; ++a)
 #pragma unroll
-            for (int m = 0; m < ND; ++m) {
-                double v = 0.0;
-#pragma unroll
-                for (int r = 0; r < ND; ++r) v += nu[r] * ps[(r * ND + a) * ND + m];
-                hs[a][m] = v;
+            for (int m = 0; m < ND; ++m)
                 xr[a][m] = A + (int64_t)rowidx[(slot[k1 * ND + m] >> 1) * ND + a] * W + n;
-            }
         const int code = bcu[x];
         const bool use_asym = !((code == 2 && elim[i]) || (code == 3 && elim[ND + i]));
         const double *xu = A + (int64_t)rowidx[x] * W + n;

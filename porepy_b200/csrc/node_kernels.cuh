@@ -320,7 +320,24 @@ PB_HD void mpfa_node(Team &t, const PlanView &P, const GeoView &G, const MpfaPar
     const int32_t *pfc = P.pos_fc + P.posfc_ptr[s];
     const int32_t *pfb = P.pos_fb + P.posfb_ptr[s];
     for (int u = t.warp(); u < nsf; u += t.nwarps()) {
-        const int side1 = sides[u] & 0xFFFF;  // unique side = smaller cell index (_fvutils.py:163)
+        // The reference takes the flux from the side with the smaller cell index
+        // (_fvutils.py:163).  Flux continuity makes both sides give the same number; in the
+        // continuity-point formulation the side with the SMALLER transmissibilities is the
+        // well-conditioned one (on the high-permeability side the gradient is a difference
+        // of nearly equal pressures), so evaluate from that side.
+        int side1 = sides[u] & 0xFFFF;
+        {
+            const int side2 = (sides[u] >> 16) & 0xFFFF;
+            if (side2 != 0xFFFF) {
+                double n1 = 0.0, n2 = 0.0;
+#pragma unroll
+                for (int m2 = 0; m2 < ND; ++m2) {
+                    n1 += fabs(Tk[side1 * ND + m2]);
+                    n2 += fabs(Tk[side2 * ND + m2]);
+                }
+                if (n2 < n1) side1 = side2;
+            }
+        }
         const int k1 = side1 / ND, m1 = side1 - k1 * ND;
         const double *T1 = Tk + k1 * ND * ND + m1 * ND;
         const double *R1 = Rk + k1 * ND * ND + m1 * ND;

@@ -1,0 +1,152 @@
+"""Sharding of one grid's interaction regions across GPUs (one process per GPU).
+
+The assembly needs no data-path collective: interaction regions (nodes) are independent and a
+face row is complete as soon as all nodes of the face have been processed.  The decomposition
+is the reference's own memory-splitting scheme (``_fvutils.subproblems``, reference
+src/porepy/numerics/fv/_fvutils.py:414-539; overlap rows removed by
+``remove_nonlocal_contribution`` :542, mpfa.py:301-304) with the simplification that every face
+row is produced by exactly one shard (no averaging over repeated faces, mpfa.py:357-372):
+
+* cells are partitioned (coordinate slabs, the structured analogue of
+  ``pp.partition.partition``, grids/partition.py:269);
+* shard p takes the NODES of its cells and every cell touching those nodes (one halo layer):
+  all interaction regions of the faces of its own cells are then complete;
+* shard p keeps the rows of the faces of its own cells; a face shared by two shards is kept
+  by the lower rank.  Cell rows (Biot's divergence-type terms) are kept for own cells.
+
+``Shard.to_global`` maps the kept rows into global numbering; concatenating (summing) the
+shards' matrices reproduces the unsplit discretization (tests/test_shard*.py; parity with
+applications/test_utils/common_xpfa_tests.py:832-957 "split == unsplit").
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import scipy.sparse as sps
+
+from .grid import Grid
+
+
+def partition_cells(g, nparts: int, axis: int | None = None) -> np.ndarray:
+    """Equal-count coordinate slabs.  Returns part id per cell."""
+    cc = np.asarray(g.cell_centers)
+    if axis is None:
+        axis = int(np.argmax(np.ptp(cc, axis=1)))
+    order = np.argsort(cc[axis], kind="stable")
+    part = np.empty(g.num_cells, dtype=np.int64)
+    bounds = np.linspace(0, g.num_cells, nparts + 1).astype(np.int64)
+    for p in range(nparts):
+        part[order[bounds[p]:bounds[p + 1]]] = p
+    return part
+
+
+@dataclass
+class Shard:
+    rank: int
+    grid: Grid              # local sub-grid (own cells + one halo layer)
+    cells: np.ndarray       # local -> global cell
+    faces: np.ndarray       # local -> global face
+    nodes: np.ndarray       # local -> global node
+    own_cell: np.ndarray    # bool per local cell
+    own_face: np.ndarray    # bool per local face: rows this shard keeps
+    cut_face: np.ndarray    # bool per local face: artificial boundary of the overlap
+    num_global: tuple       # (nc, nf, nn) of the global grid
+
+    def restrict_cell_array(self, a: np.ndarray) -> np.ndarray:
+        """(..., nc_global) -> (..., nc_local)."""
+        return np.ascontiguousarray(a[..., self.cells])
+
+    def restrict_face_array(self, a: np.ndarray) -> np.ndarray:
+        return np.ascontiguousarray(a[..., self.faces])
+
+    def to_global(self, m, rows: str, cols: str, br: int = 1, bc: int = 1) -> sps.csr_matrix:
+        """Embed a local matrix into global numbering, keeping only this shard's rows.
+        rows/cols in {"face", "cell"}; br/bc = block sizes (nd for vector quantities)."""
+        nc, nf, _ = self.num_global
+        rmap, rkeep, nr = (self.faces, self.own_face, nf) if rows == "face" else (self.cells, self.own_cell, nc)
+        cmap, ncg = (self.faces, nf) if cols == "face" else (self.cells, nc)
+        m = sps.coo_matrix(m)
+        lr, li = np.divmod(m.row, br)
+        lc, lj = np.divmod(m.col, bc)
+        keep = rkeep[lr]
+        return sps.coo_matrix((m.data[keep], (rmap[lr[keep]] * br + li[keep], cmap[lc[keep]] * bc + lj[keep])),
+                              shape=(nr * br, ncg * bc)).tocsr()
+
+
+def extract_shard(g, part: np.ndarray, rank: int) -> Shard:
+    cf = sps.csc_matrix(g.cell_faces)
+    fn = sps.csc_matrix(g.face_nodes)
+    nc, nf, nn = g.num_cells, g.num_faces, g.num_nodes
+    own = part == rank
+    # nodes of own cells
+    cell_nodes = (abs(fn) @ abs(cf)).tocsc()  # nn x nc
+    cell_nodes.data[:] = 1
+    own_nodes = np.zeros(nn, bool)
+    own_nodes[np.unique(cell_nodes[:, np.flatnonzero(own)].indices)] = True
+    # all cells touching an own node
+    touch = np.asarray((cell_nodes.T @ own_nodes.astype(np.float64))).ravel() > 0
+    cells = np.flatnonzero(touch)
+    sub_cf = cf[:, cells]
+    faces = np.unique(sub_cf.indices)
+    sub_cf = sub_cf.tocsr()[faces].tocsc()
+    sub_fn = fn[:, faces]
+    nodes = np.unique(sub_fn.indices)
+    sub_fn = sub_fn.tocsr()[nodes].tocsc()
+    # keep the stored node order inside each face (face_nodes column order defines sub-face ids)
+    fn_sorted = sps.csc_matrix(fn)
+    lg = Grid(g.dim, np.asarray(g.nodes)[:, nodes], sub_fn, sub_cf, name=getattr(g, "name", "Grid"))
+    lg.set_geometry(np.asarray(g.face_normals)[:, faces], np.asarray(g.face_centers)[:, faces],
+                    np.asarray(g.face_areas)[faces], np.asarray(g.cell_centers)[:, cells],
+                    np.asarray(g.cell_volumes)[cells])
+    del fn_sorted
+    glob_bnd = np.zeros(nf, bool)
+    glob_bnd[g.get_all_boundary_faces()] = True
+    loc_single = np.asarray(abs(lg.cell_faces).sum(axis=1)).ravel() == 1
+    cut = loc_single & ~glob_bnd[faces]
+    if "fracture_faces" in g.tags:
+        lg.tags["fracture_faces"] = np.asarray(g.tags["fracture_faces"], bool)[faces]
+    lg.tags["domain_boundary_faces"] = loc_single & ~lg.tags["fracture_faces"]
+    own_cell = own[cells]
+    # faces of own cells; shared faces go to the lower rank
+    acf = abs(cf).tocsr()
+    face_min_part = np.full(nf, np.iinfo(np.int64).max)
+    coo = acf.tocoo()
+    np.minimum.at(face_min_part, coo.row, part[coo.col])
+    own_face_glob = np.zeros(nf, bool)
+    own_face_glob[np.unique(cf[:, np.flatnonzero(own)].indices)] = True
+    own_face_glob &= face_min_part == rank
+    return Shard(rank, lg, cells, faces, nodes, own_cell, own_face_glob[faces], cut, (nc, nf, nn))
+
+
+def restrict_scalar_bc(bc, shard: Shard):
+    """Boundary condition of the sub-grid: the global flags on true boundary faces, Neumann on
+    the artificial cut faces (their rows are discarded; cf. Mpfa._bc_for_subgrid, mpfa.py:1580)."""
+    from types import SimpleNamespace
+    f = shard.faces
+    out = SimpleNamespace(bc_type="scalar", num_faces=f.size)
+    out.is_dir = np.asarray(bc.is_dir, bool)[f].copy()
+    out.is_rob = np.asarray(bc.is_rob, bool)[f].copy()
+    out.is_neu = np.asarray(bc.is_neu, bool)[f].copy()
+    out.is_internal = np.asarray(getattr(bc, "is_internal", np.zeros(bc.is_dir.shape[-1], bool)), bool)[f].copy()
+    out.robin_weight = np.asarray(bc.robin_weight, float)[f].copy()
+    out.is_dir[shard.cut_face] = False
+    out.is_rob[shard.cut_face] = False
+    out.is_neu[shard.cut_face] = True
+    return out
+
+
+def restrict_vector_bc(bc, shard: Shard):
+    from types import SimpleNamespace
+    f = shard.faces
+    out = SimpleNamespace(bc_type="vectorial", num_faces=f.size)
+    out.is_dir = np.asarray(bc.is_dir, bool)[:, f].copy()
+    out.is_rob = np.asarray(bc.is_rob, bool)[:, f].copy()
+    out.is_neu = np.asarray(bc.is_neu, bool)[:, f].copy()
+    out.is_internal = np.asarray(bc.is_internal, bool)[f].copy()
+    out.robin_weight = np.asarray(bc.robin_weight, float)[:, :, f].copy()
+    out.basis = np.asarray(bc.basis, float)[:, :, f].copy()
+    out.is_dir[:, shard.cut_face] = False
+    out.is_rob[:, shard.cut_face] = False
+    out.is_neu[:, shard.cut_face] = True
+    return out

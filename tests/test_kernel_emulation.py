@@ -20,6 +20,13 @@ def test_mpfa_node_routine(name):
     out = p.mpfa(c.raw["K"], scalar_codes(c.bc, c.g.num_faces), c.bc.robin_weight, c.eta)
     err, key = max_rel_err(c.mats, out)
     assert err < TOL, (key, err)
+    # the solved problem (incl. the kappa = 1e+-6 contrast case): relative 2-norm
+    import scipy.sparse.linalg as spla
+    div = c.g.divergence(1)
+    A = div @ out["flux"]
+    b = -div @ (out["bound_flux"] @ c.raw["bc_values"])
+    sol = spla.spsolve(sps.csc_matrix(A), b)
+    assert np.linalg.norm(sol - c.raw["solution"]) <= 1e-9 * np.linalg.norm(c.raw["solution"])
 
 
 @pytest.mark.parametrize("name", case_names("mpsa_") + case_names("biot_"))

@@ -62,6 +62,11 @@ int pb_set_device(int device);
 /* kernels launched by this library since load (bench.py's gpu_launches evidence). */
 int64_t pb_launch_count(void);
 
+/* Page-locked host buffers for the CSR value arrays the *_download calls fill (full PCIe rate;
+ * pageable NumPy buffers go through the driver's staging copies).  The caller frees them. */
+int pb_host_alloc(uint64_t bytes, void **out);
+void pb_host_free(void *p);
+
 /* ---- plan: sub-cell topology + output patterns --------------------------------------- */
 /* Replaces _fvutils.SubcellTopology.__init__ (numerics/fv/_fvutils.py:51-172), the
  * sub-face pairing (:163-172, pair_over_subfaces :183-216), cell_node_blocks /
@@ -83,6 +88,13 @@ int pb_plan_sizes(const pb_plan *p, int64_t *num_subcells, int64_t *num_subfaces
 /* base pattern `which` (PB_PAT_*): nrows and nnz; then copy indptr (nrows+1) / indices (nnz). */
 int pb_plan_pattern_size(const pb_plan *p, int which, int64_t *nrows, int64_t *nnz);
 int pb_plan_pattern_get(const pb_plan *p, int which, int32_t *indptr, int32_t *indices);
+
+/* Block expansion of base pattern `which` into br x bc blocks (row r*br+i, column c*bc+j), built
+ * on the device and copied to the caller's buffers: indptr (nrows*br+1), indices (br*bc*nnz).
+ * The value of block entry (i,j) of base entry q of base row r lives at
+ * br*bc*indptr[r] + i*bc*len_r + (q-indptr[r])*bc + j -- the layout the kernels scatter into.
+ * PB_ENOTIMPL when br*bc*nnz does not fit int32. */
+int pb_plan_pattern_expanded(pb_plan *p, int which, int br, int bc, int32_t *indptr, int32_t *indices);
 
 /* Geometry the path reads from pp.Grid (grids/grid.py:32): nodes (3 x nn), face_normals /
  * face_centers (3 x nf), cell_centers (3 x nc) row-major as numpy stores them; face_areas (nf),

@@ -27,12 +27,15 @@ _SIGNATURES = {
     "pb_device_count": (C.c_int, []),
     "pb_set_device": (C.c_int, [C.c_int]),
     "pb_launch_count": (C.c_int64, []),
+    "pb_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
+    "pb_host_free": (None, [C.c_void_p]),
     "pb_plan_create": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, _i32p, _i32p, _i8p,
                                  _i32p, _i32p, C.POINTER(C.c_void_p)]),
     "pb_plan_destroy": (None, [C.c_void_p]),
     "pb_plan_sizes": (C.c_int, [C.c_void_p, _i64p, _i64p, _i64p, _i32p, _i32p]),
     "pb_plan_pattern_size": (C.c_int, [C.c_void_p, C.c_int, _i64p, _i64p]),
     "pb_plan_pattern_get": (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p]),
+    "pb_plan_pattern_expanded": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _i32p, _i32p]),
     "pb_plan_set_geometry": (C.c_int, [C.c_void_p] + [_f64p] * 6),
     "pb_mpfa_upload": (C.c_int, [C.c_void_p, _f64p, _u8p, _f64p, C.c_double]),
     "pb_mpfa_assemble": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _f32p]),
@@ -105,3 +108,41 @@ def require_gpu() -> None:
     lib = load()
     if lib.pb_device_count() < 1:
         raise RuntimeError("porepy_b200: no CUDA device visible and there is no CPU fallback")
+
+
+# ------------------------------------------------------------------------------------------
+# page-locked host buffers (pooled: cudaHostAlloc is slow, discretize() is called repeatedly)
+# ------------------------------------------------------------------------------------------
+import weakref  # noqa: E402
+
+_POOL: dict = {}
+_POOL_BYTES = [0]
+_POOL_CAP = int(os.environ.get("POREB200_PINNED_POOL_BYTES", 64 << 30))
+
+
+def _release(ptr: int, nbytes: int) -> None:
+    if _lib is None:
+        return
+    if _POOL_BYTES[0] + nbytes <= _POOL_CAP:
+        _POOL.setdefault(nbytes, []).append(ptr)
+        _POOL_BYTES[0] += nbytes
+    else:
+        _lib.pb_host_free(C.c_void_p(ptr))
+
+
+def pinned_empty(n: int, dtype=np.float64) -> np.ndarray:
+    """Uninitialised 1-D array in page-locked host memory; returned to a pool when the array
+    (and every view of it, e.g. a scipy matrix's ``data``) is garbage collected."""
+    lib = load()
+    nbytes = max(int(n) * np.dtype(dtype).itemsize, 8)
+    free = _POOL.get(nbytes)
+    if free:
+        ptr = free.pop()
+        _POOL_BYTES[0] -= nbytes
+    else:
+        out = C.c_void_p()
+        check(lib.pb_host_alloc(nbytes, C.byref(out)))
+        ptr = out.value
+    buf = (C.c_char * nbytes).from_address(ptr)
+    weakref.finalize(buf, _release, ptr, nbytes)
+    return np.frombuffer(buf, dtype=dtype, count=int(n))

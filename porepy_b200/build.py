@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libporeb200.so")
 SOURCES = ["api.cu", "spmv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-Xcompiler", "-fopenmp"]
 
 
 def _nvcc() -> str:
@@ -42,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         subprocess.check_call(cmd)
         objs.append(obj)
     subprocess.check_call([_nvcc(), "-shared", "-o", LIB, *objs, "-gencode",
-                           "arch=compute_100a,code=sm_100a"])
+                           "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fopenmp", "-lgomp"])
     return LIB
 
 

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -50,6 +51,15 @@ extern "C" int pb_set_device(int device) {
     return PB_OK;
 }
 
+extern "C" int pb_host_alloc(uint64_t bytes, void **out) {
+    if (!out) return fail(PB_EINVAL, "null pointer");
+    CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 8, cudaHostAllocDefault));
+    return PB_OK;
+}
+extern "C" void pb_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 // ------------------------------------------------------------------------------------
 // device buffers
 // ------------------------------------------------------------------------------------
@@ -87,10 +97,33 @@ struct DevBuf {
     T *as() const { return (T *)p; }
 };
 
+// Solver configurations (node_kernels.cuh).  A node goes to the first one that fits.
+using Cfg0 = RegGJ<1, 12, 2, 4>;   // team 32  : MPFA hexahedral nodes (12 x 45)
+using Cfg1 = RegGJ<4, 9, 2, 4>;    // team 128 : MPSA hexahedral nodes (36 x 61)
+using Cfg2 = RegGJ<4, 9, 3, 3>;    // team 128 : Biot hexahedral nodes
+using Cfg3 = RegGJ<4, 10, 5, 3>;   // team 128 : MPFA tetrahedral nodes (36 x 133)
+using Cfg4 = RegGJ<8, 14, 6, 1>;   // team 256 : MPSA tetrahedral nodes (108 x 181)
+using Cfg5 = RegGJ<16, 7, 8, 1>;   // team 512 : Biot tetrahedral nodes
+using Cfg6 = SmemGJ;               // team 256 : anything else (in-memory Gauss-Jordan)
+using Cfg7 = RegGJ<12, 9, 6, 1>;   // team 384 : alternative for cfg 4 (POREB200_CFG4=384)
+struct SolverCfg { int team, max_n, max_w; };
+static const SolverCfg kCfg[] = {
+    {Cfg0::team, Cfg0::max_n, Cfg0::max_w}, {Cfg1::team, Cfg1::max_n, Cfg1::max_w},
+    {Cfg2::team, Cfg2::max_n, Cfg2::max_w}, {Cfg3::team, Cfg3::max_n, Cfg3::max_w},
+    {Cfg4::team, Cfg4::max_n, Cfg4::max_w}, {Cfg5::team, Cfg5::max_n, Cfg5::max_w},
+    {Cfg6::team, 1 << 30, 1 << 30},         {Cfg7::team, Cfg7::max_n, Cfg7::max_w},
+};
+static const int kNumCfg = 8;      // cfg 6 is the catch-all; 7 only by request
+static const int kCatchAll = 6;
+
 struct NodeClass {
+    int cfg = 0;
     int team = 32;
     int n = 0;
-    int64_t smem_doubles = 0;  // per team
+    bool a_global = false;     // A lives in a global-memory workspace (does not fit shared memory)
+    int64_t a_doubles = 0;     // per team
+    int64_t rest_doubles = 0;  // per team
+    int64_t scr_doubles = 0;   // per team (solver scratch, first in the team's region)
     DevBuf nodes;
 };
 
@@ -107,7 +140,7 @@ struct pb_plan {
     bool have_geo = false;
     PlanView view{};
     GeoView geo{};
-    DevBuf err;
+    DevBuf err, a_ws;
     // mpfa
     std::vector<NodeClass> mpfa_cls;
     DevBuf perm, bc, robw;
@@ -131,32 +164,43 @@ struct pb_plan {
 // ------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------
-template <int ND, int TEAM>
-__global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM)
+// shared memory of one team: [solver scratch | index lists, sub-cell products ... | A]
+template <int ND, class Solver>
+__global__ void __launch_bounds__(Solver::team == 32 ? 128 : Solver::team, Solver::min_blocks)
     mpfa_kernel(PlanView P, GeoView G, MpfaParams prm, MpfaOut o, const int32_t *__restrict__ nodes,
-                int n_nodes, int smem_doubles, int *err) {
+                int n_nodes, int scr_doubles, int rest_doubles, int a_doubles, double *a_ws, int *err) {
     extern __shared__ double smem[];
+    constexpr int TEAM = Solver::team;
     GpuTeam<TEAM> t;
     const int teams_per_block = blockDim.x / TEAM;
     const int team_in_block = threadIdx.x / TEAM;
-    double *smd = smem + (size_t)team_in_block * smem_doubles;
+    double *scratch = smem;
+    if (TEAM == 32) scratch += (size_t)team_in_block * (scr_doubles + rest_doubles + (a_ws ? 0 : a_doubles));
+    double *rest = scratch + scr_doubles;
+    double *A = a_ws ? a_ws + ((size_t)blockIdx.x * teams_per_block + team_in_block) * a_doubles
+                     : rest + rest_doubles;
     for (int i = blockIdx.x * teams_per_block + team_in_block; i < n_nodes;
          i += gridDim.x * teams_per_block)
-        mpfa_node<ND>(t, P, G, prm, o, (int64_t)nodes[i], smd, err);
+        mpfa_node<ND, Solver>(t, P, G, prm, o, (int64_t)nodes[i], A, rest, scratch, err);
 }
 
-template <int ND, int TEAM>
-__global__ void __launch_bounds__(TEAM == 32 ? 128 : TEAM)
+template <int ND, class Solver>
+__global__ void __launch_bounds__(Solver::team == 32 ? 128 : Solver::team, Solver::min_blocks)
     mpsa_kernel(PlanView P, GeoView G, MpsaParams prm, MpsaOut o, const int32_t *__restrict__ nodes,
-                int n_nodes, int smem_doubles, int *err) {
+                int n_nodes, int scr_doubles, int rest_doubles, int a_doubles, double *a_ws, int *err) {
     extern __shared__ double smem[];
+    constexpr int TEAM = Solver::team;
     GpuTeam<TEAM> t;
     const int teams_per_block = blockDim.x / TEAM;
     const int team_in_block = threadIdx.x / TEAM;
-    double *smd = smem + (size_t)team_in_block * smem_doubles;
+    double *scratch = smem;
+    if (TEAM == 32) scratch += (size_t)team_in_block * (scr_doubles + rest_doubles + (a_ws ? 0 : a_doubles));
+    double *rest = scratch + scr_doubles;
+    double *A = a_ws ? a_ws + ((size_t)blockIdx.x * teams_per_block + team_in_block) * a_doubles
+                     : rest + rest_doubles;
     for (int i = blockIdx.x * teams_per_block + team_in_block; i < n_nodes;
          i += gridDim.x * teams_per_block)
-        mpsa_node<ND>(t, P, G, prm, o, (int64_t)nodes[i], smd, err);
+        mpsa_node<ND, Solver>(t, P, G, prm, o, (int64_t)nodes[i], A, rest, scratch, err);
 }
 
 static const size_t kMaxSmem = 227 * 1024;
@@ -165,41 +209,111 @@ static const int kSMs = 148;
 // ------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------
-static int team_for(int n_unknowns) {
-    if (n_unknowns <= 16) return 32;
-    if (n_unknowns <= 40) return 64;
-    if (n_unknowns <= 80) return 128;
-    return 256;
+static int64_t cfg_scratch(int cfg, int n) {
+    switch (cfg) {
+        case 0: return Cfg0::scratch_doubles_c();
+        case 1: return Cfg1::scratch_doubles_c();
+        case 2: return Cfg2::scratch_doubles_c();
+        case 3: return Cfg3::scratch_doubles_c();
+        case 4: return Cfg4::scratch_doubles_c();
+        case 5: return Cfg5::scratch_doubles_c();
+        case 7: return Cfg7::scratch_doubles_c();
+        default: return n;
+    }
 }
 
+// size_of(nsf, nsc, nb, &n, &w, &a_doubles, &rest_doubles)
 template <class F>
-static int build_classes(pb_plan *p, std::vector<NodeClass> &out, int unknowns_per_sf, F smem_of) {
+static int build_classes(pb_plan *p, std::vector<NodeClass> &out, F size_of) {
     const HostPlan &H = p->H;
-    const int teams[4] = {32, 64, 128, 256};
-    std::vector<int32_t> lists[4];
-    int64_t smem[4] = {0, 0, 0, 0};
+    const char *alt = getenv("POREB200_CFG4");
+    const bool use7 = alt && atoi(alt) == 384;
+    // key: cfg*2 + a_global
+    std::vector<int32_t> lists[2 * kNumCfg];
+    int64_t amax[2 * kNumCfg] = {0}, rmax[2 * kNumCfg] = {0}, smax[2 * kNumCfg] = {0};
     for (int64_t s = 0; s < H.nn; ++s) {
         int nsc = H.node_sc_ptr[s + 1] - H.node_sc_ptr[s];
         int nsf = H.node_sf_ptr[s + 1] - H.node_sf_ptr[s];
         if (nsf == 0) continue;
-        int t = team_for(nsf * unknowns_per_sf);
-        int ci = t == 32 ? 0 : t == 64 ? 1 : t == 128 ? 2 : 3;
-        int64_t need = smem_of(nsf, nsc, H.node_nb[s]);
-        // small teams share a CTA 4-ways: move up a class when 4 teams would not fit
-        while (ci < 3 && need * 8 * (teams[ci] == 32 ? 4 : 1) > (int64_t)kMaxSmem) ++ci;
-        lists[ci].push_back((int32_t)s);
-        smem[ci] = std::max(smem[ci], need);
+        int n = 0, w = 0;
+        int64_t a = 0, r = 0;
+        size_of(nsf, nsc, H.node_nb[s], &n, &w, &a, &r);
+        int cfg = 0;
+        while (cfg < kCatchAll && (n > kCfg[cfg].max_n || w > kCfg[cfg].max_w)) ++cfg;
+        if (cfg == 4 && use7 && n <= kCfg[7].max_n && w <= kCfg[7].max_w) cfg = 7;
+        const int64_t scr = cfg_scratch(cfg, n);
+        const int tpb = kCfg[cfg].team == 32 ? 4 : 1;
+        bool glob = (size_t)(a + r + scr) * 8 * tpb > kMaxSmem;
+        if (glob && (size_t)(r + scr) * 8 * tpb > kMaxSmem)
+            return fail(PB_ENOTIMPL, "interaction region at node " + std::to_string(s) +
+                                         " is too large for this build (" + std::to_string(nsf) +
+                                         " sub-faces)");
+        int key = cfg * 2 + (glob ? 1 : 0);
+        lists[key].push_back((int32_t)s);
+        amax[key] = std::max(amax[key], a);
+        rmax[key] = std::max(rmax[key], r);
+        smax[key] = std::max(smax[key], scr);
     }
     out.clear();
-    for (int ci = 0; ci < 4; ++ci) {
-        if (lists[ci].empty()) continue;
+    for (int key = 0; key < 2 * kNumCfg; ++key) {
+        if (lists[key].empty()) continue;
         out.emplace_back();
         NodeClass &c = out.back();
-        c.team = teams[ci];
-        c.n = (int)lists[ci].size();
-        c.smem_doubles = smem[ci];
-        if (c.nodes.upload(lists[ci], p->stream) != cudaSuccess) return fail(PB_ECUDA, "upload of node list failed");
+        c.cfg = key / 2;
+        c.a_global = key & 1;
+        c.team = kCfg[c.cfg].team;
+        c.n = (int)lists[key].size();
+        c.a_doubles = amax[key];
+        c.rest_doubles = rmax[key];
+        c.scr_doubles = smax[key];
+        if (!c.a_global) {
+            // the class maxima of A and of the rest may come from different nodes
+            const int tpb = c.team == 32 ? 4 : 1;
+            if ((size_t)(c.a_doubles + c.rest_doubles + c.scr_doubles) * 8 * tpb > kMaxSmem) c.a_global = true;
+        }
+        if (c.nodes.upload(lists[key], p->stream) != cudaSuccess) return fail(PB_ECUDA, "upload of node list failed");
     }
+    return PB_OK;
+}
+
+// launch one class with kernel template KERNEL<ND, Solver>
+#define PB_LAUNCH_CFG(KERNEL, ND, ...)                                              \
+    switch (c.cfg) {                                                                \
+        case 0: rc = launch_one(KERNEL<ND, Cfg0>, c, p, __VA_ARGS__); break;        \
+        case 1: rc = launch_one(KERNEL<ND, Cfg1>, c, p, __VA_ARGS__); break;        \
+        case 2: rc = launch_one(KERNEL<ND, Cfg2>, c, p, __VA_ARGS__); break;        \
+        case 3: rc = launch_one(KERNEL<ND, Cfg3>, c, p, __VA_ARGS__); break;        \
+        case 4: rc = launch_one(KERNEL<ND, Cfg4>, c, p, __VA_ARGS__); break;        \
+        case 5: rc = launch_one(KERNEL<ND, Cfg5>, c, p, __VA_ARGS__); break;        \
+        case 7: rc = launch_one(KERNEL<ND, Cfg7>, c, p, __VA_ARGS__); break;        \
+        default: rc = launch_one(KERNEL<ND, Cfg6>, c, p, __VA_ARGS__); break;       \
+    }
+
+template <class K, class Prm, class Out>
+static int launch_one(K kernel, const NodeClass &c, pb_plan *p, const Prm &prm, const Out &o) {
+    const int blk = c.team == 32 ? 128 : c.team;
+    const int tpb = blk / c.team;
+    const size_t smem = (size_t)(c.scr_doubles + c.rest_doubles + (c.a_global ? 0 : c.a_doubles)) *
+                        sizeof(double) * tpb;
+    if (smem > kMaxSmem)
+        return fail(PB_ENOTIMPL, "interaction region needs " + std::to_string(smem) +
+                                     " B of shared memory (> 227 KB)");
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, blk, smem));
+    if (per_sm < 1) per_sm = 1;
+    int64_t need = ((int64_t)c.n + tpb - 1) / tpb;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)kSMs * per_sm));
+    double *ws = nullptr;
+    if (c.a_global) {
+        CUDA_TRY(p->a_ws.ensure((size_t)grid * tpb * c.a_doubles * sizeof(double)));
+        ws = p->a_ws.as<double>();
+    }
+    kernel<<<grid, blk, smem, p->stream>>>(p->view, p->geo, prm, o, c.nodes.as<int32_t>(), c.n,
+                                           (int)c.scr_doubles, (int)c.rest_doubles,
+                                           (int)c.a_doubles, ws, p->err.as<int>());
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
     return PB_OK;
 }
 
@@ -255,8 +369,12 @@ extern "C" int pb_plan_create(int nd, int64_t nc, int64_t nf, int64_t nn, const 
     v.pos_cc = p->pos_cc.as<int32_t>(); v.pos_cb = p->pos_cb.as<int32_t>();
     v.fc_indptr = p->fc_indptr.as<int32_t>(); v.fb_indptr = p->fb_indptr.as<int32_t>();
     v.cc_indptr = p->cc_indptr.as<int32_t>(); v.cb_indptr = p->cb_indptr.as<int32_t>();
-    rc = build_classes(p, p->mpfa_cls, 1,
-                       [&](int nsf, int nsc, int nb) { return mpfa_smem_doubles(nd, nsf, nsc, nb); });
+    rc = build_classes(p, p->mpfa_cls, [&](int nsf, int nsc, int nb, int *n, int *w, int64_t *a, int64_t *r) {
+        *n = nsf;
+        *w = mpfa_width(nd, nsf, nsc, nb);
+        *a = mpfa_A_doubles(nd, nsf, nsc, nb);
+        *r = mpfa_rest_doubles(nd, nsf, nsc, nb);
+    });
     if (rc) { delete p; return rc; }
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail("sync", e);
     *out = p;
@@ -295,6 +413,55 @@ extern "C" int pb_plan_pattern_get(const pb_plan *p, int which, int32_t *indptr,
     const Csr &c = p->H.pat[which];
     std::copy(c.indptr.begin(), c.indptr.end(), indptr);
     std::copy(c.indices.begin(), c.indices.end(), indices);
+    return PB_OK;
+}
+
+// one warp per base row; lanes run over the row's expanded entries (coalesced stores)
+__global__ void expand_pattern_kernel(int64_t nrows, const int32_t *__restrict__ ip,
+                                      const int32_t *__restrict__ ix, int br, int bc,
+                                      int32_t *__restrict__ nip, int32_t *__restrict__ nix) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < nrows; r += nwarps) {
+        const int64_t b = ip[r], len = ip[r + 1] - b;
+        const int64_t base = (int64_t)br * bc * b, rowlen = len * bc;
+        for (int i = 0; i < br; ++i) {
+            if (lane == 0) nip[r * br + i] = (int32_t)(base + i * rowlen);
+            for (int64_t t = lane; t < rowlen; t += 32) {
+                const int64_t q = t / bc;
+                const int j = (int)(t - q * bc);
+                nix[base + i * rowlen + t] = ix[b + q] * bc + j;
+            }
+        }
+    }
+    if (warp == 0 && lane == 0) nip[nrows * br] = (int32_t)((int64_t)br * bc * ip[nrows]);
+}
+
+extern "C" int pb_plan_pattern_expanded(pb_plan *p, int which, int br, int bc, int32_t *indptr,
+                                        int32_t *indices) {
+    if (!p || which < 0 || which > 3 || br < 1 || bc < 1 || !indptr || !indices)
+        return fail(PB_EINVAL, "bad arguments");
+    const Csr &c = p->H.pat[which];
+    const int64_t nnz = c.nnz() * br * bc;
+    if (nnz >= 0x7FFFFFFFll || c.ncols * bc >= 0x7FFFFFFFll)
+        return fail(PB_ENOTIMPL, "expanded pattern does not fit int32 indices");
+    DevBuf *bip = which == 0 ? &p->fc_indptr : which == 1 ? &p->fb_indptr : which == 2 ? &p->cc_indptr : &p->cb_indptr;
+    DevBuf dix, nip, nix;
+    cudaStream_t st = p->stream;
+    CUDA_TRY(dix.upload(c.indices, st));
+    CUDA_TRY(nip.ensure((c.nrows * br + 1) * sizeof(int32_t)));
+    CUDA_TRY(nix.ensure((nnz ? nnz : 1) * sizeof(int32_t)));
+    const int block = 256;
+    int64_t need = (c.nrows * 32 + block - 1) / block;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)kSMs * 16));
+    expand_pattern_kernel<<<grid, block, 0, st>>>(c.nrows, bip->as<int32_t>(), dix.as<int32_t>(), br, bc,
+                                                  nip.as<int32_t>(), nix.as<int32_t>());
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(indptr, nip.p, (c.nrows * br + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (nnz) CUDA_TRY(cudaMemcpyAsync(indices, nix.p, nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return PB_OK;
 }
 
@@ -380,42 +547,7 @@ extern "C" int pb_mpfa_assemble(pb_plan *p, int want_flux, int want_trace, int w
                    p->have_robw ? p->robw.as<double>() : nullptr, p->eta};
     for (const NodeClass &c : p->mpfa_cls) {
         int rc = PB_OK;
-        int *err = p->err.as<int>();
-        auto go = [&](auto kernel) {
-            const int team = c.team;
-            const int blk = team == 32 ? 128 : team;
-            const int tpb = blk / team;
-            const size_t smem = (size_t)c.smem_doubles * sizeof(double) * tpb;
-            if (smem > kMaxSmem)
-                return fail(PB_ENOTIMPL, "interaction region needs " + std::to_string(smem) +
-                                             " B of shared memory (> 227 KB)");
-            CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int per_sm = 1;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, blk, smem));
-            if (per_sm < 1) per_sm = 1;
-            int64_t need = ((int64_t)c.n + tpb - 1) / tpb;
-            int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)kSMs * per_sm));
-            kernel<<<grid, blk, smem, st>>>(p->view, p->geo, prm, o, c.nodes.as<int32_t>(), c.n,
-                                            (int)c.smem_doubles, err);
-            g_launches++;
-            CUDA_TRY(cudaGetLastError());
-            return (int)PB_OK;
-        };
-        if (nd == 3) {
-            switch (c.team) {
-                case 32: rc = go(mpfa_kernel<3, 32>); break;
-                case 64: rc = go(mpfa_kernel<3, 64>); break;
-                case 128: rc = go(mpfa_kernel<3, 128>); break;
-                default: rc = go(mpfa_kernel<3, 256>); break;
-            }
-        } else {
-            switch (c.team) {
-                case 32: rc = go(mpfa_kernel<2, 32>); break;
-                case 64: rc = go(mpfa_kernel<2, 64>); break;
-                case 128: rc = go(mpfa_kernel<2, 128>); break;
-                default: rc = go(mpfa_kernel<2, 256>); break;
-            }
-        }
+        if (nd == 3) { PB_LAUNCH_CFG(mpfa_kernel, 3, prm, o) } else { PB_LAUNCH_CFG(mpfa_kernel, 2, prm, o) }
         if (rc) return rc;
     }
     CUDA_TRY(cudaEventRecord(p->e1, st));
@@ -468,8 +600,12 @@ extern "C" int pb_mpsa_upload(pb_plan *p, const double *stiffness, const uint8_t
     p->n_alpha = n_alpha;
     p->veta = eta;
     if (p->mpsa_cls_nalpha != n_alpha) {
-        int rc = build_classes(p, p->mpsa_cls, nd, [&](int nsf, int nsc, int nb) {
-            return mpsa_smem_doubles(nd, nsf, nsc, nb, n_alpha);
+        int rc = build_classes(p, p->mpsa_cls, [&](int nsf, int nsc, int nb, int *n, int *w, int64_t *a,
+                                                   int64_t *r) {
+            *n = nsf * nd;
+            *w = mpsa_width(nd, nsf, nsc, nb, n_alpha);
+            *a = mpsa_A_doubles(nd, nsf, nsc, nb, n_alpha);
+            *r = mpsa_rest_doubles(nd, nsf, nsc, nb, n_alpha);
         });
         if (rc) return rc;
         p->mpsa_cls_nalpha = n_alpha;
@@ -510,44 +646,9 @@ extern "C" int pb_mpsa_assemble(pb_plan *p, float *ms) {
     MpsaParams prm{p->stiff.as<double>(), p->vbc.as<uint8_t>(),
                    p->have_vrobw ? p->vrobw.as<double>() : nullptr, p->veta, p->n_alpha,
                    p->n_alpha ? p->alpha.as<double>() : nullptr};
-    int *err = p->err.as<int>();
     for (const NodeClass &c : p->mpsa_cls) {
-        auto go = [&](auto kernel) {
-            const int team = c.team;
-            const int blk = team == 32 ? 128 : team;
-            const int tpb = blk / team;
-            const size_t smem = (size_t)c.smem_doubles * sizeof(double) * tpb;
-            if (smem > kMaxSmem)
-                return fail(PB_ENOTIMPL, "interaction region needs " + std::to_string(smem) +
-                                             " B of shared memory (> 227 KB)");
-            CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int per_sm = 1;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, blk, smem));
-            if (per_sm < 1) per_sm = 1;
-            int64_t need = ((int64_t)c.n + tpb - 1) / tpb;
-            int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)kSMs * per_sm));
-            kernel<<<grid, blk, smem, st>>>(p->view, p->geo, prm, o, c.nodes.as<int32_t>(), c.n,
-                                            (int)c.smem_doubles, err);
-            g_launches++;
-            CUDA_TRY(cudaGetLastError());
-            return (int)PB_OK;
-        };
-        int rc;
-        if (nd == 3) {
-            switch (c.team) {
-                case 32: rc = go(mpsa_kernel<3, 32>); break;
-                case 64: rc = go(mpsa_kernel<3, 64>); break;
-                case 128: rc = go(mpsa_kernel<3, 128>); break;
-                default: rc = go(mpsa_kernel<3, 256>); break;
-            }
-        } else {
-            switch (c.team) {
-                case 32: rc = go(mpsa_kernel<2, 32>); break;
-                case 64: rc = go(mpsa_kernel<2, 64>); break;
-                case 128: rc = go(mpsa_kernel<2, 128>); break;
-                default: rc = go(mpsa_kernel<2, 256>); break;
-            }
-        }
+        int rc = PB_OK;
+        if (nd == 3) { PB_LAUNCH_CFG(mpsa_kernel, 3, prm, o) } else { PB_LAUNCH_CFG(mpsa_kernel, 2, prm, o) }
         if (rc) return rc;
     }
     CUDA_TRY(cudaEventRecord(p->e1, st));

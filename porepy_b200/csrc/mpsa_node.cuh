@@ -22,17 +22,20 @@
 
 namespace pb {
 
-PB_HD int64_t mpsa_smem_doubles(int nd, int nsf, int nsc, int nb, int nalpha) {
+PB_HD int mpsa_width(int nd, int nsf, int nsc, int nb, int nalpha) {
+    return (nsf * nd + nsc * nd + nb * nd + nalpha * nsc) | 1;
+}
+PB_HD int64_t mpsa_A_doubles(int nd, int nsf, int nsc, int nb, int nalpha) {
+    return (int64_t)nsf * nd * mpsa_width(nd, nsf, nsc, nb, nalpha);
+}
+PB_HD int64_t mpsa_rest_doubles(int nd, int nsf, int nsc, int nb, int nalpha) {
     const int64_t nd2 = nd * nd, n = (int64_t)nsf * nd;
     const int64_t nrhs = (int64_t)nsc * nd + (int64_t)nb * nd + (int64_t)nalpha * nsc;
-    const int64_t W = (n + nrhs) | 1;
-    int64_t d = n * W;                          // A
-    d += (int64_t)nsc * nd2 * nd2;              // PS
+    int64_t d = (int64_t)nsc * nd2 * nd2;       // PS
     d += (int64_t)nsc * nd2;                    // E
     d += nd2 * (n + (int64_t)nsc * nd);         // SA | SAc
     d += nd2 * nrhs;                            // Z
     d += nsf;                                   // invmf
-    d += n;                                     // ipiv
     d += (int64_t)nsf * nd;                     // nrm
     d += 2 * (int64_t)nsc;                      // wk, volk
     d += (int64_t)nalpha * nsc * nd2 * 2;       // NA, AE
@@ -53,9 +56,9 @@ PB_HD bool sym_mask(int p, int q) {
     return (p % (ND + 1) == 0) && (q % (ND + 1) == 0);
 }
 
-template <int ND, class Team>
+template <int ND, class Solver, class Team>
 PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaParams &prm,
-                     const MpsaOut &o, int64_t s, double *smd, int *err) {
+                     const MpsaOut &o, int64_t s, double *A, double *smd, double *scratch, int *err) {
     constexpr int ND2 = ND * ND;
     const int sc0 = P.node_sc_ptr[s], nsc = P.node_sc_ptr[s + 1] - sc0;
     const int sf0 = P.node_sf_ptr[s], nsf = P.node_sf_ptr[s + 1] - sf0;
@@ -69,15 +72,13 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
     const int W = (n + nrhs) | 1;
     const int64_t nf = P.nf, nc = P.nc, nn = P.nn;
 
-    double *A = smd;
-    double *PS = A + (int64_t)n * W;            // [k][p][a][m]
+    double *PS = smd;                           // [k][p][a][m]
     double *E = PS + nsc * ND2 * ND2;           // [k][kappa][m]
     double *SA = E + nsc * ND2;                 // [p][x], x < n
     double *SAc = SA + ND2 * n;                 // [p][k*ND+a]
     double *Z = SAc + ND2 * ncc;                // [p][c], c < nrhs
     double *invmf = Z + ND2 * nrhs;
-    double *ipiv = invmf + nsf;
-    double *nrm = ipiv + n;                     // [u][r]  n_f / m_f
+    double *nrm = invmf + nsf;                  // [u][r]  n_f / m_f
     double *wk = nrm + nsf * ND;
     double *volk = wk + nsc;
     double *NA = volk + nsc;                    // [q][k][m][i]  (n_{u(k,m)}^T alpha_k)_i
@@ -302,7 +303,7 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
     t.sync();
 
     // ---- phase 5: solve
-    if (!gauss_jordan(t, A, n, W, nrhs, rowidx, ipiv)) {
+    if (!Solver::solve(t, A, n, W, nrhs, rowidx, scratch)) {
         if (t.tid() == 0) flag_singular(err, s);
         t.sync();
         return;

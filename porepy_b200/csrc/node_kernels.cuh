@@ -133,6 +133,158 @@ PB_HD bool gauss_jordan(Team &t, double *A, int n, int W, int nrhs, int *rowidx,
     return ok;
 }
 
+// Solver policies.  `solve` leaves X(p, c) = A[rowidx[p]*W + n + c].
+struct SmemGJ {
+    // Gauss-Jordan directly on the shared (or global) memory copy of A: works for any size
+    // and on the host (kernel emulation); the slow path on the GPU.
+    static constexpr int team = 256;
+    static constexpr int min_blocks = 1;
+    static PB_HD int64_t scratch_doubles(int n) { return n; }
+    template <class Team>
+    static PB_HD bool solve(Team &t, double *A, int n, int W, int nrhs, int *rowidx, double *scratch) {
+        return gauss_jordan(t, A, n, W, nrhs, rowidx, scratch);
+    }
+};
+
+#if defined(__CUDACC__)
+// Register-tiled Gauss-Jordan.  The team is TR warps; warp w owns the rows {w + TR*x}, lane l
+// the columns {l + 32*y}: every thread keeps an RL x CL tile of the augmented matrix in
+// registers for the whole elimination (cyclic ownership keeps all threads busy while the
+// active part shrinks).  Per pivot step
+//   A  the factors of a warp's rows sit in lane (p mod 32) of the same warp -> RL shuffles
+//      broadcast them (no shared memory); lane 0 posts the warp's best unused row,
+//   B  every warp arg-maxes the TR candidates with shuffles; the owner warp scales the pivot
+//      row and posts it (one value per owned column) to shared memory,
+//   C  rank-1 update of the tile: RL*CL FMAs against CL shared loads.
+// Two barriers per step (a one-barrier variant in which every warp posts its candidate row
+// was measured 8-10 % slower on B200: profiles/r01_notes.md).  The loop over 32-column blocks
+// is unrolled so that all register indices are compile-time.
+// Requires n <= TR*RL and n + nrhs <= 32*CL.
+#define PB_GJ_CASE(X)                                                  \
+    case X:                                                            \
+        if constexpr (X < RL) {                                        \
+            const double inv = 1.0 / f[X];                             \
+            _Pragma("unroll") for (int y = py; y < CL; ++y) {          \
+                a[X][y] *= inv;                                        \
+                pw[tj + 32 * y] = a[X][y];                             \
+            }                                                          \
+        }                                                              \
+        break;
+
+template <int TR, int RL, int CL, int MINB>
+struct RegGJ {
+    static_assert(RL <= 18, "extend the PB_GJ_CASE list");
+    static constexpr int team = TR * 32;
+    static constexpr int min_blocks = MINB;
+    static __host__ __device__ constexpr int64_t scratch_doubles_c() { return 32 * CL + 32 + 16 + 2; }
+    static PB_HD int64_t scratch_doubles(int) { return scratch_doubles_c(); }
+    static constexpr int max_n = TR * RL;
+    static constexpr int max_w = 32 * CL;
+
+    template <class Team>
+    static __device__ __forceinline__ bool solve(Team &t, double *A, int n, int W, int nrhs,
+                                                 int *rowidx, double *scratch) {
+        const int ti = t.warp(), tj = t.lane();
+        const int wend = n + nrhs;
+        double a[RL][CL];
+#pragma unroll
+        for (int x = 0; x < RL; ++x)
+#pragma unroll
+            for (int y = 0; y < CL; ++y) {
+                const int r = ti + TR * x, c = tj + 32 * y;
+                a[x][y] = (r < n && c < wend) ? A[r * W + c] : 0.0;
+            }
+        double *pw = scratch;              // [32*CL] scaled pivot row
+        double *cval = pw + 32 * CL;       // [32]    per-warp pivot candidates (|value|)
+        int *crow = (int *)(cval + 32);    // [32]    ... and their rows
+        unsigned used = 0;                 // bit x: my row x has been a pivot row
+        bool ok = true;
+#pragma unroll
+        for (int py = 0; py < CL; ++py) {
+            if (py * 32 >= n) break;
+            for (int pl = 0; pl < 32; ++pl) {
+                const int p = py * 32 + pl;
+                if (p >= n) break;
+                // A: factors of my rows; candidate of my warp (two independent compare chains)
+                double f[RL];
+                double b0 = -1.0, b1 = -1.0;
+                int x0 = -1, x1 = -1;
+#pragma unroll
+                for (int x = 0; x < RL; ++x) {
+                    f[x] = __shfl_sync(0xffffffffu, a[x][py], pl);
+                    const double av = ((used >> x) & 1u) ? -1.0 : fabs(f[x]);
+                    if (x & 1) { if (av > b1) { b1 = av; x1 = x; } }
+                    else       { if (av > b0) { b0 = av; x0 = x; } }
+                }
+                if (TR > 1) {
+                    if (tj == 0) {
+                        const int bx = (b1 > b0) ? x1 : x0;
+                        cval[ti] = (b1 > b0) ? b1 : b0;
+                        crow[ti] = bx < 0 ? -1 : ti + TR * bx;
+                    }
+                    t.sync();
+                }
+                // B: pivot = arg max over the warps' candidates
+                double v;
+                int pr;
+                if (TR > 1) {
+                    v = tj < TR ? cval[tj] : -2.0;
+                    pr = tj < TR ? crow[tj] : 0x7fffffff;
+                    t.warp_argmax(v, pr);
+                } else {
+                    v = (b1 > b0) ? b1 : b0;
+                    pr = (b1 > b0) ? x1 : x0;
+                }
+                if (!(v > 0.0) || pr < 0) { ok = false; break; }  // uniform over the team
+                const int xpiv = (ti == pr % TR) ? pr / TR : -1;
+                if (xpiv >= 0) {
+                    switch (xpiv) {
+                        PB_GJ_CASE(0) PB_GJ_CASE(1) PB_GJ_CASE(2) PB_GJ_CASE(3) PB_GJ_CASE(4)
+                        PB_GJ_CASE(5) PB_GJ_CASE(6) PB_GJ_CASE(7) PB_GJ_CASE(8) PB_GJ_CASE(9)
+                        PB_GJ_CASE(10) PB_GJ_CASE(11) PB_GJ_CASE(12) PB_GJ_CASE(13) PB_GJ_CASE(14)
+                        PB_GJ_CASE(15) PB_GJ_CASE(16) PB_GJ_CASE(17)
+                        default: break;
+                    }
+                    used |= 1u << xpiv;
+                    if (tj == 0) rowidx[p] = pr;
+                }
+                t.sync();
+                // C: rank-1 update of the rows != pr, columns > p
+                double pv[CL];
+#pragma unroll
+                for (int y = py; y < CL; ++y) pv[y] = pw[tj + 32 * y];
+#pragma unroll
+                for (int x = 0; x < RL; ++x) {
+                    const double fx = f[x];
+                    if (x != xpiv && fx != 0.0) {
+                        if (tj > pl) a[x][py] -= fx * pv[py];
+#pragma unroll
+                        for (int y = py + 1; y < CL; ++y) a[x][y] -= fx * pv[y];
+                    }
+                }
+                if (TR == 1) t.sync();  // pw is reused by the next step
+            }
+            if (!ok) break;
+        }
+        t.sync();
+        if (!ok) return false;
+#pragma unroll
+        for (int x = 0; x < RL; ++x) {
+            const int r = ti + TR * x;
+            if (r < n) {
+#pragma unroll
+                for (int y = 0; y < CL; ++y) {
+                    const int c = tj + 32 * y;
+                    if (c >= n && c < wend) A[r * W + c] = a[x][y];
+                }
+            }
+        }
+        t.sync();
+        return true;
+    }
+};
+#endif
+
 // ------------------------------------------------------------------------------------
 // small dense inverse of the nd x nd matrix of distance vectors (rows d_m)
 // ------------------------------------------------------------------------------------
@@ -173,16 +325,21 @@ PB_HD bool invert_small<3>(const double (&D)[3][3], double (&E)[3][3]) {
 // MPFA
 // ------------------------------------------------------------------------------------
 // doubles of shared memory one team needs for a node with the given counts
-PB_HD int64_t mpfa_smem_doubles(int nd, int nsf, int nsc, int nb) {
-    int64_t W = (nsf + nsc + nb + nd * nsc) | 1;
-    int64_t d = (int64_t)nsf * W + 2 * (int64_t)nsc * nd * nd + 3 * (int64_t)nsf;
+PB_HD int mpfa_width(int nd, int nsf, int nsc, int nb) { return (nsf + nsc + nb + nd * nsc) | 1; }
+PB_HD int64_t mpfa_A_doubles(int nd, int nsf, int nsc, int nb) {
+    return (int64_t)nsf * mpfa_width(nd, nsf, nsc, nb);
+}
+// everything but A and the solver scratch
+PB_HD int64_t mpfa_rest_doubles(int nd, int nsf, int nsc, int nb) {
+    (void)nb;
+    int64_t d = 2 * (int64_t)nsc * nd * nd + 2 * (int64_t)nsf;
     int64_t ints = nsc + 5 * (int64_t)nsf + (int64_t)nsc * nd;
     return d + (ints + 1) / 2 + 2;
 }
 
-template <int ND, class Team>
+template <int ND, class Solver, class Team>
 PB_HD void mpfa_node(Team &t, const PlanView &P, const GeoView &G, const MpfaParams &prm,
-                     const MpfaOut &o, int64_t s, double *smd, int *err) {
+                     const MpfaOut &o, int64_t s, double *A, double *smd, double *scratch, int *err) {
     const int sc0 = P.node_sc_ptr[s], nsc = P.node_sc_ptr[s + 1] - sc0;
     const int sf0 = P.node_sf_ptr[s], nsf = P.node_sf_ptr[s + 1] - sf0;
     const int nb = P.node_nb[s];
@@ -190,13 +347,11 @@ PB_HD void mpfa_node(Team &t, const PlanView &P, const GeoView &G, const MpfaPar
     const int nrhs = nsc + nb + ND * nsc;
     const int W = (nsf + nrhs) | 1;
     const int64_t nf = P.nf, nc = P.nc, nn = P.nn;
-    double *A = smd;
-    double *Tk = A + (int64_t)nsf * W;
+    double *Tk = smd;
     double *Rk = Tk + nsc * ND * ND;
     double *invmf = Rk + nsc * ND * ND;
     double *robw = invmf + nsf;
-    double *ipiv = robw + nsf;
-    int *cell = (int *)(ipiv + nsf);
+    int *cell = (int *)(robw + nsf);
     int *face = cell + nsc;
     int *sides = face + nsf;
     int *bloc = sides + nsf;
@@ -310,7 +465,7 @@ PB_HD void mpfa_node(Team &t, const PlanView &P, const GeoView &G, const MpfaPar
     t.sync();
 
     // ---- phase 4: solve for all right-hand sides
-    if (!gauss_jordan(t, A, nsf, W, nrhs, rowidx, ipiv)) {
+    if (!Solver::solve(t, A, nsf, W, nrhs, rowidx, scratch)) {
         if (t.tid() == 0) flag_singular(err, s);
         t.sync();
         return;

@@ -57,32 +57,33 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
     P.fn_indptr.assign(fn_indptr, fn_indptr + nf + 1);
     const int64_t U = fn_indptr[nf];
     P.U = U;
-    // ---- pass 1: count sub-half-faces per node; sort faces inside each cell
+    // ---- pass 1: sort faces inside each cell; count sub-half-faces per node
     std::vector<int32_t> cfaces(cf_indices, cf_indices + cf_indptr[nc]);
     std::vector<int8_t> csign(cf_data, cf_data + cf_indptr[nc]);
+    int bad_input = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad_input)
     for (int64_t c = 0; c < nc; ++c) {
         int b = cf_indptr[c], e = cf_indptr[c + 1];
-        // insertion sort of (face, sign) by face (cells have few faces)
-        for (int i = b + 1; i < e; ++i) {
-            int32_t f = cfaces[i]; int8_t s = csign[i]; int j = i - 1;
+        for (int i = b + 1; i < e; ++i) {  // insertion sort by face (cells have few faces)
+            int32_t f = cfaces[i]; int8_t sg = csign[i]; int j = i - 1;
             while (j >= b && cfaces[j] > f) { cfaces[j + 1] = cfaces[j]; csign[j + 1] = csign[j]; --j; }
-            cfaces[j + 1] = f; csign[j + 1] = s;
+            cfaces[j + 1] = f; csign[j + 1] = sg;
         }
         for (int i = b; i < e; ++i) {
-            if (cfaces[i] < 0 || cfaces[i] >= nf) { err = "cell_faces index out of range"; return 1; }
-            if (csign[i] != 1 && csign[i] != -1) { err = "cell_faces data must be +-1"; return 1; }
+            if (cfaces[i] < 0 || cfaces[i] >= nf) bad_input |= 1;
+            if (csign[i] != 1 && csign[i] != -1) bad_input |= 2;
         }
     }
+    if (bad_input & 1) { err = "cell_faces index out of range"; return 1; }
+    if (bad_input & 2) { err = "cell_faces data must be +-1"; return 1; }
+    for (int64_t q = 0; q < U; ++q)
+        if (fn_indices[q] < 0 || fn_indices[q] >= nn) { err = "face_nodes index out of range"; return 1; }
     std::vector<int64_t> hptr(nn + 1, 0);
     int64_t H = 0;
     for (int64_t c = 0; c < nc; ++c)
         for (int i = cf_indptr[c]; i < cf_indptr[c + 1]; ++i) {
             int32_t f = cfaces[i];
-            for (int q = fn_indptr[f]; q < fn_indptr[f + 1]; ++q) {
-                int32_t s = fn_indices[q];
-                if (s < 0 || s >= nn) { err = "face_nodes index out of range"; return 1; }
-                ++hptr[s + 1]; ++H;
-            }
+            for (int q = fn_indptr[f]; q < fn_indptr[f + 1]; ++q) { ++hptr[fn_indices[q] + 1]; ++H; }
         }
     P.H = H;
     if (H % nd != 0) { err = "cells must have exactly nd faces meeting in each vertex"; return 3; }
@@ -95,17 +96,21 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
         for (int64_t c = 0; c < nc; ++c)
             for (int i = cf_indptr[c]; i < cf_indptr[c + 1]; ++i) {
                 int32_t f = cfaces[i];
-                for (int q = fn_indptr[f]; q < fn_indptr[f + 1]; ++q) {
-                    int32_t s = fn_indices[q];
-                    hf[fill[s]++] = HF{(int32_t)c, f, (int32_t)q, csign[i]};
-                }
+                for (int q = fn_indptr[f]; q < fn_indptr[f + 1]; ++q)
+                    hf[fill[fn_indices[q]]++] = HF{(int32_t)c, f, (int32_t)q, csign[i]};
             }
     }
-    // ---- sub-cells / sub-faces per node
+    // ---- sub-cells / sub-faces per node (offsets known up front -> nodes are independent)
     const int64_t S = H / nd;
     P.S = S;
     P.node_sc_ptr.assign(nn + 1, 0);
     P.node_sf_ptr.assign(nn + 1, 0);
+    for (int64_t s = 0; s <= nn; ++s) {
+        if (hptr[s] % nd != 0) { err = "cells must have exactly nd faces meeting in each vertex"; return 3; }
+        P.node_sc_ptr[s] = (int32_t)(hptr[s] / nd);
+    }
+    for (int64_t q = 0; q < U; ++q) ++P.node_sf_ptr[fn_indices[q] + 1];
+    for (int64_t s = 0; s < nn; ++s) P.node_sf_ptr[s + 1] += P.node_sf_ptr[s];
     P.sc_cell.resize(S);
     P.slot_sf.resize(H);
     P.sf_face.resize(U);
@@ -113,61 +118,61 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
     P.sf_bloc.assign(U, 0xFFFF);
     P.node_nb.assign(nn, 0);
     P.sc_ncn.assign(nc, 0);
-    int64_t sc_fill = 0, sf_fill = 0;
-    std::vector<int32_t> us;
-    int bad = 0;
-    for (int64_t s = 0; s < nn; ++s) {
-        const int64_t b = hptr[s], e = hptr[s + 1];
-        const int64_t nh = e - b;
-        if (nh % nd != 0) { bad = 3; break; }
-        const int nsc = (int)(nh / nd);
-        P.node_sc_ptr[s] = (int32_t)sc_fill;
-        P.node_sf_ptr[s] = (int32_t)sf_fill;
-        // unique sub-faces (ids u) of the node, ascending
-        us.resize(nh);
-        for (int64_t i = 0; i < nh; ++i) us[i] = hf[b + i].u;
-        std::sort(us.begin(), us.end());
-        us.erase(std::unique(us.begin(), us.end()), us.end());
-        const int nsf = (int)us.size();
-        if (nsf > 32767 || nsc > 21000) { err = "interaction region too large"; return 1; }
-        for (int k = 0; k < nsc; ++k) {
-            const HF *h = &hf[b + (int64_t)k * nd];
-            for (int m = 1; m < nd; ++m)
-                if (h[m].c != h[0].c) bad = 3;
-            if (k > 0 && h[0].c == hf[b + (int64_t)(k - 1) * nd].c) bad = 3;
-            if (bad) break;
-            P.sc_cell[sc_fill + k] = h[0].c;
-            ++P.sc_ncn[h[0].c];
-            for (int m = 0; m < nd; ++m) {
-                int lu = (int)(std::lower_bound(us.begin(), us.end(), h[m].u) - us.begin());
-                P.slot_sf[(sc_fill + k) * nd + m] = (uint16_t)((lu << 1) | (h[m].sg < 0 ? 1 : 0));
-                uint32_t &sd = P.sf_sides[sf_fill + lu];
-                uint32_t side = (uint32_t)(k * nd + m);
-                if ((sd & 0xFFFFu) == 0xFFFFu) sd = (sd & 0xFFFF0000u) | side;
-                else if ((sd >> 16) == 0xFFFFu) sd = (sd & 0xFFFFu) | (side << 16);
-                else { err = "face with more than two neighbouring cells"; return 1; }
+    int bad = 0, mx_sf = 0, mx_sc = 0, mx_nb = 0;
+#pragma omp parallel
+    {
+        std::vector<int32_t> us;
+#pragma omp for schedule(dynamic, 512) reduction(| : bad) reduction(max : mx_sf, mx_sc, mx_nb)
+        for (int64_t s = 0; s < nn; ++s) {
+            const int64_t b = hptr[s], e = hptr[s + 1];
+            const int64_t nh = e - b;
+            const int nsc = (int)(nh / nd);
+            const int64_t sc_fill = P.node_sc_ptr[s], sf_fill = P.node_sf_ptr[s];
+            us.resize(nh);
+            for (int64_t i = 0; i < nh; ++i) us[i] = hf[b + i].u;
+            std::sort(us.begin(), us.end());
+            us.erase(std::unique(us.begin(), us.end()), us.end());
+            const int nsf = (int)us.size();
+            if (nsf != P.node_sf_ptr[s + 1] - sf_fill) { bad |= 4; continue; }
+            if (nsf > 32767 || nsc > 21000) { bad |= 8; continue; }
+            int lbad = 0;
+            for (int k = 0; k < nsc && !lbad; ++k) {
+                const HF *h = &hf[b + (int64_t)k * nd];
+                for (int m = 1; m < nd; ++m)
+                    if (h[m].c != h[0].c) lbad = 3;
+                if (k > 0 && h[0].c == hf[b + (int64_t)(k - 1) * nd].c) lbad = 3;
+                if (lbad) break;
+                P.sc_cell[sc_fill + k] = h[0].c;
+                for (int m = 0; m < nd; ++m) {
+                    int lu = (int)(std::lower_bound(us.begin(), us.end(), h[m].u) - us.begin());
+                    P.slot_sf[(sc_fill + k) * nd + m] = (uint16_t)((lu << 1) | (h[m].sg < 0 ? 1 : 0));
+                    uint32_t &sd = P.sf_sides[sf_fill + lu];
+                    uint32_t side = (uint32_t)(k * nd + m);
+                    if ((sd & 0xFFFFu) == 0xFFFFu) sd = (sd & 0xFFFF0000u) | side;
+                    else if ((sd >> 16) == 0xFFFFu) sd = (sd & 0xFFFFu) | (side << 16);
+                    else lbad = 16;
+                }
             }
+            if (lbad) { bad |= lbad; continue; }
+            int nb = 0;
+            for (int lu = 0; lu < nsf; ++lu) {
+                int32_t u = us[lu];
+                int32_t f = (int32_t)(std::upper_bound(fn_indptr, fn_indptr + nf + 1, u) - fn_indptr) - 1;
+                P.sf_face[sf_fill + lu] = f;
+                if ((P.sf_sides[sf_fill + lu] >> 16) == 0xFFFFu) P.sf_bloc[sf_fill + lu] = (uint16_t)nb++;
+            }
+            P.node_nb[s] = nb;
+            mx_sf = std::max(mx_sf, nsf);
+            mx_sc = std::max(mx_sc, nsc);
+            mx_nb = std::max(mx_nb, nb);
         }
-        if (bad) break;
-        int nb = 0;
-        for (int lu = 0; lu < nsf; ++lu) {
-            int32_t u = us[lu];
-            // face of sub-face u: largest f with fn_indptr[f] <= u
-            int32_t f = (int32_t)(std::upper_bound(fn_indptr, fn_indptr + nf + 1, u) - fn_indptr) - 1;
-            P.sf_face[sf_fill + lu] = f;
-            if ((P.sf_sides[sf_fill + lu] >> 16) == 0xFFFFu) P.sf_bloc[sf_fill + lu] = (uint16_t)nb++;
-        }
-        P.node_nb[s] = nb;
-        P.max_nsf = std::max(P.max_nsf, nsf);
-        P.max_nsc = std::max(P.max_nsc, nsc);
-        P.max_nb = std::max(P.max_nb, nb);
-        sc_fill += nsc;
-        sf_fill += nsf;
     }
-    if (bad) { err = "cells must have exactly nd faces meeting in each vertex"; return 3; }
-    P.node_sc_ptr[nn] = (int32_t)sc_fill;
-    P.node_sf_ptr[nn] = (int32_t)sf_fill;
-    if (sf_fill != U) { err = "face_nodes holds nodes without neighbouring cells"; return 1; }
+    if (bad & 3) { err = "cells must have exactly nd faces meeting in each vertex"; return 3; }
+    if (bad & 4) { err = "face_nodes holds nodes without neighbouring cells"; return 1; }
+    if (bad & 8) { err = "interaction region too large"; return 1; }
+    if (bad & 16) { err = "face with more than two neighbouring cells"; return 1; }
+    P.max_nsf = mx_sf; P.max_nsc = mx_sc; P.max_nb = mx_nb;
+    for (int64_t q = 0; q < S; ++q) ++P.sc_ncn[P.sc_cell[q]];
 
     // ---- adjacency: face -> nodes is fn; cell -> nodes from the sub-cells
     std::vector<int32_t> cn_ptr(nc + 1, 0), cn_idx(S);
@@ -182,6 +187,7 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
     std::vector<int32_t> nbf_ptr(nn + 1, 0), nbf_idx;
     for (int64_t s = 0; s < nn; ++s) nbf_ptr[s + 1] = nbf_ptr[s] + P.node_nb[s];
     nbf_idx.resize(nbf_ptr[nn]);
+#pragma omp parallel for schedule(static)
     for (int64_t s = 0; s < nn; ++s)
         for (int32_t q = P.node_sf_ptr[s]; q < P.node_sf_ptr[s + 1]; ++q)
             if (P.sf_bloc[q] != 0xFFFF) nbf_idx[nbf_ptr[s] + P.sf_bloc[q]] = P.sf_face[q];
@@ -192,19 +198,22 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
                      Csr &out) {
         out.nrows = nrows; out.ncols = ncols;
         out.indptr.assign(nrows + 1, 0);
-        std::vector<int32_t> tmp;
-        // two passes (count, fill) to avoid a big temporary
         for (int pass = 0; pass < 2; ++pass) {
-            for (int64_t r = 0; r < nrows; ++r) {
-                tmp.clear();
-                for (int32_t q = row_nodes_ptr[r]; q < row_nodes_ptr[r + 1]; ++q) {
-                    int32_t s = row_nodes[q];
-                    tmp.insert(tmp.end(), col_idx + col_ptr[s], col_idx + col_ptr[s + 1]);
+#pragma omp parallel
+            {
+                std::vector<int32_t> tmp;
+#pragma omp for schedule(dynamic, 1024)
+                for (int64_t r = 0; r < nrows; ++r) {
+                    tmp.clear();
+                    for (int32_t q = row_nodes_ptr[r]; q < row_nodes_ptr[r + 1]; ++q) {
+                        int32_t s = row_nodes[q];
+                        tmp.insert(tmp.end(), col_idx + col_ptr[s], col_idx + col_ptr[s + 1]);
+                    }
+                    std::sort(tmp.begin(), tmp.end());
+                    tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+                    if (pass == 0) out.indptr[r + 1] = (int32_t)tmp.size();
+                    else std::copy(tmp.begin(), tmp.end(), out.indices.begin() + out.indptr[r]);
                 }
-                std::sort(tmp.begin(), tmp.end());
-                tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-                if (pass == 0) out.indptr[r + 1] = (int32_t)tmp.size();
-                else std::copy(tmp.begin(), tmp.end(), out.indices.begin() + out.indptr[r]);
             }
             if (pass == 0) {
                 int64_t acc = 0;
@@ -243,6 +252,7 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
         const int32_t *b = A.indices.data() + A.indptr[r], *e = A.indices.data() + A.indptr[r + 1];
         return (int32_t)(std::lower_bound(b, e, c) - A.indices.data());
     };
+#pragma omp parallel for schedule(dynamic, 512)
     for (int64_t s = 0; s < nn; ++s) {
         const int32_t *cells = P.sc_cell.data() + P.node_sc_ptr[s];
         const int32_t *faces = P.sf_face.data() + P.node_sf_ptr[s];

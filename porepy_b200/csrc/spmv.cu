@@ -112,6 +112,24 @@ extern "C" int pb_csr_create(int64_t nrows, int64_t ncols, int64_t nnz, const in
     }
     double mean = nrows ? (double)nnz / (double)nrows : 0.0;
     a->tpr = mean <= 3 ? 2 : mean <= 6 ? 4 : mean <= 24 ? 8 : mean <= 48 ? 16 : 32;
+    // pick the lanes-per-row that is fastest for THIS matrix (a few launches, once per matrix)
+    if (nnz > (1 << 20)) {
+        cudaMemsetAsync(a->x, 0, (ncols ? ncols : 1) * sizeof(double), a->stream);
+        float best = 1e30f;
+        int best_tpr = a->tpr;
+        const int cands[4] = {4, 8, 16, 32};
+        for (int ci = 0; ci < 4; ++ci) {
+            a->tpr = cands[ci];
+            float ms = 1e30f;
+            if (launch_spmv(a, a->x, a->y, a->stream) != PB_OK) break;
+            cudaEventRecord(a->e0, a->stream);
+            for (int i = 0; i < 3; ++i) launch_spmv(a, a->x, a->y, a->stream);
+            cudaEventRecord(a->e1, a->stream);
+            if (cudaEventSynchronize(a->e1) == cudaSuccess) cudaEventElapsedTime(&ms, a->e0, a->e1);
+            if (ms < best) { best = ms; best_tpr = cands[ci]; }
+        }
+        a->tpr = best_tpr;
+    }
     *out = a;
     return PB_OK;
 }

@@ -154,10 +154,18 @@ class DevicePlan:
             if br == 1 and bc == 1:
                 self._expanded[key] = (ip, ix)
             else:
-                nip, nix = block_expand(ip, ix, br, bc)
                 ncols = {0: self.nc, 1: self.nf, 2: self.nc, 3: self.nf}[which] * bc
-                dt = _index_dtype(int(nip[-1]), ncols)
-                self._expanded[key] = (nip.astype(dt), nix.astype(dt))
+                nnz = int(ix.size) * br * bc
+                if max(nnz, ncols) < 2**31 - 1:
+                    # expansion on the device, D2H into page-locked buffers
+                    nip = _lib.pinned_empty((ip.size - 1) * br + 1, np.int32)
+                    nix = _lib.pinned_empty(max(nnz, 1), np.int32)
+                    _lib.check(self.lib.pb_plan_pattern_expanded(
+                        self.h, which, br, bc, _lib.ptr(nip, _lib._i32p), _lib.ptr(nix, _lib._i32p)))
+                    self._expanded[key] = (nip, nix[:nnz])
+                else:  # beyond int32: host expansion with 64-bit indices
+                    nip, nix = block_expand(ip, ix, br, bc)
+                    self._expanded[key] = (nip, nix)
         return self._expanded[key]
 
     def matrix(self, which: int, br: int, bc: int, data: np.ndarray) -> sps.csr_matrix:
@@ -197,12 +205,12 @@ class DevicePlan:
         nd = self.nd
         nfc, nfb = self.nnz(0), self.nnz(1)
         bufs = {
-            "flux": np.empty(nfc) if flux else None,
-            "bound_flux": np.empty(nfb) if flux else None,
-            "bound_pressure_cell": np.empty(nfc) if trace else None,
-            "bound_pressure_face": np.empty(nfb) if trace else None,
-            "vector_source": np.empty(nfc * nd) if (flux and vector_source) else None,
-            "bound_pressure_vector_source": np.empty(nfc * nd) if (trace and vector_source) else None,
+            "flux": _lib.pinned_empty(nfc) if flux else None,
+            "bound_flux": _lib.pinned_empty(nfb) if flux else None,
+            "bound_pressure_cell": _lib.pinned_empty(nfc) if trace else None,
+            "bound_pressure_face": _lib.pinned_empty(nfb) if trace else None,
+            "vector_source": _lib.pinned_empty(nfc * nd) if (flux and vector_source) else None,
+            "bound_pressure_vector_source": _lib.pinned_empty(nfc * nd) if (trace and vector_source) else None,
         }
         _lib.check(self.lib.pb_mpfa_download(self.h, *[_lib.ptr(b, _lib._f64p) for b in bufs.values()]))
         shape = {"flux": (0, 1, 1), "bound_flux": (1, 1, 1), "bound_pressure_cell": (0, 1, 1),
@@ -237,7 +245,8 @@ class DevicePlan:
         nd = self.nd
         nd2 = nd * nd
         nfc, nfb = self.nnz(0), self.nnz(1)
-        bufs = [np.empty(nfc * nd2), np.empty(nfb * nd2), np.empty(nfc * nd2), np.empty(nfb * nd2)]
+        bufs = [_lib.pinned_empty(nfc * nd2), _lib.pinned_empty(nfb * nd2), _lib.pinned_empty(nfc * nd2),
+                _lib.pinned_empty(nfb * nd2)]
         _lib.check(self.lib.pb_mpsa_download(self.h, *[_lib.ptr(b, _lib._f64p) for b in bufs]))
         return {
             "stress": self.matrix(0, nd, nd, bufs[0]),
@@ -249,8 +258,8 @@ class DevicePlan:
     def biot_download(self, q: int) -> dict:
         nd = self.nd
         nfc, ncc, ncb = self.nnz(0), self.nnz(2), self.nnz(3)
-        bufs = [np.empty(ncc * nd), np.empty(ncb * nd), np.empty(nfc * nd), np.empty(ncc),
-                np.empty(nfc * nd)]
+        bufs = [_lib.pinned_empty(ncc * nd), _lib.pinned_empty(ncb * nd), _lib.pinned_empty(nfc * nd),
+                _lib.pinned_empty(ncc), _lib.pinned_empty(nfc * nd)]
         _lib.check(self.lib.pb_biot_download(self.h, q, *[_lib.ptr(b, _lib._f64p) for b in bufs]))
         return {
             "displacement_divergence": self.matrix(2, 1, nd, bufs[0]),

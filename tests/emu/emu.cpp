@@ -80,13 +80,17 @@ int emu_mpfa(void *h, const double *nodes, const double *fnorm, const double *fc
     int64_t need = 0;
     for (int64_t s = 0; s < P.nn; ++s) {
         int nsc = P.node_sc_ptr[s + 1] - P.node_sc_ptr[s], nsf = P.node_sf_ptr[s + 1] - P.node_sf_ptr[s];
-        need = std::max(need, mpfa_smem_doubles(P.nd, nsf, nsc, P.node_nb[s]));
+        need = std::max(need, mpfa_A_doubles(P.nd, nsf, nsc, P.node_nb[s]) +
+                                  mpfa_rest_doubles(P.nd, nsf, nsc, P.node_nb[s]) + nsf);
     }
     std::vector<double> sm(need + 8);
     CpuTeam t;
     for (int64_t s = 0; s < P.nn; ++s) {
-        if (P.nd == 3) mpfa_node<3>(t, P, G, prm, o, s, sm.data(), &err);
-        else mpfa_node<2>(t, P, G, prm, o, s, sm.data(), &err);
+        int nsc = P.node_sc_ptr[s + 1] - P.node_sc_ptr[s], nsf = P.node_sf_ptr[s + 1] - P.node_sf_ptr[s];
+        double *rest = sm.data() + mpfa_A_doubles(P.nd, nsf, nsc, P.node_nb[s]);
+        double *scr = rest + mpfa_rest_doubles(P.nd, nsf, nsc, P.node_nb[s]);
+        if (P.nd == 3) mpfa_node<3, SmemGJ>(t, P, G, prm, o, s, sm.data(), rest, scr, &err);
+        else mpfa_node<2, SmemGJ>(t, P, G, prm, o, s, sm.data(), rest, scr, &err);
     }
     return err == INT_MAX ? 0 : 2;
 }
@@ -110,13 +114,17 @@ int emu_mpsa(void *h, const double *nodes, const double *fnorm, const double *fc
     int64_t need = 0;
     for (int64_t s = 0; s < P.nn; ++s) {
         int nsc = P.node_sc_ptr[s + 1] - P.node_sc_ptr[s], nsf = P.node_sf_ptr[s + 1] - P.node_sf_ptr[s];
-        need = std::max(need, mpsa_smem_doubles(P.nd, nsf, nsc, P.node_nb[s], n_alpha));
+        need = std::max(need, mpsa_A_doubles(P.nd, nsf, nsc, P.node_nb[s], n_alpha) +
+                                  mpsa_rest_doubles(P.nd, nsf, nsc, P.node_nb[s], n_alpha) + (int64_t)nsf * P.nd);
     }
     std::vector<double> sm(need + 8);
     CpuTeam t;
     for (int64_t s = 0; s < P.nn; ++s) {
-        if (P.nd == 3) mpsa_node<3>(t, P, G, prm, o, s, sm.data(), &err);
-        else mpsa_node<2>(t, P, G, prm, o, s, sm.data(), &err);
+        int nsc = P.node_sc_ptr[s + 1] - P.node_sc_ptr[s], nsf = P.node_sf_ptr[s + 1] - P.node_sf_ptr[s];
+        double *rest = sm.data() + mpsa_A_doubles(P.nd, nsf, nsc, P.node_nb[s], n_alpha);
+        double *scr = rest + mpsa_rest_doubles(P.nd, nsf, nsc, P.node_nb[s], n_alpha);
+        if (P.nd == 3) mpsa_node<3, SmemGJ>(t, P, G, prm, o, s, sm.data(), rest, scr, &err);
+        else mpsa_node<2, SmemGJ>(t, P, G, prm, o, s, sm.data(), rest, scr, &err);
     }
     return err == INT_MAX ? 0 : 2;
 }

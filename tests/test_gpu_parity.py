@@ -222,3 +222,58 @@ def test_spmv_matches_scipy():
     R = sps.vstack([R, sps.csr_matrix((5, 700))]).tocsr()
     x = rng.standard_normal(700)
     assert np.abs(pb.DeviceCsr(R) @ x - R @ x).max() <= 1e-12
+
+
+def test_device_pattern_expansion_matches_host():
+    from porepy_b200.fv import DevicePlan, block_expand
+    g = pb.structured_tet_grid([4, 3, 3])
+    plan = DevicePlan.for_grid(g)
+    for which in range(4):
+        ip, ix = plan.base_pattern(which)
+        for br, bc in ((3, 3), (1, 3), (3, 1)):
+            nip, nix = plan.pattern(which, br, bc)
+            hip, hix = block_expand(ip, ix, br, bc)
+            assert np.array_equal(nip, hip) and np.array_equal(nix, hix)
+
+
+def test_sharded_equals_unsplit():
+    """Two shards discretized one after the other on the GPU reproduce the unsplit matrices
+    (common_xpfa_tests.py:832-957)."""
+    from porepy_b200 import shard as sh
+    g = pb.cart_grid_3d([8, 5, 4], perturb=0.3, seed=9)
+    rng = np.random.default_rng(5)
+    k = _aniso(g.num_cells, rng)
+    bc = _mixed_scalar_bc(g)
+    C = pb.FourthOrderTensor(np.exp(0.3 * rng.standard_normal(g.num_cells)), np.ones(g.num_cells))
+    vbc = _mixed_vector_bc(g)
+    data = pb.initialize_data({}, "flow", {"second_order_tensor": k, "bc": bc})
+    pb.Mpfa("flow").discretize(g, data)
+    dm = pb.initialize_data({}, "mech", {"fourth_order_tensor": C, "bc": vbc})
+    pb.Mpsa("mech").discretize(g, dm)
+    ref = dict(data[pb.DISCRETIZATION_MATRICES]["flow"])
+    ref.update(dm[pb.DISCRETIZATION_MATRICES]["mech"])
+    part = sh.partition_cells(g, 2)
+    acc = {}
+    shapes = {"flux": ("face", "cell", 1, 1), "bound_flux": ("face", "face", 1, 1),
+              "bound_pressure_cell": ("face", "cell", 1, 1), "bound_pressure_face": ("face", "face", 1, 1),
+              "vector_source": ("face", "cell", 1, 3), "bound_pressure_vector_source": ("face", "cell", 1, 3),
+              "stress": ("face", "cell", 3, 3), "bound_stress": ("face", "face", 3, 3),
+              "bound_displacement_cell": ("face", "cell", 3, 3),
+              "bound_displacement_face": ("face", "face", 3, 3)}
+    for r in range(2):
+        s = sh.extract_shard(g, part, r)
+        d1 = pb.initialize_data({}, "flow", {
+            "second_order_tensor": pb.SecondOrderTensor.from_values(s.restrict_cell_array(k.values)),
+            "bc": sh.restrict_scalar_bc(bc, s)})
+        pb.Mpfa("flow").discretize(s.grid, d1)
+        d2 = pb.initialize_data({}, "mech", {
+            "fourth_order_tensor": pb.FourthOrderTensor.from_values(s.restrict_cell_array(C.values)),
+            "bc": sh.restrict_vector_bc(vbc, s)})
+        pb.Mpsa("mech").discretize(s.grid, d2)
+        loc = dict(d1[pb.DISCRETIZATION_MATRICES]["flow"])
+        loc.update(d2[pb.DISCRETIZATION_MATRICES]["mech"])
+        for key, m in loc.items():
+            gm = s.to_global(m, *shapes[key])
+            acc[key] = gm if key not in acc else acc[key] + gm
+    for key in ref:
+        assert rel_err(ref[key], acc[key]) < 1e-12, key

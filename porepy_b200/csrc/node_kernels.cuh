@@ -150,20 +150,20 @@ struct SmemGJ {
 // Register-tiled Gauss-Jordan.  The team is TR warps; warp w owns the rows {w + TR*x}, lane l
 // the columns {l + 32*y}: every thread keeps an RL x CL tile of the augmented matrix in
 // registers for the whole elimination (cyclic ownership keeps all threads busy while the
-// active part shrinks).  Per pivot step
-//   A  the factors of a warp's rows sit in lane (p mod 32) of the same warp -> RL shuffles
-//      broadcast them (no shared memory); lane 0 posts the warp's best unused row,
-//   B  every warp arg-maxes the TR candidates with shuffles; the owner warp scales the pivot
-//      row and posts it (one value per owned column) to shared memory,
-//   C  rank-1 update of the tile: RL*CL FMAs against CL shared loads.
-// Two barriers per step (a one-barrier variant in which every warp posts its candidate row
-// was measured 8-10 % slower on B200: profiles/r01_notes.md).  The loop over 32-column blocks
-// is unrolled so that all register indices are compile-time.
-// Requires n <= TR*RL and n + nrhs <= 32*CL.
+// active part shrinks).  Per pivot step p:
+//   A  the lane that owns column p dumps it (RL values per warp) to shared memory, together
+//      with |value| of the rows that have not been pivots yet;            -- barrier --
+//   B  every warp finds the pivot row from the dumped column (<= 4 shared loads per lane and
+//      one packed-key warp arg-max); the owner warp scales the pivot row and posts it (one
+//      value per owned column);                                            -- barrier --
+//   C  rank-1 update of the tile: the row factors are broadcast shared loads of the dumped
+//      column, RL*CL FMAs against RL + CL shared loads.
+// The column dump is double-buffered (step p+1's dump may overtake slow readers of step p).
+// The loop over 32-column blocks is unrolled so that all register indices are compile-time.
+// Requires n <= TR*RL <= 255 and n + nrhs <= 32*CL.
 #define PB_GJ_CASE(X)                                                  \
     case X:                                                            \
         if constexpr (X < RL) {                                        \
-            const double inv = 1.0 / f[X];                             \
             _Pragma("unroll") for (int y = py; y < CL; ++y) {          \
                 a[X][y] *= inv;                                        \
                 pw[tj + 32 * y] = a[X][y];                             \
@@ -174,12 +174,14 @@ struct SmemGJ {
 template <int TR, int RL, int CL, int MINB>
 struct RegGJ {
     static_assert(RL <= 18, "extend the PB_GJ_CASE list");
+    static_assert(TR * RL <= 255, "row index must fit the 8-bit key field");
     static constexpr int team = TR * 32;
     static constexpr int min_blocks = MINB;
-    static __host__ __device__ constexpr int64_t scratch_doubles_c() { return 32 * CL + 32 + 16 + 2; }
-    static PB_HD int64_t scratch_doubles(int) { return scratch_doubles_c(); }
     static constexpr int max_n = TR * RL;
     static constexpr int max_w = 32 * CL;
+    static constexpr int NP = ((max_n + 31) / 32) * 32;  // padded column length
+    static __host__ __device__ constexpr int64_t scratch_doubles_c() { return 32 * CL + 4 * NP + 2; }
+    static PB_HD int64_t scratch_doubles(int) { return scratch_doubles_c(); }
 
     template <class Team>
     static __device__ __forceinline__ bool solve(Team &t, double *A, int n, int W, int nrhs,
@@ -194,50 +196,49 @@ struct RegGJ {
                 const int r = ti + TR * x, c = tj + 32 * y;
                 a[x][y] = (r < n && c < wend) ? A[r * W + c] : 0.0;
             }
-        double *pw = scratch;              // [32*CL] scaled pivot row
-        double *cval = pw + 32 * CL;       // [32]    per-warp pivot candidates (|value|)
-        int *crow = (int *)(cval + 32);    // [32]    ... and their rows
-        unsigned used = 0;                 // bit x: my row x has been a pivot row
+        double *pw = scratch;             // [32*CL]  scaled pivot row
+        double *col = pw + 32 * CL;       // [2][NP]  pivot column (factors), by physical row
+        double *cab = col + 2 * NP;       // [2][NP]  |pivot column| of rows still unused, else 0
+        for (int i = t.tid(); i < 4 * NP; i += t.size()) col[i] = 0.0;
+        t.sync();
+        unsigned used = 0;  // bit x: my row x has been a pivot row
         bool ok = true;
+        // dump of column 0 (step 0's phase A); later dumps are issued as look-ahead inside phase C
+        if (tj == 0) {
+#pragma unroll
+            for (int x = 0; x < RL; ++x) {
+                col[ti + TR * x] = a[x][0];
+                cab[ti + TR * x] = fabs(a[x][0]);
+            }
+        }
 #pragma unroll
         for (int py = 0; py < CL; ++py) {
             if (py * 32 >= n) break;
             for (int pl = 0; pl < 32; ++pl) {
                 const int p = py * 32 + pl;
                 if (p >= n) break;
-                // A: factors of my rows; candidate of my warp (two independent compare chains)
-                double f[RL];
-                double b0 = -1.0, b1 = -1.0;
-                int x0 = -1, x1 = -1;
+                const int buf = p & 1;
+                double *fc = col + buf * NP;
+                double *ca = cab + buf * NP;
+                t.sync();
+                // B: pivot = arg max |column| over unused rows (every warp redundantly)
+                unsigned long long key = 0ull;
 #pragma unroll
-                for (int x = 0; x < RL; ++x) {
-                    f[x] = __shfl_sync(0xffffffffu, a[x][py], pl);
-                    const double av = ((used >> x) & 1u) ? -1.0 : fabs(f[x]);
-                    if (x & 1) { if (av > b1) { b1 = av; x1 = x; } }
-                    else       { if (av > b0) { b0 = av; x0 = x; } }
+                for (int q = 0; q < NP / 32; ++q) {
+                    unsigned long long k = (unsigned long long)__double_as_longlong(ca[tj + 32 * q]);
+                    k = (k & ~0xFFull) | (unsigned)(tj + 32 * q);
+                    key = k > key ? k : key;
                 }
-                if (TR > 1) {
-                    if (tj == 0) {
-                        const int bx = (b1 > b0) ? x1 : x0;
-                        cval[ti] = (b1 > b0) ? b1 : b0;
-                        crow[ti] = bx < 0 ? -1 : ti + TR * bx;
-                    }
-                    t.sync();
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = k2 > key ? k2 : key;
                 }
-                // B: pivot = arg max over the warps' candidates
-                double v;
-                int pr;
-                if (TR > 1) {
-                    v = tj < TR ? cval[tj] : -2.0;
-                    pr = tj < TR ? crow[tj] : 0x7fffffff;
-                    t.warp_argmax(v, pr);
-                } else {
-                    v = (b1 > b0) ? b1 : b0;
-                    pr = (b1 > b0) ? x1 : x0;
-                }
-                if (!(v > 0.0) || pr < 0) { ok = false; break; }  // uniform over the team
+                if ((key >> 8) == 0ull) { ok = false; break; }  // zero column: uniform over the team
+                const int pr = (int)(key & 0xFFull);
                 const int xpiv = (ti == pr % TR) ? pr / TR : -1;
                 if (xpiv >= 0) {
+                    const double inv = 1.0 / fc[pr];
                     switch (xpiv) {
                         PB_GJ_CASE(0) PB_GJ_CASE(1) PB_GJ_CASE(2) PB_GJ_CASE(3) PB_GJ_CASE(4)
                         PB_GJ_CASE(5) PB_GJ_CASE(6) PB_GJ_CASE(7) PB_GJ_CASE(8) PB_GJ_CASE(9)
@@ -249,20 +250,45 @@ struct RegGJ {
                     if (tj == 0) rowidx[p] = pr;
                 }
                 t.sync();
-                // C: rank-1 update of the rows != pr, columns > p
+                // C1: rank-1 update of the pivot's own 32-column block (holds column p+1 as well)
                 double pv[CL];
 #pragma unroll
                 for (int y = py; y < CL; ++y) pv[y] = pw[tj + 32 * y];
+                double fx[RL];
 #pragma unroll
                 for (int x = 0; x < RL; ++x) {
-                    const double fx = f[x];
-                    if (x != xpiv && fx != 0.0) {
-                        if (tj > pl) a[x][py] -= fx * pv[py];
+                    fx[x] = (x != xpiv) ? fc[ti + TR * x] : 0.0;
+                    if (tj > pl) a[x][py] -= fx[x] * pv[py];
+                }
+                // A' (look-ahead): dump column p+1 for the next step when it is in this block
+                const bool la = (pl < 31) && (p + 1 < n);
+                double *fc2 = col + (buf ^ 1) * NP;
+                double *ca2 = cab + (buf ^ 1) * NP;
+                if (la && tj == pl + 1) {
 #pragma unroll
-                        for (int y = py + 1; y < CL; ++y) a[x][y] -= fx * pv[y];
+                    for (int x = 0; x < RL; ++x) {
+                        const double v = a[x][py];
+                        fc2[ti + TR * x] = v;
+                        ca2[ti + TR * x] = ((used >> x) & 1u) ? 0.0 : fabs(v);
                     }
                 }
-                if (TR == 1) t.sync();  // pw is reused by the next step
+                // C2: the remaining column blocks
+#pragma unroll
+                for (int x = 0; x < RL; ++x) {
+                    if (fx[x] != 0.0) {
+#pragma unroll
+                        for (int y = py + 1; y < CL; ++y) a[x][y] -= fx[x] * pv[y];
+                    }
+                }
+                if (!la && p + 1 < n && tj == 0) {  // first column of the next block
+#pragma unroll
+                    for (int x = 0; x < RL; ++x) {
+                        const double v = a[x][py + 1 < CL ? py + 1 : py];
+                        fc2[ti + TR * x] = v;
+                        ca2[ti + TR * x] = ((used >> x) & 1u) ? 0.0 : fabs(v);
+                    }
+                }
+                if (TR == 1) t.sync();
             }
             if (!ok) break;
         }

@@ -14,6 +14,9 @@
 // drops exact zeros): row f of FACE_CELL holds every cell sharing a node with face f, etc.
 #pragma once
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -43,6 +46,8 @@ struct HostPlan {
     // per-node maps local (row, col) -> position in the base pattern's data array
     std::vector<int64_t> posfc_ptr, posfb_ptr, poscc_ptr, poscb_ptr;  // nn+1 each
     std::vector<int32_t> pos_fc, pos_fb, pos_cc, pos_cb;
+    std::vector<int32_t> nbf_ptr, nbf_idx;     // boundary faces of each node (local order)
+    std::vector<int32_t> cn_ptr, cn_idx;       // nodes of each cell
     int32_t max_nsf = 0, max_nsc = 0, max_nb = 0;
 };
 
@@ -50,7 +55,16 @@ struct HostPlan {
 inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int32_t *cf_indptr,
                            const int32_t *cf_indices, const int8_t *cf_data,
                            const int32_t *fn_indptr, const int32_t *fn_indices, HostPlan &P,
-                           std::string &err) {
+                           std::string &err, bool build_pos_maps = true, bool build_patterns = true) {
+    const bool timing = getenv("POREB200_PLAN_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[plan] %-28s %8.1f ms\n", what,
+                std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     if (nd != 2 && nd != 3) { err = "nd must be 2 or 3"; return 1; }
     if (nc <= 0 || nf <= 0 || nn <= 0) { err = "empty grid"; return 1; }
     P.nd = nd; P.nc = nc; P.nf = nf; P.nn = nn;
@@ -78,6 +92,7 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
     if (bad_input & 2) { err = "cell_faces data must be +-1"; return 1; }
     for (int64_t q = 0; q < U; ++q)
         if (fn_indices[q] < 0 || fn_indices[q] >= nn) { err = "face_nodes index out of range"; return 1; }
+    lap("sort faces in cells");
     std::vector<int64_t> hptr(nn + 1, 0);
     int64_t H = 0;
     for (int64_t c = 0; c < nc; ++c)
@@ -100,6 +115,7 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
                     hf[fill[fn_indices[q]]++] = HF{(int32_t)c, f, (int32_t)q, csign[i]};
             }
     }
+    lap("bucket by node");
     // ---- sub-cells / sub-faces per node (offsets known up front -> nodes are independent)
     const int64_t S = H / nd;
     P.S = S;
@@ -167,6 +183,7 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
             mx_nb = std::max(mx_nb, nb);
         }
     }
+    lap("per-node topology");
     if (bad & 3) { err = "cells must have exactly nd faces meeting in each vertex"; return 3; }
     if (bad & 4) { err = "face_nodes holds nodes without neighbouring cells"; return 1; }
     if (bad & 8) { err = "interaction region too large"; return 1; }
@@ -192,6 +209,7 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
         for (int32_t q = P.node_sf_ptr[s]; q < P.node_sf_ptr[s + 1]; ++q)
             if (P.sf_bloc[q] != 0xFFFF) nbf_idx[nbf_ptr[s] + P.sf_bloc[q]] = P.sf_face[q];
 
+    lap("adjacency");
     // ---- patterns: union over the nodes of a row entity of the node's column entities
     auto build = [&](int64_t nrows, int64_t ncols, const int32_t *row_nodes_ptr,
                      const int32_t *row_nodes, const int32_t *col_ptr, const int32_t *col_idx,
@@ -227,12 +245,19 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
         }
         return 0;
     };
+    P.nbf_ptr = nbf_ptr;
+    P.nbf_idx = nbf_idx;
+    P.cn_ptr = cn_ptr;
+    P.cn_idx = cn_idx;
     int rc = 0;
+    if (build_patterns) {
     rc |= build(nf, nc, fn_indptr, fn_indices, P.node_sc_ptr.data(), P.sc_cell.data(), P.pat[0]);
     rc |= build(nf, nf, fn_indptr, fn_indices, nbf_ptr.data(), nbf_idx.data(), P.pat[1]);
     rc |= build(nc, nc, cn_ptr.data(), cn_idx.data(), P.node_sc_ptr.data(), P.sc_cell.data(), P.pat[2]);
     rc |= build(nc, nf, cn_ptr.data(), cn_idx.data(), nbf_ptr.data(), nbf_idx.data(), P.pat[3]);
+    }
     if (rc) { err = "pattern exceeds 2^31 entries; split the grid"; return 1; }
+    lap("patterns");
 
     // ---- per-node position maps
     P.posfc_ptr.assign(nn + 1, 0); P.posfb_ptr.assign(nn + 1, 0);
@@ -246,6 +271,7 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
         P.poscc_ptr[s + 1] = P.poscc_ptr[s] + nsc * nsc;
         P.poscb_ptr[s + 1] = P.poscb_ptr[s] + nsc * nb;
     }
+    if (!build_pos_maps) { lap("position map offsets"); return 0; }  // filled on the device (api.cu)
     P.pos_fc.resize(P.posfc_ptr[nn]); P.pos_fb.resize(P.posfb_ptr[nn]);
     P.pos_cc.resize(P.poscc_ptr[nn]); P.pos_cb.resize(P.poscb_ptr[nn]);
     auto find = [](const Csr &A, int32_t r, int32_t c) -> int32_t {
@@ -273,6 +299,7 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
                 P.pos_cb[P.poscb_ptr[s] + (int64_t)k * nb + b] = find(P.pat[3], cells[k], bfs[b]);
         }
     }
+    lap("position maps");
     return 0;
 }
 

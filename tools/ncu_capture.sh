@@ -1,7 +1,8 @@
 #!/bin/bash
 # usage: tools/ncu_capture.sh <name> <launch-skip> <workload>   (runs on the GPU box)
-# Captures ONE launch with ncu --set full, exports the raw and source pages as CSV into
-# gpurun_out/ and drops the (20 MB) .ncu-rep so that gpurun_out stays under the 64 MiB cap.
+# Captures ONE launch with ncu --set full, exports the raw / source (SASS and CUDA-C views) /
+# details pages into gpurun_out/ and drops the (20 MB) .ncu-rep so that gpurun_out stays under
+# the 64 MiB cap.
 set -e
 name=$1; skip=$2; wl=$3
 mkdir -p gpurun_out /tmp/ncu
@@ -9,5 +10,6 @@ ncu --set full --clock-control none --import-source on --launch-skip $skip --lau
     -o /tmp/ncu/$name python tools/profile_run.py $wl 1 | tail -1
 ncu -i /tmp/ncu/$name.ncu-rep --page raw --csv > gpurun_out/${name}_raw.csv
 ncu -i /tmp/ncu/$name.ncu-rep --page source --csv > gpurun_out/${name}_source.csv 2>/dev/null || true
+ncu -i /tmp/ncu/$name.ncu-rep --page source --print-source cuda --csv > gpurun_out/${name}_cuda.csv 2>/dev/null || true
 ncu -i /tmp/ncu/$name.ncu-rep --page details > gpurun_out/${name}_details.txt
 ls -la gpurun_out/${name}_*

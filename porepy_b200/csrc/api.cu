@@ -106,10 +106,10 @@ using Cfg0 = RegGJ<1, 12, 2, 4>;   // team 32  : MPFA hexahedral nodes (12 x 45)
 using Cfg1 = RegGJ<4, 9, 2, 4>;    // team 128 : MPSA hexahedral nodes (36 x 61)
 using Cfg2 = RegGJ<4, 9, 3, 3>;    // team 128 : Biot hexahedral nodes
 using Cfg3 = RegGJ<4, 10, 5, 3>;   // team 128 : MPFA tetrahedral nodes (36 x 133)
-using Cfg4 = RegGJ<8, 14, 6, 1>;   // team 256 : MPSA tetrahedral nodes (108 x 181)
+using Cfg4 = TileGJ<7, 2, 24, 1>;  // team 224 : MPSA tetrahedral nodes (108 x 181), FP64 tensor cores (DMMA)
 using Cfg5 = RegGJ<16, 7, 8, 1>;   // team 512 : Biot tetrahedral nodes
 using Cfg6 = SmemGJ;               // team 256 : anything else (in-memory Gauss-Jordan)
-using Cfg7 = RegGJ<16, 7, 6, 1>;   // team 512 : alternative for cfg 4 (POREB200_CFG4=384)
+using Cfg7 = RegGJ<8, 14, 6, 1>;   // team 256 : scalar register-tiled alternative for cfg 4 (POREB200_CFG4=reg)
 struct SolverCfg { int team, max_n, max_w; };
 static const SolverCfg kCfg[] = {
     {Cfg0::team, Cfg0::max_n, Cfg0::max_w}, {Cfg1::team, Cfg1::max_n, Cfg1::max_w},
@@ -232,7 +232,7 @@ template <class F>
 static int build_classes(pb_plan *p, std::vector<NodeClass> &out, F size_of) {
     const HostPlan &H = p->H;
     const char *alt = getenv("POREB200_CFG4");
-    const bool use7 = alt && atoi(alt) == 384;
+    const bool use7 = alt && strcmp(alt, "reg") == 0;
     // key: cfg*2 + a_global
     std::vector<int32_t> lists[2 * kNumCfg];
     int64_t amax[2 * kNumCfg] = {0}, rmax[2 * kNumCfg] = {0}, smax[2 * kNumCfg] = {0};

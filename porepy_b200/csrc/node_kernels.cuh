@@ -311,6 +311,267 @@ struct RegGJ {
 };
 #endif
 
+#if defined(__CUDACC__)
+// Blocked Gauss-Jordan on FP64 tensor cores (DMMA, mma.sync.m8n8k4.f64 -- tcgen05 has no FP64
+// kind).  The augmented matrix lives in registers as 8x8 accumulator tiles: warp w owns row
+// tile w (8 rows) and all NCT column tiles (2 doubles per lane and tile).  Pivots are taken four
+// at a time (a panel = half a column tile):
+//   S1  every warp dumps its 8x4 slice of the panel to shared memory;            -- barrier --
+//   S2  warp 0 runs partial pivoting on the n x 4 panel in registers (packed-key warp arg-max
+//       per column), inverts the 4x4 pivot block A11 and publishes rows + A11^-1;  -- barrier --
+//   S3  the owners post the four raw pivot rows;                                  -- barrier --
+//   S4  all threads form R = A11^-1 * (pivot rows), one column each;              -- barrier --
+//   S5  block update  A22 -= A21 * R : the A fragment (8x4 slice of the panel) comes from the
+//       warp's own tile by two shuffles, the B fragment is one conflict-free shared load, one
+//       DMMA per tile; the pivot rows are overwritten with R.
+// Block Gauss-Jordan identity: [A11 A12; A21 A22] -> [I A11^-1 A12; 0 A22 - A21 A11^-1 A12].
+// 4 barriers per 4 pivots instead of 8, and 256 FMAs per issued math instruction instead of 32.
+__device__ __forceinline__ void pb_dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+template <int NW, int RT, int NCT, int MINB>
+struct TileGJ {
+    // NW warps; warp w owns the row tiles {w + NW*rt, rt < RT} (8 rows each) and all NCT column
+    // tiles.  (A variant with a dedicated panel warp factorizing panel q+1 during the block update
+    // of panel q was measured no faster on B200 and is not kept: profiles/r01_notes.md.)
+    static_assert(NCT % 2 == 0, "padded row stride must be 4 mod 16");
+    static constexpr int team = NW * 32;
+    static constexpr int min_blocks = MINB;
+    static constexpr int NRT = NW * RT;
+    static constexpr int max_n = NRT * 8;
+    static constexpr int max_w = NCT * 8;
+    static constexpr int NP = ((max_n + 31) / 32) * 32;  // rows of the panel buffer
+    static constexpr int NI = NP / 32;
+    static constexpr int WP = NCT * 8 + 4;               // stride of the pivot-row buffers
+    static_assert(NP <= 256, "row index must fit the 8-bit key field");
+    static __host__ __device__ constexpr int64_t scratch_doubles_c() {
+        return NP * 4 + 2 * 4 * WP + 16 + (8 + NP) / 2 + 4;
+    }
+    static PB_HD int64_t scratch_doubles(int) { return scratch_doubles_c(); }
+
+    // partial pivoting on the n x 4 panel held in P0 (one warp); publishes the pivot rows, the
+    // inverse of the 4x4 pivot block and the bookkeeping
+    static __device__ __forceinline__ void factor_panel(int l, const double *P0, int *usedf, int *prs,
+                                                        double *Ainv, int *rowidx, int p0, int pw) {
+        double v[NI][4];
+        bool us[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int rr = l + 32 * i;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[i][j] = P0[rr * 4 + j];
+            us[i] = usedf[rr] != 0;
+        }
+        int mypr[4] = {-1, -1, -1, -1};
+        bool sing = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < pw && !sing) {
+                // pivot choice on float-rounded magnitudes (24-bit keys, row in the low byte):
+                // one redux.sync instead of five 64-bit shuffle rounds
+                unsigned key = 0u;
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    const float av = fminf(fabsf((float)v[i][j]), 3.0e38f);
+                    unsigned k = (__float_as_uint(av) & ~0xFFu) | (unsigned)(l + 32 * i);
+                    if (us[i] || !(av > 0.0f)) k = 0u;
+                    key = k > key ? k : key;
+                }
+                key = __reduce_max_sync(0xffffffffu, key);
+                if ((key >> 8) == 0u) { sing = true; }
+                else {
+                    const int pr = (int)(key & 0xFFu);
+                    mypr[j] = pr;
+                    const int ol = pr & 31, os = pr >> 5;
+                    double prow[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        double x = 0.0;
+#pragma unroll
+                        for (int i = 0; i < NI; ++i)
+                            if (i == os) x = v[i][jj];
+                        prow[jj] = __shfl_sync(0xffffffffu, x, ol);
+                    }
+                    const double inv = __drcp_rn(prow[j]);
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) {
+                        const bool me = (l == ol) && (i == os);
+                        if (me) us[i] = true;
+                        else {
+                            const double f = v[i][j] * inv;
+#pragma unroll
+                            for (int jj = j + 1; jj < 4; ++jj) v[i][jj] -= f * prow[jj];
+                        }
+                    }
+                }
+            }
+        }
+        // A11 = original panel entries of the pivot rows (identity for missing pivots);
+        // 4x4 inverse, one element per lane (lane = 4*row + col), shuffles for the broadcasts
+        const int mj = (l >> 2) & 3, mi = l & 3;
+        int prj = -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j == mj) prj = mypr[j];
+        double m = (prj >= 0) ? ((mi < pw) ? P0[prj * 4 + mi] : 0.0) : (mi == mj ? 1.0 : 0.0);
+        double iv = (mi == mj) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double inv = __drcp_rn(__shfl_sync(0xffffffffu, m, k * 4 + k));
+            if (mj == k) { m *= inv; iv *= inv; }
+            const double mk = __shfl_sync(0xffffffffu, m, k * 4 + mi);
+            const double ik = __shfl_sync(0xffffffffu, iv, k * 4 + mi);
+            const double f = __shfl_sync(0xffffffffu, m, mj * 4 + k);
+            if (mj != k) { m -= f * mk; iv -= f * ik; }
+        }
+        if (l < 16) Ainv[l] = iv;
+        if (l == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                prs[j] = mypr[j];
+                if (mypr[j] >= 0) { usedf[mypr[j]] = 1; rowidx[p0 + j] = mypr[j]; }
+            }
+            if (sing) prs[4] = 1;
+        }
+    }
+
+    template <class Team>
+    static __device__ __forceinline__ bool solve(Team &t, double *A, int n, int W, int nrhs,
+                                                 int *rowidx, double *scratch) {
+        const int ti = t.warp(), l = t.lane();
+        const int gr = l >> 2, gc = (l & 3) * 2;
+        const int wend = n + nrhs;
+        double c[RT][NCT][2];
+#pragma unroll
+        for (int rt = 0; rt < RT; ++rt) {
+            const int myrow = 8 * (ti + NW * rt) + gr;
+#pragma unroll
+            for (int tc = 0; tc < NCT; ++tc) {
+                const int col = 8 * tc + gc;
+                c[rt][tc][0] = (myrow < n && col < wend) ? A[myrow * W + col] : 0.0;
+                c[rt][tc][1] = (myrow < n && col + 1 < wend) ? A[myrow * W + col + 1] : 0.0;
+            }
+        }
+        double *P0 = scratch;              // [NP][4]  panel columns
+        double *Raw = P0 + NP * 4;         // [4][WP]  raw pivot rows
+        double *R = Raw + 4 * WP;          // [4][WP]  A11^-1 * pivot rows
+        double *Ainv = R + 4 * WP;         // [4][4]
+        int *prs = (int *)(Ainv + 16);     // [4] pivot rows of the panel, [4] = singular flag
+        int *usedf = prs + 8;              // [NP]
+        for (int i = t.tid(); i < NP; i += t.size()) usedf[i] = i < n ? 0 : 1;
+        for (int i = t.tid(); i < NP * 4; i += t.size()) P0[i] = 0.0;
+        if (t.tid() == 0) prs[4] = 0;
+        t.sync();
+        const int npanel = (n + 3) >> 2;
+        bool ok = true;
+#pragma unroll
+        for (int tcp = 0; tcp < NRT && tcp < NCT; ++tcp) {
+            for (int half = 0; half < 2; ++half) {
+                const int q = 2 * tcp + half;
+                if (q >= npanel || !ok) break;
+                const int p0 = 4 * q;
+                const int pw = (n - p0) < 4 ? (n - p0) : 4;
+                // S1: dump my 8x4 slices of the panel
+                if (((l & 3) >> 1) == half) {
+                    const int j0 = 2 * (l & 1);
+#pragma unroll
+                    for (int rt = 0; rt < RT; ++rt) {
+                        const int myrow = 8 * (ti + NW * rt) + gr;
+                        P0[myrow * 4 + j0] = c[rt][tcp][0];
+                        P0[myrow * 4 + j0 + 1] = c[rt][tcp][1];
+                    }
+                }
+                t.sync();
+                // S2: panel factorization by warp 0
+                if (ti == 0) factor_panel(l, P0, usedf, prs, Ainv, rowidx, p0, pw);
+                t.sync();
+                ok = prs[4] == 0;  // uniform over the team
+                if (!ok) break;
+                // S3: owners post the raw pivot rows (column tiles >= tcp)
+                int myp[RT];
+#pragma unroll
+                for (int rt = 0; rt < RT; ++rt) {
+                    const int myrow = 8 * (ti + NW * rt) + gr;
+                    myp[rt] = -1;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (prs[j] == myrow) myp[rt] = j;
+                    if (myp[rt] >= 0) {
+#pragma unroll
+                        for (int tc = tcp; tc < NCT; ++tc) {
+                            Raw[myp[rt] * WP + 8 * tc + gc] = c[rt][tc][0];
+                            Raw[myp[rt] * WP + 8 * tc + gc + 1] = c[rt][tc][1];
+                        }
+                    }
+                }
+                t.sync();
+                // S4: R = A11^-1 * Raw, one column per thread
+                for (int col = 8 * tcp + t.tid(); col < NCT * 8; col += t.size()) {
+                    double raw[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) raw[i] = (i < pw) ? Raw[i * WP + col] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        double x = 0.0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) x += Ainv[j * 4 + i] * raw[i];
+                        R[j * WP + col] = (j < pw) ? x : 0.0;
+                    }
+                }
+                t.sync();
+                // S5: A22 -= A21 * R  (one DMMA per tile), pivot rows <- R
+                {
+                    const int k = l & 3;
+                    const int src = (l & ~3) | (2 * half + (k >> 1));
+                    double af[RT];
+#pragma unroll
+                    for (int rt = 0; rt < RT; ++rt) {
+                        const double v0 = __shfl_sync(0xffffffffu, c[rt][tcp][0], src);
+                        const double v1 = __shfl_sync(0xffffffffu, c[rt][tcp][1], src);
+                        af[rt] = (k < pw) ? -((k & 1) ? v1 : v0) : 0.0;
+                    }
+                    const double *rb = R + k * WP + (l >> 2);
+#pragma unroll
+                    for (int tc = tcp; tc < NCT; ++tc) {
+                        const double bf = rb[8 * tc];
+#pragma unroll
+                        for (int rt = 0; rt < RT; ++rt) pb_dmma(c[rt][tc], af[rt], bf);
+                    }
+#pragma unroll
+                    for (int rt = 0; rt < RT; ++rt)
+                        if (myp[rt] >= 0) {
+#pragma unroll
+                            for (int tc = tcp; tc < NCT; ++tc) {
+                                c[rt][tc][0] = R[myp[rt] * WP + 8 * tc + gc];
+                                c[rt][tc][1] = R[myp[rt] * WP + 8 * tc + gc + 1];
+                            }
+                        }
+                }
+            }
+        }
+        t.sync();
+        if (!ok) return false;
+#pragma unroll
+        for (int rt = 0; rt < RT; ++rt) {
+            const int myrow = 8 * (ti + NW * rt) + gr;
+#pragma unroll
+            for (int tc = 0; tc < NCT; ++tc) {
+                const int col = 8 * tc + gc;
+                if (myrow < n) {
+                    if (col >= n && col < wend) A[myrow * W + col] = c[rt][tc][0];
+                    if (col + 1 >= n && col + 1 < wend) A[myrow * W + col + 1] = c[rt][tc][1];
+                }
+            }
+        }
+        t.sync();
+        return true;
+    }
+};
+#endif
+
 // ------------------------------------------------------------------------------------
 // small dense inverse of the nd x nd matrix of distance vectors (rows d_m)
 // ------------------------------------------------------------------------------------

@@ -39,7 +39,7 @@ PB_HD int64_t mpsa_rest_doubles(int nd, int nsf, int nsc, int nb, int nalpha) {
     d += (int64_t)nsf * nd;                     // nrm
     d += 2 * (int64_t)nsc;                      // wk, volk
     d += (int64_t)nalpha * nsc * nd2 * 2;       // NA, AE
-    int64_t ints = nsc + 3 * (int64_t)nsf + (int64_t)nsf * nd + n + (int64_t)nsc * nd + 2 * nd;
+    int64_t ints = nsc + 4 * (int64_t)nsf + (int64_t)nsf * nd + n + (int64_t)nsc * nd + 2 * nd;
     return d + (ints + 1) / 2 + 2;
 }
 
@@ -91,6 +91,7 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
     int *rowidx = bcu + nsf * ND;
     int *slot = rowidx + n;
     int *elim = slot + nsc * ND;                // [i] neumann, [ND+i] robin
+    int *sidesel = elim + 2 * ND;               // [u] side the traction is evaluated from
 
     // ---- phase 1: lists
     for (int k = t.tid(); k < nsc; k += t.size()) cell[k] = P.sc_cell[sc0 + k];
@@ -233,6 +234,34 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
     }
     t.sync();
 
+    // ---- phase 3b: side each sub-face's traction is evaluated from.  The reference takes the
+    // side with the smaller cell index (mpsa.py:1782-1832); traction continuity makes both sides
+    // agree, and the softer side is the well-conditioned one in the continuity-point formulation
+    // (see the MPFA routine), so pick the side with the smaller |n . (C o S) D^-1|.
+    for (int u = t.tid(); u < nsf; u += t.size()) {
+        const int s1 = sides[u] & 0xFFFF, s2 = (sides[u] >> 16) & 0xFFFF;
+        int pick = s1;
+        if (s2 != 0xFFFF) {
+            const double *nu = nrm + u * ND;
+            double w1 = 0.0, w2 = 0.0;
+            const double *p1 = PS + (s1 / ND) * ND2 * ND2, *p2 = PS + (s2 / ND) * ND2 * ND2;
+            for (int i = 0; i < ND; ++i)
+                for (int am = 0; am < ND2; ++am) {
+                    double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+                    for (int r = 0; r < ND; ++r) {
+                        a1 += nu[r] * p1[(i * ND + r) * ND2 + am];
+                        a2 += nu[r] * p2[(i * ND + r) * ND2 + am];
+                    }
+                    w1 += fabs(a1);
+                    w2 += fabs(a2);
+                }
+            if (w2 < w1) pick = s2;
+        }
+        sidesel[u] = pick;
+    }
+    t.sync();
+
     // ---- phase 4: one row per (sub-face, component)
     for (int x = t.tid(); x < n; x += t.size()) {
         const int u = x / ND, i = x - u * ND;
@@ -323,40 +352,20 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
     const int32_t *pfb = P.pos_fb + P.posfb_ptr[s];
     for (int x = t.warp(); x < n; x += t.nwarps()) {
         const int u = x / ND, i = x - u * ND;
-        // The reference takes the traction from the side with the smaller cell index
-        // (mpsa.py:1782-1832).  Traction continuity makes both sides agree; evaluate from the
-        // softer side, which is the well-conditioned one in the continuity-point formulation
-        // (see the MPFA routine).
         const double *nu = nrm + u * ND;
-        int side1 = sides[u] & 0xFFFF;
+        const int side1 = sidesel[u];
         double hs[ND][ND];  // [a][m] coefficient of ubar_{u(k1,m),a}
         {
-            const int side2 = (sides[u] >> 16) & 0xFFFF;
-            double nrm1 = 0.0, nrm2 = 0.0, h2[ND][ND];
             const double *ps1 = PS + ((side1 / ND) * ND2 + i * ND) * ND2;
-            const double *ps2 = PS + ((side2 == 0xFFFF ? 0 : side2 / ND) * ND2 + i * ND) * ND2;
 #pragma unroll
             for (int a = 0; a < ND; ++a)
 #pragma unroll
                 for (int m = 0; m < ND; ++m) {
-                    double v = 0.0, w = 0.0;
+                    double v = 0.0;
 #pragma unroll
-                    for (int r = 0; r < ND; ++r) {
-                        v += nu[r] * ps1[(r * ND + a) * ND + m];
-                        w += nu[r] * ps2[(r * ND + a) * ND + m];
-                    }
+                    for (int r = 0; r < ND; ++r) v += nu[r] * ps1[(r * ND + a) * ND + m];
                     hs[a][m] = v;
-                    h2[a][m] = w;
-                    nrm1 += fabs(v);
-                    nrm2 += fabs(w);
                 }
-            if (side2 != 0xFFFF && nrm2 < nrm1) {
-                side1 = side2;
-#pragma unroll
-                for (int a = 0; a < ND; ++a)
-#pragma unroll
-                    for (int m = 0; m < ND; ++m) hs[a][m] = h2[a][m];
-            }
         }
         const int k1 = side1 / ND, m1 = side1 - k1 * ND;
         const double *xr[ND][ND];

@@ -395,15 +395,18 @@ struct TileGJ {
                             if (i == os) x = v[i][jj];
                         prow[jj] = __shfl_sync(0xffffffffu, x, ol);
                     }
-                    const double inv = __drcp_rn(prow[j]);
+                    // fraction-free elimination: the panel copy is only used to CHOOSE the pivots
+                    // (A11^-1 is formed from the original entries below), and scaling every row by
+                    // the same pivot does not change the arg-max -> no reciprocal on the critical path
+                    const double piv = prow[j];
 #pragma unroll
                     for (int i = 0; i < NI; ++i) {
                         const bool me = (l == ol) && (i == os);
                         if (me) us[i] = true;
                         else {
-                            const double f = v[i][j] * inv;
+                            const double f = v[i][j];
 #pragma unroll
-                            for (int jj = j + 1; jj < 4; ++jj) v[i][jj] -= f * prow[jj];
+                            for (int jj = j + 1; jj < 4; ++jj) v[i][jj] = v[i][jj] * piv - f * prow[jj];
                         }
                     }
                 }

@@ -1,0 +1,215 @@
+"""Row-distributed SpMV with halo exchange and a BiCGStab solve on top of it -- the "next" row
+of the scope table: the reference only has direct solvers
+(``SolutionStrategy.solve_linear_system``, reference src/porepy/models/solution_strategy.py:830-884);
+at 10^6 3-D cells those dominate the run time, and the north star asks for the Newton SpMV /
+residual with NCCL used only for ghost entries and Krylov dot products.
+
+One process per GPU.  Cells (rows and columns) are assigned to ranks by an ``owner`` array
+(e.g. ``porepy_b200.shard.partition_cells``).  Every rank keeps the rows of its own cells in a
+device-resident CSR (``DeviceCsr``) with columns renumbered as [own cells | ghost cells]; one SpMV =
+pack + neighbour exchange of the ghost entries (``torch.distributed`` point-to-point, NCCL on GPUs)
++ the local ``csr_spmv_kernel`` on torch's current stream.  Dot products are local dots + one
+all-reduce of 1-2 scalars.
+
+The local SpMV runs through ``pb_csr_spmv_dev`` on raw device pointers of torch tensors (torch is
+plumbing: memory + collectives).  For the CPU (gloo) tests of the host logic a ``matvec`` stand-in
+can be injected; the product default has no CPU path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sps
+
+
+@dataclass
+class LocalSystem:
+    """This rank's rows of a row-distributed matrix."""
+
+    rank: int
+    world: int
+    owned: np.ndarray            # global ids of own cells (ascending)
+    ghosts: np.ndarray           # global ids of ghost columns, grouped by owner rank
+    a_local: sps.csr_matrix      # (n_own, n_own + n_ghost), local column numbering
+    recv_counts: list            # ghosts received from each rank
+    send_index: list             # per rank: local indices (into own) to send
+    extra: dict = field(default_factory=dict)
+
+
+def build_local_system(a, owner: np.ndarray, rank: int, world: int, group=None) -> LocalSystem:
+    """Split ``a`` (global scipy CSR, same on every rank) by rows; collective (exchanges the ghost lists)."""
+    a = sps.csr_matrix(a)
+    owner = np.asarray(owner)
+    owned = np.flatnonzero(owner == rank)
+    rows = a[owned]
+    cols = np.unique(rows.indices)
+    gh = cols[owner[cols] != rank]
+    gh = gh[np.lexsort((gh, owner[gh]))]  # grouped by owner, ascending inside
+    n_own = owned.size
+    g2l = np.full(a.shape[1], -1, dtype=np.int64)
+    g2l[owned] = np.arange(n_own)
+    g2l[gh] = n_own + np.arange(gh.size)
+    a_local = sps.csr_matrix((rows.data, g2l[rows.indices], rows.indptr), shape=(n_own, n_own + gh.size))
+    a_local.sort_indices()
+    need = [gh[owner[gh] == q] for q in range(world)]  # what I need from q
+    recv_counts = [int(x.size) for x in need]
+    if world > 1:
+        import torch.distributed as dist
+        all_need = [None] * world
+        dist.all_gather_object(all_need, [x.tolist() for x in need], group=group)
+        send_index = [g2l[np.asarray(all_need[q][rank], dtype=np.int64)] for q in range(world)]
+    else:
+        send_index = [np.zeros(0, dtype=np.int64)]
+    return LocalSystem(rank, world, owned, gh, a_local, recv_counts, send_index)
+
+
+class DistributedOperator:
+    """y_own = (A x)_own with x distributed; torch tensors (cuda float64; cpu only with a stand-in)."""
+
+    def __init__(self, loc: LocalSystem, device, matvec=None, group=None):
+        import torch
+        self.torch = torch
+        self.loc, self.device, self.group = loc, device, group
+        self.n_own = loc.owned.size
+        self.n_ghost = loc.ghosts.size
+        self.xbuf = torch.zeros(self.n_own + self.n_ghost, dtype=torch.float64, device=device)
+        self.send_idx = [torch.as_tensor(ix, dtype=torch.int64, device=device) for ix in loc.send_index]
+        self.halo_bytes = 8 * sum(int(ix.numel()) for ix in self.send_idx)
+        if matvec is not None:
+            self._matvec = matvec  # test stand-in (host logic checks under gloo)
+            self.dev_csr = None
+        else:
+            if torch.device(device).type != "cuda":
+                raise RuntimeError("porepy_b200.krylov: the SpMV kernel needs a CUDA device (no CPU path)")
+            from .sparse import DeviceCsr
+            self.dev_csr = DeviceCsr(loc.a_local)
+            self._matvec = None
+
+    def exchange(self, x_own):
+        """Fill xbuf = [x_own | ghosts] (neighbour exchange of the ghost entries)."""
+        torch = self.torch
+        self.xbuf[: self.n_own].copy_(x_own)
+        if self.loc.world == 1:
+            return self.xbuf
+        import torch.distributed as dist
+        ops, off = [], self.n_own
+        sends = []
+        for q in range(self.loc.world):
+            if q == self.loc.rank:
+                continue
+            if self.send_idx[q].numel():
+                buf = x_own.index_select(0, self.send_idx[q]).contiguous()
+                sends.append(buf)
+                ops.append(dist.P2POp(dist.isend, buf, q, group=self.group))
+        for q in range(self.loc.world):
+            cnt = self.loc.recv_counts[q]
+            if q != self.loc.rank and cnt:
+                ops.append(dist.P2POp(dist.irecv, self.xbuf[off:off + cnt], q, group=self.group))
+            off += cnt
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return self.xbuf
+
+    def matvec(self, x_own, out=None):
+        torch = self.torch
+        xb = self.exchange(x_own)
+        if out is None:
+            out = torch.empty(self.n_own, dtype=torch.float64, device=self.device)
+        if self._matvec is not None:
+            out.copy_(self._matvec(xb))
+        else:
+            stream = torch.cuda.current_stream().cuda_stream
+            self.dev_csr.spmv_device(xb.data_ptr(), out.data_ptr(), stream)
+        return out
+
+    def dots(self, pairs):
+        """Global dot products of several (a, b) pairs with ONE all-reduce."""
+        torch = self.torch
+        v = torch.stack([torch.dot(a, b) for a, b in pairs])
+        if self.loc.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(v, group=self.group)
+        return v
+
+
+def bicgstab(op: DistributedOperator, b_own, x0=None, tol: float = 1e-10, maxiter: int = 2000,
+             diag_own=None):
+    """Right-preconditioned (Jacobi, optional) BiCGStab on the distributed operator.
+    Returns (x_own, info) with info = {"iterations", "relres", "converged", "spmv", "allreduce"}."""
+    torch = op.torch
+    x = torch.zeros_like(b_own) if x0 is None else x0.clone()
+    minv = None if diag_own is None else 1.0 / diag_own
+    r = b_own - op.matvec(x) if x0 is not None else b_own.clone()
+    rhat = r.clone()
+    bnorm = float(torch.sqrt(op.dots([(b_own, b_own)])[0]))
+    if bnorm == 0.0:
+        return x, {"iterations": 0, "relres": 0.0, "converged": True, "spmv": 0, "allreduce": 1}
+    rho = alpha = omega = 1.0
+    v = torch.zeros_like(r)
+    p = torch.zeros_like(r)
+    nspmv, nred, relres = 0, 1, 1.0
+    for it in range(1, maxiter + 1):
+        rho_new = float(op.dots([(rhat, r)])[0])
+        nred += 1
+        if rho_new == 0.0:
+            break
+        beta = (rho_new / rho) * (alpha / omega)
+        p = r + beta * (p - omega * v)
+        ph = p if minv is None else p * minv
+        v = op.matvec(ph)
+        nspmv += 1
+        alpha = rho_new / float(op.dots([(rhat, v)])[0])
+        nred += 1
+        s = r - alpha * v
+        sh = s if minv is None else s * minv
+        t = op.matvec(sh)
+        nspmv += 1
+        d = op.dots([(t, s), (t, t), (s, s)])
+        nred += 1
+        tt = float(d[1])
+        omega = float(d[0]) / tt if tt > 0 else 0.0
+        x = x + alpha * ph + omega * sh
+        r = s - omega * t
+        rho = rho_new
+        relres = float(torch.sqrt(op.dots([(r, r)])[0])) / bnorm
+        nred += 1
+        if relres < tol or omega == 0.0:
+            return x, {"iterations": it, "relres": relres, "converged": relres < tol, "spmv": nspmv,
+                       "allreduce": nred}
+    return x, {"iterations": maxiter, "relres": relres, "converged": False, "spmv": nspmv, "allreduce": nred}
+
+
+def solve(a, b, owner=None, tol: float = 1e-10, maxiter: int = 2000, jacobi: bool = True, device=None,
+          matvec_factory=None):
+    """Solve A x = b.  Single process: everything on cuda:0.  Under torch.distributed: ``a``/``b`` are
+    the global system on every rank, ``owner`` assigns cells to ranks; returns the OWN part of x,
+    the own global ids and the solver info."""
+    import torch
+    rank, world = 0, 1
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    a = sps.csr_matrix(a)
+    if owner is None:
+        owner = np.zeros(a.shape[0], dtype=np.int64)
+        if world > 1:
+            owner = (np.arange(a.shape[0]) * world) // a.shape[0]
+    loc = build_local_system(a, owner, rank, world)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu"
+    mv = None if matvec_factory is None else matvec_factory(loc)
+    op = DistributedOperator(loc, device, matvec=mv)
+    b_own = torch.as_tensor(np.asarray(b)[loc.owned], dtype=torch.float64, device=device)
+    diag = None
+    if jacobi:
+        dg = a.diagonal()[loc.owned]
+        if np.all(dg != 0):
+            diag = torch.as_tensor(dg, dtype=torch.float64, device=device)
+    x, info = bicgstab(op, b_own, tol=tol, maxiter=maxiter, diag_own=diag)
+    info["halo_bytes_per_spmv"] = op.halo_bytes
+    return x, loc.owned, info

@@ -347,6 +347,7 @@ struct TileGJ {
     static constexpr int NI = NP / 32;
     static constexpr int WP = NCT * 8 + 4;               // stride of the pivot-row buffers
     static_assert(NP <= 256, "row index must fit the 8-bit key field");
+    static_assert(NI <= 8, "extend the PB_PICK list");
     static __host__ __device__ constexpr int64_t scratch_doubles_c() {
         return NP * 4 + 2 * 4 * WP + 16 + (8 + NP) / 2 + 4;
     }
@@ -375,10 +376,10 @@ struct TileGJ {
                 unsigned key = 0u;
 #pragma unroll
                 for (int i = 0; i < NI; ++i) {
-                    const float av = fminf(fabsf((float)v[i][j]), 3.0e38f);
-                    unsigned k = (__float_as_uint(av) & ~0xFFu) | (unsigned)(l + 32 * i);
-                    if (us[i] || !(av > 0.0f)) k = 0u;
-                    key = k > key ? k : key;
+                    // (float)inf / nan keys would win the max; a finite panel is guaranteed by the
+                    // row scaling, and a NaN panel ends as "singular" through the reciprocal below
+                    unsigned k = (__float_as_uint(fabsf((float)v[i][j])) & 0x7FFFFF00u) | (unsigned)(l + 32 * i);
+                    key = (!us[i] && k > key) ? k : key;
                 }
                 key = __reduce_max_sync(0xffffffffu, key);
                 if ((key >> 8) == 0u) { sing = true; }
@@ -387,13 +388,21 @@ struct TileGJ {
                     mypr[j] = pr;
                     const int ol = pr & 31, os = pr >> 5;
                     double prow[4];
+                    {
+                        double x[4] = {0.0, 0.0, 0.0, 0.0};
+                        switch (os) {  // warp-uniform: a jump instead of NI*4 predicated selects
+#define PB_PICK(I)                                                        \
+    case I:                                                               \
+        if constexpr (I < NI) {                                           \
+            x[0] = v[I][0]; x[1] = v[I][1]; x[2] = v[I][2]; x[3] = v[I][3]; \
+        }                                                                 \
+        break;
+                            PB_PICK(0) PB_PICK(1) PB_PICK(2) PB_PICK(3) PB_PICK(4) PB_PICK(5) PB_PICK(6) PB_PICK(7)
+#undef PB_PICK
+                            default: break;
+                        }
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        double x = 0.0;
-#pragma unroll
-                        for (int i = 0; i < NI; ++i)
-                            if (i == os) x = v[i][jj];
-                        prow[jj] = __shfl_sync(0xffffffffu, x, ol);
+                        for (int jj = 0; jj < 4; ++jj) prow[jj] = __shfl_sync(0xffffffffu, x[jj], ol);
                     }
                     // fraction-free elimination: the panel copy is only used to CHOOSE the pivots
                     // (A11^-1 is formed from the original entries below), and scaling every row by

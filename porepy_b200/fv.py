@@ -326,10 +326,11 @@ class _Base:
         self.discretize(sd, data)
 
     def _check_unsupported(self, params: dict) -> None:
-        pa = params.get("partition_arguments")
-        # partition_arguments bound the reference's working set; the kernels stream over nodes
-        # and never materialise the global block-diagonal inverse, so the key is accepted and ignored.
-        del pa
+        """``partition_arguments`` bound the reference's working set (``_fvutils.py:358-411``); the
+        kernels stream over nodes and never materialise the global block-diagonal inverse, so the
+        key is accepted and ignored.  ``specified_cells/faces/nodes`` select a partial update in the
+        reference; here the whole grid is re-discretized (same matrices)."""
+        return None
 
 
 class Mpfa(_Base):

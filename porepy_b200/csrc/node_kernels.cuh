@@ -355,8 +355,64 @@ struct TileGJ {
 
     // partial pivoting on the n x 4 panel held in P0 (one warp); publishes the pivot rows, the
     // inverse of the 4x4 pivot block and the bookkeeping
+    // 4x4 inverse of the pivot block, one element per lane (lane = 4*row + col; lanes >= 16 mirror
+    // lanes 0..15), Gauss-Jordan in the given row order, shuffles for the broadcasts.
+    // Returns max |inverse entry| (inf / nan when the block is not invertible in that order).
+    static __device__ __forceinline__ double invert_block(int l, double m, double &iv) {
+        const int mj = (l >> 2) & 3, mi = l & 3;
+        iv = (mi == mj) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double inv = __drcp_rn(__shfl_sync(0xffffffffu, m, k * 4 + k));
+            if (mj == k) { m *= inv; iv *= inv; }
+            const double mk = __shfl_sync(0xffffffffu, m, k * 4 + mi);
+            const double ik = __shfl_sync(0xffffffffu, iv, k * 4 + mi);
+            const double f = __shfl_sync(0xffffffffu, m, mj * 4 + k);
+            if (mj != k) { m -= f * mk; iv -= f * ik; }
+        }
+        double g = fabs(iv);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const double g2 = __shfl_xor_sync(0xffffffffu, g, o);
+            g = (g2 > g || !(g2 == g2)) ? g2 : g;  // propagate nan
+        }
+        return g;
+    }
+
+    // Pivot choice for one panel (one warp).  Fast path: the panel's natural rows p0..p0+3 (the
+    // "diagonal block") are accepted as pivot block when they are unused and the inverse of the
+    // block is tame (max |entry| <= kGrowth; rows are scaled to unit 1-norm) -- threshold block
+    // pivoting: no search, ~6x shorter dependent chain.  Otherwise: partial pivoting on the n x 4
+    // panel (packed-key warp arg-max per column).  Publishes the pivot rows, A11^-1 and bookkeeping.
+    static constexpr double kGrowth = 64.0;
     static __device__ __forceinline__ void factor_panel(int l, const double *P0, int *usedf, int *prs,
                                                         double *Ainv, int *rowidx, int p0, int pw) {
+        const int mj = (l >> 2) & 3, mi = l & 3;
+        int mypr[4] = {-1, -1, -1, -1};
+        bool sing = false;
+        double iv;
+        // ---- fast path
+        {
+            const bool bad = (mj < pw) && (usedf[p0 + mj] != 0);
+            const bool any_used = __any_sync(0xffffffffu, bad);
+            double m = (mj < pw) ? ((mi < pw) ? P0[(p0 + mj) * 4 + mi] : 0.0) : (mi == mj ? 1.0 : 0.0);
+            const double growth = invert_block(l, m, iv);
+            if (!any_used && growth <= kGrowth) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < pw) mypr[j] = p0 + j;
+                if (l < 16) Ainv[l] = iv;
+                if (l == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        prs[j] = mypr[j];
+                        if (mypr[j] >= 0) { usedf[mypr[j]] = 1; rowidx[p0 + j] = mypr[j]; }
+                    }
+                }
+                return;
+            }
+        }
+        // ---- partial pivoting on the panel
         double v[NI][4];
         bool us[NI];
 #pragma unroll
@@ -366,8 +422,6 @@ struct TileGJ {
             for (int j = 0; j < 4; ++j) v[i][j] = P0[rr * 4 + j];
             us[i] = usedf[rr] != 0;
         }
-        int mypr[4] = {-1, -1, -1, -1};
-        bool sing = false;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (j < pw && !sing) {
@@ -376,8 +430,6 @@ struct TileGJ {
                 unsigned key = 0u;
 #pragma unroll
                 for (int i = 0; i < NI; ++i) {
-                    // (float)inf / nan keys would win the max; a finite panel is guaranteed by the
-                    // row scaling, and a NaN panel ends as "singular" through the reciprocal below
                     unsigned k = (__float_as_uint(fabsf((float)v[i][j])) & 0x7FFFFF00u) | (unsigned)(l + 32 * i);
                     key = (!us[i] && k > key) ? k : key;
                 }
@@ -421,24 +473,14 @@ struct TileGJ {
                 }
             }
         }
-        // A11 = original panel entries of the pivot rows (identity for missing pivots);
-        // 4x4 inverse, one element per lane (lane = 4*row + col), shuffles for the broadcasts
-        const int mj = (l >> 2) & 3, mi = l & 3;
+        // A11 = original panel entries of the pivot rows (identity for missing pivots)
         int prj = -1;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (j == mj) prj = mypr[j];
-        double m = (prj >= 0) ? ((mi < pw) ? P0[prj * 4 + mi] : 0.0) : (mi == mj ? 1.0 : 0.0);
-        double iv = (mi == mj) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double inv = __drcp_rn(__shfl_sync(0xffffffffu, m, k * 4 + k));
-            if (mj == k) { m *= inv; iv *= inv; }
-            const double mk = __shfl_sync(0xffffffffu, m, k * 4 + mi);
-            const double ik = __shfl_sync(0xffffffffu, iv, k * 4 + mi);
-            const double f = __shfl_sync(0xffffffffu, m, mj * 4 + k);
-            if (mj != k) { m -= f * mk; iv -= f * ik; }
-        }
+        const double m = (prj >= 0) ? ((mi < pw) ? P0[prj * 4 + mi] : 0.0) : (mi == mj ? 1.0 : 0.0);
+        const double growth = invert_block(l, m, iv);
+        if (!(growth < 1e300)) sing = true;  // inf / nan
         if (l < 16) Ainv[l] = iv;
         if (l == 0) {
 #pragma unroll

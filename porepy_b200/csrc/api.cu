@@ -105,7 +105,7 @@ struct DevBuf {
 using Cfg0 = RegGJ<1, 12, 2, 4>;   // team 32  : MPFA hexahedral nodes (12 x 45)
 using Cfg1 = TileGJ<5, 1, 8, 3>;   // team 160 : MPSA hexahedral nodes (36 x 61), DMMA
 using Cfg2 = TileGJ<5, 1, 12, 3>;  // team 160 : Biot hexahedral nodes, DMMA
-using Cfg3 = RegGJ<4, 10, 5, 3>;   // team 128 : MPFA tetrahedral nodes (36 x 133)
+using Cfg3 = TileGJ<5, 1, 18, 3>;  // team 160 : MPFA tetrahedral nodes (36 x 133), DMMA
 using Cfg4 = TileGJ<7, 2, 24, 1>;  // team 224 : MPSA tetrahedral nodes (108 x 181), FP64 tensor cores (DMMA)
 using Cfg5 = RegGJ<16, 7, 8, 1>;   // team 512 : Biot tetrahedral nodes
 using Cfg6 = SmemGJ;               // team 256 : anything else (in-memory Gauss-Jordan)

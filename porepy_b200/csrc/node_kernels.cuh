@@ -385,6 +385,19 @@ struct TileGJ {
     // pivoting: no search, ~6x shorter dependent chain.  Otherwise: partial pivoting on the n x 4
     // panel (packed-key warp arg-max per column).  Publishes the pivot rows, A11^-1 and bookkeeping.
     static constexpr double kGrowth = 64.0;
+    // fast-path test, executed by EVERY warp redundantly (same inputs -> same decision): no
+    // serialized section and no extra barrier on the common path
+    static __device__ __forceinline__ bool try_diagonal_block(int l, const double *P0, const int *usedf,
+                                                              int p0, int pw, double &iv) {
+        const int mj = (l >> 2) & 3, mi = l & 3;
+        const bool bad = (mj < pw) && (usedf[p0 + mj] != 0);
+        const bool any_used = __any_sync(0xffffffffu, bad);
+        const double m = (mj < pw) ? ((mi < pw) ? P0[(p0 + mj) * 4 + mi] : 0.0) : (mi == mj ? 1.0 : 0.0);
+        const double growth = invert_block(l, m, iv);
+        return !any_used && growth <= kGrowth;
+    }
+
+    template <bool TRY_FAST>
     static __device__ __forceinline__ void factor_panel(int l, const double *P0, int *usedf, int *prs,
                                                         double *Ainv, int *rowidx, int p0, int pw) {
         const int mj = (l >> 2) & 3, mi = l & 3;
@@ -392,7 +405,7 @@ struct TileGJ {
         bool sing = false;
         double iv;
         // ---- fast path
-        {
+        if (TRY_FAST) {
             const bool bad = (mj < pw) && (usedf[p0 + mj] != 0);
             const bool any_used = __any_sync(0xffffffffu, bad);
             double m = (mj < pw) ? ((mi < pw) ? P0[(p0 + mj) * 4 + mi] : 0.0) : (mi == mj ? 1.0 : 0.0);
@@ -528,7 +541,8 @@ struct TileGJ {
                 if (q >= npanel || !ok) break;
                 const int p0 = 4 * q;
                 const int pw = (n - p0) < 4 ? (n - p0) : 4;
-                // S1: dump my 8x4 slices of the panel
+                // S1: dump my 8x4 slices of the panel; the owners of the panel's natural rows
+                // p0..p0+3 post them as raw pivot rows right away (speculation for the fast path)
                 if (((l & 3) >> 1) == half) {
                     const int j0 = 2 * (l & 1);
 #pragma unroll
@@ -538,21 +552,12 @@ struct TileGJ {
                         P0[myrow * 4 + j0 + 1] = c[rt][tcp][1];
                     }
                 }
-                t.sync();
-                // S2: panel factorization by warp 0
-                if (ti == 0) factor_panel(l, P0, usedf, prs, Ainv, rowidx, p0, pw);
-                t.sync();
-                ok = prs[4] == 0;  // uniform over the team
-                if (!ok) break;
-                // S3: owners post the raw pivot rows (column tiles >= tcp)
                 int myp[RT];
 #pragma unroll
                 for (int rt = 0; rt < RT; ++rt) {
                     const int myrow = 8 * (ti + NW * rt) + gr;
-                    myp[rt] = -1;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (prs[j] == myrow) myp[rt] = j;
+                    const int j = myrow - p0;
+                    myp[rt] = (j >= 0 && j < pw) ? j : -1;
                     if (myp[rt] >= 0) {
 #pragma unroll
                         for (int tc = tcp; tc < NCT; ++tc) {
@@ -562,6 +567,36 @@ struct TileGJ {
                     }
                 }
                 t.sync();
+                // S2: every warp tests the diagonal block (threshold block pivoting)
+                double iv;
+                const bool fast = try_diagonal_block(l, P0, usedf, p0, pw, iv);
+                if (fast) {
+                    if (l < 16) Ainv[l] = iv;  // every warp writes the same 16 values
+                    __syncwarp();
+                } else {
+                    // rare: partial pivoting on the panel by warp 0, then the owners re-post the rows
+                    t.sync();  // all warps have read usedf / P0 for the test
+                    if (ti == 0) factor_panel<false>(l, P0, usedf, prs, Ainv, rowidx, p0, pw);
+                    t.sync();
+                    ok = prs[4] == 0;  // uniform over the team
+                    if (!ok) break;
+#pragma unroll
+                    for (int rt = 0; rt < RT; ++rt) {
+                        const int myrow = 8 * (ti + NW * rt) + gr;
+                        myp[rt] = -1;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (prs[j] == myrow) myp[rt] = j;
+                        if (myp[rt] >= 0) {
+#pragma unroll
+                            for (int tc = tcp; tc < NCT; ++tc) {
+                                Raw[myp[rt] * WP + 8 * tc + gc] = c[rt][tc][0];
+                                Raw[myp[rt] * WP + 8 * tc + gc + 1] = c[rt][tc][1];
+                            }
+                        }
+                    }
+                    t.sync();
+                }
                 // S4: R = A11^-1 * Raw, one column per thread
                 for (int col = 8 * tcp + t.tid(); col < NCT * 8; col += t.size()) {
                     double raw[4];
@@ -577,6 +612,10 @@ struct TileGJ {
                 }
                 t.sync();
                 // S5: A22 -= A21 * R  (one DMMA per tile), pivot rows <- R
+                if (fast && t.tid() < pw) {  // bookkeeping of the fast path (after every warp's test)
+                    usedf[p0 + t.tid()] = 1;
+                    rowidx[p0 + t.tid()] = p0 + t.tid();
+                }
                 {
                     const int k = l & 3;
                     const int src = (l & ~3) | (2 * half + (k >> 1));

@@ -102,7 +102,7 @@ struct DevBuf {
 };
 
 // Solver configurations (node_kernels.cuh).  A node goes to the first one that fits.
-using Cfg0 = RegGJ<1, 12, 2, 4>;   // team 32  : MPFA hexahedral nodes (12 x 45)
+using Cfg0 = TileGJ<1, 2, 6, 4>;   // team 32  : MPFA hexahedral nodes (12 x 45), DMMA, one warp per node
 using Cfg1 = TileGJ<5, 1, 8, 3>;   // team 160 : MPSA hexahedral nodes (36 x 61), DMMA
 using Cfg2 = TileGJ<5, 1, 12, 3>;  // team 160 : Biot hexahedral nodes, DMMA
 using Cfg3 = TileGJ<5, 1, 18, 3>;  // team 160 : MPFA tetrahedral nodes (36 x 133), DMMA

@@ -104,7 +104,7 @@ struct DevBuf {
 // Solver configurations (node_kernels.cuh).  A node goes to the first one that fits.
 using Cfg0 = TileGJ<1, 2, 6, 4>;   // team 32  : MPFA hexahedral nodes (12 x 45), DMMA, one warp per node
 using Cfg1 = TileGJ<2, 3, 8, 6>;   // team 64  : MPSA hexahedral nodes (36 x 61), DMMA
-using Cfg2 = TileGJ<5, 1, 12, 3>;  // team 160 : Biot hexahedral nodes, DMMA
+using Cfg2 = TileGJ<2, 3, 12, 4>;  // team 64  : Biot hexahedral nodes, DMMA
 using Cfg3 = TileGJ<5, 1, 18, 3>;  // team 160 : MPFA tetrahedral nodes (36 x 133), DMMA
 using Cfg4 = TileGJ<7, 2, 24, 1>;  // team 224 : MPSA tetrahedral nodes (108 x 181), FP64 tensor cores (DMMA)
 using Cfg5 = RegGJ<16, 7, 8, 1>;   // team 512 : Biot tetrahedral nodes

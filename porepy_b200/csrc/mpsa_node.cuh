@@ -339,12 +339,37 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
     }
 
     // ---- phase 6: Z[p][c] = SigmaA[p] applied to the solution (+ direct cell-displacement term)
+#if defined(__CUDA_ARCH__)
+    // (ND2 x n) * (n x nrhs) on the FP64 tensor cores: one 8x8 tile of Z per warp iteration
+    {
+        const int l = t.lane();
+        const int ntr = (ND2 + 7) / 8, ntc = (nrhs + 7) / 8;
+        for (int tile = t.warp(); tile < ntr * ntc; tile += t.nwarps()) {
+            const int tr = tile / ntc, tc = tile - tr * ntc;
+            const int row = 8 * tr + (l >> 2);
+            const int colb = 8 * tc + (l >> 2);
+            double acc[2] = {0.0, 0.0};
+            for (int k0 = 0; k0 < n; k0 += 4) {
+                const int k = k0 + (l & 3);
+                const double a = (row < ND2 && k < n) ? SA[row * n + k] : 0.0;
+                const double b = (k < n && colb < nrhs) ? A[(int64_t)rowidx[k] * W + n + colb] : 0.0;
+                pb_dmma(acc, a, b);
+            }
+            const int c0 = 8 * tc + 2 * (l & 3);
+            if (row < ND2) {
+                if (c0 < nrhs) Z[row * nrhs + c0] = acc[0] + (c0 < ncc ? SAc[row * ncc + c0] : 0.0);
+                if (c0 + 1 < nrhs) Z[row * nrhs + c0 + 1] = acc[1] + (c0 + 1 < ncc ? SAc[row * ncc + c0 + 1] : 0.0);
+            }
+        }
+    }
+#else
     for (int it = t.tid(); it < ND2 * nrhs; it += t.size()) {
         const int p = it / nrhs, c = it - p * nrhs;
         double v = (c < ncc) ? SAc[p * ncc + c] : 0.0;
         for (int x = 0; x < n; ++x) v += SA[p * n + x] * A[(int64_t)rowidx[x] * W + n + c];
         Z[it] = v;
     }
+#endif
     t.sync();
 
     // ---- phase 7: face rows (traction from the unique side, displacement trace)

@@ -145,7 +145,7 @@ struct pb_plan {
     bool have_geo = false;
     PlanView view{};
     GeoView geo{};
-    DevBuf err, a_ws;
+    DevBuf err, a_ws, repack_tmp;
     // mpfa
     std::vector<NodeClass> mpfa_cls;
     DevBuf perm, bc, robw;
@@ -689,6 +689,30 @@ extern "C" int pb_plan_pattern_expanded(pb_plan *p, int which, int br, int bc, i
     return PB_OK;
 }
 
+// (ncomp, n) row-major -> (n, ncomp): one contiguous record per entity for the per-sub-cell gathers
+__global__ void repack_kernel(const double *__restrict__ in, double *__restrict__ out, int ncomp, int64_t n) {
+    const int64_t total = (int64_t)ncomp * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / ncomp;
+        const int comp = (int)(i - e * ncomp);
+        out[i] = in[(int64_t)comp * n + e];
+    }
+}
+
+static int upload_repacked(pb_plan *p, DevBuf &dst, const double *host, int ncomp, int64_t n) {
+    DevBuf &tmp = p->repack_tmp;
+    cudaStream_t st = p->stream;
+    CUDA_TRY(tmp.upload(host, (size_t)ncomp * n, st));
+    CUDA_TRY(dst.ensure((size_t)ncomp * n * sizeof(double)));
+    const int64_t total = (int64_t)ncomp * n;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)kSMs * 32));
+    repack_kernel<<<grid, 256, 0, st>>>(tmp.as<double>(), dst.as<double>(), ncomp, n);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PB_OK;
+}
+
 extern "C" int pb_plan_set_geometry(pb_plan *p, const double *nodes, const double *face_normals,
                                     const double *face_centers, const double *face_areas,
                                     const double *cell_centers, const double *cell_volumes) {
@@ -696,15 +720,17 @@ extern "C" int pb_plan_set_geometry(pb_plan *p, const double *nodes, const doubl
         return fail(PB_EINVAL, "null pointer");
     const HostPlan &H = p->H;
     cudaStream_t st = p->stream;
-    CUDA_TRY(p->nodes.upload(nodes, 3 * H.nn, st));
-    CUDA_TRY(p->fnorm.upload(face_normals, 3 * H.nf, st));
-    CUDA_TRY(p->fcent.upload(face_centers, 3 * H.nf, st));
+    int rc;
+    if ((rc = upload_repacked(p, p->nodes, nodes, 3, H.nn))) return rc;
+    if ((rc = upload_repacked(p, p->fnorm, face_normals, 3, H.nf))) return rc;
+    if ((rc = upload_repacked(p, p->fcent, face_centers, 3, H.nf))) return rc;
+    if ((rc = upload_repacked(p, p->ccent, cell_centers, 3, H.nc))) return rc;
     CUDA_TRY(p->farea.upload(face_areas, H.nf, st));
-    CUDA_TRY(p->ccent.upload(cell_centers, 3 * H.nc, st));
     CUDA_TRY(p->cvol.upload(cell_volumes, H.nc, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     p->geo = GeoView{p->nodes.as<double>(), p->fnorm.as<double>(), p->fcent.as<double>(),
-                     p->farea.as<double>(), p->ccent.as<double>(), p->cvol.as<double>()};
+                     p->farea.as<double>(), p->ccent.as<double>(), p->cvol.as<double>(),
+                     1, 3, 1, 3, 1, 3};
     p->have_geo = true;
     return PB_OK;
 }
@@ -732,7 +758,7 @@ extern "C" int pb_mpfa_upload(pb_plan *p, const double *perm, const uint8_t *bc,
     if (!p->have_geo) return fail(PB_EINVAL, "pb_plan_set_geometry has not been called");
     const HostPlan &H = p->H;
     cudaStream_t st = p->stream;
-    CUDA_TRY(p->perm.upload(perm, 9 * H.nc, st));
+    { int rcp = upload_repacked(p, p->perm, perm, 9, H.nc); if (rcp) return rcp; }
     CUDA_TRY(p->bc.upload(bc, H.nf, st));
     p->have_robw = robin_weight != nullptr;
     if (robin_weight) CUDA_TRY(p->robw.upload(robin_weight, H.nf, st));
@@ -768,7 +794,7 @@ extern "C" int pb_mpfa_assemble(pb_plan *p, int want_flux, int want_trace, int w
     int init = INT_MAX;
     CUDA_TRY(cudaMemcpyAsync(p->err.p, &init, sizeof(int), cudaMemcpyHostToDevice, st));
     MpfaParams prm{p->perm.as<double>(), p->bc.as<uint8_t>(),
-                   p->have_robw ? p->robw.as<double>() : nullptr, p->eta};
+                   p->have_robw ? p->robw.as<double>() : nullptr, p->eta, 1, 9};
     for (const NodeClass &c : p->mpfa_cls) {
         int rc = PB_OK;
         if (nd == 3) { PB_LAUNCH_CFG(mpfa_kernel, 3, prm, o) } else { PB_LAUNCH_CFG(mpfa_kernel, 2, prm, o) }
@@ -816,11 +842,21 @@ extern "C" int pb_mpsa_upload(pb_plan *p, const double *stiffness, const uint8_t
     const HostPlan &H = p->H;
     const int nd = H.nd;
     cudaStream_t st = p->stream;
-    CUDA_TRY(p->stiff.upload(stiffness, 81 * H.nc, st));
+    { int rcs = upload_repacked(p, p->stiff, stiffness, 81, H.nc); if (rcs) return rcs; }
     CUDA_TRY(p->vbc.upload(bc, (size_t)nd * H.nf, st));
     p->have_vrobw = robin_weight != nullptr;
     if (robin_weight) CUDA_TRY(p->vrobw.upload(robin_weight, (size_t)nd * nd * H.nf, st));
-    if (n_alpha) CUDA_TRY(p->alpha.upload(alpha, (size_t)n_alpha * 9 * H.nc, st));
+    if (n_alpha) {
+        CUDA_TRY(p->alpha.ensure((size_t)n_alpha * 9 * H.nc * sizeof(double)));
+        for (int q = 0; q < n_alpha; ++q) {
+            DevBuf one;
+            int rca = upload_repacked(p, one, alpha + (size_t)q * 9 * H.nc, 9, H.nc);
+            if (rca) return rca;
+            CUDA_TRY(cudaMemcpyAsync(p->alpha.as<double>() + (size_t)q * 9 * H.nc, one.p,
+                                     (size_t)9 * H.nc * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+    }
     p->n_alpha = n_alpha;
     p->veta = eta;
     if (p->mpsa_cls_nalpha != n_alpha) {
@@ -869,7 +905,7 @@ extern "C" int pb_mpsa_assemble(pb_plan *p, float *ms) {
     CUDA_TRY(cudaMemcpyAsync(p->err.p, &init, sizeof(int), cudaMemcpyHostToDevice, st));
     MpsaParams prm{p->stiff.as<double>(), p->vbc.as<uint8_t>(),
                    p->have_vrobw ? p->vrobw.as<double>() : nullptr, p->veta, p->n_alpha,
-                   p->n_alpha ? p->alpha.as<double>() : nullptr};
+                   p->n_alpha ? p->alpha.as<double>() : nullptr, 1, 81, 1, 9, 9 * H.nc};
     for (const NodeClass &c : p->mpsa_cls) {
         int rc = PB_OK;
         if (nd == 3) { PB_LAUNCH_CFG(mpsa_kernel, 3, prm, o) } else { PB_LAUNCH_CFG(mpsa_kernel, 2, prm, o) }

@@ -112,7 +112,7 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
                 if (code == 0) code = 2;
             }
             bcu[u * ND + i] = code;
-            nrm[u * ND + i] = G.fnorm[i * nf + f] * im;
+            nrm[u * ND + i] = G.fnorm[i * G.face_cs + f * G.face_es] * im;
         }
     }
     for (int x = t.tid(); x < n; x += t.size()) rowidx[x] = x;
@@ -126,8 +126,8 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
         double xc[ND], xs[ND], D[ND][ND], Ei[ND][ND];
 #pragma unroll
         for (int i = 0; i < ND; ++i) {
-            xc[i] = G.ccent[i * nc + c];
-            xs[i] = G.nodes[i * nn + s];
+            xc[i] = G.ccent[i * G.cell_cs + c * G.cell_es];
+            xs[i] = G.nodes[i * G.node_cs + s * G.node_es];
         }
 #pragma unroll
         for (int m = 0; m < ND; ++m) {
@@ -136,7 +136,7 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
             const double e = (bloc[u] >= 0) ? 0.0 : prm.eta;
 #pragma unroll
             for (int i = 0; i < ND; ++i) {
-                const double xf = G.fcent[i * nf + f];
+                const double xf = G.fcent[i * G.face_cs + f * G.face_es];
                 D[m][i] = xf + e * (xs[i] - xf) - xc[i];
             }
         }
@@ -147,12 +147,12 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
             for (int m = 0; m < ND; ++m) E[k * ND2 + q * ND + m] = Ei[q][m];
         volk[k] = G.cvol[c] / (double)P.sc_ncn[c];
         for (int q = 0; q < nal; ++q) {
-            const double *al = prm.alpha + (int64_t)q * 9 * nc;
+            const double *al = prm.alpha + (int64_t)q * prm.alpha_stride;
             double a2[ND][ND];
 #pragma unroll
             for (int a = 0; a < ND; ++a)
 #pragma unroll
-                for (int b = 0; b < ND; ++b) a2[a][b] = al[(3 * a + b) * nc + c];
+                for (int b = 0; b < ND; ++b) a2[a][b] = al[(3 * a + b) * prm.alpha_cs + c * prm.alpha_es];
 #pragma unroll
             for (int m = 0; m < ND; ++m) {
                 const int u = slot[k * ND + m] >> 1;
@@ -194,13 +194,13 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
         const int k = it / ND2, p = it - k * ND2;
         const int64_t c = cell[k];
         const int pi = p / ND, pr = p - pi * ND;
-        const double *Crow = prm.stiff + (int64_t)c9<ND>(pi, pr) * 9 * nc + c;  // C[p9][q9][c]
+        const double *Crow = prm.stiff + (int64_t)c9<ND>(pi, pr) * 9 * prm.stiff_cs + c * prm.stiff_es;  // C[p9][q9][c]
 #pragma unroll
         for (int a = 0; a < ND; ++a) {
             double cs[ND];
 #pragma unroll
             for (int q = 0; q < ND; ++q)
-                cs[q] = sym_mask<ND>(p, a * ND + q) ? Crow[(int64_t)c9<ND>(a, q) * nc] : 0.0;
+                cs[q] = sym_mask<ND>(p, a * ND + q) ? Crow[(int64_t)c9<ND>(a, q) * prm.stiff_cs] : 0.0;
 #pragma unroll
             for (int m = 0; m < ND; ++m) {
                 double v = 0.0;
@@ -215,11 +215,11 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
         const int pi = p / ND, pr = p - pi * ND;
         for (int k = 0; k < nsc; ++k) {
             const int64_t c = cell[k];
-            const double *Crow = prm.stiff + (int64_t)c9<ND>(pi, pr) * 9 * nc + c;
+            const double *Crow = prm.stiff + (int64_t)c9<ND>(pi, pr) * 9 * prm.stiff_cs + c * prm.stiff_es;
             double ca[ND];
 #pragma unroll
             for (int q = 0; q < ND; ++q)
-                ca[q] = sym_mask<ND>(p, a * ND + q) ? 0.0 : wk[k] * Crow[(int64_t)c9<ND>(a, q) * nc];
+                ca[q] = sym_mask<ND>(p, a * ND + q) ? 0.0 : wk[k] * Crow[(int64_t)c9<ND>(a, q) * prm.stiff_cs];
             double sum = 0.0;
 #pragma unroll
             for (int m = 0; m < ND; ++m) {

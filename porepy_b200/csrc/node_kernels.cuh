@@ -768,10 +768,10 @@ PB_HD void mpfa_node(Team &t, const PlanView &P, const GeoView &G, const MpfaPar
         double xc[ND], xs[ND], K[ND][ND], D[ND][ND], R[ND][ND], E[ND][ND];
 #pragma unroll
         for (int i = 0; i < ND; ++i) {
-            xc[i] = G.ccent[i * nc + c];
-            xs[i] = G.nodes[i * nn + s];
+            xc[i] = G.ccent[i * G.cell_cs + c * G.cell_es];
+            xs[i] = G.nodes[i * G.node_cs + s * G.node_es];
 #pragma unroll
-            for (int j = 0; j < ND; ++j) K[i][j] = prm.perm[(i * 3 + j) * nc + c];
+            for (int j = 0; j < ND; ++j) K[i][j] = prm.perm[(i * 3 + j) * prm.perm_cs + c * prm.perm_es];
         }
 #pragma unroll
         for (int m = 0; m < ND; ++m) {
@@ -781,9 +781,9 @@ PB_HD void mpfa_node(Team &t, const PlanView &P, const GeoView &G, const MpfaPar
             double nrm[ND];
 #pragma unroll
             for (int i = 0; i < ND; ++i) {
-                const double xf = G.fcent[i * nf + f];
+                const double xf = G.fcent[i * G.face_cs + f * G.face_es];
                 D[m][i] = xf + e * (xs[i] - xf) - xc[i];
-                nrm[i] = G.fnorm[i * nf + f] * invmf[u];
+                nrm[i] = G.fnorm[i * G.face_cs + f * G.face_es] * invmf[u];
             }
 #pragma unroll
             for (int j = 0; j < ND; ++j) {

@@ -28,15 +28,20 @@ struct PlanView {
 };
 
 // geometry as pp.Grid stores it: (3, n) row-major -> component i of entity e at [i*n + e]
+// Vector arrays are addressed as base[component * cs + entity * es]: (cs, es) = (n, 1) for the
+// reference's (3, n) row-major layout (what the host emulation passes), (1, 3) after the device-side
+// repack into entity-major records (one 24-byte record per point instead of three sectors).
 struct GeoView {
     const double *nodes, *fnorm, *fcent, *farea, *ccent, *cvol;
+    int64_t node_cs, node_es, face_cs, face_es, cell_cs, cell_es;
 };
 
 struct MpfaParams {
-    const double *perm;   // (3,3,nc)
+    const double *perm;   // (3,3,nc): entry (i,j) of cell c at [(3i+j)*perm_cs + c*perm_es]
     const uint8_t *bc;    // nf
     const double *robw;   // nf or null
     double eta;
+    int64_t perm_cs, perm_es;
 };
 
 struct MpfaOut {
@@ -50,6 +55,8 @@ struct MpsaParams {
     double eta;
     int n_alpha;
     const double *alpha;  // n_alpha x (3,3,nc)
+    int64_t stiff_cs, stiff_es;  // entry (p9,q9) of cell c at [(9*p9+q9)*stiff_cs + c*stiff_es]
+    int64_t alpha_cs, alpha_es, alpha_stride;  // tensor q at alpha + q*alpha_stride
 };
 
 #define PB_MAX_ALPHA 4

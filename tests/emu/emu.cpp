@@ -73,8 +73,8 @@ int emu_mpfa(void *h, const double *nodes, const double *fnorm, const double *fc
              double *bpc, double *bpf, double *vs, double *bpvs) {
     Emu *e = (Emu *)h;
     PlanView P = view_of(e->P);
-    GeoView G{nodes, fnorm, fcent, farea, ccent, cvol};
-    MpfaParams prm{perm, bc, robw, eta};
+    GeoView G{nodes, fnorm, fcent, farea, ccent, cvol, P.nn, 1, P.nf, 1, P.nc, 1};
+    MpfaParams prm{perm, bc, robw, eta, P.nc, 1};
     MpfaOut o{flux, bflux, bpc, bpf, vs, bpvs};
     int err = INT_MAX;
     int64_t need = 0;
@@ -103,8 +103,8 @@ int emu_mpsa(void *h, const double *nodes, const double *fnorm, const double *fc
              double **sg, double **cons, double **bdp) {
     Emu *e = (Emu *)h;
     PlanView P = view_of(e->P);
-    GeoView G{nodes, fnorm, fcent, farea, ccent, cvol};
-    MpsaParams prm{stiff, bc, robw, eta, n_alpha, alpha};
+    GeoView G{nodes, fnorm, fcent, farea, ccent, cvol, P.nn, 1, P.nf, 1, P.nc, 1};
+    MpsaParams prm{stiff, bc, robw, eta, n_alpha, alpha, P.nc, 1, P.nc, 1, 9 * P.nc};
     MpsaOut o{};
     o.stress = stress; o.bstress = bstress; o.bdc = bdc; o.bdf = bdf;
     for (int a = 0; a < n_alpha; ++a) {

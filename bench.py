@@ -220,6 +220,18 @@ def main():
         return
     args.warmup = max(args.warmup, 3)
 
+    # Only the JSON line may reach stdout: libraries (NCCL prints its version banner on the first
+    # communicator) write to fd 1, so park fd 1 on stderr until the line is printed.
+    sys.stdout.flush()
+    _saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: str) -> None:
+        sys.stdout.flush()
+        os.dup2(_saved_stdout_fd, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
     import torch
     import porepy_b200 as pb
     from porepy_b200 import _lib
@@ -420,7 +432,7 @@ def main():
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "spmv": spmv, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -18,7 +18,13 @@ plan = pb.DevicePlan.for_grid(g)
 eta = pb.determine_eta(g)
 plan.mpfa_upload(k.values, scalar_bc_codes(bc, g.num_faces), None, eta)
 codes, robw = vector_bc_codes(vbc, 3, g.num_faces)
-plan.mpsa_upload(C.values, codes, robw, eta)
+alphas = []
+if os.environ.get("PB_BIOT"):
+    import numpy as np
+    a = np.zeros((3, 3, g.num_cells))
+    a[0, 0] = a[1, 1] = a[2, 2] = 0.8
+    alphas = [a]
+plan.mpsa_upload(C.values, codes, robw, eta, alphas)
 for _ in range(reps):
     a = plan.mpfa_assemble()
     b = plan.mpsa_assemble()

@@ -96,3 +96,37 @@ def test_boundary_condition_defaults():
     assert bc.is_dir.sum() == 3 and bc.is_neu.sum() == g.get_all_boundary_faces().size - 3
     vb = pb.BoundaryConditionVectorial(g)
     assert vb.is_neu.shape == (3, g.num_faces) and vb.robin_weight.shape == (3, 3, g.num_faces)
+
+
+def test_bc_encoding_and_error_behaviour():
+    """Host-side encoding of the reference's BC objects and its exception parity."""
+    from porepy_b200.fv import scalar_bc_codes, vector_bc_codes
+    g = pb.cart_grid_3d([2, 2, 2])
+    bf = g.get_all_boundary_faces()
+    bc = pb.BoundaryCondition(g, bf[:4], ["dir", "rob", "neu", "dir"])
+    bc.is_internal[bf[3]] = True  # internal (fracture) faces are Neumann for MPFA (mpfa.py:1452-1454)
+    codes = scalar_bc_codes(bc, g.num_faces)
+    assert codes[bf[0]] == 1 and codes[bf[1]] == 3 and codes[bf[2]] == 2 and codes[bf[3]] == 2
+    assert (codes[np.setdiff1d(np.arange(g.num_faces), bf)] == 0).all()
+    vb = pb.BoundaryConditionVectorial(g, bf[:2], ["dir", "rob"])
+    vcodes, robw = vector_bc_codes(vb, 3, g.num_faces)
+    assert vcodes.shape == (3, g.num_faces) and (vcodes[:, bf[0]] == 1).all() and robw.shape == (3, 3, g.num_faces)
+    with pytest.raises(AttributeError):  # mpsa.py:823: "MPSA must be given a vectorial boundary condition"
+        vector_bc_codes(bc, 3, g.num_faces)
+    vb.basis[0, 1, bf[0]] = 0.5
+    with pytest.raises(NotImplementedError):
+        vector_bc_codes(vb, 3, g.num_faces)
+
+
+def test_determine_eta_follows_the_reference_rule():
+    assert pb.determine_eta(pb.cart_grid_3d([1, 1, 1])) == 0.0
+    assert pb.determine_eta(pb.structured_tet_grid([1, 1, 1])) == pytest.approx(1.0 / 3.0)
+
+
+def test_biot_class_keys_and_assembly_refusal():
+    b = pb.Biot("mech")
+    keys = {k: v for k, v in vars(b).items() if k.endswith("_matrix_key")}
+    assert keys["bound_displacement_divergence_matrix_key"] == "boundary_displacement_divergence"
+    assert keys["consistency_matrix_key"] == "mpsa_consistency"
+    with pytest.raises(NotImplementedError):  # biot.py:125-149
+        b.assemble_matrix_rhs(None, {})

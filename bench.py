@@ -159,8 +159,19 @@ def cpu_oracle_throughput(kind, procs, reps=1):
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_oracle_worker, [(kind, dims, 100 * i, reps) for i in range(procs)])
+    # one process per core, one BLAS/OpenMP thread per process (the children inherit the environment)
+    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    for k in saved:
+        os.environ[k] = "1"
+    try:
+        with ctx.Pool(procs) as pool:
+            res = pool.map(_oracle_worker, [(kind, dims, 100 * i, reps) for i in range(procs)])
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     wall = time.perf_counter() - t0
     cells = sum(r[0] for r in res)
     # worker-side time excludes interpreter start-up; use the slowest worker

@@ -40,6 +40,8 @@ WORKLOADS = {
     "cart32": ("cart", (32, 32, 32), "MPFA+MPSA assembly, Cartesian 32^3 = 32,768 cells (config[0])"),
     "tet100k": ("tet", (26, 26, 26), "MPFA+MPSA assembly, structured tetrahedral grid 26^3 x 6 = 105,456 cells"),
     "tet10k": ("tet", (12, 12, 12), "MPFA+MPSA assembly, structured tetrahedral grid 12^3 x 6 = 10,368 cells"),
+    "tet384": ("tet", (4, 4, 4), "tooling: 384 tets (compute-sanitizer runs)"),
+    "cart512": ("cart", (8, 8, 8), "tooling: 512 hexes (compute-sanitizer runs)"),
 }
 CPU_SAMPLE = {"tet": (5, 5, 5), "cart": (12, 12, 12)}
 
@@ -184,7 +186,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     kind, dims, desc = WORKLOADS[args.workload]
-    procs = max(1, os.cpu_count() or 1)  # all host threads: one oracle process per core
+    # one oracle process per core up to 32: on the 128-core B200 host 128 processes measured SLOWER
+    # (13.7k cells/s) than 32 (39k cells/s) -- the batched NumPy/LAPACK oracle is memory bound
+    procs = max(1, min(os.cpu_count() or 1, 32))
     for _ in range(max(args.warmup, 0) and 1):
         _oracle_worker((kind, (3, 3, 3), 0, 1))
     vals = []

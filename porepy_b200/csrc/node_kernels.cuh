@@ -349,7 +349,7 @@ struct TileGJ {
     static_assert(NP <= 256, "row index must fit the 8-bit key field");
     static_assert(NI <= 8, "extend the PB_PICK list");
     static __host__ __device__ constexpr int64_t scratch_doubles_c() {
-        return NP * 4 + 2 * 4 * WP + 16 + (8 + NP) / 2 + 4;
+        return NP * 4 + 2 * 4 * WP + 16 * (NW + 1) + (8 + NP) / 2 + 4;
     }
     static PB_HD int64_t scratch_doubles(int) { return scratch_doubles_c(); }
 
@@ -525,8 +525,8 @@ struct TileGJ {
         double *P0 = scratch;              // [NP][4]  panel columns
         double *Raw = P0 + NP * 4;         // [4][WP]  raw pivot rows
         double *R = Raw + 4 * WP;          // [4][WP]  A11^-1 * pivot rows
-        double *Ainv = R + 4 * WP;         // [4][4]
-        int *prs = (int *)(Ainv + 16);     // [4] pivot rows of the panel, [4] = singular flag
+        double *Ainv = R + 4 * WP;         // [NW+1][4][4]: copy 0 = slow-path result, copy 1+w = warp w's own
+        int *prs = (int *)(Ainv + 16 * (NW + 1));  // [4] pivot rows of the panel, [4] = singular flag
         int *usedf = prs + 8;              // [NP]
         for (int i = t.tid(); i < NP; i += t.size()) usedf[i] = i < n ? 0 : 1;
         for (int i = t.tid(); i < NP * 4; i += t.size()) P0[i] = 0.0;
@@ -570,9 +570,12 @@ struct TileGJ {
                 // S2: every warp tests the diagonal block (threshold block pivoting)
                 double iv;
                 const bool fast = try_diagonal_block(l, P0, usedf, p0, pw, iv);
+                const double *ainv = Ainv;  // slow path: warp 0's result, published behind a barrier
                 if (fast) {
-                    if (l < 16) Ainv[l] = iv;  // every warp writes the same 16 values
+                    double *mine = Ainv + 16 * (ti + 1);  // private copy: no cross-warp sharing
+                    if (l < 16) mine[l] = iv;
                     __syncwarp();
+                    ainv = mine;
                 } else {
                     // rare: partial pivoting on the panel by warp 0, then the owners re-post the rows
                     t.sync();  // all warps have read usedf / P0 for the test
@@ -606,7 +609,7 @@ struct TileGJ {
                     for (int j = 0; j < 4; ++j) {
                         double x = 0.0;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) x += Ainv[j * 4 + i] * raw[i];
+                        for (int i = 0; i < 4; ++i) x += ainv[j * 4 + i] * raw[i];
                         R[j * WP + col] = (j < pw) ? x : 0.0;
                     }
                 }

@@ -402,7 +402,7 @@ def main():
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
-        "note": "latency/FP64-FMA bound, not HBM bound (SURVEY §8d); fp64 figures alongside",
+        "note": "latency bound (serial pivot chain per interaction region), neither HBM nor FP64 bound (SURVEY §8d); fp64 figures alongside",
         "fp64_gflops_achieved": (fl_mpsa if dom == "mpsa" else fl_mpfa) / (dom_ms * 1e-3) / 1e9,
         "fp64_peak_nominal_gflops": 40000.0,
         "fp64_frac_of_nominal": (fl_mpsa if dom == "mpsa" else fl_mpfa) / (dom_ms * 1e-3) / 1e9 / 40000.0,

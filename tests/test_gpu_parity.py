@@ -277,3 +277,30 @@ def test_sharded_equals_unsplit():
             acc[key] = gm if key not in acc else acc[key] + gm
     for key in ref:
         assert rel_err(ref[key], acc[key]) < 1e-12, key
+
+
+@pytest.mark.parametrize("make", [lambda: pb.cart_grid_3d([5, 4, 4], perturb=0.3, seed=8),
+                                  lambda: pb.structured_tet_grid([2, 2, 3])])
+def test_high_contrast_vs_oracle(make):
+    """Six orders of magnitude of contrast in permeability and stiffness between neighbouring cells
+    (test_mpfa.py:140-251 pattern): the threshold block pivoting must hold the 1e-10 entrywise bar."""
+    from oracle import fv_oracle as fo
+    g = make()
+    rng = np.random.default_rng(21)
+    nc = g.num_cells
+    kk = np.where(rng.random(nc) < 0.5, 1e-3, 1e3)
+    k = pb.SecondOrderTensor(kk)
+    bc = _mixed_scalar_bc(g)
+    data = pb.initialize_data({}, "flow", {"second_order_tensor": k, "bc": bc})
+    pb.Mpfa("flow").discretize(g, data)
+    ref = fo.mpfa(g, k.values, bc, pb.determine_eta(g))
+    err, key = max_rel_err(ref, data[pb.DISCRETIZATION_MATRICES]["flow"])
+    assert err < TOL, (key, err)
+    mu = np.where(rng.random(nc) < 0.5, 1e-3, 1e3)
+    C = pb.FourthOrderTensor(mu, 2.0 * mu)
+    vbc = _mixed_vector_bc(g)
+    dm = pb.initialize_data({}, "mech", {"fourth_order_tensor": C, "bc": vbc})
+    pb.Mpsa("mech").discretize(g, dm)
+    refm = fo.mpsa(g, C.values, vbc, pb.determine_eta(g))
+    err, key = max_rel_err(refm, dm[pb.DISCRETIZATION_MATRICES]["mech"])
+    assert err < TOL, (key, err)

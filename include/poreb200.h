@@ -125,6 +125,14 @@ int pb_mpfa_download(pb_plan *p, double *flux, double *bound_flux, double *bound
                      double *bound_pressure_face, double *vector_source,
                      double *bound_pressure_vector_source);
 
+/* Device-side system of the flow problem, replacing the host scipy products of
+ * FVElliptic.assemble_matrix_rhs (numerics/fv/fv_elliptic.py:67-112):
+ *   A = div @ flux  on the CELL_CELL pattern, kept in HBM as a device CSR handle, no D2H of the matrices;
+ *   b = -div @ (bound_flux @ bc_values) [- div @ (vector_source @ v)]   (host vectors in/out).
+ * Needs a preceding pb_mpfa_assemble with the flux terms (and the vector source when v != NULL). */
+int pb_mpfa_system(pb_plan *p, struct pb_csr **out);
+int pb_mpfa_rhs(pb_plan *p, const double *bc_values, const double *vector_source, double *rhs);
+
 /* ---- MPSA / Biot ------------------------------------------------------------------------ */
 /* Replaces Mpsa._stress_discretization (numerics/fv/mpsa.py:531-781),
  * _create_inverse_gradient_matrix (:784-930), _tensor_vector_prod (:1520-1675),
@@ -157,6 +165,9 @@ typedef struct pb_csr pb_csr; /* device-resident CSR matrix */
 int pb_csr_create(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t *indptr,
                   const int32_t *indices, const double *data, pb_csr **out);
 void pb_csr_destroy(pb_csr *a);
+/* copy a device-resident matrix back (indptr nrows+1, indices nnz, data nnz); sizes via pb_csr_shape */
+int pb_csr_shape(const pb_csr *a, int64_t *nrows, int64_t *ncols, int64_t *nnz);
+int pb_csr_download(pb_csr *a, int32_t *indptr, int32_t *indices, double *data);
 /* host vectors in/out (H2D + kernel + D2H) */
 int pb_csr_spmv(pb_csr *a, const double *x, double *y);
 /* device pointers (e.g. torch tensors' data_ptr()); stream = cudaStream_t as integer (0 = default) */

@@ -40,6 +40,8 @@ _SIGNATURES = {
     "pb_mpfa_upload": (C.c_int, [C.c_void_p, _f64p, _u8p, _f64p, C.c_double]),
     "pb_mpfa_assemble": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _f32p]),
     "pb_mpfa_download": (C.c_int, [C.c_void_p] + [_f64p] * 6),
+    "pb_mpfa_system": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pb_mpfa_rhs": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p]),
     "pb_mpsa_upload": (C.c_int, [C.c_void_p, _f64p, _u8p, _f64p, C.c_double, C.c_int, _f64p]),
     "pb_mpsa_assemble": (C.c_int, [C.c_void_p, _f32p]),
     "pb_mpsa_download": (C.c_int, [C.c_void_p] + [_f64p] * 4),
@@ -47,6 +49,8 @@ _SIGNATURES = {
     "pb_csr_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _i32p, _i32p, _f64p,
                                 C.POINTER(C.c_void_p)]),
     "pb_csr_destroy": (None, [C.c_void_p]),
+    "pb_csr_shape": (C.c_int, [C.c_void_p, _i64p, _i64p, _i64p]),
+    "pb_csr_download": (C.c_int, [C.c_void_p, _i32p, _i32p, _f64p]),
     "pb_csr_spmv": (C.c_int, [C.c_void_p, _f64p, _f64p]),
     "pb_csr_spmv_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "pb_csr_spmv_bench": (C.c_int, [C.c_void_p, C.c_int, _f32p]),

@@ -138,7 +138,7 @@ struct pb_plan {
     // plan arrays
     DevBuf fn_indptr, node_sc_ptr, sc_cell, node_sf_ptr, sf_face, sf_sides, sf_bloc, slot_sf, node_nb,
         sc_ncn, posfc_ptr, posfb_ptr, poscc_ptr, poscb_ptr, pos_fc, pos_fb, pos_cc, pos_cb, fc_indptr,
-        fb_indptr, cc_indptr, cb_indptr, pat_idx[4], nbf_ptr, nbf_idx, cn_ptr, cn_idx;
+        fb_indptr, cc_indptr, cb_indptr, pat_idx[4], nbf_ptr, nbf_idx, cn_ptr, cn_idx, face_cells;
     int64_t pat_rows[4] = {0, 0, 0, 0}, pat_cols[4] = {0, 0, 0, 0}, pat_nnz[4] = {0, 0, 0, 0};
     // geometry
     DevBuf nodes, fnorm, fcent, farea, ccent, cvol;
@@ -826,6 +826,138 @@ extern "C" int pb_mpfa_download(pb_plan *p, double *flux, double *bound_flux, do
     if ((rc = dl(p, p->o_vs, vs, nfc * H.nd))) return rc;
     if ((rc = dl(p, p->o_bpvs, bpvs, nfc * H.nd))) return rc;
     CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// device-side flow system  A = div @ flux,  b = -div @ (bound_flux @ bc [+ vector_source @ v])
+// ------------------------------------------------------------------------------------
+struct pb_csr;
+int pb_csr_from_device_pattern_(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t *indptr_dev,
+                                const int32_t *indices_dev, pb_csr **out);  // spmv.cu
+double *pb_csr_data_(pb_csr *a);
+
+// one warp per face: every entry (f, k) of the flux row goes to row c of A for the one or two
+// cells c of the face, with the sign of cell_faces[f, c] (= div[c, f]); position by binary search
+// in the CELL_CELL row (the flux row's columns are a subset of it)
+__global__ void div_flux_kernel(int64_t nf, const int32_t *__restrict__ fc_ip, const int32_t *__restrict__ fc_ix,
+                                const double *__restrict__ flux, const int32_t *__restrict__ face_cells,
+                                const int32_t *__restrict__ cc_ip, const int32_t *__restrict__ cc_ix,
+                                double *__restrict__ a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t f = warp; f < nf; f += nwarps) {
+        for (int sd = 0; sd < 2; ++sd) {
+            const int32_t enc = face_cells[2 * f + sd];  // (cell << 1) | (sign < 0), -1 = none
+            if (enc < 0) continue;
+            const int c = enc >> 1;
+            const double sg = (enc & 1) ? -1.0 : 1.0;
+            const int b = cc_ip[c], e = cc_ip[c + 1];
+            for (int q = fc_ip[f] + lane; q < fc_ip[f + 1]; q += 32) {
+                const int k = fc_ix[q];
+                int lo = b, hi = e;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (cc_ix[mid] < k) lo = mid + 1; else hi = mid;
+                }
+                atomicAdd(a + lo, sg * flux[q]);
+            }
+        }
+    }
+}
+
+// y[f] = sum_q vals[q*blk + j] * x[cols[q]*blk + j]   (blk = 1: bound_flux @ bc; blk = nd: vector_source @ v)
+__global__ void face_row_dot_kernel(int64_t nf, const int32_t *__restrict__ ip, const int32_t *__restrict__ ix,
+                                    const double *__restrict__ vals, int blk, const double *__restrict__ x,
+                                    double *__restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t f = warp; f < nf; f += nwarps) {
+        double acc = 0.0;
+        const int64_t b = ip[f], e = ip[f + 1];
+        for (int64_t t = b * blk + lane; t < e * blk; t += 32) {
+            const int64_t q = t / blk;
+            const int j = (int)(t - q * blk);
+            acc += vals[t] * x[(int64_t)ix[q] * blk + j];
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) y[f] += acc;
+    }
+}
+
+// rhs[c] = - sum_{f of c} sign * w[f]
+__global__ void neg_div_kernel(int64_t nf, const int32_t *__restrict__ face_cells, const double *__restrict__ w,
+                               double *__restrict__ rhs) {
+    for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x)
+        for (int sd = 0; sd < 2; ++sd) {
+            const int32_t enc = face_cells[2 * f + sd];
+            if (enc >= 0) atomicAdd(rhs + (enc >> 1), ((enc & 1) ? 1.0 : -1.0) * w[f]);
+        }
+}
+
+static int ensure_face_cells(pb_plan *p) {
+    if (p->face_cells.p) return PB_OK;
+    CUDA_TRY(p->face_cells.upload(p->H.face_cells, p->stream));
+    return PB_OK;
+}
+
+extern "C" int pb_mpfa_system(pb_plan *p, pb_csr **out) {
+    if (!p || !out) return fail(PB_EINVAL, "null pointer");
+    if (!p->o_flux.p) return fail(PB_EINVAL, "pb_mpfa_assemble (flux terms) has not been called");
+    const HostPlan &H = p->H;
+    int rc = ensure_face_cells(p);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    pb_csr *a = nullptr;
+    rc = pb_csr_from_device_pattern_(H.nc, H.nc, p->pat_nnz[2], p->cc_indptr.as<int32_t>(),
+                                     p->pat_idx[2].as<int32_t>(), &a);
+    if (rc) return rc;
+    const int block = 256;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((H.nf * 32 + block - 1) / block, (int64_t)kSMs * 16));
+    div_flux_kernel<<<grid, block, 0, p->stream>>>(H.nf, p->fc_indptr.as<int32_t>(), p->pat_idx[0].as<int32_t>(),
+                                                   p->o_flux.as<double>(), p->face_cells.as<int32_t>(),
+                                                   p->cc_indptr.as<int32_t>(), p->pat_idx[2].as<int32_t>(),
+                                                   pb_csr_data_(a));
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    *out = a;
+    return PB_OK;
+}
+
+extern "C" int pb_mpfa_rhs(pb_plan *p, const double *bc_values, const double *vector_source, double *rhs) {
+    if (!p || !bc_values || !rhs) return fail(PB_EINVAL, "null pointer");
+    if (!p->o_bflux.p) return fail(PB_EINVAL, "pb_mpfa_assemble (flux terms) has not been called");
+    if (vector_source && !p->o_vs.p) return fail(PB_EINVAL, "vector source terms were not assembled");
+    const HostPlan &H = p->H;
+    cudaStream_t st = p->stream;
+    int rc = ensure_face_cells(p);
+    if (rc) return rc;
+    DevBuf bc, vs, w, r;
+    CUDA_TRY(bc.upload(bc_values, (size_t)H.nf, st));
+    CUDA_TRY(w.ensure((size_t)H.nf * sizeof(double)));
+    CUDA_TRY(r.ensure((size_t)H.nc * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(w.p, 0, (size_t)H.nf * sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(r.p, 0, (size_t)H.nc * sizeof(double), st));
+    const int block = 256;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((H.nf * 32 + block - 1) / block, (int64_t)kSMs * 16));
+    face_row_dot_kernel<<<grid, block, 0, st>>>(H.nf, p->fb_indptr.as<int32_t>(), p->pat_idx[1].as<int32_t>(),
+                                                p->o_bflux.as<double>(), 1, bc.as<double>(), w.as<double>());
+    g_launches++;
+    if (vector_source) {
+        CUDA_TRY(vs.upload(vector_source, (size_t)H.nc * H.nd, st));
+        face_row_dot_kernel<<<grid, block, 0, st>>>(H.nf, p->fc_indptr.as<int32_t>(), p->pat_idx[0].as<int32_t>(),
+                                                    p->o_vs.as<double>(), H.nd, vs.as<double>(), w.as<double>());
+        g_launches++;
+    }
+    int grid2 = (int)std::max<int64_t>(1, std::min<int64_t>((H.nf + block - 1) / block, (int64_t)kSMs * 16));
+    neg_div_kernel<<<grid2, block, 0, st>>>(H.nf, p->face_cells.as<int32_t>(), w.as<double>(), r.as<double>());
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(rhs, r.p, (size_t)H.nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return PB_OK;
 }
 

@@ -48,6 +48,7 @@ struct HostPlan {
     std::vector<int32_t> pos_fc, pos_fb, pos_cc, pos_cb;
     std::vector<int32_t> nbf_ptr, nbf_idx;     // boundary faces of each node (local order)
     std::vector<int32_t> cn_ptr, cn_idx;       // nodes of each cell
+    std::vector<int32_t> face_cells;           // 2*nf: (cell << 1) | (cell_faces sign < 0), -1 = no second cell
     int32_t max_nsf = 0, max_nsc = 0, max_nb = 0;
 };
 
@@ -93,6 +94,14 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
     for (int64_t q = 0; q < U; ++q)
         if (fn_indices[q] < 0 || fn_indices[q] >= nn) { err = "face_nodes index out of range"; return 1; }
     lap("sort faces in cells");
+    P.face_cells.assign(2 * nf, -1);
+    for (int64_t c = 0; c < nc; ++c)
+        for (int i = cf_indptr[c]; i < cf_indptr[c + 1]; ++i) {
+            const int32_t f = cfaces[i];
+            const int32_t enc = (int32_t)((c << 1) | (csign[i] < 0 ? 1 : 0));
+            if (P.face_cells[2 * f] < 0) P.face_cells[2 * f] = enc;
+            else P.face_cells[2 * f + 1] = enc;
+        }
     std::vector<int64_t> hptr(nn + 1, 0);
     int64_t H = 0;
     for (int64_t c = 0; c < nc; ++c)

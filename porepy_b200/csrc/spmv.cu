@@ -134,6 +134,53 @@ extern "C" int pb_csr_create(int64_t nrows, int64_t ncols, int64_t nnz, const in
     return PB_OK;
 }
 
+extern "C" int pb_csr_shape(const pb_csr *a, int64_t *nrows, int64_t *ncols, int64_t *nnz) {
+    if (!a) return pb_fail_(PB_EINVAL, "null matrix");
+    if (nrows) *nrows = a->nrows;
+    if (ncols) *ncols = a->ncols;
+    if (nnz) *nnz = a->nnz;
+    return PB_OK;
+}
+
+extern "C" int pb_csr_download(pb_csr *a, int32_t *indptr, int32_t *indices, double *data) {
+    if (!a || !indptr || !indices || !data) return pb_fail_(PB_EINVAL, "null pointer");
+    CUDA_TRY(cudaMemcpy(indptr, a->indptr, (a->nrows + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (a->nnz) {
+        CUDA_TRY(cudaMemcpy(indices, a->indices, a->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(data, a->data, a->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return PB_OK;
+}
+
+// matrix whose pattern is copied from device arrays and whose values the caller fills (api.cu)
+int pb_csr_from_device_pattern_(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t *indptr_dev,
+                                const int32_t *indices_dev, pb_csr **out) {
+    pb_csr *a = new pb_csr;
+    a->nrows = nrows; a->ncols = ncols; a->nnz = nnz;
+    auto bail = [&](cudaError_t e) {
+        std::string m = cudaGetErrorString(e);
+        pb_csr_destroy(a);
+        return pb_fail_(PB_ECUDA, m);
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreate(&a->e0)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreate(&a->e1)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&a->indptr, (nrows + 1) * sizeof(int32_t))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&a->indices, (nnz ? nnz : 1) * sizeof(int32_t))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&a->data, (nnz ? nnz : 1) * sizeof(double))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&a->x, (ncols ? ncols : 1) * sizeof(double))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&a->y, (nrows ? nrows : 1) * sizeof(double))) != cudaSuccess) return bail(e);
+    if ((e = cudaMemcpy(a->indptr, indptr_dev, (nrows + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice)) != cudaSuccess) return bail(e);
+    if (nnz && (e = cudaMemcpy(a->indices, indices_dev, nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice)) != cudaSuccess) return bail(e);
+    if ((e = cudaMemset(a->data, 0, (nnz ? nnz : 1) * sizeof(double))) != cudaSuccess) return bail(e);
+    double mean = nrows ? (double)nnz / (double)nrows : 0.0;
+    a->tpr = mean <= 3 ? 2 : mean <= 6 ? 4 : mean <= 24 ? 8 : mean <= 48 ? 16 : 32;
+    *out = a;
+    return PB_OK;
+}
+double *pb_csr_data_(pb_csr *a) { return a->data; }
+
 extern "C" int pb_csr_spmv(pb_csr *a, const double *x, double *y) {
     if (!a || !x || !y) return pb_fail_(PB_EINVAL, "null pointer");
     CUDA_TRY(cudaMemcpyAsync(a->x, x, a->ncols * sizeof(double), cudaMemcpyHostToDevice, a->stream));

@@ -218,6 +218,22 @@ class DevicePlan:
                  "bound_pressure_vector_source": (0, 1, nd)}
         return {k: self.matrix(*shape[k], v) for k, v in bufs.items() if v is not None}
 
+    def mpfa_system(self):
+        """A = div @ flux assembled and kept on the device (``DeviceCsr``); needs ``mpfa_assemble``."""
+        from .sparse import DeviceCsr
+        h = C.c_void_p()
+        _lib.check(self.lib.pb_mpfa_system(self.h, C.byref(h)))
+        return DeviceCsr.from_handle(h)
+
+    def mpfa_rhs(self, bc_values, vector_source=None) -> np.ndarray:
+        """b = -div @ (bound_flux @ bc_values) [- div @ (vector_source_discr @ vector_source)]."""
+        bv = _lib.f64(bc_values)
+        vs = None if vector_source is None else _lib.f64(vector_source)
+        rhs = np.empty(self.nc)
+        _lib.check(self.lib.pb_mpfa_rhs(self.h, _lib.ptr(bv, _lib._f64p), _lib.ptr(vs, _lib._f64p),
+                                        _lib.ptr(rhs, _lib._f64p)))
+        return rhs
+
     # ---- MPSA / Biot
     def mpsa_upload(self, stiff, codes, robw, eta, alphas=()) -> None:
         stiff = _lib.f64(stiff)
@@ -392,6 +408,17 @@ class Mpfa(_Base):
         if "vector_source" in params:
             rhs -= div @ (mats[self.vector_source_matrix_key] @ params["vector_source"])
         return matrix, rhs
+
+
+    def assemble_matrix_rhs_device(self, sd, data: dict):
+        """Device-resident counterpart of ``assemble_matrix_rhs``: ``A = div @ flux`` is formed on the GPU
+        from the values of the last ``discretize`` (still in HBM) and returned as a ``DeviceCsr`` -- no D2H
+        of the matrices; ``b`` comes back as a host vector.  Feed both to ``porepy_b200.krylov``."""
+        params = data[PARAMETERS][self.keyword]
+        plan = DevicePlan.for_grid(sd)
+        a = plan.mpfa_system()
+        b = plan.mpfa_rhs(params["bc_values"], params.get("vector_source"))
+        return a, b
 
 
 class Mpsa(_Base):

@@ -31,6 +31,24 @@ class DeviceCsr:
         self.h = h
         self.lib = lib
 
+    @classmethod
+    def from_handle(cls, h) -> "DeviceCsr":
+        """Wrap a matrix that was assembled on the device (e.g. ``DevicePlan.mpfa_system``)."""
+        lib = _lib.load()
+        self = cls.__new__(cls)
+        nr, ncl, nz = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(lib.pb_csr_shape(h, C.byref(nr), C.byref(ncl), C.byref(nz)))
+        self.shape, self.nnz, self.h, self.lib = (nr.value, ncl.value), nz.value, h, lib
+        return self
+
+    def to_scipy(self) -> sps.csr_matrix:
+        ip = np.empty(self.shape[0] + 1, np.int32)
+        ix = np.empty(max(self.nnz, 1), np.int32)
+        da = np.empty(max(self.nnz, 1), np.float64)
+        _lib.check(self.lib.pb_csr_download(self.h, _lib.ptr(ip, _lib._i32p), _lib.ptr(ix, _lib._i32p),
+                                            _lib.ptr(da, _lib._f64p)))
+        return sps.csr_matrix((da[:self.nnz], ix[:self.nnz], ip), shape=self.shape)
+
     def __del__(self):
         h = getattr(self, "h", None)
         if h is not None and h.value:

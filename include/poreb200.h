@@ -132,6 +132,11 @@ int pb_mpfa_download(pb_plan *p, double *flux, double *bound_flux, double *bound
  * Needs a preceding pb_mpfa_assemble with the flux terms (and the vector source when v != NULL). */
 int pb_mpfa_system(pb_plan *p, struct pb_csr **out);
 int pb_mpfa_rhs(pb_plan *p, const double *bc_values, const double *vector_source, double *rhs);
+/* Same for mechanics (Mpsa.assemble_matrix_rhs, numerics/fv/mpsa.py:486-529): A = div_nd @ stress
+ * (nd x nd blocks on the CELL_CELL pattern, row c*nd+i, column k*nd+j) as a device CSR and
+ * b = -div_nd @ (bound_stress @ bc_values) + source  (bc_values: nf*nd face-major, source: nc*nd). */
+int pb_mpsa_system(pb_plan *p, struct pb_csr **out);
+int pb_mpsa_rhs(pb_plan *p, const double *bc_values, const double *source, double *rhs);
 
 /* ---- MPSA / Biot ------------------------------------------------------------------------ */
 /* Replaces Mpsa._stress_discretization (numerics/fv/mpsa.py:531-781),

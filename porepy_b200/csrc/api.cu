@@ -962,6 +962,139 @@ extern "C" int pb_mpfa_rhs(pb_plan *p, const double *bc_values, const double *ve
 }
 
 // ------------------------------------------------------------------------------------
+// device-side mechanics system  A = div_nd @ stress,  b = -div_nd @ (bound_stress @ bc) + source
+// ------------------------------------------------------------------------------------
+// one warp per face; block layouts as documented at pb_plan_pattern_expanded
+__global__ void div_stress_kernel(int64_t nf, int nd, const int32_t *__restrict__ fc_ip,
+                                  const int32_t *__restrict__ fc_ix, const double *__restrict__ stress,
+                                  const int32_t *__restrict__ face_cells, const int32_t *__restrict__ cc_ip,
+                                  const int32_t *__restrict__ cc_ix, double *__restrict__ a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nd2 = nd * nd;
+    for (int64_t f = warp; f < nf; f += nwarps) {
+        const int64_t fb = fc_ip[f], flen = fc_ip[f + 1] - fb;
+        for (int sd = 0; sd < 2; ++sd) {
+            const int32_t enc = face_cells[2 * f + sd];
+            if (enc < 0) continue;
+            const int c = enc >> 1;
+            const double sg = (enc & 1) ? -1.0 : 1.0;
+            const int64_t cb = cc_ip[c], clen = cc_ip[c + 1] - cb;
+            for (int64_t t = lane; t < flen * nd2; t += 32) {
+                const int64_t q = t / nd2;
+                const int ij = (int)(t - q * nd2);
+                const int i = ij / nd, j = ij - i * nd;
+                const int k = fc_ix[fb + q];
+                int64_t lo = cb, hi = cb + clen;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (cc_ix[mid] < k) lo = mid + 1; else hi = mid;
+                }
+                const double v = stress[nd2 * fb + (int64_t)i * nd * flen + q * nd + j];
+                atomicAdd(a + nd2 * cb + (int64_t)i * nd * clen + (lo - cb) * nd + j, sg * v);
+            }
+        }
+    }
+}
+
+// w[f*nd+i] = sum over block entries of bound_stress row (f,i) times bc
+__global__ void bound_stress_dot_kernel(int64_t nf, int nd, const int32_t *__restrict__ ip,
+                                        const int32_t *__restrict__ ix, const double *__restrict__ vals,
+                                        const double *__restrict__ x, double *__restrict__ w) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nd2 = nd * nd;
+    for (int64_t r = warp; r < nf * nd; r += nwarps) {
+        const int64_t f = r / nd;
+        const int i = (int)(r - f * nd);
+        const int64_t b = ip[f], len = ip[f + 1] - b;
+        double acc = 0.0;
+        for (int64_t t = lane; t < len * nd; t += 32) {
+            const int64_t q = t / nd;
+            const int j = (int)(t - q * nd);
+            acc += vals[nd2 * b + (int64_t)i * nd * len + t] * x[(int64_t)ix[b + q] * nd + j];
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) w[r] = acc;
+    }
+}
+
+__global__ void neg_div_nd_kernel(int64_t nf, int nd, const int32_t *__restrict__ face_cells,
+                                  const double *__restrict__ w, double *__restrict__ rhs) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nf * nd; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = r / nd;
+        const int i = (int)(r - f * nd);
+        for (int sd = 0; sd < 2; ++sd) {
+            const int32_t enc = face_cells[2 * f + sd];
+            if (enc >= 0) atomicAdd(rhs + (int64_t)(enc >> 1) * nd + i, ((enc & 1) ? 1.0 : -1.0) * w[r]);
+        }
+    }
+}
+
+extern "C" int pb_mpsa_system(pb_plan *p, pb_csr **out) {
+    if (!p || !out) return fail(PB_EINVAL, "null pointer");
+    if (!p->o_stress.p) return fail(PB_EINVAL, "pb_mpsa_assemble has not been called");
+    const HostPlan &H = p->H;
+    const int nd = H.nd, nd2 = nd * nd;
+    if ((int64_t)p->pat_nnz[2] * nd2 >= 0x7FFFFFFFll) return fail(PB_ENOTIMPL, "system matrix does not fit int32 indices");
+    int rc = ensure_face_cells(p);
+    if (rc) return rc;
+    cudaStream_t st = p->stream;
+    // block-expanded CELL_CELL pattern on the device
+    DevBuf nip, nix;
+    CUDA_TRY(nip.ensure((size_t)(H.nc * nd + 1) * sizeof(int32_t)));
+    CUDA_TRY(nix.ensure((size_t)std::max<int64_t>(1, p->pat_nnz[2] * nd2) * sizeof(int32_t)));
+    const int block = 256;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((H.nc * 32 + block - 1) / block, (int64_t)kSMs * 16));
+    expand_pattern_kernel<<<grid, block, 0, st>>>(H.nc, p->cc_indptr.as<int32_t>(), p->pat_idx[2].as<int32_t>(), nd, nd,
+                                                  nip.as<int32_t>(), nix.as<int32_t>());
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));
+    pb_csr *a = nullptr;
+    rc = pb_csr_from_device_pattern_(H.nc * nd, H.nc * nd, p->pat_nnz[2] * nd2, nip.as<int32_t>(), nix.as<int32_t>(), &a);
+    if (rc) return rc;
+    int grid2 = (int)std::max<int64_t>(1, std::min<int64_t>((H.nf * 32 + block - 1) / block, (int64_t)kSMs * 16));
+    div_stress_kernel<<<grid2, block, 0, st>>>(H.nf, nd, p->fc_indptr.as<int32_t>(), p->pat_idx[0].as<int32_t>(),
+                                               p->o_stress.as<double>(), p->face_cells.as<int32_t>(),
+                                               p->cc_indptr.as<int32_t>(), p->pat_idx[2].as<int32_t>(), pb_csr_data_(a));
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *out = a;
+    return PB_OK;
+}
+
+extern "C" int pb_mpsa_rhs(pb_plan *p, const double *bc_values, const double *source, double *rhs) {
+    if (!p || !bc_values || !rhs) return fail(PB_EINVAL, "null pointer");
+    if (!p->o_bstress.p) return fail(PB_EINVAL, "pb_mpsa_assemble has not been called");
+    const HostPlan &H = p->H;
+    const int nd = H.nd;
+    cudaStream_t st = p->stream;
+    int rc = ensure_face_cells(p);
+    if (rc) return rc;
+    DevBuf bc, w, r;
+    CUDA_TRY(bc.upload(bc_values, (size_t)H.nf * nd, st));
+    CUDA_TRY(w.ensure((size_t)H.nf * nd * sizeof(double)));
+    CUDA_TRY(r.ensure((size_t)H.nc * nd * sizeof(double)));
+    if (source) CUDA_TRY(cudaMemcpyAsync(r.p, source, (size_t)H.nc * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    else CUDA_TRY(cudaMemsetAsync(r.p, 0, (size_t)H.nc * nd * sizeof(double), st));
+    const int block = 256;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((H.nf * nd * 32 + block - 1) / block, (int64_t)kSMs * 16));
+    bound_stress_dot_kernel<<<grid, block, 0, st>>>(H.nf, nd, p->fb_indptr.as<int32_t>(), p->pat_idx[1].as<int32_t>(),
+                                                    p->o_bstress.as<double>(), bc.as<double>(), w.as<double>());
+    int grid2 = (int)std::max<int64_t>(1, std::min<int64_t>((H.nf * nd + block - 1) / block, (int64_t)kSMs * 16));
+    neg_div_nd_kernel<<<grid2, block, 0, st>>>(H.nf, nd, p->face_cells.as<int32_t>(), w.as<double>(), r.as<double>());
+    g_launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(rhs, r.p, (size_t)H.nc * nd * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------
 // MPSA / Biot
 // ------------------------------------------------------------------------------------
 extern "C" int pb_mpsa_upload(pb_plan *p, const double *stiffness, const uint8_t *bc,

@@ -234,6 +234,22 @@ class DevicePlan:
                                         _lib.ptr(rhs, _lib._f64p)))
         return rhs
 
+    def mpsa_system(self):
+        """A = div_nd @ stress assembled and kept on the device (``DeviceCsr``); needs ``mpsa_assemble``."""
+        from .sparse import DeviceCsr
+        h = C.c_void_p()
+        _lib.check(self.lib.pb_mpsa_system(self.h, C.byref(h)))
+        return DeviceCsr.from_handle(h)
+
+    def mpsa_rhs(self, bc_values, source=None) -> np.ndarray:
+        """b = -div_nd @ (bound_stress @ bc_values) + source   (mpsa.py:486-529)."""
+        bv = _lib.f64(bc_values)
+        src = None if source is None else _lib.f64(source)
+        rhs = np.empty(self.nc * self.nd)
+        _lib.check(self.lib.pb_mpsa_rhs(self.h, _lib.ptr(bv, _lib._f64p), _lib.ptr(src, _lib._f64p),
+                                        _lib.ptr(rhs, _lib._f64p)))
+        return rhs
+
     # ---- MPSA / Biot
     def mpsa_upload(self, stiff, codes, robw, eta, alphas=()) -> None:
         stiff = _lib.f64(stiff)
@@ -475,6 +491,12 @@ class Mpsa(_Base):
         mats.update(out)
         self.last_timing = dict(plan_s=t1 - t0, upload_s=t2 - t1, kernel_ms=ms,
                                 assemble_s=t3 - t2, download_s=t4 - t3)
+
+    def assemble_matrix_rhs_device(self, sd, data: dict):
+        """Device-resident counterpart of ``assemble_matrix_rhs`` (see ``Mpfa.assemble_matrix_rhs_device``)."""
+        params = data[PARAMETERS][self.keyword]
+        plan = DevicePlan.for_grid(sd)
+        return plan.mpsa_system(), plan.mpsa_rhs(params["bc_values"], params.get("source"))
 
     def assemble_matrix_rhs(self, sd, data: dict):
         """mpsa.py:486-529."""

@@ -340,3 +340,28 @@ def test_device_side_flow_system_and_solve():
     xs, info = kr.bicgstab(op, torch.as_tensor(b_dev, device="cuda"), tol=1e-11, diag_own=diag)
     ref = spla.spsolve(sps.csc_matrix(A_host), b_host)
     assert info["converged"] and np.linalg.norm(xs.cpu().numpy() - ref) <= 1e-8 * np.linalg.norm(ref)
+
+
+def test_device_side_mechanics_system():
+    """A = div_nd @ stress and b = -div_nd @ (bound_stress @ bc) + source assembled on the device equal
+    the host products of mpsa.py:486-529."""
+    g = pb.cart_grid_3d([6, 5, 4], perturb=0.3, seed=2)
+    rng = np.random.default_rng(5)
+    nc = g.num_cells
+    C = pb.FourthOrderTensor(np.exp(0.4 * rng.standard_normal(nc)), np.exp(0.4 * rng.standard_normal(nc)))
+    vbc = _mixed_vector_bc(g)
+    bv = np.zeros((3, g.num_faces))
+    bf = g.get_all_boundary_faces()
+    bv[:, bf] = rng.random((3, bf.size))
+    src = rng.standard_normal(3 * nc)
+    data = pb.initialize_data({}, "mech", {"fourth_order_tensor": C, "bc": vbc,
+                                           "bc_values": bv.ravel("F"), "source": src})
+    d = pb.Mpsa("mech")
+    d.discretize(g, data)
+    A_host, b_host = d.assemble_matrix_rhs(g, data)
+    A_dev, b_dev = d.assemble_matrix_rhs_device(g, data)
+    assert A_dev.shape == A_host.shape
+    assert rel_err(A_host, A_dev.to_scipy()) < 1e-13
+    assert np.abs(b_dev - b_host).max() <= 1e-12 * np.abs(b_host).max()
+    x = rng.standard_normal(3 * nc)
+    assert np.abs(A_dev @ x - A_host @ x).max() <= 1e-12 * np.abs(A_host @ x).max()

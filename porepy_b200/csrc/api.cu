@@ -595,6 +595,15 @@ extern "C" int pb_plan_create(int nd, int64_t nc, int64_t nf, int64_t nn, const 
     });
     if (rc) { delete p; return rc; }
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail("sync", e);
+    // the host copies of the node-major lists are only needed for the uploads above
+    if ((e = p->face_cells.upload(H.face_cells, st)) != cudaSuccess) return bail("face_cells", e);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail("sync", e);
+    {
+        auto drop = [](auto &v) { v.clear(); v.shrink_to_fit(); };
+        drop(H.sc_cell); drop(H.sf_face); drop(H.sf_sides); drop(H.sf_bloc); drop(H.slot_sf); drop(H.sc_ncn);
+        drop(H.posfc_ptr); drop(H.posfb_ptr); drop(H.poscc_ptr); drop(H.poscb_ptr);
+        drop(H.nbf_ptr); drop(H.nbf_idx); drop(H.cn_ptr); drop(H.cn_idx); drop(H.face_cells); drop(H.fn_indptr);
+    }
     if (getenv("POREB200_PLAN_TIMING"))
         fprintf(stderr, "[plan] total incl. upload          %8.1f ms\n",
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count());
@@ -898,9 +907,8 @@ __global__ void neg_div_kernel(int64_t nf, const int32_t *__restrict__ face_cell
 }
 
 static int ensure_face_cells(pb_plan *p) {
-    if (p->face_cells.p) return PB_OK;
-    CUDA_TRY(p->face_cells.upload(p->H.face_cells, p->stream));
-    return PB_OK;
+    if (p->face_cells.p) return PB_OK;  // uploaded by pb_plan_create
+    return fail(PB_EINVAL, "plan has no face->cell table");
 }
 
 extern "C" int pb_mpfa_system(pb_plan *p, pb_csr **out) {

@@ -205,7 +205,11 @@ __global__ void __launch_bounds__(Solver::team == 32 ? 128 : Solver::team, Solve
                      : rest + rest_doubles;
     for (int i = blockIdx.x * teams_per_block + team_in_block; i < n_nodes;
          i += gridDim.x * teams_per_block)
-        mpsa_node<ND, Solver>(t, P, G, prm, o, (int64_t)nodes[i], A, rest, scratch, err);
+    {
+        const int inext = i + gridDim.x * teams_per_block;  // prefetched into L2 during this region's output phase
+        const int64_t s_next = inext < n_nodes ? (int64_t)nodes[inext] : -1;
+        mpsa_node<ND, Solver>(t, P, G, prm, o, (int64_t)nodes[i], A, rest, scratch, err, s_next);
+    }
 }
 
 static const size_t kMaxSmem = 227 * 1024;

@@ -58,7 +58,8 @@ PB_HD bool sym_mask(int p, int q) {
 
 template <int ND, class Solver, class Team>
 PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaParams &prm,
-                     const MpsaOut &o, int64_t s, double *A, double *smd, double *scratch, int *err) {
+                     const MpsaOut &o, int64_t s, double *A, double *smd, double *scratch, int *err,
+                     int64_t s_next = -1) {
     constexpr int ND2 = ND * ND;
     const int sc0 = P.node_sc_ptr[s], nsc = P.node_sc_ptr[s + 1] - sc0;
     const int sf0 = P.node_sf_ptr[s], nsf = P.node_sf_ptr[s + 1] - sf0;
@@ -338,6 +339,19 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
         return;
     }
 
+#if defined(__CUDA_ARCH__)
+    // software prefetch of the NEXT region's inputs into L2 (three dependent stages spread over
+    // phases 6-7 so that no stage waits): pointers here, lists after phase 6, records after phase 7
+    int pf_sc0 = 0, pf_nsc = 0, pf_sf0 = 0, pf_nsf = 0;
+    int64_t pf_pos0 = 0;
+    if (s_next >= 0) {
+        pf_sc0 = P.node_sc_ptr[s_next];
+        pf_nsc = P.node_sc_ptr[s_next + 1] - pf_sc0;
+        pf_sf0 = P.node_sf_ptr[s_next];
+        pf_nsf = P.node_sf_ptr[s_next + 1] - pf_sf0;
+        pf_pos0 = P.posfc_ptr[s_next];
+    }
+#endif
     // ---- phase 6: Z[p][c] = SigmaA[p] applied to the solution (+ direct cell-displacement term)
 #if defined(__CUDA_ARCH__)
     // (ND2 x n) * (n x nrhs) on the FP64 tensor cores: one 8x8 tile of Z per warp iteration
@@ -372,79 +386,152 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
 #endif
     t.sync();
 
+#if defined(__CUDA_ARCH__)
+    int pf_cell = -1, pf_face = -1;
+    if (t.tid() < pf_nsc) pf_cell = P.sc_cell[pf_sc0 + t.tid()];
+    if (t.tid() < pf_nsf) {
+        pf_face = P.sf_face[pf_sf0 + t.tid()];
+        if ((t.tid() & 7) == 0) {
+            pb_prefetch_l2(P.sf_sides + pf_sf0 + t.tid());
+            pb_prefetch_l2(P.sf_bloc + pf_sf0 + t.tid());
+        }
+    }
+    if (t.tid() * 16 < pf_nsc * ND) pb_prefetch_l2(P.slot_sf + (int64_t)pf_sc0 * ND + t.tid() * 16);
+    for (int64_t off = (int64_t)t.tid() * 32; off < (int64_t)pf_nsf * pf_nsc; off += (int64_t)t.size() * 32)
+        pb_prefetch_l2(P.pos_fc + pf_pos0 + off);
+#endif
     // ---- phase 7: face rows (traction from the unique side, displacement trace)
     const int32_t *pfc = P.pos_fc + P.posfc_ptr[s];
     const int32_t *pfb = P.pos_fb + P.posfb_ptr[s];
-    for (int x = t.warp(); x < n; x += t.nwarps()) {
-        const int u = x / ND, i = x - u * ND;
+    // one warp per sub-face, lanes over the right-hand-side columns, the nd components of the
+    // row inside: the 9 solution rows of the selected sub-cell and the CSR position are loaded
+    // once per (sub-face, column) instead of once per component
+    for (int u = t.warp(); u < nsf; u += t.nwarps()) {
         const double *nu = nrm + u * ND;
         const int side1 = sidesel[u];
-        double hs[ND][ND];  // [a][m] coefficient of ubar_{u(k1,m),a}
-        {
-            const double *ps1 = PS + ((side1 / ND) * ND2 + i * ND) * ND2;
+        const int k1 = side1 / ND, m1 = side1 - k1 * ND;
+        double hs[ND][ND][ND];  // [i][a][m] coefficient of ubar_{u(k1,m),a} in component i
+        double hsum[ND][ND];    // [i][a] = sum_m hs[i][a][m]
 #pragma unroll
-            for (int a = 0; a < ND; ++a)
+        for (int i = 0; i < ND; ++i) {
+            const double *ps1 = PS + (k1 * ND2 + i * ND) * ND2;
+#pragma unroll
+            for (int a = 0; a < ND; ++a) {
+                double sm = 0.0;
 #pragma unroll
                 for (int m = 0; m < ND; ++m) {
                     double v = 0.0;
 #pragma unroll
                     for (int r = 0; r < ND; ++r) v += nu[r] * ps1[(r * ND + a) * ND + m];
-                    hs[a][m] = v;
+                    hs[i][a][m] = v;
+                    sm += v;
                 }
+                hsum[i][a] = sm;
+            }
         }
-        const int k1 = side1 / ND, m1 = side1 - k1 * ND;
-        const double *xr[ND][ND];
+        int xo[ND][ND];  // offsets of the solution rows of ubar_{u(k1,m),a}
 #pragma unroll
         for (int a = 0; a < ND; ++a)
 #pragma unroll
-            for (int m = 0; m < ND; ++m)
-                xr[a][m] = A + (int64_t)rowidx[(slot[k1 * ND + m] >> 1) * ND + a] * W + n;
-        const int code = bcu[x];
-        const bool use_asym = !((code == 2 && elim[i]) || (code == 3 && elim[ND + i]));
-        const double *xu = A + (int64_t)rowidx[x] * W + n;
+            for (int m = 0; m < ND; ++m) xo[a][m] = rowidx[(slot[k1 * ND + m] >> 1) * ND + a] * W + n;
+        bool use_asym[ND];
+        int uo[ND];
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+            const int code = bcu[u * ND + i];
+            use_asym[i] = !((code == 2 && elim[i]) || (code == 3 && elim[ND + i]));
+            uo[i] = rowidx[u * ND + i] * W + n;
+        }
         const double im = invmf[u];
         const int64_t f = face[u];
         const int64_t fc0 = P.fc_indptr[f], fcl = P.fc_indptr[f + 1] - fc0;
         const int64_t fb0 = P.fb_indptr[f], fbl = P.fb_indptr[f + 1] - fb0;
         for (int c = t.lane(); c < nrhs; c += t.lanes()) {
-            double hk = 0.0;
+            double hk[ND], tr[ND];
+#pragma unroll
+            for (int i = 0; i < ND; ++i) hk[i] = 0.0;
 #pragma unroll
             for (int a = 0; a < ND; ++a)
 #pragma unroll
-                for (int m = 0; m < ND; ++m) hk += hs[a][m] * xr[a][m][c];
-            if (use_asym) {
+                for (int m = 0; m < ND; ++m) {
+                    const double xv = A[xo[a][m] + c];
 #pragma unroll
-                for (int r = 0; r < ND; ++r) hk += nu[r] * Z[(i * ND + r) * nrhs + c];
+                    for (int i = 0; i < ND; ++i) hk[i] += hs[i][a][m] * xv;
+                }
+#pragma unroll
+            for (int i = 0; i < ND; ++i) {
+                if (use_asym[i]) {
+#pragma unroll
+                    for (int r = 0; r < ND; ++r) hk[i] += nu[r] * Z[(i * ND + r) * nrhs + c];
+                }
+                tr[i] = A[uo[i] + c] * im;
             }
-            const double tr = xu[c] * im;
             if (c < ncc) {
                 const int k = c / ND, j = c - k * ND;
                 if (k == k1) {  // direct dependence of the own sub-cell's gradient on u_{k1,j}
 #pragma unroll
-                    for (int m = 0; m < ND; ++m) hk -= hs[j][m];
+                    for (int i = 0; i < ND; ++i) {
+                        double hj = hsum[i][0];
+#pragma unroll
+                        for (int a = 1; a < ND; ++a) hj = (j == a) ? hsum[i][a] : hj;
+                        hk[i] -= hj;
+                    }
                 }
                 const int64_t pb = pfc[u * nsc + k];
-                const int64_t pos = ND2 * fc0 + (int64_t)i * ND * fcl + (pb - fc0) * ND + j;
-                if (o.stress) red_add(o.stress + pos, hk);
-                if (o.bdc) red_add(o.bdc + pos, tr);
+                const int64_t pos = ND2 * fc0 + (pb - fc0) * ND + j;
+#pragma unroll
+                for (int i = 0; i < ND; ++i) {
+                    if (o.stress) red_add(o.stress + pos + (int64_t)i * ND * fcl, hk[i]);
+                    if (o.bdc) red_add(o.bdc + pos + (int64_t)i * ND * fcl, tr[i]);
+                }
             } else if (c < ncc + nbc) {
                 const int cb = c - ncc;
                 const int b = cb / ND, j = cb - b * ND;
                 const int64_t pb = pfb[u * nb + b];
-                const int64_t pos = ND2 * fb0 + (int64_t)i * ND * fbl + (pb - fb0) * ND + j;
-                if (o.bstress) red_add(o.bstress + pos, hk);
-                if (o.bdf) red_add(o.bdf + pos, tr);
+                const int64_t pos = ND2 * fb0 + (pb - fb0) * ND + j;
+#pragma unroll
+                for (int i = 0; i < ND; ++i) {
+                    if (o.bstress) red_add(o.bstress + pos + (int64_t)i * ND * fbl, hk[i]);
+                    if (o.bdf) red_add(o.bdf + pos + (int64_t)i * ND * fbl, tr[i]);
+                }
             } else {
                 const int cq = c - ncc - nbc;
                 const int q = cq / nsc, k = cq - q * nsc;
-                if (k == k1) hk -= NA[((q * nsc + k1) * ND + m1) * ND + i];  // biot.py:853-855
                 const int64_t pb = pfc[u * nsc + k];
-                const int64_t pos = ND * fc0 + (int64_t)i * fcl + (pb - fc0);
-                if (o.sg[q]) red_add(o.sg[q] + pos, hk);
-                if (o.bdp[q]) red_add(o.bdp[q] + pos, tr);
+                const int64_t pos = ND * fc0 + (pb - fc0);
+#pragma unroll
+                for (int i = 0; i < ND; ++i) {
+                    double h = hk[i];
+                    if (k == k1) h -= NA[((q * nsc + k1) * ND + m1) * ND + i];  // biot.py:853-855
+                    if (o.sg[q]) red_add(o.sg[q] + pos + (int64_t)i * fcl, h);
+                    if (o.bdp[q]) red_add(o.bdp[q] + pos + (int64_t)i * fcl, tr[i]);
+                }
             }
         }
     }
+#if defined(__CUDA_ARCH__)
+    if (pf_cell >= 0) {
+        if (prm.stiff_cs == 1) {
+            const double *rec = prm.stiff + (int64_t)pf_cell * prm.stiff_es;
+#pragma unroll
+            for (int b = 0; b < 81; b += 16) pb_prefetch_l2(rec + b);
+            pb_prefetch_l2(rec + 80);
+        }
+        if (G.cell_cs == 1) pb_prefetch_l2(G.ccent + (int64_t)pf_cell * G.cell_es);
+        pb_prefetch_l2(G.cvol + pf_cell);
+        pb_prefetch_l2(P.sc_ncn + pf_cell);
+    }
+    if (pf_face >= 0) {
+        if (G.face_cs == 1) {
+            pb_prefetch_l2(G.fnorm + (int64_t)pf_face * G.face_es);
+            pb_prefetch_l2(G.fcent + (int64_t)pf_face * G.face_es);
+        }
+        pb_prefetch_l2(P.fn_indptr + pf_face);
+        pb_prefetch_l2(P.fc_indptr + pf_face);
+#pragma unroll
+        for (int i = 0; i < ND; ++i) pb_prefetch_l2(prm.bc + (int64_t)i * nf + pf_face);
+    }
+#endif
     // ---- phase 8 (Biot): cell rows  dv_K . G_K  (biot.py:1054-1135)
     if (nal > 0) {
         const int32_t *pcc = P.pos_cc + P.poscc_ptr[s];

@@ -671,6 +671,12 @@ struct TileGJ {
 // ------------------------------------------------------------------------------------
 // small dense inverse of the nd x nd matrix of distance vectors (rows d_m)
 // ------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pb_prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+#endif
+
 template <int ND>
 PB_HD bool invert_small(const double (&D)[ND][ND], double (&E)[ND][ND]);
 

@@ -37,7 +37,7 @@ PB_HD int64_t mpsa_rest_doubles(int nd, int nsf, int nsc, int nb, int nalpha) {
     d += nd2 * nrhs;                            // Z
     d += nsf;                                   // invmf
     d += (int64_t)nsf * nd;                     // nrm
-    d += 2 * (int64_t)nsc;                      // wk, volk
+    d += (int64_t)nsc;                          // volk
     d += (int64_t)nalpha * nsc * nd2 * 2;       // NA, AE
     int64_t ints = nsc + 4 * (int64_t)nsf + (int64_t)nsf * nd + n + (int64_t)nsc * nd + 2 * nd;
     return d + (ints + 1) / 2 + 2;
@@ -80,8 +80,7 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
     double *Z = SAc + ND2 * ncc;                // [p][c], c < nrhs
     double *invmf = Z + ND2 * nrhs;
     double *nrm = invmf + nsf;                  // [u][r]  n_f / m_f
-    double *wk = nrm + nsf * ND;
-    double *volk = wk + nsc;
+    double *volk = nrm + nsf * ND;
     double *NA = volk + nsc;                    // [q][k][m][i]  (n_{u(k,m)}^T alpha_k)_i
     double *AE = NA + nal * nsc * ND2;          // [q][k][a][m]  sum_kappa alpha_k[a][kappa] E_k[kappa][m]
     int *cell = (int *)(AE + nal * nsc * ND2);
@@ -172,23 +171,6 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
         }
     }
     t.sync();
-    // node-volume weights w_K (mpsa.py:1619-1640) and the elimination flags
-    if (t.tid() == 0) {
-        double tot = 0.0;
-        for (int k = 0; k < nsc; ++k) tot += volk[k];
-        for (int k = 0; k < nsc; ++k) wk[k] = volk[k] / tot;
-        for (int i = 0; i < ND; ++i) {
-            int cn = 0, cr = 0;
-            for (int u = 0; u < nsf; ++u) {
-                cn += bcu[u * ND + i] == 2;
-                cr += bcu[u * ND + i] == 3;
-            }
-            elim[i] = nsc < cn;
-            elim[ND + i] = nsc < cr;
-        }
-    }
-    t.sync();
-
     // ---- phase 3: PS[k][p][a][m] = sum_kappa (C o S)[p,(a,kappa)] E[kappa][m];
     //               SA[p][(u,a)]  += w_k sum_kappa (C o !S)[p,(a,kappa)] E[kappa][m]
     for (int it = t.tid(); it < nsc * ND2; it += t.size()) {
@@ -211,27 +193,42 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
             }
         }
     }
-    for (int it = t.tid(); it < ND2 * ND; it += t.size()) {
-        const int p = it / ND, a = it - p * ND;
+    // one item per (p, a, sub-cell); a sub-face entry of SigmaA receives one contribution per side
+    // (<= 2, so the sum does not depend on the order).  Node-volume weights w_K = vol_K / sum vol
+    // (mpsa.py:1619-1640) are formed on the fly.
+    for (int it = t.tid(); it < ND2 * ND * nsc; it += t.size()) {
+        const int pa = it / nsc, k = it - pa * nsc;
+        const int p = pa / ND, a = pa - p * ND;
         const int pi = p / ND, pr = p - pi * ND;
-        for (int k = 0; k < nsc; ++k) {
-            const int64_t c = cell[k];
-            const double *Crow = prm.stiff + (int64_t)c9<ND>(pi, pr) * 9 * prm.stiff_cs + c * prm.stiff_es;
-            double ca[ND];
+        double tot = 0.0;
+        for (int j = 0; j < nsc; ++j) tot += volk[j];
+        const double w = volk[k] / tot;
+        const int64_t c = cell[k];
+        const double *Crow = prm.stiff + (int64_t)c9<ND>(pi, pr) * 9 * prm.stiff_cs + c * prm.stiff_es;
+        double ca[ND];
 #pragma unroll
-            for (int q = 0; q < ND; ++q)
-                ca[q] = sym_mask<ND>(p, a * ND + q) ? 0.0 : wk[k] * Crow[(int64_t)c9<ND>(a, q) * prm.stiff_cs];
-            double sum = 0.0;
+        for (int q = 0; q < ND; ++q)
+            ca[q] = sym_mask<ND>(p, a * ND + q) ? 0.0 : w * Crow[(int64_t)c9<ND>(a, q) * prm.stiff_cs];
+        double sum = 0.0;
 #pragma unroll
-            for (int m = 0; m < ND; ++m) {
-                double v = 0.0;
+        for (int m = 0; m < ND; ++m) {
+            double v = 0.0;
 #pragma unroll
-                for (int q = 0; q < ND; ++q) v += ca[q] * E[k * ND2 + q * ND + m];
-                SA[p * n + (slot[k * ND + m] >> 1) * ND + a] += v;
-                sum += v;
-            }
-            SAc[p * ncc + k * ND + a] = -sum;
+            for (int q = 0; q < ND; ++q) v += ca[q] * E[k * ND2 + q * ND + m];
+            team_add(SA + p * n + (slot[k * ND + m] >> 1) * ND + a, v);
+            sum += v;
         }
+        SAc[p * ncc + k * ND + a] = -sum;
+    }
+    // elimination flags of _eliminate_ncasym (mpsa.py:1932-2000), one thread per component
+    for (int i = t.tid(); i < ND; i += t.size()) {
+        int cn = 0, cr = 0;
+        for (int u = 0; u < nsf; ++u) {
+            cn += bcu[u * ND + i] == 2;
+            cr += bcu[u * ND + i] == 3;
+        }
+        elim[i] = nsc < cn;
+        elim[ND + i] = nsc < cr;
     }
     t.sync();
 

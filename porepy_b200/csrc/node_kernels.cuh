@@ -72,6 +72,15 @@ PB_HD void red_add(double *p, double v) {
 #endif
 }
 
+// add into the team's shared staging area from concurrent threads
+PB_HD void team_add(double *p, double v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+
 PB_HD void flag_singular(int *err, int64_t node) {
 #if defined(__CUDA_ARCH__)
     atomicMin(err, (int)node);

@@ -357,11 +357,15 @@ class _Base:
         and gives the same matrices."""
         self.discretize(sd, data)
 
-    def _check_unsupported(self, params: dict) -> None:
+    def _check_unsupported(self, params: dict, sd=None) -> None:
         """``partition_arguments`` bound the reference's working set (``_fvutils.py:358-411``); the
         kernels stream over nodes and never materialise the global block-diagonal inverse, so the
         key is accepted and ignored.  ``specified_cells/faces/nodes`` select a partial update in the
-        reference; here the whole grid is re-discretized (same matrices)."""
+        reference; here the whole grid is re-discretized (same matrices).  Periodic face pairs
+        (``_fvutils.py:95-140``) are not merged by the topology plan: refuse rather than discretize
+        the pair as two boundaries."""
+        if sd is not None and getattr(sd, "periodic_face_map", None) is not None:
+            raise NotImplementedError("periodic boundaries (sd.periodic_face_map) are not supported")
         return None
 
 
@@ -397,7 +401,7 @@ class Mpfa(_Base):
             raise NotImplementedError("ambient_dimension != sd.dim is not supported")
         if np.asarray(bc.is_dir).shape[-1] != sd.num_faces:
             raise NotImplementedError("sub-face boundary conditions are not supported")
-        self._check_unsupported(params)
+        self._check_unsupported(params, sd)
         t0 = time.perf_counter()
         plan = DevicePlan.for_grid(sd)
         codes = scalar_bc_codes(bc, sd.num_faces)
@@ -468,7 +472,7 @@ class Mpsa(_Base):
             raise NotImplementedError("reconstruction_eta != mpsa_eta is not supported")
         if np.asarray(bc.is_dir).shape[-1] != sd.num_faces:
             raise NotImplementedError("sub-face boundary conditions are not supported")
-        self._check_unsupported(params)
+        self._check_unsupported(params, sd)
         alphas = self._alphas(sd, params)
         t0 = time.perf_counter()
         plan = DevicePlan.for_grid(sd)

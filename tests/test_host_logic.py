@@ -130,3 +130,14 @@ def test_biot_class_keys_and_assembly_refusal():
     assert keys["consistency_matrix_key"] == "mpsa_consistency"
     with pytest.raises(NotImplementedError):  # biot.py:125-149
         b.assemble_matrix_rhs(None, {})
+
+
+def test_periodic_grids_are_refused():
+    """Periodic face pairs are merged by the reference's SubcellTopology (_fvutils.py:95-140);
+    the topology plan does not, so the operator must refuse them (before touching the device)."""
+    g = pb.cart_grid_3d([2, 2, 2])
+    g.periodic_face_map = np.array([[0], [2]])
+    data = pb.initialize_data({}, "flow", {"second_order_tensor": pb.SecondOrderTensor(np.ones(8)),
+                                           "bc": pb.BoundaryCondition(g)})
+    with pytest.raises(NotImplementedError):
+        pb.Mpfa("flow").discretize(g, data)

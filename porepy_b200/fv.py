@@ -64,6 +64,63 @@ def _index_dtype(nnz: int, ncols: int):
     return np.int32 if max(nnz, ncols) < 2**31 - 1 else np.int64
 
 
+# ------------------------------------------------------------------------------------------
+# 2-D grids embedded in 3-D (fracture planes)
+# ------------------------------------------------------------------------------------------
+
+
+def plane_frame(sd, tol: float = 1e-5):
+    """Rotation ``R`` (3, 3) with rows (t1, t2, n) that maps a planar 2-D grid into its own
+    plane, or ``None`` when the grid already lies in a plane z = const.
+
+    The reference rotates such grids with ``map_geometry.map_grid`` before discretizing
+    (numerics/fv/mpfa.py:733-754).  Any in-plane basis gives the same matrices (the scheme is
+    invariant under rotations and reflections), so the frame is taken from the principal axes
+    of the node cloud."""
+    x = np.asarray(sd.nodes, dtype=np.float64)
+    xc = x - x.mean(axis=1, keepdims=True)
+    w, v = np.linalg.eigh(xc @ xc.T)          # ascending: v[:, 0] is the plane normal
+    n = v[:, 0]
+    extent = np.sqrt(max(w[2], 0.0) / max(x.shape[1], 1)) + 1e-300
+    if np.abs(n @ xc).max() > tol * max(extent, np.abs(xc).max()):
+        raise ValueError("2-D grid is not planar")
+    if abs(abs(n[2]) - 1.0) <= 1e-14 and np.ptp(x[2]) <= 1e-12 * max(1.0, np.abs(x).max()):
+        return None
+    t1 = v[:, 2]
+    t2 = np.cross(n, t1)
+    return np.vstack((t1, t2 / np.linalg.norm(t2), n))
+
+
+def plan_geometry(sd):
+    """The six geometry arrays the plan reads, and the rotation applied to them (None for 3-D
+    grids and for 2-D grids in a plane z = const)."""
+    arrs = [sd.nodes, sd.face_normals, sd.face_centers, sd.face_areas, sd.cell_centers, sd.cell_volumes]
+    rot = plane_frame(sd) if int(sd.dim) == 2 else None
+    if rot is not None:
+        for i in (0, 1, 2, 4):
+            a = rot @ np.asarray(arrs[i], dtype=np.float64)
+            a[2] = 0.0
+            arrs[i] = a
+    return [_lib.f64(a) for a in arrs], rot
+
+
+def rotate_second_order(values: np.ndarray, rot: np.ndarray) -> np.ndarray:
+    """R K R^T per cell for (3, 3, nc) values (mpfa.py:749-754; the kernels read the leading
+    nd x nd block)."""
+    return np.einsum("ia,abc,jb->ijc", rot, np.asarray(values, dtype=np.float64), rot)
+
+
+def lift_vector_source(ip: np.ndarray, ix: np.ndarray, data: np.ndarray, rows: np.ndarray, nc: int):
+    """(nf, 2 nc) vector-source matrix in the plane's coordinates -> (nf, 3 nc) in the ambient
+    space: every (face, cell) pair of in-plane coefficients is multiplied by the two in-plane
+    rows of the rotation (mpfa.py:423-466).  ``ip, ix`` is the FACE x CELL base pattern,
+    ``data`` holds the two coefficients of each base entry consecutively."""
+    d3 = np.asarray(data, dtype=np.float64).reshape(-1, 2) @ np.asarray(rows, dtype=np.float64)
+    dt = _index_dtype(3 * int(ix.size), 3 * nc)
+    cols = (ix.astype(dt)[:, None] * 3 + np.arange(3, dtype=dt)).ravel()
+    return sps.csr_matrix((d3.ravel(), cols, ip.astype(dt) * 3), shape=(ip.size - 1, 3 * nc))
+
+
 class DevicePlan:
     """Device-resident sub-cell topology + output patterns of one grid (``pb_plan``).
 
@@ -97,6 +154,7 @@ class DevicePlan:
         self.fingerprint = (self.nd, self.nc, self.nf, self.nn, int(cf.nnz), int(fn.nnz))
         self._base = {}
         self._expanded = {}
+        self.rotation = None
 
     def __del__(self):
         h = getattr(self, "h", None)
@@ -122,14 +180,9 @@ class DevicePlan:
         return plan
 
     def set_geometry(self, sd) -> None:
-        if self.nd == 2:
-            z = np.asarray(sd.nodes)[2]
-            if np.ptp(z) > 1e-12 * max(1.0, np.abs(sd.nodes).max()):
-                raise NotImplementedError(
-                    "2-D grids must lie in the xy-plane (the rotation of mpfa.py:733-754 is "
-                    "not part of this build)")
-        arrs = [_lib.f64(a) for a in (sd.nodes, sd.face_normals, sd.face_centers, sd.face_areas,
-                                      sd.cell_centers, sd.cell_volumes)]
+        """Upload the geometry.  2-D grids embedded in 3-D are rotated into their own plane first
+        (``plan_geometry``); ``self.rotation`` keeps the rotation for the callers."""
+        arrs, self.rotation = plan_geometry(sd)
         _lib.check(self.lib.pb_plan_set_geometry(self.h, *[_lib.ptr(a, _lib._f64p) for a in arrs]))
 
     # ---- patterns
@@ -396,9 +449,9 @@ class Mpfa(_Base):
             eta = determine_eta(sd)
         if np.asarray(eta).size != 1:
             raise NotImplementedError("sub-face valued mpfa_eta is not supported")
-        amb = params.get("ambient_dimension", sd.dim)
-        if amb != sd.dim:
-            raise NotImplementedError("ambient_dimension != sd.dim is not supported")
+        amb = int(params.get("ambient_dimension", sd.dim))
+        if amb != sd.dim and not (sd.dim == 2 and amb == 3):
+            raise NotImplementedError(f"ambient_dimension={amb} for a {sd.dim}-d grid is not supported")
         if np.asarray(bc.is_dir).shape[-1] != sd.num_faces:
             raise NotImplementedError("sub-face boundary conditions are not supported")
         self._check_unsupported(params, sd)
@@ -407,11 +460,21 @@ class Mpfa(_Base):
         codes = scalar_bc_codes(bc, sd.num_faces)
         robw = np.asarray(bc.robin_weight, float) if np.any(codes == _lib.BC_ROB) else None
         t1 = time.perf_counter()
-        plan.mpfa_upload(k.values, codes, robw, float(np.asarray(eta).ravel()[0]))
+        kvals = k.values
+        if plan.rotation is not None:  # fracture plane: mpfa.py:733-754
+            if amb != 3:
+                raise NotImplementedError("a 2-D grid outside the xy-plane needs ambient_dimension=3")
+            kvals = rotate_second_order(kvals, plan.rotation)
+        plan.mpfa_upload(kvals, codes, robw, float(np.asarray(eta).ravel()[0]))
         t2 = time.perf_counter()
         ms = plan.mpfa_assemble()
         t3 = time.perf_counter()
         out = plan.mpfa_download()
+        if sd.dim == 2 and amb == 3:  # vector source back to the ambient space, mpfa.py:423-466
+            rows = (np.eye(3) if plan.rotation is None else plan.rotation)[:2]
+            ip, ix = plan.base_pattern(0)
+            for key in (self.vector_source_matrix_key, self.bound_pressure_vector_source_matrix_key):
+                out[key] = lift_vector_source(ip, ix, out[key].data, rows, sd.num_cells)
         t4 = time.perf_counter()
         mats.update(out)
         self.last_timing = dict(plan_s=t1 - t0, upload_s=t2 - t1, kernel_ms=ms,
@@ -476,6 +539,11 @@ class Mpsa(_Base):
         alphas = self._alphas(sd, params)
         t0 = time.perf_counter()
         plan = DevicePlan.for_grid(sd)
+        if plan.rotation is not None:
+            # the reference discretizes in the local frame of map_grid without rotating the stiffness
+            # back (mpsa.py:2005-2040): frame dependent, and not a use case (mechanics lives on the
+            # top-dimensional grid)
+            raise NotImplementedError("MPSA on a 2-D grid outside the xy-plane is not supported")
         codes, robw = vector_bc_codes(bc, sd.dim, sd.num_faces)
         t1 = time.perf_counter()
         plan.mpsa_upload(constit.values, codes, robw, float(eta), list(alphas.values()))

@@ -18,10 +18,10 @@ Use in a model (the mixin override of constitutive_laws.py:1078,3003,3506)::
         def darcy_flux_discretization(self, subdomains):
             return b200.MpfaAd(self.darcy_keyword, subdomains)
 
-Scope: the GPU path covers the top-dimensional subdomains (3-D grids, and 2-D grids lying in
-the xy-plane), which hold > 99 % of the cells of a mixed-dimensional grid.  Fracture /
-intersection grids (embedded 2-D planes, 1-D lines, 0-D points) are handed to the reference's
-own implementation (its TPFA fallback for 1-D, mpfa.py:690-712), exactly as ``pp.Mpfa`` would.
+Scope: the GPU path covers the top-dimensional subdomains (3-D grids, 2-D grids lying in the
+xy-plane) and, for the flux discretization, 2-D fracture planes embedded in 3-D.  Intersection
+grids (1-D lines, 0-D points) are handed to the reference's own implementation (its TPFA
+fallback, mpfa.py:690-712), exactly as ``pp.Mpfa`` would.
 """
 from __future__ import annotations
 
@@ -35,10 +35,14 @@ from . import fv
 logger = logging.getLogger(__name__)
 
 
-def _gpu_scope(sd) -> bool:
+def _gpu_scope(sd, flow: bool = False) -> bool:
+    """3-D grids; 2-D grids in a plane z = const; for the flux discretization also 2-D fracture
+    planes embedded in 3-D (rotated into their plane on the host, fv.plane_frame)."""
     if sd.dim == 3:
         return True
     if sd.dim == 2:
+        if flow:
+            return True
         z = np.asarray(sd.nodes)[2]
         return bool(np.ptp(z) <= 1e-12 * max(1.0, float(np.abs(sd.nodes).max())))
     return False
@@ -53,7 +57,7 @@ def plugin(pp) -> SimpleNamespace:
             fv.Mpfa.__init__(self, keyword)
 
         def discretize(self, sd, data) -> None:
-            if _gpu_scope(sd) and not hasattr(sd, "periodic_face_map"):
+            if _gpu_scope(sd, flow=True) and not hasattr(sd, "periodic_face_map"):
                 fv.Mpfa.discretize(self, sd, data)
             else:
                 logger.info("B200 Mpfa: %s-d subdomain outside the GPU scope -> reference path", sd.dim)

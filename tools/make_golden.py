@@ -154,6 +154,45 @@ def case_mpfa(name, kind, robin, seed, contrast=False):
     print(name, "nc", nc, "nf", g.num_faces)
 
 
+def tilt_rotation(rng):
+    """A generic rotation (proper orthogonal matrix) from a seeded QR factorization."""
+    q, r = np.linalg.qr(rng.standard_normal((3, 3)))
+    q = q * np.sign(np.diag(r))
+    if np.linalg.det(q) < 0:
+        q[:, 0] *= -1
+    return q
+
+
+def case_mpfa_embedded(name, kind, seed, tilt):
+    """2-D grid embedded in 3-D (a fracture plane): the reference rotates it into its own plane
+    (mpfa.py:733-754) and maps the vector source back to the ambient space (mpfa.py:423-466)."""
+    rng = np.random.default_rng(seed)
+    g = make_grid(kind, rng)
+    nc = g.num_cells
+    bc = scalar_bc(g, rng, robin=True)   # labels from the untilted face centres
+    if tilt:
+        Q = tilt_rotation(rng)
+        g.nodes = Q @ g.nodes + np.array([[0.3], [-0.2], [0.7]])
+        g.compute_geometry()
+    k = pp.SecondOrderTensor(1 + rng.random(nc), 1 + rng.random(nc), 1 + rng.random(nc),
+                             0.3 * rng.random(nc), 0.3 * rng.random(nc), 0.3 * rng.random(nc))
+    data = pp.initialize_data({}, "flow", {"second_order_tensor": k, "bc": bc, "mpfa_inverter": "python",
+                                            "ambient_dimension": 3})
+    discr = pp.Mpfa("flow")
+    discr.discretize(g, data)
+    M = data[pp.DISCRETIZATION_MATRICES]["flow"]
+    d = grid_arrays(g)
+    d.update(kind=np.array("mpfa"), K=k.values, bc_is_dir=bc.is_dir, bc_is_neu=bc.is_neu,
+             bc_is_rob=bc.is_rob, bc_is_internal=bc.is_internal,
+             bc_robin_weight=np.asarray(bc.robin_weight, float), ambient_dimension=np.int64(3),
+             eta=np.float64(pp.numerics.fv._fvutils.determine_eta(g)))
+    for key in ("flux", "bound_flux", "bound_pressure_cell", "bound_pressure_face",
+                "vector_source", "bound_pressure_vector_source"):
+        put_matrix(d, key, M[key])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "nc", nc, "nf", g.num_faces, "vector_source", M["vector_source"].shape)
+
+
 def case_mpsa(name, kind, robin, seed, biot=False):
     rng = np.random.default_rng(seed)
     g = make_grid(kind, rng)
@@ -191,24 +230,34 @@ def case_mpsa(name, kind, robin, seed, biot=False):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    case_mpfa("mpfa_cart3d", "cart3d", False, 1)
-    case_mpfa("mpfa_cart3d_robin", "cart3d", True, 2)
-    case_mpfa("mpfa_cart3d_pert", "cart3d_pert", False, 3)
-    case_mpfa("mpfa_cart3d_contrast", "cart3d", False, 4, contrast=True)
-    case_mpfa("mpfa_tet3d_robin", "tet3d", True, 5)
-    case_mpfa("mpfa_tet3d_delaunay", "tet3d_delaunay", False, 6)
-    case_mpfa("mpfa_cart2d", "cart2d", True, 7)
-    case_mpfa("mpfa_tri2d", "tri2d", False, 8)
-    case_mpsa("mpsa_cart3d", "cart3d", False, 11)
-    case_mpsa("mpsa_cart3d_robin", "cart3d", True, 12)
-    case_mpsa("mpsa_cart3d_pert", "cart3d_pert", False, 13)
-    case_mpsa("mpsa_tet3d", "tet3d", False, 14)
-    case_mpsa("mpsa_tet3d_delaunay", "tet3d_delaunay", False, 15)
-    case_mpsa("mpsa_cart2d_robin", "cart2d", True, 16)
-    case_mpsa("mpsa_tri2d", "tri2d", False, 17)
-    case_mpsa("biot_cart3d", "cart3d", False, 21, biot=True)
-    case_mpsa("biot_tet3d_robin", "tet3d", True, 22, biot=True)
-    case_mpsa("biot_cart2d", "cart2d", False, 23, biot=True)
+    only = sys.argv[1] if len(sys.argv) > 1 else ""   # optional fixture-name prefix
+    cases = [
+        (case_mpfa, ("mpfa_cart3d", "cart3d", False, 1), {}),
+        (case_mpfa, ("mpfa_cart3d_robin", "cart3d", True, 2), {}),
+        (case_mpfa, ("mpfa_cart3d_pert", "cart3d_pert", False, 3), {}),
+        (case_mpfa, ("mpfa_cart3d_contrast", "cart3d", False, 4), {"contrast": True}),
+        (case_mpfa, ("mpfa_tet3d_robin", "tet3d", True, 5), {}),
+        (case_mpfa, ("mpfa_tet3d_delaunay", "tet3d_delaunay", False, 6), {}),
+        (case_mpfa, ("mpfa_cart2d", "cart2d", True, 7), {}),
+        (case_mpfa, ("mpfa_tri2d", "tri2d", False, 8), {}),
+        (case_mpsa, ("mpsa_cart3d", "cart3d", False, 11), {}),
+        (case_mpsa, ("mpsa_cart3d_robin", "cart3d", True, 12), {}),
+        (case_mpsa, ("mpsa_cart3d_pert", "cart3d_pert", False, 13), {}),
+        (case_mpsa, ("mpsa_tet3d", "tet3d", False, 14), {}),
+        (case_mpsa, ("mpsa_tet3d_delaunay", "tet3d_delaunay", False, 15), {}),
+        (case_mpsa, ("mpsa_cart2d_robin", "cart2d", True, 16), {}),
+        (case_mpsa, ("mpsa_tri2d", "tri2d", False, 17), {}),
+        (case_mpsa, ("biot_cart3d", "cart3d", False, 21), {"biot": True}),
+        (case_mpsa, ("biot_tet3d_robin", "tet3d", True, 22), {"biot": True}),
+        (case_mpsa, ("biot_cart2d", "cart2d", False, 23), {"biot": True}),
+        # fracture planes: 2-D grids embedded in 3-D (prefix keeps them out of the "mpfa_*" sweeps)
+        (case_mpfa_embedded, ("embedded_tri2d_tilted", "tri2d", 31, True), {}),
+        (case_mpfa_embedded, ("embedded_cart2d_tilted", "cart2d", 32, True), {}),
+        (case_mpfa_embedded, ("embedded_cart2d_xy", "cart2d", 33, False), {}),
+    ]
+    for fn, args, kw in cases:
+        if args[0].startswith(only):
+            fn(*args, **kw)
 
 
 if __name__ == "__main__":

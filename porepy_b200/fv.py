@@ -401,6 +401,10 @@ class _Base:
         self.keyword = keyword
         self.last_timing: dict = {}
 
+    def __repr__(self) -> str:
+        """numerics/discretization.py:21-25."""
+        return f"Discretization of type {self.__class__.__name__} with keyword {self.keyword}"
+
     def _key(self) -> str:
         return self.keyword + "_"
 

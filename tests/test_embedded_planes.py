@@ -5,7 +5,7 @@ reference (tools/make_golden.py, ``embedded_*`` fixtures).
 
 CPU part: ``porepy_b200.fv.Mpfa.discretize`` is driven end to end with the device plan replaced by
 the host build of the same node routines (tests/emu) -- this covers all of the host logic that
-the feature adds.  GPU part: the same call on the real plan."""
+the feature adds.  The same call on the real plan is tests/test_zz_fracture_planes_gpu.py."""
 from types import SimpleNamespace
 
 import numpy as np
@@ -91,16 +91,6 @@ def test_tilted_plane_needs_the_ambient_dimension(monkeypatch):
     del p["ambient_dimension"]
     with pytest.raises(NotImplementedError):
         fv.Mpfa("flow").discretize(c.g, pb.initialize_data({}, "flow", p))
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", CASES)
-def test_fracture_plane_flux_discretization_gpu(name):
-    c = load_case(name)
-    data = pb.initialize_data({}, "flow", _params(c))
-    pb.Mpfa("flow").discretize(c.g, data)
-    err, key = max_rel_err(c.mats, data[pb.DISCRETIZATION_MATRICES]["flow"])
-    assert err < TOL, (key, err)
 
 
 def test_mechanics_on_a_tilted_plane_is_refused(monkeypatch):

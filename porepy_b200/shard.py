@@ -150,3 +150,89 @@ def restrict_vector_bc(bc, shard: Shard):
     out.is_rob[:, shard.cut_face] = False
     out.is_neu[:, shard.cut_face] = True
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# one call per rank: restrict the parameters, discretize the shard, embed the kept rows
+# ------------------------------------------------------------------------------------------
+
+# key -> (row entity, column entity, row block, column block); "nd" is replaced by the grid dimension
+_LAYOUT = {
+    "flux": ("face", "cell", 1, 1), "bound_flux": ("face", "face", 1, 1),
+    "bound_pressure_cell": ("face", "cell", 1, 1), "bound_pressure_face": ("face", "face", 1, 1),
+    "vector_source": ("face", "cell", 1, "nd"), "bound_pressure_vector_source": ("face", "cell", 1, "nd"),
+    "stress": ("face", "cell", "nd", "nd"), "bound_stress": ("face", "face", "nd", "nd"),
+    "bound_displacement_cell": ("face", "cell", "nd", "nd"),
+    "bound_displacement_face": ("face", "face", "nd", "nd"),
+    "displacement_divergence": ("cell", "cell", 1, "nd"),
+    "boundary_displacement_divergence": ("cell", "face", 1, "nd"),
+    "scalar_gradient": ("face", "cell", "nd", 1), "mpsa_consistency": ("cell", "cell", 1, 1),
+    "bound_displacement_pressure": ("face", "cell", "nd", 1),
+}
+
+
+def restrict_parameters(params: dict, shard: Shard) -> dict:
+    """Parameter dictionary of the shard's sub-grid: cell tensors restricted to its cells, boundary
+    conditions to its faces (cut faces -> Neumann), everything else passed through."""
+    from .params import FourthOrderTensor, SecondOrderTensor
+    out = {}
+    for key, val in params.items():
+        if key == "second_order_tensor":
+            out[key] = SecondOrderTensor.from_values(shard.restrict_cell_array(val.values))
+        elif key == "fourth_order_tensor":
+            out[key] = FourthOrderTensor.from_values(shard.restrict_cell_array(val.values))
+        elif key == "bc":
+            vec = np.asarray(val.is_dir).ndim == 2
+            out[key] = restrict_vector_bc(val, shard) if vec else restrict_scalar_bc(val, shard)
+        elif key == "scalar_vector_mappings":
+            out[key] = {k: (SecondOrderTensor.from_values(shard.restrict_cell_array(a.values))
+                            if hasattr(a, "values") else a) for k, a in val.items()}
+        elif key == "bc_values":
+            arr = np.asarray(val)
+            nd = arr.size // shard.num_global[1]
+            out[key] = arr.reshape(-1, nd)[shard.faces].ravel() if nd > 1 else arr[shard.faces]
+        else:
+            out[key] = val
+    return out
+
+
+def discretize_shard(discr, g, data: dict, part: np.ndarray, rank: int) -> dict:
+    """Discretize this rank's share of ``g`` with ``discr`` (``Mpfa``, ``Mpsa`` or ``Biot``): the
+    interaction regions of the rank's nodes on its sub-grid, then the rows of its own faces /
+    cells in GLOBAL numbering.  Returns ``{key: csr}`` (Biot's coupling keys: ``{key: {kw: csr}}``)
+    of global shape holding only this rank's rows; the sum over ranks is the unsplit discretization.
+    No communication.  ``data`` is the global data dictionary (``initialize_data``); the global
+    ``mpfa_eta`` / ``mpsa_eta`` is fixed from the GLOBAL grid so that all shards agree."""
+    from .fv import determine_eta
+    from .params import DISCRETIZATION_MATRICES, PARAMETERS, initialize_data
+    kw = discr.keyword
+    shard = extract_shard(g, part, rank)
+    params = restrict_parameters(data[PARAMETERS][kw], shard)
+    eta_key = "mpfa_eta" if "second_order_tensor" in params else "mpsa_eta"
+    params.setdefault(eta_key, determine_eta(g))
+    local = initialize_data({}, kw, params)
+    discr.discretize(shard.grid, local)
+    nd = int(g.dim)
+    out = {}
+    for key, m in local[DISCRETIZATION_MATRICES][kw].items():
+        rows, cols, br, bc = _LAYOUT[key]
+        br, bc = (nd if br == "nd" else br), (nd if bc == "nd" else bc)
+        if isinstance(m, dict):
+            out[key] = {k: shard.to_global(v, rows, cols, br, bc) for k, v in m.items()}
+        else:
+            out[key] = shard.to_global(m, rows, cols, br, bc)
+    return out
+
+
+def sum_shards(parts: list) -> dict:
+    """Combine the per-rank results of ``discretize_shard`` (e.g. after ``gather_object``)."""
+    acc: dict = {}
+    for p in parts:
+        for key, m in p.items():
+            if isinstance(m, dict):
+                d = acc.setdefault(key, {})
+                for k, v in m.items():
+                    d[k] = v if k not in d else d[k] + v
+            else:
+                acc[key] = m if key not in acc else acc[key] + m
+    return acc

@@ -180,3 +180,57 @@ def _mpsa(self, stiff, bc_codes, robw, eta, alpha=None):
 
 
 EmuPlan.mpsa = _mpsa
+
+
+
+class EmuBackedPlan:
+    """Stand-in for ``porepy_b200.fv.DevicePlan`` with the calls the operator classes make, backed by
+    the host build of the node routines.  TEST INFRASTRUCTURE: lets the CPU tests drive
+    ``fv.Mpfa / Mpsa / Biot.discretize`` end to end (host logic + the kernels' source)."""
+
+    def __init__(self, sd):
+        from types import SimpleNamespace
+        from porepy_b200 import fv
+        arrs, self.rotation = fv.plan_geometry(sd)
+        proxy = SimpleNamespace(dim=sd.dim, num_cells=sd.num_cells, num_faces=sd.num_faces,
+                                num_nodes=sd.num_nodes, cell_faces=sd.cell_faces, face_nodes=sd.face_nodes,
+                                nodes=arrs[0], face_normals=arrs[1], face_centers=arrs[2],
+                                face_areas=arrs[3], cell_centers=arrs[4], cell_volumes=arrs[5])
+        self.emu = EmuPlan(proxy)
+        self.nd, self.nc = int(sd.dim), sd.num_cells
+
+    @classmethod
+    def for_grid(cls, sd):
+        return cls(sd)
+
+    def base_pattern(self, which):
+        return self.emu.pat[which]
+
+    def mpfa_upload(self, perm, codes, robw, eta):
+        self._mpfa = (perm, codes, robw, eta)
+
+    def mpfa_assemble(self, *a):
+        self._out = self.emu.mpfa(*self._mpfa)
+        return 0.0
+
+    def mpfa_download(self, *a):
+        return self._out
+
+    def mpsa_upload(self, stiff, codes, robw, eta, alphas=()):
+        self._mpsa = (stiff, codes, robw, eta, {q: a for q, a in enumerate(alphas)})
+
+    def mpsa_assemble(self):
+        stiff, codes, robw, eta, al = self._mpsa
+        if robw is not None:
+            robw = np.asarray(robw)[:self.nd, :self.nd]
+        self._mout = self.emu.mpsa(stiff, codes, robw, eta, alpha=al or None)
+        return 0.0
+
+    def mpsa_download(self):
+        return {k: self._mout[k] for k in ("stress", "bound_stress", "bound_displacement_cell",
+                                           "bound_displacement_face")}
+
+    def biot_download(self, q):
+        return {k: self._mout[k][q] for k in ("displacement_divergence", "boundary_displacement_divergence",
+                                              "scalar_gradient", "mpsa_consistency",
+                                              "bound_displacement_pressure")}

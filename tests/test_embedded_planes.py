@@ -6,14 +6,13 @@ reference (tools/make_golden.py, ``embedded_*`` fixtures).
 CPU part: ``porepy_b200.fv.Mpfa.discretize`` is driven end to end with the device plan replaced by
 the host build of the same node routines (tests/emu) -- this covers all of the host logic that
 the feature adds.  The same call on the real plan is tests/test_zz_fracture_planes_gpu.py."""
-from types import SimpleNamespace
-
 import numpy as np
 import pytest
 
 import porepy_b200 as pb
 from porepy_b200 import fv
 from cases import max_rel_err
+from emu_binding import EmuBackedPlan
 from golden_io import case_names, load_case
 
 TOL = 1e-10
@@ -23,37 +22,6 @@ CASES = case_names("embedded_")
 def _params(c):
     k = pb.SecondOrderTensor.from_values(c.raw["K"])
     return {"second_order_tensor": k, "bc": c.bc, "ambient_dimension": int(c.raw["ambient_dimension"])}
-
-
-class EmuBackedPlan:
-    """Stand-in for fv.DevicePlan with the calls Mpfa.discretize makes (test infrastructure)."""
-
-    def __init__(self, sd):
-        from emu_binding import EmuPlan
-        arrs, self.rotation = fv.plan_geometry(sd)
-        proxy = SimpleNamespace(dim=sd.dim, num_cells=sd.num_cells, num_faces=sd.num_faces,
-                                num_nodes=sd.num_nodes, cell_faces=sd.cell_faces, face_nodes=sd.face_nodes,
-                                nodes=arrs[0], face_normals=arrs[1], face_centers=arrs[2],
-                                face_areas=arrs[3], cell_centers=arrs[4], cell_volumes=arrs[5])
-        self.emu = EmuPlan(proxy)
-        self.nc = sd.num_cells
-
-    @classmethod
-    def for_grid(cls, sd):
-        return cls(sd)
-
-    def base_pattern(self, which):
-        return self.emu.pat[which]
-
-    def mpfa_upload(self, perm, codes, robw, eta):
-        self.args = (perm, codes, robw, eta)
-
-    def mpfa_assemble(self):
-        self.out = self.emu.mpfa(*self.args)
-        return 0.0
-
-    def mpfa_download(self):
-        return self.out
 
 
 def test_plane_frame_is_a_rotation_into_the_plane():

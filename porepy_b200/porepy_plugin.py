@@ -18,6 +18,9 @@ Use in a model (the mixin override of constitutive_laws.py:1078,3003,3506)::
         def darcy_flux_discretization(self, subdomains):
             return b200.MpfaAd(self.darcy_keyword, subdomains)
 
+    class B200Poromechanics(b200.ModelMixin, pp.Poromechanics):   # all hooks at once
+        pass
+
 Scope: the GPU path covers the top-dimensional subdomains (3-D grids, 2-D grids lying in the
 xy-plane) and, for the flux discretization, 2-D fracture planes embedded in 3-D.  Intersection
 grids (1-D lines, 0-D points) are handed to the reference's own implementation (its TPFA
@@ -125,4 +128,33 @@ def plugin(pp) -> SimpleNamespace:
                     ["displacement_divergence", "bound_displacement_divergence", "scalar_gradient",
                      "bound_pressure", "consistency"])
 
-    return SimpleNamespace(Mpfa=Mpfa, Mpsa=Mpsa, Biot=Biot, MpfaAd=MpfaAd, MpsaAd=MpsaAd, BiotAd=BiotAd)
+    class ModelMixin:
+        """Put FIRST among the bases of a PorePy model class to route its flux / stress
+        discretizations through the GPU classes::
+
+            class Model(b200.ModelMixin, Geometry, BoundaryConditions, pp.Poromechanics): ...
+
+        Overrides the constitutive-law hooks (models/constitutive_laws.py:1078, 2425, 3003, 3506)
+        and relaxes the exact-type check of ``add_nonlinear_diffusive_flux_discretization``
+        (models/solution_strategy.py:505-524: ``type(x) in [pp.Mpfa, pp.Tpfa]``) to ``isinstance``,
+        which the plugin's subclasses satisfy."""
+
+        def darcy_flux_discretization(self, subdomains):
+            return MpfaAd(self.darcy_keyword, subdomains)
+
+        def fourier_flux_discretization(self, subdomains):
+            return MpfaAd(self.fourier_keyword, subdomains)
+
+        def stress_discretization(self, subdomains):
+            stock = super().stress_discretization(subdomains)
+            cls = BiotAd if isinstance(stock, pp.ad.BiotAd) else MpsaAd
+            return cls(self.stress_keyword, subdomains)
+
+        def add_nonlinear_diffusive_flux_discretization(self, discretization) -> None:
+            if not isinstance(discretization._discr, (pp.Mpfa, pp.Tpfa)):
+                raise TypeError(f"Expecting an Mpfa or Tpfa discretization, got {type(discretization._discr)}")
+            if discretization not in self._nonlinear_diffusive_flux_discretizations:
+                self._nonlinear_diffusive_flux_discretizations.append(discretization)
+
+    return SimpleNamespace(Mpfa=Mpfa, Mpsa=Mpsa, Biot=Biot, MpfaAd=MpfaAd, MpsaAd=MpsaAd, BiotAd=BiotAd,
+                           ModelMixin=ModelMixin)

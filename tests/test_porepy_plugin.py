@@ -66,3 +66,132 @@ def test_parameter_mirrors_match_reference(pp):
     r = pp.BoundaryCondition(g, bf[:5], ["dir"] * 5)
     m = pb.BoundaryCondition(g, bf[:5], ["dir"] * 5)
     assert np.array_equal(r.is_dir, m.is_dir) and np.array_equal(r.is_neu, m.is_neu)
+
+
+# ---- whole PorePy models on the plugin classes (device plan -> host build of the kernels) ---------
+
+
+class _Geometry:
+    def set_domain(self):
+        import porepy as pp
+        self._domain = pp.Domain({"xmin": 0, "xmax": 1, "ymin": 0, "ymax": 1, "zmin": 0, "zmax": 1})
+
+    def grid_type(self):
+        return "cartesian"
+
+    def meshing_arguments(self):
+        return {"cell_size": 0.25}
+
+
+class _VerticalFracture:
+    def set_fractures(self):
+        import porepy as pp
+        pts = np.array([[0.5, 0.5, 0.5, 0.5], [0.25, 0.75, 0.75, 0.25], [0.25, 0.25, 0.75, 0.75]])
+        self._fractures = [pp.PlaneFracture(pts)]
+
+
+class _HeterogeneousPermeability:
+    def permeability(self, subdomains):
+        import porepy as pp
+        vals = []
+        for sd in subdomains:
+            rng = np.random.default_rng(sd.num_cells)
+            nc = sd.num_cells
+            t = np.zeros((3, 3, nc))
+            t[0, 0], t[1, 1], t[2, 2] = 1 + rng.random((3, nc))
+            o = 0.3 * rng.random((3, nc))
+            t[0, 1] = t[1, 0] = o[0]
+            t[0, 2] = t[2, 0] = o[1]
+            t[1, 2] = t[2, 1] = o[2]
+            vals.append(t.reshape(9, nc).ravel("F"))
+        return pp.wrap_as_dense_ad_array(np.hstack(vals) if vals else np.zeros(0), name="permeability")
+
+
+class _FlowBC:
+    def bc_type_darcy_flux(self, sd):
+        import porepy as pp
+        sides = self.domain_boundary_sides(sd)
+        return pp.BoundaryCondition(sd, sides.west + sides.east, "dir")
+
+    def bc_values_pressure(self, bg):
+        sides = self.domain_boundary_sides(bg)
+        v = np.zeros(bg.num_cells)
+        v[sides.west] = 1.0
+        return v
+
+
+class _MechBC:
+    def bc_type_mechanics(self, sd):
+        import porepy as pp
+        sides = self.domain_boundary_sides(sd)
+        bc = pp.BoundaryConditionVectorial(sd, sides.west + sides.bottom, "dir")
+        bc.internal_to_dirichlet(sd)
+        return bc
+
+    def bc_values_stress(self, bg):
+        sides = self.domain_boundary_sides(bg)
+        v = np.zeros((3, bg.num_cells))
+        v[2, sides.top] = -1e-3 * bg.cell_volumes[sides.top]
+        return v.ravel("F")
+
+
+def _solve(pp, cls):
+    model = cls({"times_to_export": [], "time_manager": pp.TimeManager([0, 1.0], 0.5, constant_dt=True)})
+    pp.run_time_dependent_model(model, {"prepare_simulation": True})
+    return model.equation_system.get_variable_values(iterate_index=0)
+
+
+@pytest.fixture()
+def emu_plan(monkeypatch):
+    from emu_binding import EmuBackedPlan
+    from porepy_b200 import fv
+    monkeypatch.setattr(fv, "DevicePlan", EmuBackedPlan)
+
+
+def test_single_phase_flow_model_with_a_fracture(pp, emu_plan):
+    """pp.SinglePhaseFlow on a 3-D grid with a vertical fracture (a 2-D plane embedded in 3-D) and
+    anisotropic heterogeneous permeability: same solution with the plugin discretization as with the
+    stock one.  The 3-D matrix and the fracture plane go through porepy_b200, the rest is PorePy."""
+    from porepy_b200.porepy_plugin import plugin
+    b = plugin(pp)
+    seen = []
+    stock = b.Mpfa.discretize
+
+    def spy(self, sd, data):
+        seen.append(sd.dim)
+        return stock(self, sd, data)
+    b.Mpfa.discretize = spy
+
+    class Stock(_Geometry, _VerticalFracture, _HeterogeneousPermeability, _FlowBC, pp.SinglePhaseFlow):
+        pass
+
+    class Plugged(b.ModelMixin, _Geometry, _VerticalFracture, _HeterogeneousPermeability, _FlowBC,
+                  pp.SinglePhaseFlow):
+        pass
+    ref, got = _solve(pp, Stock), _solve(pp, Plugged)
+    assert sorted(set(seen)) == [2, 3]
+    assert np.ptp(ref) > 0.5
+    assert np.linalg.norm(ref - got) <= 1e-10 * np.linalg.norm(ref)
+
+
+def test_poromechanics_model(pp, emu_plan):
+    """pp.Poromechanics (Biot coupling, two time steps): flux and stress discretizations swapped by the
+    model mixin, identical solution vector (pressure + displacement)."""
+    from porepy_b200.porepy_plugin import plugin
+    b = plugin(pp)
+    seen = []
+    for cls in (b.Mpfa, b.Biot):
+        def spy(self, sd, data, _stock=cls.discretize, _name=cls.__name__):
+            seen.append(_name)
+            return _stock(self, sd, data)
+        cls.discretize = spy
+
+    class Stock(_Geometry, _HeterogeneousPermeability, _FlowBC, _MechBC, pp.Poromechanics):
+        pass
+
+    class Plugged(b.ModelMixin, _Geometry, _HeterogeneousPermeability, _FlowBC, _MechBC, pp.Poromechanics):
+        pass
+    ref, got = _solve(pp, Stock), _solve(pp, Plugged)
+    assert {"Mpfa", "Biot"} <= set(seen)
+    assert np.abs(ref).max() > 0
+    assert np.linalg.norm(ref - got) <= 1e-9 * np.linalg.norm(ref)

@@ -195,3 +195,36 @@ def test_poromechanics_model(pp, emu_plan):
     assert {"Mpfa", "Biot"} <= set(seen)
     assert np.abs(ref).max() > 0
     assert np.linalg.norm(ref - got) <= 1e-9 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("family", ["MomentumBalance", "Thermoporomechanics", "MassAndEnergyBalance"])
+def test_other_model_families(pp, emu_plan, family):
+    """MPSA alone (MomentumBalance), Biot + Darcy + Fourier fluxes (Thermoporomechanics), and Darcy +
+    Fourier fluxes on a 3-D matrix with a fracture plane (MassAndEnergyBalance): the mixin routes
+    every flux / stress discretization of the model and the solution vector is unchanged."""
+    from porepy_b200.porepy_plugin import plugin
+    b = plugin(pp)
+    seen = set()
+    for cls in (b.Mpfa, b.Mpsa, b.Biot):
+        def spy(self, sd, data, _stock=cls.discretize, _name=cls.__name__):
+            seen.add((_name, self.keyword, sd.dim))
+            return _stock(self, sd, data)
+        cls.discretize = spy
+    extra = {"MomentumBalance": (_Geometry, _MechBC),
+             "Thermoporomechanics": (_Geometry, _HeterogeneousPermeability, _FlowBC, _MechBC),
+             "MassAndEnergyBalance": (_Geometry, _VerticalFracture, _HeterogeneousPermeability, _FlowBC)}[family]
+    expect = {"MomentumBalance": {("Mpsa", "mechanics", 3)},
+              "Thermoporomechanics": {("Biot", "mechanics", 3), ("Mpfa", "flow", 3)},
+              "MassAndEnergyBalance": {("Mpfa", "flow", 3), ("Mpfa", "flow", 2)}}[family]
+    base = getattr(pp, family)
+
+    class Stock(*extra, base):
+        pass
+
+    class Plugged(b.ModelMixin, *extra, base):
+        pass
+    ref, got = _solve(pp, Stock), _solve(pp, Plugged)
+    assert expect <= seen
+    assert any(kw.startswith("fourier") for _, kw, _ in seen) or family == "MomentumBalance"
+    assert np.linalg.norm(ref) > 0
+    assert np.linalg.norm(ref - got) <= 1e-9 * np.linalg.norm(ref)

@@ -21,6 +21,8 @@ Use in a model (the mixin override of constitutive_laws.py:1078,3003,3506)::
     class B200Poromechanics(b200.ModelMixin, pp.Poromechanics):   # all hooks at once
         pass
 
+    b200.install()        # or: rebind pp.Mpfa / pp.Mpsa / pp.Biot, stock models unchanged
+
 Scope: the GPU path covers the top-dimensional subdomains (3-D grids, 2-D grids lying in the
 xy-plane) and, for the flux discretization, 2-D fracture planes embedded in 3-D.  Intersection
 grids (1-D lines, 0-D points) are handed to the reference's own implementation (its TPFA
@@ -53,55 +55,60 @@ def _gpu_scope(sd, flow: bool = False) -> bool:
 
 def plugin(pp) -> SimpleNamespace:
     """Build the plugin classes against the given ``porepy`` module."""
+    # the reference classes as they are NOW: the plugin keeps working if the caller afterwards rebinds
+    # pp.Mpfa etc. to the plugin classes (e.g. to run the reference's own tests on them)
+    RefMpfa, RefMpsa, RefBiot = pp.Mpfa, pp.Mpsa, pp.Biot
+    RefMpfaAd, RefMpsaAd, RefBiotAd = pp.ad.MpfaAd, pp.ad.MpsaAd, pp.ad.BiotAd
 
-    class Mpfa(fv.Mpfa, pp.Mpfa):
-        def __init__(self, keyword: str) -> None:
-            pp.Mpfa.__init__(self, keyword)
-            fv.Mpfa.__init__(self, keyword)
+    def _core(name, gpu_cls, ref_cls, flow):
+        """Subclass of the reference core whose ``discretize`` runs on the GPU.  Anything the GPU
+        classes refuse (``NotImplementedError``: periodic faces, sub-face boundary conditions, rotated
+        boundary bases, ...) and every subdomain outside the GPU scope goes to the reference's own
+        implementation -- the plugin IS a subclass of it -- with a log line."""
 
-        def discretize(self, sd, data) -> None:
-            if _gpu_scope(sd, flow=True) and not hasattr(sd, "periodic_face_map"):
-                fv.Mpfa.discretize(self, sd, data)
-            else:
-                logger.info("B200 Mpfa: %s-d subdomain outside the GPU scope -> reference path", sd.dim)
-                pp.Mpfa.discretize(self, sd, data)
-
-        def assemble_matrix_rhs(self, sd, data):
-            return pp.Mpfa.assemble_matrix_rhs(self, sd, data)
-
-        def update_discretization(self, sd, data) -> None:
-            self.discretize(sd, data)
-
-    class Mpsa(fv.Mpsa, pp.Mpsa):
-        def __init__(self, keyword: str) -> None:
-            pp.Mpsa.__init__(self, keyword)
-            fv.Mpsa.__init__(self, keyword)
+        if name == "Biot":  # biot.py:77 has a default keyword, the others do not
+            def __init__(self, keyword: str = "mechanics") -> None:
+                ref_cls.__init__(self, keyword)
+                gpu_cls.__init__(self, keyword)
+        else:
+            def __init__(self, keyword: str) -> None:
+                ref_cls.__init__(self, keyword)
+                gpu_cls.__init__(self, keyword)
 
         def discretize(self, sd, data) -> None:
-            if _gpu_scope(sd):
-                fv.Mpsa.discretize(self, sd, data)
+            params = data[pp.PARAMETERS][self.keyword]
+            if any(params.get(k) is not None for k in ("specified_cells", "specified_faces", "specified_nodes")):
+                # partial (re)discretization of a few cells (_fvutils.py:308-355): a local host-side
+                # update with its own bookkeeping (active_cells / active_faces); the reference's job
+                logger.info("B200 %s: partial update -> reference path", name)
+            elif _gpu_scope(sd, flow=flow) and not hasattr(sd, "periodic_face_map"):
+                try:
+                    gpu_cls.discretize(self, sd, data)
+                    return
+                except NotImplementedError as e:
+                    logger.info("B200 %s: %s -> reference path", name, e)
             else:
-                pp.Mpsa.discretize(self, sd, data)
-
-        def assemble_matrix_rhs(self, sd, data):
-            return pp.Mpsa.assemble_matrix_rhs(self, sd, data)
+                logger.info("B200 %s: %s-d subdomain outside the GPU scope -> reference path", name, sd.dim)
+            ref_cls.discretize(self, sd, data)
 
         def update_discretization(self, sd, data) -> None:
-            self.discretize(sd, data)
-
-    class Biot(fv.Biot, pp.Biot):
-        def __init__(self, keyword: str = "mechanics") -> None:
-            pp.Biot.__init__(self, keyword)
-            fv.Biot.__init__(self, keyword)
-
-        def discretize(self, sd, data) -> None:
-            if _gpu_scope(sd):
-                fv.Biot.discretize(self, sd, data)
+            # the reference's update (index maps after a grid change, modified cells;
+            # discretization.py:54-105) is host-side bookkeeping around discretize(): keep it when the
+            # caller provides that information, otherwise re-discretize (on the GPU)
+            if "update_discretization" in data:
+                ref_cls.update_discretization(self, sd, data)
             else:
-                pp.Biot.discretize(self, sd, data)
+                self.discretize(sd, data)
 
-        def update_discretization(self, sd, data) -> None:
-            self.discretize(sd, data)
+        body = {"__init__": __init__, "discretize": discretize, "update_discretization": update_discretization,
+                "__doc__": f"pp.{name} with the GPU discretization (porepy_b200.fv.{name})."}
+        if name != "Biot":
+            body["assemble_matrix_rhs"] = lambda self, sd, data: ref_cls.assemble_matrix_rhs(self, sd, data)
+        return type(name, (gpu_cls, ref_cls), body)
+
+    Mpfa = _core("Mpfa", fv.Mpfa, RefMpfa, True)
+    Mpsa = _core("Mpsa", fv.Mpsa, RefMpsa, False)
+    Biot = _core("Biot", fv.Biot, RefBiot, False)
 
     def _rewrap(obj, discr, subdomains, coupling_terms=None):
         obj._discretization = discr
@@ -111,17 +118,17 @@ def plugin(pp) -> SimpleNamespace:
             pp.ad.wrap_discretization(obj=obj, discr=discr, subdomains=subdomains,
                                       coupling_terms=coupling_terms)
 
-    class MpfaAd(pp.ad.MpfaAd):
+    class MpfaAd(RefMpfaAd):
         def __init__(self, keyword, subdomains):
             super().__init__(keyword, subdomains)
             _rewrap(self, Mpfa(keyword), subdomains)
 
-    class MpsaAd(pp.ad.MpsaAd):
+    class MpsaAd(RefMpsaAd):
         def __init__(self, keyword, subdomains):
             super().__init__(keyword, subdomains)
             _rewrap(self, Mpsa(keyword), subdomains)
 
-    class BiotAd(pp.ad.BiotAd):
+    class BiotAd(RefBiotAd):
         def __init__(self, keyword, subdomains):
             super().__init__(keyword, subdomains)
             _rewrap(self, Biot(keyword), subdomains,
@@ -147,14 +154,25 @@ def plugin(pp) -> SimpleNamespace:
 
         def stress_discretization(self, subdomains):
             stock = super().stress_discretization(subdomains)
-            cls = BiotAd if isinstance(stock, pp.ad.BiotAd) else MpsaAd
+            cls = BiotAd if isinstance(stock, RefBiotAd) else MpsaAd
             return cls(self.stress_keyword, subdomains)
 
         def add_nonlinear_diffusive_flux_discretization(self, discretization) -> None:
-            if not isinstance(discretization._discr, (pp.Mpfa, pp.Tpfa)):
+            if not isinstance(discretization._discr, (RefMpfa, pp.Tpfa)):
                 raise TypeError(f"Expecting an Mpfa or Tpfa discretization, got {type(discretization._discr)}")
             if discretization not in self._nonlinear_diffusive_flux_discretizations:
                 self._nonlinear_diffusive_flux_discretizations.append(discretization)
 
+    def install() -> None:
+        """Rebind ``pp.Mpfa / pp.Mpsa / pp.Biot`` to the plugin classes for the whole process.  The AD
+        wrappers look the cores up at construction time (``pp.Mpfa(keyword)``,
+        numerics/ad/discretizations.py:192-206) and the models' exact-type checks compare with
+        ``pp.Mpfa``, so every stock model then discretizes through porepy_b200 without any change to
+        the model classes (this is how tools/run_reference_tests.py runs the reference's own tests)."""
+        pp.Mpfa, pp.Mpsa, pp.Biot = Mpfa, Mpsa, Biot
+
+    def uninstall() -> None:
+        pp.Mpfa, pp.Mpsa, pp.Biot = RefMpfa, RefMpsa, RefBiot
+
     return SimpleNamespace(Mpfa=Mpfa, Mpsa=Mpsa, Biot=Biot, MpfaAd=MpfaAd, MpsaAd=MpsaAd, BiotAd=BiotAd,
-                           ModelMixin=ModelMixin)
+                           ModelMixin=ModelMixin, install=install, uninstall=uninstall)

@@ -394,6 +394,61 @@ def vector_bc_codes(bc, nd: int, nf: int):
 # ------------------------------------------------------------------------------------------
 
 
+def active_indices(sd, params: dict):
+    """Cells of the sub-grid to discretize and faces whose rows are (re)computed, from
+    ``specified_cells / specified_faces / specified_nodes`` (``_fvutils.find_active_indices``,
+    _fvutils.py:308-355, and ``cell_ind_for_partial_update``, :1260-1462).  Cells mode: the faces
+    touching a node of the given cells, and every cell touching a node of those faces.  Faces mode
+    (split faces): the faces sharing a node with the given ones, and two layers of cells around
+    them.  Nodes mode (gradual build-up): the cells touching the given nodes, and the faces all of
+    whose nodes are given.  Writes ``active_cells`` / ``active_faces`` into ``params``."""
+    nc, nf, nn = sd.num_cells, sd.num_faces, sd.num_nodes
+    spec = [params.get(k) for k in ("specified_cells", "specified_faces", "specified_nodes")]
+    if all(v is None for v in spec):
+        cells, faces = np.arange(nc), np.arange(nf)
+        params["active_cells"], params["active_faces"] = cells, faces
+        return cells, faces
+    fn = abs(sps.csr_matrix(sd.face_nodes)).astype(np.float64)      # nn x nf
+    cf = abs(sps.csr_matrix(sd.cell_faces)).astype(np.float64)      # nf x nc
+    cn = (fn @ cf).tocsr()                                          # nn x nc
+
+    def mask(n, idx):
+        m = np.zeros(n)
+        m[np.asarray(idx, dtype=np.int64)] = 1.0
+        return m
+
+    active_faces = np.zeros(nf, bool)
+    cell_ind = np.zeros(nc, bool)
+    if spec[0] is not None:
+        vert = (cn @ mask(nc, spec[0])) > 0
+        active_faces |= (fn.T @ vert.astype(np.float64)) > 0
+        vert |= (fn @ active_faces.astype(np.float64)) > 0
+        cell_ind |= (cn.T @ vert.astype(np.float64)) > 0
+    if spec[1] is not None:
+        pvert = (fn @ mask(nf, spec[1])) > 0
+        active_faces |= (fn.T @ pvert.astype(np.float64)) > 0
+        anodes = (fn @ active_faces.astype(np.float64)) > 0
+        pcells = (cn.T @ anodes.astype(np.float64)) > 0
+        anodes |= (cn @ pcells.astype(np.float64)) > 0
+        cell_ind |= (cn.T @ anodes.astype(np.float64)) > 0
+    if spec[2] is not None:
+        vert = mask(nn, spec[2])
+        cell_ind |= (cn.T @ vert) > 0
+        active_faces |= np.asarray(fn.T @ vert).ravel() == np.asarray(fn.sum(axis=0)).ravel()
+    cells, faces = np.flatnonzero(cell_ind), np.flatnonzero(active_faces)
+    params["active_cells"], params["active_faces"] = cells, faces
+    return cells, faces
+
+
+def _replace_rows(old, new, keep_entity: np.ndarray):
+    """``old`` with the rows of the flagged entities (block rows) replaced by those of ``new``."""
+    old = sps.csr_matrix(old)
+    new = sps.csr_matrix(new)
+    br = new.shape[0] // keep_entity.size
+    stay = sps.diags(np.repeat(~keep_entity, br).astype(np.float64))
+    return (stay @ old + new).tocsr()
+
+
 class _Base:
     """numerics/discretization.py:12-121."""
 
@@ -408,17 +463,47 @@ class _Base:
     def _key(self) -> str:
         return self.keyword + "_"
 
+    def discretize(self, sd, data: dict) -> None:
+        """Full discretization, or -- with ``specified_cells / specified_faces / specified_nodes`` in
+        the parameters -- the reference's partial one (mpfa.py:176-201,468-508; biot.py:326-342,
+        614-712): the sub-grid of the active cells is discretized as a whole (same kernels), the rows
+        of the active faces (and, for Biot's cell-row terms, of the cells next to them) are embedded
+        in global numbering, all other rows are zero -- or, with ``update_discretization = True``,
+        keep the values already stored.  ``active_cells`` / ``active_faces`` are written back to the
+        parameter dictionary as the reference does (_fvutils.py:346-353)."""
+        params = data[PARAMETERS][self.keyword]
+        mats = data.setdefault(DISCRETIZATION_MATRICES, {}).setdefault(self.keyword, {})
+        cells, faces = active_indices(sd, params)
+        if cells.size == sd.num_cells and faces.size == sd.num_faces:
+            mats.update(self._discretize_grid(sd, params))
+            return
+        from . import shard as _shard
+        keep_faces = np.zeros(sd.num_faces, bool)
+        keep_faces[faces] = True
+        keep_cells = np.asarray(abs(sps.csr_matrix(sd.cell_faces)).T @ keep_faces.astype(np.float64)).ravel() > 0
+        sub = _shard.extract_cells(sd, cells, keep_faces, keep_cells)
+        local = _shard.restrict_parameters(params, sub)
+        local.setdefault(self._eta_key, determine_eta(sd))
+        out = {key: _shard.embed(sub, key, m) for key, m in self._discretize_grid(sub.grid, local).items()}
+        if params.get("update_discretization", False):
+            for key, new in out.items():
+                keep = keep_faces if _shard._LAYOUT[key][0] == "face" else keep_cells
+                if isinstance(new, dict):
+                    mats[key] = {k: _replace_rows(mats[key][k], v, keep) for k, v in new.items()}
+                else:
+                    mats[key] = _replace_rows(mats[key], new, keep)
+        else:
+            mats.update(out)
+
     def update_discretization(self, sd, data: dict) -> None:
-        """numerics/discretization.py:54.  The reference re-discretizes only around
-        ``specified_cells/faces/nodes``; a full pass on the GPU is cheaper than the bookkeeping,
-        and gives the same matrices."""
+        """numerics/discretization.py:54: re-discretize (the partial path of ``discretize`` applies when
+        ``specified_cells/faces/nodes`` are set)."""
         self.discretize(sd, data)
 
     def _check_unsupported(self, params: dict, sd=None) -> None:
         """``partition_arguments`` bound the reference's working set (``_fvutils.py:358-411``); the
         kernels stream over nodes and never materialise the global block-diagonal inverse, so the
-        key is accepted and ignored.  ``specified_cells/faces/nodes`` select a partial update in the
-        reference; here the whole grid is re-discretized (same matrices).  Periodic face pairs
+        key is accepted and ignored.  Periodic face pairs
         (``_fvutils.py:95-140``) are not merged by the topology plan: refuse rather than discretize
         the pair as two boundaries."""
         if sd is not None and getattr(sd, "periodic_face_map", None) is not None:
@@ -441,11 +526,11 @@ class Mpfa(_Base):
     def ndof(self, sd) -> int:
         return sd.num_cells
 
-    def discretize(self, sd, data: dict) -> None:
-        """mpfa.py:65.  Reads ``second_order_tensor``, ``bc``, optional ``mpfa_eta`` and
-        ``ambient_dimension``; writes the six matrices of mpfa.py:496-508."""
-        params = data[PARAMETERS][self.keyword]
-        mats = data.setdefault(DISCRETIZATION_MATRICES, {}).setdefault(self.keyword, {})
+    _eta_key = "mpfa_eta"
+
+    def _discretize_grid(self, sd, params: dict) -> dict:
+        """mpfa.py:65 on the whole of ``sd``.  Reads ``second_order_tensor``, ``bc``, optional
+        ``mpfa_eta`` and ``ambient_dimension``; returns the six matrices of mpfa.py:496-508."""
         k = params["second_order_tensor"]
         bc = params["bc"]
         eta = params.get("mpfa_eta", None)
@@ -480,9 +565,9 @@ class Mpfa(_Base):
             for key in (self.vector_source_matrix_key, self.bound_pressure_vector_source_matrix_key):
                 out[key] = lift_vector_source(ip, ix, out[key].data, rows, sd.num_cells)
         t4 = time.perf_counter()
-        mats.update(out)
         self.last_timing = dict(plan_s=t1 - t0, upload_s=t2 - t1, kernel_ms=ms,
                                 assemble_s=t3 - t2, download_s=t4 - t3)
+        return out
 
     def assemble_matrix_rhs(self, sd, data: dict):
         """fv_elliptic.py:67-112: A = div @ flux, b = -div @ bound_flux @ bc_values
@@ -524,11 +609,11 @@ class Mpsa(_Base):
     def _alphas(self, sd, params):
         return {}
 
-    def discretize(self, sd, data: dict) -> None:
-        """mpsa.py:121 (and biot.py:247 through ``_alphas``).  Reads ``fourth_order_tensor``,
-        ``bc`` (vectorial), optional ``mpsa_eta``."""
-        params = data[PARAMETERS][self.keyword]
-        mats = data.setdefault(DISCRETIZATION_MATRICES, {}).setdefault(self.keyword, {})
+    _eta_key = "mpsa_eta"
+
+    def _discretize_grid(self, sd, params: dict) -> dict:
+        """mpsa.py:121 (and biot.py:247 through ``_alphas``) on the whole of ``sd``.  Reads
+        ``fourth_order_tensor``, ``bc`` (vectorial), optional ``mpsa_eta``."""
         constit = params["fourth_order_tensor"]
         bc = params["bc"]
         eta = params.get("mpsa_eta", None)
@@ -564,9 +649,9 @@ class Mpsa(_Base):
                     coupled[name][key] = m
             out.update(coupled)
         t4 = time.perf_counter()
-        mats.update(out)
         self.last_timing = dict(plan_s=t1 - t0, upload_s=t2 - t1, kernel_ms=ms,
                                 assemble_s=t3 - t2, download_s=t4 - t3)
+        return out
 
     def assemble_matrix_rhs_device(self, sd, data: dict):
         """Device-resident counterpart of ``assemble_matrix_rhs`` (see ``Mpfa.assemble_matrix_rhs_device``)."""

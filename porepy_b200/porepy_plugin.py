@@ -76,12 +76,7 @@ def plugin(pp) -> SimpleNamespace:
                 gpu_cls.__init__(self, keyword)
 
         def discretize(self, sd, data) -> None:
-            params = data[pp.PARAMETERS][self.keyword]
-            if any(params.get(k) is not None for k in ("specified_cells", "specified_faces", "specified_nodes")):
-                # partial (re)discretization of a few cells (_fvutils.py:308-355): a local host-side
-                # update with its own bookkeeping (active_cells / active_faces); the reference's job
-                logger.info("B200 %s: partial update -> reference path", name)
-            elif _gpu_scope(sd, flow=flow) and not hasattr(sd, "periodic_face_map"):
+            if _gpu_scope(sd, flow=flow) and not hasattr(sd, "periodic_face_map"):
                 try:
                     gpu_cls.discretize(self, sd, data)
                     return

@@ -74,49 +74,56 @@ class Shard:
                               shape=(nr * br, ncg * bc)).tocsr()
 
 
-def extract_shard(g, part: np.ndarray, rank: int) -> Shard:
+def extract_cells(g, cells: np.ndarray, keep_faces: np.ndarray, keep_cells: np.ndarray, rank: int = 0) -> Shard:
+    """Sub-grid of the given (sorted, global) cells as a ``Shard`` that keeps the rows of the global
+    faces / cells flagged in ``keep_faces`` / ``keep_cells`` (bool per global entity).  The reference's
+    ``pp.partition.extract_subgrid`` (grids/partition.py) + ``subgrid_to_grid_mapping``."""
     cf = sps.csc_matrix(g.cell_faces)
     fn = sps.csc_matrix(g.face_nodes)
     nc, nf, nn = g.num_cells, g.num_faces, g.num_nodes
-    own = part == rank
-    # nodes of own cells
-    cell_nodes = (abs(fn) @ abs(cf)).tocsc()  # nn x nc
-    cell_nodes.data[:] = 1
-    own_nodes = np.zeros(nn, bool)
-    own_nodes[np.unique(cell_nodes[:, np.flatnonzero(own)].indices)] = True
-    # all cells touching an own node
-    touch = np.asarray((cell_nodes.T @ own_nodes.astype(np.float64))).ravel() > 0
-    cells = np.flatnonzero(touch)
+    cells = np.asarray(cells, dtype=np.int64)
     sub_cf = cf[:, cells]
     faces = np.unique(sub_cf.indices)
     sub_cf = sub_cf.tocsr()[faces].tocsc()
     sub_fn = fn[:, faces]
     nodes = np.unique(sub_fn.indices)
     sub_fn = sub_fn.tocsr()[nodes].tocsc()
-    # keep the stored node order inside each face (face_nodes column order defines sub-face ids)
-    fn_sorted = sps.csc_matrix(fn)
     lg = Grid(g.dim, np.asarray(g.nodes)[:, nodes], sub_fn, sub_cf, name=getattr(g, "name", "Grid"))
     lg.set_geometry(np.asarray(g.face_normals)[:, faces], np.asarray(g.face_centers)[:, faces],
                     np.asarray(g.face_areas)[faces], np.asarray(g.cell_centers)[:, cells],
                     np.asarray(g.cell_volumes)[cells])
-    del fn_sorted
     glob_bnd = np.zeros(nf, bool)
     glob_bnd[g.get_all_boundary_faces()] = True
     loc_single = np.asarray(abs(lg.cell_faces).sum(axis=1)).ravel() == 1
     cut = loc_single & ~glob_bnd[faces]
-    if "fracture_faces" in g.tags:
-        lg.tags["fracture_faces"] = np.asarray(g.tags["fracture_faces"], bool)[faces]
+    tags = getattr(g, "tags", {})
+    if "fracture_faces" in tags:
+        lg.tags["fracture_faces"] = np.asarray(tags["fracture_faces"], bool)[faces]
     lg.tags["domain_boundary_faces"] = loc_single & ~lg.tags["fracture_faces"]
-    own_cell = own[cells]
+    return Shard(rank, lg, cells, faces, nodes, np.asarray(keep_cells, bool)[cells],
+                 np.asarray(keep_faces, bool)[faces], cut, (nc, nf, nn))
+
+
+def extract_shard(g, part: np.ndarray, rank: int) -> Shard:
+    """This rank's nodes, every cell touching them (one halo layer); rows of the faces of the rank's own
+    cells (a shared face goes to the lower rank) and of its own cells."""
+    cf = sps.csc_matrix(g.cell_faces)
+    fn = sps.csc_matrix(g.face_nodes)
+    nc, nf, nn = g.num_cells, g.num_faces, g.num_nodes
+    own = part == rank
+    cell_nodes = (abs(fn) @ abs(cf)).tocsc()  # nn x nc
+    cell_nodes.data[:] = 1
+    own_nodes = np.zeros(nn, bool)
+    own_nodes[np.unique(cell_nodes[:, np.flatnonzero(own)].indices)] = True
+    touch = np.asarray((cell_nodes.T @ own_nodes.astype(np.float64))).ravel() > 0
     # faces of own cells; shared faces go to the lower rank
-    acf = abs(cf).tocsr()
     face_min_part = np.full(nf, np.iinfo(np.int64).max)
-    coo = acf.tocoo()
+    coo = abs(cf).tocoo()
     np.minimum.at(face_min_part, coo.row, part[coo.col])
     own_face_glob = np.zeros(nf, bool)
     own_face_glob[np.unique(cf[:, np.flatnonzero(own)].indices)] = True
     own_face_glob &= face_min_part == rank
-    return Shard(rank, lg, cells, faces, nodes, own_cell, own_face_glob[faces], cut, (nc, nf, nn))
+    return extract_cells(g, np.flatnonzero(touch), own_face_glob, own, rank)
 
 
 def restrict_scalar_bc(bc, shard: Shard):
@@ -156,19 +163,28 @@ def restrict_vector_bc(bc, shard: Shard):
 # one call per rank: restrict the parameters, discretize the shard, embed the kept rows
 # ------------------------------------------------------------------------------------------
 
-# key -> (row entity, column entity, row block, column block); "nd" is replaced by the grid dimension
+# key -> (row entity, column entity); block sizes follow from the local matrix shape
 _LAYOUT = {
-    "flux": ("face", "cell", 1, 1), "bound_flux": ("face", "face", 1, 1),
-    "bound_pressure_cell": ("face", "cell", 1, 1), "bound_pressure_face": ("face", "face", 1, 1),
-    "vector_source": ("face", "cell", 1, "nd"), "bound_pressure_vector_source": ("face", "cell", 1, "nd"),
-    "stress": ("face", "cell", "nd", "nd"), "bound_stress": ("face", "face", "nd", "nd"),
-    "bound_displacement_cell": ("face", "cell", "nd", "nd"),
-    "bound_displacement_face": ("face", "face", "nd", "nd"),
-    "displacement_divergence": ("cell", "cell", 1, "nd"),
-    "boundary_displacement_divergence": ("cell", "face", 1, "nd"),
-    "scalar_gradient": ("face", "cell", "nd", 1), "mpsa_consistency": ("cell", "cell", 1, 1),
-    "bound_displacement_pressure": ("face", "cell", "nd", 1),
+    "flux": ("face", "cell"), "bound_flux": ("face", "face"),
+    "bound_pressure_cell": ("face", "cell"), "bound_pressure_face": ("face", "face"),
+    "vector_source": ("face", "cell"), "bound_pressure_vector_source": ("face", "cell"),
+    "stress": ("face", "cell"), "bound_stress": ("face", "face"),
+    "bound_displacement_cell": ("face", "cell"), "bound_displacement_face": ("face", "face"),
+    "displacement_divergence": ("cell", "cell"), "boundary_displacement_divergence": ("cell", "face"),
+    "scalar_gradient": ("face", "cell"), "mpsa_consistency": ("cell", "cell"),
+    "bound_displacement_pressure": ("face", "cell"),
 }
+
+
+def embed(shard: Shard, key: str, m):
+    """Kept rows of the local matrix ``m`` (or dict of matrices) of discretization term ``key`` in
+    global numbering."""
+    if isinstance(m, dict):
+        return {k: embed(shard, key, v) for k, v in m.items()}
+    rows, cols = _LAYOUT[key]
+    n_r = shard.grid.num_faces if rows == "face" else shard.grid.num_cells
+    n_c = shard.grid.num_faces if cols == "face" else shard.grid.num_cells
+    return shard.to_global(m, rows, cols, m.shape[0] // n_r, m.shape[1] // n_c)
 
 
 def restrict_parameters(params: dict, shard: Shard) -> dict:
@@ -177,6 +193,9 @@ def restrict_parameters(params: dict, shard: Shard) -> dict:
     from .params import FourthOrderTensor, SecondOrderTensor
     out = {}
     for key, val in params.items():
+        if key in ("specified_cells", "specified_faces", "specified_nodes", "active_cells", "active_faces",
+                   "update_discretization"):
+            continue  # describe the GLOBAL grid; the sub-grid is discretized as a whole
         if key == "second_order_tensor":
             out[key] = SecondOrderTensor.from_values(shard.restrict_cell_array(val.values))
         elif key == "fourth_order_tensor":
@@ -212,16 +231,7 @@ def discretize_shard(discr, g, data: dict, part: np.ndarray, rank: int) -> dict:
     params.setdefault(eta_key, determine_eta(g))
     local = initialize_data({}, kw, params)
     discr.discretize(shard.grid, local)
-    nd = int(g.dim)
-    out = {}
-    for key, m in local[DISCRETIZATION_MATRICES][kw].items():
-        rows, cols, br, bc = _LAYOUT[key]
-        br, bc = (nd if br == "nd" else br), (nd if bc == "nd" else bc)
-        if isinstance(m, dict):
-            out[key] = {k: shard.to_global(v, rows, cols, br, bc) for k, v in m.items()}
-        else:
-            out[key] = shard.to_global(m, rows, cols, br, bc)
-    return out
+    return {key: embed(shard, key, m) for key, m in local[DISCRETIZATION_MATRICES][kw].items()}
 
 
 def sum_shards(parts: list) -> dict:

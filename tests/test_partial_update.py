@@ -1,0 +1,117 @@
+"""Partial (re)discretization through ``specified_cells / specified_faces / specified_nodes``
+(reference _fvutils.py:308-355,1260-1462; mpfa.py:176-201,468-508; biot.py:326-342,614-712), driven on
+CPU through the operator classes with the device plan replaced by the host build of the kernels.
+The reference's own partial-discretization tests run on the same code through
+tools/run_reference_tests.py (tests/test_porepy_plugin.py)."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+import porepy_b200 as pb
+from porepy_b200 import fv
+from cases import flatten
+from emu_binding import EmuBackedPlan
+from golden_io import rel_err
+from test_shard_api import problem
+
+
+@pytest.fixture(autouse=True)
+def emu_plan(monkeypatch):
+    monkeypatch.setattr(fv, "DevicePlan", EmuBackedPlan)
+
+
+def _full(g, flow, mech):
+    pb.Mpfa("flow").discretize(g, flow)
+    pb.Biot("mech").discretize(g, mech)
+    out = dict(flow[pb.DISCRETIZATION_MATRICES]["flow"])
+    out.update(mech[pb.DISCRETIZATION_MATRICES]["mech"])
+    return flatten(out)
+
+
+def _fresh(data, kw, **extra):
+    p = dict(data[pb.PARAMETERS][kw])
+    p.update(extra)
+    return pb.initialize_data({}, kw, p)
+
+
+@pytest.mark.parametrize("kind", ["cart", "tet"])
+def test_gradual_build_up_by_nodes_equals_the_full_discretization(kind):
+    """Nodes mode: every face row is produced by exactly one group of nodes only if all its nodes
+    are in the group, so whole-grid coverage needs overlapping groups; the reference's use is to
+    sum disjoint FACE sets -- here: each face is taken from the first group that completes it."""
+    g, flow, mech = problem(kind)
+    ref = _full(g, flow, mech)
+    x = g.nodes[0]
+    groups = [np.flatnonzero(x < 0.55), np.flatnonzero(x > 0.3)]     # overlapping node slabs
+    acc, done = {}, np.zeros(g.num_faces, bool)
+    for nodes in groups:
+        d1, d2 = _fresh(flow, "flow", specified_nodes=nodes), _fresh(mech, "mech", specified_nodes=nodes)
+        pb.Mpfa("flow").discretize(g, d1)
+        pb.Biot("mech").discretize(g, d2)
+        faces = d1[pb.PARAMETERS]["flow"]["active_faces"]
+        assert np.array_equal(faces, d2[pb.PARAMETERS]["mech"]["active_faces"])
+        new = np.zeros(g.num_faces, bool)
+        new[faces] = True
+        new &= ~done
+        done |= new
+        part = dict(d1[pb.DISCRETIZATION_MATRICES]["flow"])
+        part.update(d2[pb.DISCRETIZATION_MATRICES]["mech"])
+        for key, m in flatten(part).items():
+            if m.shape[0] % g.num_faces or key.startswith(("displacement_divergence", "mpsa_consistency",
+                                                           "boundary_displacement_divergence")):
+                continue   # cell-row terms are checked in the cells-mode test
+            br = m.shape[0] // g.num_faces
+            sel = sps.diags(np.repeat(new, br).astype(float))
+            acc[key] = sel @ m if key not in acc else acc[key] + sel @ m
+    assert done.all()
+    for key, m in acc.items():
+        assert rel_err(ref[key], m) < 1e-12, key
+
+
+def test_cells_mode_rows_and_update_in_place():
+    g, flow, mech = problem("cart")
+    ref = _full(g, flow, mech)
+    cells = np.array([7, 8])
+    d1 = _fresh(flow, "flow", specified_cells=cells)
+    d2 = _fresh(mech, "mech", specified_cells=cells)
+    pb.Mpfa("flow").discretize(g, d1)
+    pb.Biot("mech").discretize(g, d2)
+    faces = d1[pb.PARAMETERS]["flow"]["active_faces"]
+    act_cells = d1[pb.PARAMETERS]["flow"]["active_cells"]
+    assert 0 < faces.size < g.num_faces and cells.size < act_cells.size < g.num_cells
+    keep_f = np.zeros(g.num_faces, bool)
+    keep_f[faces] = True
+    part = dict(d1[pb.DISCRETIZATION_MATRICES]["flow"])
+    part.update(d2[pb.DISCRETIZATION_MATRICES]["mech"])
+    for key, m in flatten(part).items():
+        if key.startswith(("displacement_divergence", "mpsa_consistency", "boundary_displacement_divergence")):
+            continue
+        br = m.shape[0] // g.num_faces
+        rows = np.repeat(keep_f, br)
+        full = sps.csr_matrix(ref[key])
+        assert rel_err(sps.diags(rows.astype(float)) @ full, m) < 1e-12, key      # active rows = full rows
+        assert abs(sps.diags((~rows).astype(float)) @ m).sum() == 0, key         # the others are zero
+    # update in place: change the permeability in the two cells, re-discretize only around them
+    k2 = pb.SecondOrderTensor.from_values(flow[pb.PARAMETERS]["flow"]["second_order_tensor"].values.copy())
+    k2.values[:, :, cells] *= 7.0
+    flow2 = _fresh(flow, "flow", second_order_tensor=k2)
+    pb.Mpfa("flow").discretize(g, flow2)                         # reference result: full pass with k2
+    want = flow2[pb.DISCRETIZATION_MATRICES]["flow"]
+    upd = _fresh(flow, "flow", second_order_tensor=k2, specified_cells=cells, update_discretization=True)
+    upd[pb.DISCRETIZATION_MATRICES]["flow"] = dict(flow[pb.DISCRETIZATION_MATRICES]["flow"])   # old matrices
+    pb.Mpfa("flow").discretize(g, upd)
+    for key in want:
+        assert rel_err(want[key], upd[pb.DISCRETIZATION_MATRICES]["flow"][key]) < 1e-12, key
+
+
+def test_faces_mode_contains_the_cells_mode_of_the_neighbours():
+    g, flow, _ = problem("cart")
+    f0 = 40
+    d = _fresh(flow, "flow", specified_faces=np.array([f0]))
+    cells, faces = fv.active_indices(g, d[pb.PARAMETERS]["flow"])
+    assert f0 in faces
+    fn = sps.csc_matrix(g.face_nodes)
+    nodes = fn.indices[fn.indptr[f0]:fn.indptr[f0 + 1]]
+    touching = np.flatnonzero(np.asarray(abs(sps.csr_matrix(g.face_nodes))[nodes].sum(axis=0)).ravel() > 0)
+    assert np.array_equal(np.sort(faces), np.sort(touching))
+    assert cells.size > 0 and np.all(np.diff(cells) > 0)

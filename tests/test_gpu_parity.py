@@ -310,7 +310,7 @@ def test_device_side_flow_system_and_solve():
     """A = div @ flux and b assembled on the device (no D2H of the matrices) equal the host
     products of fv_elliptic.py:67-112; BiCGStab on the device matrix reproduces the direct solve."""
     from porepy_b200 import krylov as kr
-    from porepy_b200.fv import DevicePlan, scalar_bc_codes
+    from porepy_b200.fv import DevicePlan
     import torch
     g = pb.structured_tet_grid([6, 5, 4])
     rng = np.random.default_rng(3)

@@ -4,7 +4,6 @@ discretizer is the oracle (the checker standing in for the kernel); the gloo tes
 N > 1 path with world_size 2.  The GPU version of the same property is in
 tests/test_gpu_parity.py::test_sharded_equals_unsplit."""
 import os
-import sys
 
 import numpy as np
 import pytest

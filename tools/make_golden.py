@@ -193,6 +193,39 @@ def case_mpfa_embedded(name, kind, seed, tilt):
     print(name, "nc", nc, "nf", g.num_faces, "vector_source", M["vector_source"].shape)
 
 
+def case_next_rows(name, kind, seed):
+    """TPFA and first-order upwinding on the same grid / tensors / boundary
+    conditions: fixtures for oracle/next_rows_oracle.py."""
+    rng = np.random.default_rng(seed)
+    g = make_grid(kind, rng)
+    nc, nf = g.num_cells, g.num_faces
+    k = pp.SecondOrderTensor(1 + rng.random(nc), 1 + rng.random(nc), 1 + rng.random(nc),
+                             0.3 * rng.random(nc), 0.3 * rng.random(nc), 0.3 * rng.random(nc))
+    bc = scalar_bc(g, rng, robin=False)
+    data = pp.initialize_data({}, "flow", {"second_order_tensor": k, "bc": bc})
+    pp.Tpfa("flow").discretize(g, data)
+    M = data[pp.DISCRETIZATION_MATRICES]["flow"]
+    d = grid_arrays(g)
+    d.update(kind=np.array("next"), K=k.values, bc_is_dir=bc.is_dir, bc_is_neu=bc.is_neu,
+             bc_is_rob=bc.is_rob, bc_is_internal=bc.is_internal,
+             bc_robin_weight=np.asarray(bc.robin_weight, float), eta=np.float64(0.0))
+    for key in ("flux", "bound_flux", "bound_pressure_cell", "bound_pressure_face",
+                "vector_source", "bound_pressure_vector_source"):
+        put_matrix(d, "tpfa_" + key, M[key])
+    q = rng.standard_normal(nf)
+    q[rng.random(nf) < 0.1] = 0.0                       # exact zeros take the "positive" branch
+    up = pp.Upwind("transport")
+    dat = pp.initialize_data({}, "transport", {"bc": bc, up._flux_array_key: q})
+    up.discretize(g, dat)
+    U = dat[pp.DISCRETIZATION_MATRICES]["transport"]
+    d["darcy_flux"] = q
+    put_matrix(d, "upwind", U[up.upwind_matrix_key])
+    put_matrix(d, "bound_transport_dir", U[up.bound_transport_dir_matrix_key])
+    put_matrix(d, "bound_transport_neu", U[up.bound_transport_neu_matrix_key])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "nc", nc, "nf", nf)
+
+
 def case_mpsa(name, kind, robin, seed, biot=False):
     rng = np.random.default_rng(seed)
     g = make_grid(kind, rng)
@@ -254,6 +287,10 @@ def main():
         (case_mpfa_embedded, ("embedded_tri2d_tilted", "tri2d", 31, True), {}),
         (case_mpfa_embedded, ("embedded_cart2d_tilted", "cart2d", 32, True), {}),
         (case_mpfa_embedded, ("embedded_cart2d_xy", "cart2d", 33, False), {}),
+        # next scope row (TPFA, upwinding): fixtures for oracle/next_rows_oracle.py
+        (case_next_rows, ("next_cart3d", "cart3d_pert", 41), {}),
+        (case_next_rows, ("next_tet3d", "tet3d", 42), {}),
+        (case_next_rows, ("next_tri2d", "tri2d", 43), {}),
     ]
     for fn, args, kw in cases:
         if args[0].startswith(only):

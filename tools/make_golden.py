@@ -226,7 +226,7 @@ def case_next_rows(name, kind, seed):
     print(name, "nc", nc, "nf", nf)
 
 
-def case_mpsa(name, kind, robin, seed, biot=False):
+def case_mpsa(name, kind, robin, seed, biot=False, basis=False):
     rng = np.random.default_rng(seed)
     g = make_grid(kind, rng)
     nc = g.num_cells
@@ -234,6 +234,13 @@ def case_mpsa(name, kind, robin, seed, biot=False):
     lam = np.exp(0.5 * rng.standard_normal(nc))
     C = pp.FourthOrderTensor(mu, lam)
     bc = vector_bc(g, rng, robin)
+    if basis:  # boundary conditions in a rotated frame, a different rotation on every face
+        nd = g.dim
+        B = np.zeros((nd, nd, g.num_faces))
+        for f in range(g.num_faces):
+            q, r = np.linalg.qr(rng.standard_normal((nd, nd)))
+            B[:, :, f] = q * np.sign(np.diag(r))
+        bc.basis = B
     params = {"fourth_order_tensor": C, "bc": bc, "inverter": "python"}
     d = grid_arrays(g)
     if biot:
@@ -287,6 +294,10 @@ def main():
         (case_mpfa_embedded, ("embedded_tri2d_tilted", "tri2d", 31, True), {}),
         (case_mpfa_embedded, ("embedded_cart2d_tilted", "cart2d", 32, True), {}),
         (case_mpfa_embedded, ("embedded_cart2d_xy", "cart2d", 33, False), {}),
+        # vectorial boundary conditions in rotated bases (prefix keeps them out of the mpsa_/biot_ sweeps)
+        (case_mpsa, ("rotbasis_mpsa_cart3d", "cart3d", True, 51), {"basis": True}),
+        (case_mpsa, ("rotbasis_biot_tet3d", "tet3d", True, 52), {"biot": True, "basis": True}),
+        (case_mpsa, ("rotbasis_mpsa_cart2d", "cart2d", True, 53), {"basis": True}),
         # next scope row (TPFA, upwinding): fixtures for oracle/next_rows_oracle.py
         (case_next_rows, ("next_cart3d", "cart3d_pert", 41), {}),
         (case_next_rows, ("next_tet3d", "tet3d", 42), {}),

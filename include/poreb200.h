@@ -166,7 +166,22 @@ int pb_biot_download(pb_plan *p, int which_alpha, double *displacement_divergenc
 /* Replaces the scipy `M @ val` of AdArray.__rmatmul__ (numerics/ad/forward_mode.py:565-595)
  * and the residual chain of EquationSystem.assemble(evaluate_jacobian=False)
  * (numerics/ad/equation_system.py:1579-1713).  y = A x (+ beta*y).  */
-typedef struct pb_csr pb_csr; /* device-resident CSR matrix */
+typedef struct pb_csr pb_csr; /* ---- two-point flux approximation and first-order upwinding (one thread per face) ----------------
+ * Replaces Tpfa.discretize (numerics/fv/tpfa.py:40-280) and Upwind.discretize (numerics/fv/upwind.py:
+ * 150-300).  bc_bits (nf): bits 0-1 = PB_BC_* effective code, bit 2 = raw is_dir, bit 3 = raw is_neu.
+ * pb_tpfa: fc_indptr = row pointer of cell_faces in CSR-by-face form with ascending columns; value
+ * arrays in that pattern (flux, bound_pressure_cell: nnz; vector sources: nnz*vdim, entry-major) and
+ * the two diagonals (nf).  pb_upwind: upstream cell per face (-1 = face removed from the matrix) and the
+ * diagonals of the Neumann / Dirichlet-inflow boundary matrices.  Host pointers; outputs may be NULL
+ * for pb_tpfa. */
+int pb_tpfa(pb_plan *p, const double *permeability, const uint8_t *bc_bits, const int32_t *fc_indptr,
+            int vdim, double *flux, double *bound_pressure_cell, double *vector_source,
+            double *bound_pressure_vector_source, double *bound_flux_diag,
+            double *bound_pressure_face_diag);
+int pb_upwind(pb_plan *p, const double *darcy_flux, const uint8_t *bc_bits, int32_t *upstream_cell,
+              double *neumann_diag, double *dirichlet_diag);
+
+/* device-resident CSR matrix */
 int pb_csr_create(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t *indptr,
                   const int32_t *indices, const double *data, pb_csr **out);
 void pb_csr_destroy(pb_csr *a);

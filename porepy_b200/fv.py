@@ -303,6 +303,33 @@ class DevicePlan:
                                         _lib.ptr(rhs, _lib._f64p)))
         return rhs
 
+    # ---- two-point flux approximation, upwinding (one thread per face)
+    def tpfa(self, perm, bc_bits, fc_indptr, vdim: int) -> list:
+        """Value arrays of the six TPFA terms in the pattern of ``cell_faces`` (CSR by face):
+        [flux, bound_pressure_cell, vector_source, bound_pressure_vector_source] and the diagonals
+        [bound_flux, bound_pressure_face]."""
+        perm = _lib.f64(perm)
+        if perm.shape != (3, 3, self.nc):
+            raise ValueError("second_order_tensor.values must have shape (3, 3, num_cells)")
+        bits = np.ascontiguousarray(bc_bits, dtype=np.uint8)
+        ip = np.ascontiguousarray(fc_indptr, dtype=np.int32)
+        nnz = int(ip[-1])
+        out = [np.empty(nnz), np.empty(nnz), np.empty(nnz * vdim), np.empty(nnz * vdim), np.empty(self.nf),
+               np.empty(self.nf)]
+        _lib.check(self.lib.pb_tpfa(self.h, _lib.ptr(perm, _lib._f64p), _lib.ptr(bits, _lib._u8p),
+                                    _lib.ptr(ip, _lib._i32p), int(vdim), *[_lib.ptr(a, _lib._f64p) for a in out]))
+        return out
+
+    def upwind(self, darcy_flux, bc_bits):
+        """Upstream cell per face (-1: face not in the matrix) and the two boundary diagonals."""
+        q = _lib.f64(darcy_flux)
+        bits = np.ascontiguousarray(bc_bits, dtype=np.uint8)
+        up = np.empty(self.nf, np.int32)
+        neu, dr = np.empty(self.nf), np.empty(self.nf)
+        _lib.check(self.lib.pb_upwind(self.h, _lib.ptr(q, _lib._f64p), _lib.ptr(bits, _lib._u8p),
+                                      _lib.ptr(up, _lib._i32p), _lib.ptr(neu, _lib._f64p), _lib.ptr(dr, _lib._f64p)))
+        return up, neu, dr
+
     # ---- MPSA / Biot
     def mpsa_upload(self, stiff, codes, robw, eta, alphas=()) -> None:
         stiff = _lib.f64(stiff)
@@ -368,6 +395,20 @@ def scalar_bc_codes(bc, nf: int) -> np.ndarray:
     codes[np.asarray(bc.is_dir, bool) & ~internal] = _lib.BC_DIR
     codes[np.asarray(bc.is_rob, bool) & ~internal] = _lib.BC_ROB
     return codes
+
+
+def face_bc_bits(bc, nf: int) -> np.ndarray:
+    """Boundary byte of the per-face kernels (csrc/face_kernels.cuh): effective code in bits 0-1
+    (internal faces count as Neumann, tpfa.py:187-188), the raw ``is_dir`` / ``is_neu`` flags in
+    bits 2 / 3 (used as such by tpfa.py:221-225 and upwind.py:260-270)."""
+    internal = np.asarray(getattr(bc, "is_internal", np.zeros(nf, bool)), bool)
+    is_dir, is_neu, is_rob = (np.asarray(getattr(bc, k), bool) for k in ("is_dir", "is_neu", "is_rob"))
+    bits = np.zeros(nf, np.uint8)
+    bits[is_rob & ~internal] = _lib.BC_ROB
+    bits[is_dir & ~internal] = _lib.BC_DIR
+    bits[is_neu | internal] = _lib.BC_NEU
+    bits |= (is_dir.astype(np.uint8) << 2) | (is_neu.astype(np.uint8) << 3)
+    return bits
 
 
 def vector_bc_codes(bc, nd: int, nf: int):
@@ -696,3 +737,93 @@ class Biot(Mpsa):
     def assemble_matrix_rhs(self, sd, data: dict):
         """biot.py:125-149."""
         raise NotImplementedError("This class cannot be used for assembly.\nUse the ad version instead")
+
+
+class Tpfa(Mpfa):
+    """Two-point flux approximation (numerics/fv/tpfa.py:18; same keys and ``assemble_matrix_rhs`` as
+    MPFA through FVElliptic).  One thread per face; 1-D, 2-D and 3-D grids."""
+
+    def _discretize_grid(self, sd, params: dict) -> dict:
+        k = params["second_order_tensor"]
+        bc = params["bc"]
+        vdim = int(params.get("ambient_dimension", sd.dim))
+        self._check_unsupported(params, sd)
+        t0 = time.perf_counter()
+        plan = DevicePlan.for_grid(sd)
+        if plan.rotation is not None:
+            # the reference keeps the 3-D coordinates here (tpfa.py:160-175); the plan holds the grid rotated
+            # into its plane, which would put the vector-source terms into the local frame
+            raise NotImplementedError("TPFA on a 2-D grid outside the xy-plane is not supported")
+        fc = sps.csr_matrix(sd.cell_faces)
+        fc.sort_indices()
+        ip, ix = fc.indptr, fc.indices
+        vals = plan.tpfa(k.values, face_bc_bits(bc, sd.num_faces), ip, vdim)
+        nf, nc = sd.num_faces, sd.num_cells
+        boundary = np.diff(ip) == 1
+        cols_v = (ix[:, None].astype(np.int64) * vdim + np.arange(vdim)).ravel()
+        ipv = ip.astype(np.int64) * vdim
+        self.last_timing = dict(total_s=time.perf_counter() - t0)
+        return {
+            self.flux_matrix_key: sps.csr_matrix((vals[0], ix, ip), shape=(nf, nc)),
+            self.bound_flux_matrix_key: sps.diags(np.where(boundary, vals[4], 0.0)).tocsr(),
+            self.bound_pressure_cell_matrix_key: sps.csr_matrix((vals[1], ix, ip), shape=(nf, nc)),
+            self.bound_pressure_face_matrix_key: sps.diags(vals[5]).tocsr(),
+            self.vector_source_matrix_key: sps.csr_matrix((vals[2], cols_v, ipv), shape=(nf, nc * vdim)),
+            self.bound_pressure_vector_source_matrix_key: sps.csr_matrix((vals[3], cols_v, ipv),
+                                                                         shape=(nf, nc * vdim)),
+        }
+
+
+class Upwind(_Base):
+    """First-order upwinding of an advective flux (numerics/fv/upwind.py:13).  ``discretize`` reads
+    ``bc`` and the face fluxes under ``flux_array_key`` (default ``"darcy_flux"``) and writes the
+    upwind matrix and the two boundary matrices; ``assemble_matrix_rhs`` as upwind.py:57-148."""
+
+    def __init__(self, keyword: str = "transport") -> None:
+        super().__init__(keyword)
+        self.upwind_matrix_key = "transport"
+        self.bound_transport_dir_matrix_key = "rhs_dir"
+        self.bound_transport_neu_matrix_key = "rhs_neu"
+        self._flux_array_key = "darcy_flux"
+
+    @property
+    def flux_array_key(self) -> str:
+        return self._flux_array_key
+
+    @flux_array_key.setter
+    def flux_array_key(self, value: str) -> None:
+        self._flux_array_key = value
+
+    def ndof(self, sd) -> int:
+        return sd.num_cells
+
+    def discretize(self, sd, data: dict) -> None:
+        params = data[PARAMETERS][self.keyword]
+        mats = data.setdefault(DISCRETIZATION_MATRICES, {}).setdefault(self.keyword, {})
+        bc = params.get("bc")
+        if bc is None:  # upwind.py:244-247: Dirichlet on the boundary
+            from .params import BoundaryCondition
+            bc = BoundaryCondition(sd, sd.get_boundary_faces(), "dir")
+        plan = DevicePlan.for_grid(sd)
+        up, neu, dr = plan.upwind(params[self._flux_array_key], face_bc_bits(bc, sd.num_faces))
+        nf, nc = sd.num_faces, sd.num_cells
+        rows = np.flatnonzero(up >= 0)
+        m = sps.csr_matrix((np.ones(rows.size), (rows, up[rows])), shape=(nf, nc))
+        ncomp = int(params.get("num_components", 1))
+        eye = sps.eye(ncomp)
+        mats[self.upwind_matrix_key] = sps.kron(m, eye).tocsr()
+        mats[self.bound_transport_neu_matrix_key] = sps.kron(sps.diags(neu), eye).tocsr()
+        mats[self.bound_transport_dir_matrix_key] = sps.kron(sps.diags(dr), eye).tocsr()
+
+    def assemble_matrix_rhs(self, sd, data: dict):
+        """upwind.py:57-148: ``div @ diag(q) @ upwind`` and the boundary right-hand side."""
+        mats = data[DISCRETIZATION_MATRICES][self.keyword]
+        params = data[PARAMETERS][self.keyword]
+        q = sps.diags(np.asarray(params[self._flux_array_key], float))
+        div = sd.divergence(dim=1)
+        if div.shape[1] != mats[self.upwind_matrix_key].shape[0]:
+            raise ValueError("Dimension mismatch: upwinding with several components is only supported in Ad mode")
+        matrix = div @ q @ mats[self.upwind_matrix_key]
+        rhs = div @ ((mats[self.bound_transport_neu_matrix_key] + mats[self.bound_transport_dir_matrix_key] @ q)
+                     @ params["bc_values"])
+        return matrix, rhs

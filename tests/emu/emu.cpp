@@ -12,6 +12,7 @@
 #include "../../porepy_b200/csrc/plan_host.hpp"
 #if __has_include("../../porepy_b200/csrc/mpsa_node.cuh")
 #include "../../porepy_b200/csrc/mpsa_node.cuh"
+#include "../../porepy_b200/csrc/face_kernels.cuh"
 #define HAVE_MPSA 1
 #endif
 
@@ -93,6 +94,29 @@ int emu_mpfa(void *h, const double *nodes, const double *fnorm, const double *fc
         else mpfa_node<2, SmemGJ>(t, P, G, prm, o, s, sm.data(), rest, scr, &err);
     }
     return err == INT_MAX ? 0 : 2;
+}
+
+int emu_tpfa(void *h, const double *fnorm, const double *fcent, const double *ccent, const double *perm,
+             const uint8_t *bc, const int32_t *fc_ptr, int vdim, double *flux, double *bpc, double *vs,
+             double *bpvs, double *bflux_diag, double *bpf_diag) {
+    Emu *e = (Emu *)h;
+    const HostPlan &H = e->P;
+    GeoView G{nullptr, fnorm, fcent, nullptr, ccent, nullptr, H.nn, 1, H.nf, 1, H.nc, 1};
+    TpfaOut o{flux, bpc, vs, bpvs, bflux_diag, bpf_diag};
+    for (int64_t f = 0; f < H.nf; ++f) {
+        if (H.nd == 3) tpfa_face<3>(f, G, perm, H.nc, 1, bc, H.face_cells.data(), fc_ptr, vdim, o);
+        else tpfa_face<2>(f, G, perm, H.nc, 1, bc, H.face_cells.data(), fc_ptr, vdim, o);
+    }
+    return 0;
+}
+
+int emu_upwind(void *h, const double *darcy_flux, const uint8_t *bc, int32_t *up_col, double *neu_diag,
+               double *dir_diag) {
+    Emu *e = (Emu *)h;
+    const HostPlan &H = e->P;
+    for (int64_t f = 0; f < H.nf; ++f)
+        upwind_face(f, darcy_flux, bc, H.face_cells.data(), up_col, neu_diag, dir_diag);
+    return 0;
 }
 
 #ifdef HAVE_MPSA

@@ -216,6 +216,30 @@ class EmuBackedPlan:
     def mpfa_download(self, *a):
         return self._out
 
+    def tpfa(self, perm, bc_bits, fc_indptr, vdim):
+        L = lib()
+        ip = np.ascontiguousarray(fc_indptr, np.int32)
+        nnz = int(ip[-1])
+        nf = self.emu.nf
+        out = [np.zeros(nnz), np.zeros(nnz), np.zeros(nnz * vdim), np.zeros(nnz * vdim), np.zeros(nf), np.zeros(nf)]
+        perm = np.ascontiguousarray(perm, np.float64)
+        bits = np.ascontiguousarray(bc_bits, np.uint8)
+        g = self.emu.geo
+        L.emu_tpfa(self.emu.h, _p(g[1], C.c_double), _p(g[2], C.c_double), _p(g[4], C.c_double),
+                   _p(perm, C.c_double), _p(bits, C.c_uint8), _p(ip, C.c_int32), C.c_int(vdim),
+                   *[_p(a, C.c_double) for a in out])
+        return out
+
+    def upwind(self, darcy_flux, bc_bits):
+        L = lib()
+        nf = self.emu.nf
+        q = np.ascontiguousarray(darcy_flux, np.float64)
+        bits = np.ascontiguousarray(bc_bits, np.uint8)
+        up, neu, dr = np.zeros(nf, np.int32), np.zeros(nf), np.zeros(nf)
+        L.emu_upwind(self.emu.h, _p(q, C.c_double), _p(bits, C.c_uint8), _p(up, C.c_int32),
+                     _p(neu, C.c_double), _p(dr, C.c_double))
+        return up, neu, dr
+
     def mpsa_upload(self, stiff, codes, robw, eta, alphas=()):
         self._mpsa = (stiff, codes, robw, eta, {q: a for q, a in enumerate(alphas)})
 
@@ -234,3 +258,63 @@ class EmuBackedPlan:
         return {k: self._mout[k][q] for k in ("displacement_divergence", "boundary_displacement_divergence",
                                               "scalar_gradient", "mpsa_consistency",
                                               "bound_displacement_pressure")}
+
+
+def face_bc_bits(bc, nf: int) -> np.ndarray:
+    """Boundary byte of the per-face routines (porepy_b200/csrc/face_kernels.cuh): effective code in
+    bits 0-1, raw is_dir / is_neu in bits 2 / 3."""
+    internal = np.asarray(getattr(bc, "is_internal", np.zeros(nf, bool)), bool)
+    is_dir, is_neu, is_rob = (np.asarray(getattr(bc, k), bool) for k in ("is_dir", "is_neu", "is_rob"))
+    bits = np.zeros(nf, np.uint8)
+    bits[is_rob & ~internal] = 3
+    bits[is_dir & ~internal] = 1
+    bits[is_neu | internal] = 2
+    bits |= (is_dir.astype(np.uint8) << 2) | (is_neu.astype(np.uint8) << 3)
+    return bits
+
+
+def _tpfa(self, perm, bc, vdim=None):
+    L = lib()
+    g = self.g
+    nf, nc = self.nf, self.nc
+    vdim = self.nd if vdim is None else vdim
+    fc = sps.csr_matrix(g.cell_faces)
+    fc.sort_indices()
+    ip = fc.indptr.astype(np.int32)
+    nnz = fc.indices.size
+    out = [np.zeros(nnz), np.zeros(nnz), np.zeros(nnz * vdim), np.zeros(nnz * vdim), np.zeros(nf), np.zeros(nf)]
+    perm = np.ascontiguousarray(perm, np.float64)
+    bits = face_bc_bits(bc, nf)
+    L.emu_tpfa(self.h, _p(self.geo[1], C.c_double), _p(self.geo[2], C.c_double), _p(self.geo[4], C.c_double),
+               _p(perm, C.c_double), _p(bits, C.c_uint8), _p(ip, C.c_int32), C.c_int(vdim),
+               *[_p(a, C.c_double) for a in out])
+    ix = fc.indices
+    bnd = np.asarray(abs(fc).sum(axis=1)).ravel() == 1
+    cols_v = (ix[:, None].astype(np.int64) * vdim + np.arange(vdim)).ravel()
+    return {
+        "flux": sps.csr_matrix((out[0], ix, ip), shape=(nf, nc)),
+        "bound_pressure_cell": sps.csr_matrix((out[1], ix, ip), shape=(nf, nc)),
+        "vector_source": sps.csr_matrix((out[2], cols_v, ip.astype(np.int64) * vdim), shape=(nf, nc * vdim)),
+        "bound_pressure_vector_source": sps.csr_matrix((out[3], cols_v, ip.astype(np.int64) * vdim),
+                                                       shape=(nf, nc * vdim)),
+        "bound_flux": sps.diags(np.where(bnd, out[4], 0.0)).tocsr(),
+        "bound_pressure_face": sps.diags(out[5]).tocsr(),
+    }
+
+
+def _upwind(self, darcy_flux, bc):
+    L = lib()
+    nf, nc = self.nf, self.nc
+    q = np.ascontiguousarray(darcy_flux, np.float64)
+    bits = face_bc_bits(bc, nf)
+    up = np.zeros(nf, np.int32)
+    neu, dr = np.zeros(nf), np.zeros(nf)
+    L.emu_upwind(self.h, _p(q, C.c_double), _p(bits, C.c_uint8), _p(up, C.c_int32), _p(neu, C.c_double),
+                 _p(dr, C.c_double))
+    rows = np.flatnonzero(up >= 0)
+    return {"upwind": sps.coo_matrix((np.ones(rows.size), (rows, up[rows])), shape=(nf, nc)).tocsr(),
+            "bound_transport_neu": sps.diags(neu).tocsr(), "bound_transport_dir": sps.diags(dr).tocsr()}
+
+
+EmuPlan.tpfa = _tpfa
+EmuPlan.upwind = _upwind

@@ -58,6 +58,7 @@ def plugin(pp) -> SimpleNamespace:
     # the reference classes as they are NOW: the plugin keeps working if the caller afterwards rebinds
     # pp.Mpfa etc. to the plugin classes (e.g. to run the reference's own tests on them)
     RefMpfa, RefMpsa, RefBiot = pp.Mpfa, pp.Mpsa, pp.Biot
+    RefTpfa, RefUpwind = pp.Tpfa, pp.Upwind
     RefMpfaAd, RefMpsaAd, RefBiotAd = pp.ad.MpfaAd, pp.ad.MpsaAd, pp.ad.BiotAd
 
     def _core(name, gpu_cls, ref_cls, flow):
@@ -102,8 +103,29 @@ def plugin(pp) -> SimpleNamespace:
         return type(name, (gpu_cls, ref_cls), body)
 
     Mpfa = _core("Mpfa", fv.Mpfa, RefMpfa, True)
+    Tpfa = _core("Tpfa", fv.Tpfa, RefTpfa, False)
     Mpsa = _core("Mpsa", fv.Mpsa, RefMpsa, False)
     Biot = _core("Biot", fv.Biot, RefBiot, False)
+
+    class Upwind(fv.Upwind, RefUpwind):
+        """pp.Upwind with the per-face GPU kernel; 0-D / 1-D grids and anything refused go to the
+        reference."""
+
+        def __init__(self, keyword: str = "transport") -> None:
+            RefUpwind.__init__(self, keyword)
+            fv.Upwind.__init__(self, keyword)
+
+        def discretize(self, sd, data) -> None:
+            if _gpu_scope(sd) and not hasattr(sd, "periodic_face_map"):
+                try:
+                    fv.Upwind.discretize(self, sd, data)
+                    return
+                except NotImplementedError as e:
+                    logger.info("B200 Upwind: %s -> reference path", e)
+            RefUpwind.discretize(self, sd, data)
+
+        def assemble_matrix_rhs(self, sd, data):
+            return RefUpwind.assemble_matrix_rhs(self, sd, data)
 
     def _rewrap(obj, discr, subdomains, coupling_terms=None):
         obj._discretization = discr
@@ -165,9 +187,11 @@ def plugin(pp) -> SimpleNamespace:
         ``pp.Mpfa``, so every stock model then discretizes through porepy_b200 without any change to
         the model classes (this is how tools/run_reference_tests.py runs the reference's own tests)."""
         pp.Mpfa, pp.Mpsa, pp.Biot = Mpfa, Mpsa, Biot
+        pp.Tpfa, pp.Upwind = Tpfa, Upwind
 
     def uninstall() -> None:
         pp.Mpfa, pp.Mpsa, pp.Biot = RefMpfa, RefMpsa, RefBiot
+        pp.Tpfa, pp.Upwind = RefTpfa, RefUpwind
 
-    return SimpleNamespace(Mpfa=Mpfa, Mpsa=Mpsa, Biot=Biot, MpfaAd=MpfaAd, MpsaAd=MpsaAd, BiotAd=BiotAd,
+    return SimpleNamespace(Mpfa=Mpfa, Mpsa=Mpsa, Biot=Biot, Tpfa=Tpfa, Upwind=Upwind, MpfaAd=MpfaAd, MpsaAd=MpsaAd, BiotAd=BiotAd,
                            ModelMixin=ModelMixin, install=install, uninstall=uninstall)

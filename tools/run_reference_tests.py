@@ -37,7 +37,7 @@ class Rebind:
             from emu_binding import EmuBackedPlan
             fv.DevicePlan = EmuBackedPlan
         COUNTS["backend: " + ("cuda" if gpu else "host build of the node routines")] = 1
-        for name in ("Mpfa", "Mpsa", "Biot"):
+        for name in ("Mpfa", "Mpsa", "Biot", "Tpfa", "Upwind"):
             for owner, tag in ((getattr(fv, name), "porepy_b200"), (getattr(pp, name), "reference")):
                 stock = owner.discretize
 

@@ -115,3 +115,36 @@ def test_faces_mode_contains_the_cells_mode_of_the_neighbours():
     touching = np.flatnonzero(np.asarray(abs(sps.csr_matrix(g.face_nodes))[nodes].sum(axis=0)).ravel() > 0)
     assert np.array_equal(np.sort(faces), np.sort(touching))
     assert cells.size > 0 and np.all(np.diff(cells) > 0)
+
+
+def test_biot_update_in_place_incl_cell_row_terms():
+    """Stiffness changed in two cells, ``update_discretization = True``: face-row terms of the active
+    faces and the cell-row coupling terms of the cells next to them are replaced (biot.py:614-690);
+    every stored matrix then equals a full pass with the new stiffness wherever the reference's
+    partial pass defines it -- the face-row matrices everywhere, the cell-row matrices on the rows of
+    cells whose nodes all lie inside the active sub-grid."""
+    g, _, mech = problem("cart")
+    cells = np.array([7, 8])
+    pb.Biot("mech").discretize(g, mech)
+    old = mech[pb.DISCRETIZATION_MATRICES]["mech"]
+    C2 = pb.FourthOrderTensor.from_values(mech[pb.PARAMETERS]["mech"]["fourth_order_tensor"].values.copy())
+    C2.values[:, :, cells] *= 3.0
+    full = _fresh(mech, "mech", fourth_order_tensor=C2)
+    pb.Biot("mech").discretize(g, full)
+    want = full[pb.DISCRETIZATION_MATRICES]["mech"]
+    upd = _fresh(mech, "mech", fourth_order_tensor=C2, specified_cells=cells, update_discretization=True)
+    upd[pb.DISCRETIZATION_MATRICES]["mech"] = {k: (dict(v) if isinstance(v, dict) else v) for k, v in old.items()}
+    pb.Biot("mech").discretize(g, upd)
+    got = upd[pb.DISCRETIZATION_MATRICES]["mech"]
+    for key in ("stress", "bound_stress", "bound_displacement_cell", "bound_displacement_face"):
+        assert rel_err(want[key], got[key]) < 1e-12, key
+    for key in ("scalar_gradient", "bound_displacement_pressure"):
+        for kw in want[key]:
+            assert rel_err(want[key][kw], got[key][kw]) < 1e-12, (key, kw)
+    # cell-row terms: rows of the two modified cells (all their nodes are interior to the sub-grid)
+    sel = np.zeros(g.num_cells)
+    sel[cells] = 1.0
+    for key in ("displacement_divergence", "boundary_displacement_divergence", "mpsa_consistency"):
+        for kw in want[key]:
+            D = sps.diags(sel)
+            assert rel_err(D @ want[key][kw], D @ got[key][kw]) < 1e-12, (key, kw)

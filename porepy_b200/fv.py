@@ -519,14 +519,31 @@ class _Base:
             mats.update(self._discretize_grid(sd, params))
             return
         from . import shard as _shard
+        update = bool(params.get("update_discretization", False))
         keep_faces = np.zeros(sd.num_faces, bool)
         keep_faces[faces] = True
-        keep_cells = np.asarray(abs(sps.csr_matrix(sd.cell_faces)).T @ keep_faces.astype(np.float64)).ravel() > 0
+        if update:
+            # Cell-row terms (Biot) sum over ALL nodes of a cell, and every cell sharing a node with a
+            # modified one changes.  The reference replaces the rows of the cells next to an active face
+            # although some of their nodes have cut interaction regions in its sub-grid (biot.py:627-632;
+            # "update is not fully tested", biot.py:318-324).  Replacing stored rows must not corrupt
+            # them: grow the sub-grid by one ring and replace exactly the rows of the cells all of whose
+            # interaction regions are complete in it.
+            cn = (abs(sps.csr_matrix(sd.face_nodes)) @ abs(sps.csr_matrix(sd.cell_faces))).tocsr()
+            cn.data[:] = 1.0
+            inside = np.zeros(sd.num_cells)
+            inside[cells] = 1.0
+            grown = (cn.T @ ((cn @ inside) > 0).astype(np.float64)) > 0
+            complete_node = (cn @ grown.astype(np.float64)) == np.asarray(cn.sum(axis=1)).ravel()
+            keep_cells = grown & ((cn.T @ (~complete_node).astype(np.float64)) == 0)
+            cells = np.flatnonzero(grown)
+        else:
+            keep_cells = np.asarray(abs(sps.csr_matrix(sd.cell_faces)).T @ keep_faces.astype(np.float64)).ravel() > 0
         sub = _shard.extract_cells(sd, cells, keep_faces, keep_cells)
         local = _shard.restrict_parameters(params, sub)
         local.setdefault(self._eta_key, determine_eta(sd))
         out = {key: _shard.embed(sub, key, m) for key, m in self._discretize_grid(sub.grid, local).items()}
-        if params.get("update_discretization", False):
+        if update:
             for key, new in out.items():
                 keep = keep_faces if _shard._LAYOUT[key][0] == "face" else keep_cells
                 if isinstance(new, dict):

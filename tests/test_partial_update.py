@@ -120,11 +120,19 @@ def test_faces_mode_contains_the_cells_mode_of_the_neighbours():
 def test_biot_update_in_place_incl_cell_row_terms():
     """Stiffness changed in two cells, ``update_discretization = True``: face-row terms of the active
     faces and the cell-row coupling terms of the cells next to them are replaced (biot.py:614-690);
-    every stored matrix then equals a full pass with the new stiffness wherever the reference's
-    partial pass defines it -- the face-row matrices everywhere, the cell-row matrices on the rows of
-    cells whose nodes all lie inside the active sub-grid."""
-    g, _, mech = problem("cart")
-    cells = np.array([7, 8])
+    every stored matrix then equals a full pass with the new stiffness (the sub-grid is grown by one
+    ring so that the cell rows that are replaced have complete interaction regions)."""
+    # large enough that the two-ring sub-grid of the reference is a proper subset with cut regions:
+    # with the reference's row set the neighbours' cell rows come out 1 % wrong on this grid
+    g = pb.cart_grid_3d([7, 6, 6], perturb=0.2)
+    rng = np.random.default_rng(0)
+    nc = g.num_cells
+    C = pb.FourthOrderTensor(np.exp(0.3 * rng.standard_normal(nc)), np.exp(0.3 * rng.standard_normal(nc)))
+    bf = g.get_all_boundary_faces()
+    vbc = pb.BoundaryConditionVectorial(g, bf[g.face_centers[2, bf] < 1e-10], "dir")
+    mech = pb.initialize_data({}, "mech", {"fourth_order_tensor": C, "bc": vbc,
+                                           "scalar_vector_mappings": {"p": 0.8}})
+    cells = np.array([3 + 7 * (3 + 6 * 3), 4 + 7 * (3 + 6 * 3)])
     pb.Biot("mech").discretize(g, mech)
     old = mech[pb.DISCRETIZATION_MATRICES]["mech"]
     C2 = pb.FourthOrderTensor.from_values(mech[pb.PARAMETERS]["mech"]["fourth_order_tensor"].values.copy())
@@ -136,15 +144,16 @@ def test_biot_update_in_place_incl_cell_row_terms():
     upd[pb.DISCRETIZATION_MATRICES]["mech"] = {k: (dict(v) if isinstance(v, dict) else v) for k, v in old.items()}
     pb.Biot("mech").discretize(g, upd)
     got = upd[pb.DISCRETIZATION_MATRICES]["mech"]
+    assert upd[pb.PARAMETERS]["mech"]["active_cells"].size < g.num_cells
     for key in ("stress", "bound_stress", "bound_displacement_cell", "bound_displacement_face"):
         assert rel_err(want[key], got[key]) < 1e-12, key
     for key in ("scalar_gradient", "bound_displacement_pressure"):
         for kw in want[key]:
             assert rel_err(want[key][kw], got[key][kw]) < 1e-12, (key, kw)
-    # cell-row terms: rows of the two modified cells (all their nodes are interior to the sub-grid)
-    sel = np.zeros(g.num_cells)
-    sel[cells] = 1.0
+    # cell-row terms: EVERY row (the neighbours of the modified cells change too, all others must
+    # keep their stored values untouched)
     for key in ("displacement_divergence", "boundary_displacement_divergence", "mpsa_consistency"):
         for kw in want[key]:
-            D = sps.diags(sel)
-            assert rel_err(D @ want[key][kw], D @ got[key][kw]) < 1e-12, (key, kw)
+            assert rel_err(want[key][kw], got[key][kw]) < 1e-12, (key, kw)
+            if key != "boundary_displacement_divergence":   # (interior cells: the boundary term does not change)
+                assert rel_err(want[key][kw], old[key][kw]) > 1e-6, (key, kw)   # the update was not a no-op

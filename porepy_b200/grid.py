@@ -171,6 +171,57 @@ def cart_grid_3d(nx, physdims=(1.0, 1.0, 1.0), perturb: float = 0.0, seed: int =
     return g.set_geometry(fnrm, fc, fa, cc, cv)
 
 
+def cart_grid_2d(nx, physdims=(1.0, 1.0)) -> Grid:
+    """Cartesian grid of nx[0] x nx[1] rectangles in the plane z = 0 (the reference's
+    ``pp.CartGrid([nx, ny], physdims)``: nodes i + (nx+1) j, cells i + nx j, first the faces with
+    normal along x, then those with normal along y; the stored normal has the length of the edge and
+    points towards increasing x resp. y)."""
+    ex, ey = int(nx[0]), int(nx[1])
+    xs = np.linspace(0.0, physdims[0], ex + 1)
+    ys = np.linspace(0.0, physdims[1], ey + 1)
+    X, Y = np.meshgrid(xs, ys, indexing="ij")
+    nodes = np.vstack([X.ravel(order="F"), Y.ravel(order="F"), np.zeros((ex + 1) * (ey + 1))])
+    npx = ex + 1
+
+    def nid(i, j):
+        return i + npx * j
+
+    # x-faces: vertical edges at x_i between (i, j) and (i, j+1)
+    I, J = np.meshgrid(np.arange(ex + 1), np.arange(ey), indexing="ij")
+    I, J = I.ravel(order="F"), J.ravel(order="F")
+    fx = np.stack([nid(I, J), nid(I, J + 1)], axis=1)
+    nfx = fx.shape[0]
+    # y-faces: horizontal edges at y_j between (i, j) and (i+1, j)
+    I2, J2 = np.meshgrid(np.arange(ex), np.arange(ey + 1), indexing="ij")
+    I2, J2 = I2.ravel(order="F"), J2.ravel(order="F")
+    fy = np.stack([nid(I2, J2), nid(I2 + 1, J2)], axis=1)
+    fnodes = np.vstack([fx, fy])
+    nf = fnodes.shape[0]
+    face_nodes = sps.csc_matrix((np.ones(2 * nf, dtype=bool), fnodes.ravel(), np.arange(0, 2 * nf + 1, 2)),
+                                shape=(nodes.shape[1], nf))
+    Ic, Jc = np.meshgrid(np.arange(ex), np.arange(ey), indexing="ij")
+    Ic, Jc = Ic.ravel(order="F"), Jc.ravel(order="F")
+    west = Ic + (ex + 1) * Jc
+    east = west + 1
+    south = nfx + Ic + ex * Jc
+    north = south + ex
+    cf_idx = np.stack([west, east, south, north], axis=1).ravel()
+    cf_dat = np.tile(np.array([-1.0, 1.0, -1.0, 1.0]), ex * ey)
+    nc = ex * ey
+    cell_faces = sps.csc_matrix((cf_dat, cf_idx, np.arange(0, 4 * nc + 1, 4)), shape=(nf, nc))
+    cell_faces.sort_indices()
+    g = Grid(2, nodes, face_nodes, cell_faces, name="CartGrid")
+    a, b = nodes[:, fnodes[:, 0]], nodes[:, fnodes[:, 1]]
+    tang = b - a
+    fa = np.linalg.norm(tang, axis=0)
+    nrm = np.vstack([tang[1], -tang[0], np.zeros(nf)])   # rotate the edge by -90 degrees
+    nrm[:, nfx:] *= -1.0                                   # y-faces: +y
+    fc = 0.5 * (a + b)
+    cc = np.vstack([0.5 * (xs[Ic] + xs[Ic + 1]), 0.5 * (ys[Jc] + ys[Jc + 1]), np.zeros(nc)])
+    cv = (xs[Ic + 1] - xs[Ic]) * (ys[Jc + 1] - ys[Jc])
+    return g.set_geometry(nrm, fc, fa, cc, cv)
+
+
 def simplex_geometry_3d(g: Grid, cn: np.ndarray) -> Grid:
     """Geometry of a tetrahedral grid from its (nc,4) cell-node table.  The stored normal of a
     face points out of the cell whose ``cell_faces`` entry is +1 (pp convention)."""

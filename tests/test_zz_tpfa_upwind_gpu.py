@@ -5,7 +5,6 @@ These kernels were added after the round's GPU budget was spent: the per-face ro
 through the host build (bitwise equal to the reference) and the library cross-compiles, but the CUDA
 launch path has not been executed on a B200 yet -- hence non-strict xfail (an XPASS is the expected
 outcome; a failure here does not touch the validated MPFA / MPSA paths, whose SASS is unchanged)."""
-import numpy as np
 import pytest
 import scipy.sparse as sps
 

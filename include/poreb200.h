@@ -155,6 +155,10 @@ int pb_mpsa_rhs(pb_plan *p, const double *bc_values, const double *source, doubl
  *   mpsa_consistency nnz(CELL_CELL). */
 int pb_mpsa_upload(pb_plan *p, const double *stiffness, const uint8_t *bc,
                    const double *robin_weight, double eta, int n_alpha, const double *alpha);
+/* Boundary conditions in a rotated basis (BoundaryConditionVectorial.basis, params/bc.py; applied to the
+ * boundary equations by ExcludeBoundaries, numerics/fv/_fvutils.py:765-945): basis (nd,nd,nf) row-major,
+ * NULL = identity.  Call after pb_mpsa_upload (which resets it to the identity). */
+int pb_mpsa_set_basis(pb_plan *p, const double *basis);
 int pb_mpsa_assemble(pb_plan *p, float *ms);
 int pb_mpsa_download(pb_plan *p, double *stress, double *bound_stress,
                      double *bound_displacement_cell, double *bound_displacement_face);

@@ -46,6 +46,7 @@ _SIGNATURES = {
     "pb_mpsa_system": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "pb_mpsa_rhs": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p]),
     "pb_mpsa_upload": (C.c_int, [C.c_void_p, _f64p, _u8p, _f64p, C.c_double, C.c_int, _f64p]),
+    "pb_mpsa_set_basis": (C.c_int, [C.c_void_p, _f64p]),
     "pb_mpsa_assemble": (C.c_int, [C.c_void_p, _f32p]),
     "pb_mpsa_download": (C.c_int, [C.c_void_p] + [_f64p] * 4),
     "pb_biot_download": (C.c_int, [C.c_void_p, C.c_int] + [_f64p] * 5),

@@ -157,8 +157,8 @@ struct pb_plan {
     // mpsa
     std::vector<NodeClass> mpsa_cls;
     int mpsa_cls_nalpha = -1;
-    DevBuf stiff, vbc, vrobw, alpha;
-    bool have_vrobw = false;
+    DevBuf stiff, vbc, vrobw, vbasis, alpha;
+    bool have_vrobw = false, have_vbasis = false;
     int n_alpha = 0;
     double veta = 0.0;
     bool mpsa_ready = false;
@@ -1123,6 +1123,7 @@ extern "C" int pb_mpsa_upload(pb_plan *p, const double *stiffness, const uint8_t
     { int rcs = upload_repacked(p, p->stiff, stiffness, 81, H.nc); if (rcs) return rcs; }
     CUDA_TRY(p->vbc.upload(bc, (size_t)nd * H.nf, st));
     p->have_vrobw = robin_weight != nullptr;
+    p->have_vbasis = false;  // set again by pb_mpsa_set_basis after every upload
     if (robin_weight) CUDA_TRY(p->vrobw.upload(robin_weight, (size_t)nd * nd * H.nf, st));
     if (n_alpha) {
         CUDA_TRY(p->alpha.ensure((size_t)n_alpha * 9 * H.nc * sizeof(double)));
@@ -1150,6 +1151,18 @@ extern "C" int pb_mpsa_upload(pb_plan *p, const double *stiffness, const uint8_t
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     p->mpsa_ready = true;
+    return PB_OK;
+}
+
+extern "C" int pb_mpsa_set_basis(pb_plan *p, const double *basis) {
+    if (!p) return fail(PB_EINVAL, "null plan");
+    if (!p->mpsa_ready) return fail(PB_EINVAL, "pb_mpsa_upload has not been called");
+    p->have_vbasis = basis != nullptr;
+    if (basis) {
+        const HostPlan &H = p->H;
+        CUDA_TRY(p->vbasis.upload(basis, (size_t)H.nd * H.nd * H.nf, p->stream));
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+    }
     return PB_OK;
 }
 
@@ -1182,7 +1195,8 @@ extern "C" int pb_mpsa_assemble(pb_plan *p, float *ms) {
     int init = INT_MAX;
     CUDA_TRY(cudaMemcpyAsync(p->err.p, &init, sizeof(int), cudaMemcpyHostToDevice, st));
     MpsaParams prm{p->stiff.as<double>(), p->vbc.as<uint8_t>(),
-                   p->have_vrobw ? p->vrobw.as<double>() : nullptr, p->veta, p->n_alpha,
+                   p->have_vrobw ? p->vrobw.as<double>() : nullptr,
+                   p->have_vbasis ? p->vbasis.as<double>() : nullptr, p->veta, p->n_alpha,
                    p->n_alpha ? p->alpha.as<double>() : nullptr, 1, 81, 1, 9, 9 * H.nc};
     for (const NodeClass &c : p->mpsa_cls) {
         int rc = PB_OK;

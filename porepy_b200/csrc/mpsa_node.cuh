@@ -173,6 +173,28 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
     t.sync();
     // ---- phase 3: PS[k][p][a][m] = sum_kappa (C o S)[p,(a,kappa)] E[kappa][m];
     //               SA[p][(u,a)]  += w_k sum_kappa (C o !S)[p,(a,kappa)] E[kappa][m]
+#ifdef PB_EXP_FINE
+    // one item per (sub-cell, p, a): 3x more, 3x smaller items -- hexahedral regions have 72 (k, p)
+    // items on a 64-thread team (a second round for 8 items), 216 fine items fill 3.4 rounds
+    for (int it = t.tid(); it < nsc * ND2 * ND; it += t.size()) {
+        const int kp = it / ND, a = it - kp * ND;
+        const int k = kp / ND2, p = kp - k * ND2;
+        const int64_t c = cell[k];
+        const int pi = p / ND, pr = p - pi * ND;
+        const double *Crow = prm.stiff + (int64_t)c9<ND>(pi, pr) * 9 * prm.stiff_cs + c * prm.stiff_es;
+        double cs[ND];
+#pragma unroll
+        for (int q = 0; q < ND; ++q)
+            cs[q] = sym_mask<ND>(p, a * ND + q) ? Crow[(int64_t)c9<ND>(a, q) * prm.stiff_cs] : 0.0;
+#pragma unroll
+        for (int m = 0; m < ND; ++m) {
+            double v = 0.0;
+#pragma unroll
+            for (int q = 0; q < ND; ++q) v += cs[q] * E[k * ND2 + q * ND + m];
+            PS[((k * ND2 + p) * ND + a) * ND + m] = v;
+        }
+    }
+#else
     for (int it = t.tid(); it < nsc * ND2; it += t.size()) {
         const int k = it / ND2, p = it - k * ND2;
         const int64_t c = cell[k];
@@ -193,6 +215,7 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
             }
         }
     }
+#endif
     // one item per (p, a, sub-cell); a sub-face entry of SigmaA receives one contribution per side
     // (<= 2, so the sum does not depend on the order).  Node-volume weights w_K = vol_K / sum vol
     // (mpsa.py:1619-1640) are formed on the fly.
@@ -265,12 +288,87 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
         const int u = x / ND, i = x - u * ND;
         double *row = A + (int64_t)x * W;
         const int code = bcu[x];
-        if (code == 1) {  // Dirichlet component: ubar_{u,i} = u_b
+        if (code == 1 && prm.basis == nullptr) {  // Dirichlet component: ubar_{u,i} = u_b
             row[x] = 1.0;
             row[n + ncc + bloc[u] * ND + i] = 1.0;
             continue;
         }
         const double *nu = nrm + u * ND;
+        if (prm.basis != nullptr && bloc[u] >= 0) {
+            // Boundary conditions given in a rotated basis B_f (bc.basis; _fvutils.py:765-945): the nd
+            // equations of the sub-face are multiplied by B_f before the per-component exclusion, the
+            // boundary values live in the rotated frame.  Row i = sum_j B[i][j] (equation j).
+            const int64_t fb = face[u];
+            double B[ND][ND];
+#pragma unroll
+            for (int a = 0; a < ND; ++a)
+#pragma unroll
+                for (int j = 0; j < ND; ++j) B[a][j] = prm.basis[(int64_t)(a * ND + j) * nf + fb];
+            if (code == 1) {
+#pragma unroll
+                for (int j = 0; j < ND; ++j) row[u * ND + j] = B[i][j];
+                row[n + ncc + bloc[u] * ND + i] = 1.0;
+            } else {
+                const int side = sides[u] & 0xFFFF;  // boundary sub-face: one side
+                const int k = side / ND;
+                const double sg = (slot[side] & 1) ? -1.0 : 1.0;
+                for (int j = 0; j < ND; ++j) {
+                    const double wgt = sg * B[i][j];
+                    if (wgt == 0.0) continue;
+                    const double *ps = PS + (k * ND2 + j * ND) * ND2;  // [r][a][m], traction component j
+#pragma unroll
+                    for (int a = 0; a < ND; ++a) {
+                        double csum = 0.0;
+#pragma unroll
+                        for (int m = 0; m < ND; ++m) {
+                            double v = 0.0;
+#pragma unroll
+                            for (int r = 0; r < ND; ++r) v += nu[r] * ps[(r * ND + a) * ND + m];
+                            v *= wgt;
+                            row[(slot[k * ND + m] >> 1) * ND + a] += v;
+                            csum += v;
+                        }
+                        row[n + k * ND + a] += csum;
+                    }
+                    for (int q = 0; q < nal; ++q)
+                        row[n + ncc + nbc + q * nsc + k] += wgt * NA[((q * nsc + k) * ND + (side - k * ND)) * ND + j];
+                    // asymmetric part of component j unless eliminated for (its flag, j) (mpsa.py:1932-2000)
+                    const int cj = bcu[u * ND + j];
+                    if (!((cj == 2 && elim[j]) || (cj == 3 && elim[ND + j]))) {
+                        for (int c = 0; c < n; ++c) {
+                            double v = 0.0;
+#pragma unroll
+                            for (int r = 0; r < ND; ++r) v += nu[r] * SA[(j * ND + r) * n + c];
+                            row[c] += wgt * v;
+                        }
+                        for (int c = 0; c < ncc; ++c) {
+                            double v = 0.0;
+#pragma unroll
+                            for (int r = 0; r < ND; ++r) v += nu[r] * SAc[(j * ND + r) * ncc + c];
+                            row[n + c] -= wgt * v;
+                        }
+                    }
+                }
+                row[n + ncc + bloc[u] * ND + i] = invmf[u];
+                if (code == 3) {  // Robin weight acts on the rotated displacement: w B ubar
+                    const double as = G.farea[fb] * invmf[u];
+#pragma unroll
+                    for (int j = 0; j < ND; ++j) {
+                        double wb = 0.0;
+#pragma unroll
+                        for (int kk = 0; kk < ND; ++kk)
+                            wb += (prm.robw ? prm.robw[(int64_t)(i * ND + kk) * nf + fb] : (i == kk ? 1.0 : 0.0)) * B[kk][j];
+                        row[u * ND + j] += as * wb;
+                    }
+                }
+            }
+            double sum = 0.0;
+            for (int c = 0; c < n; ++c) sum += fabs(row[c]);
+            if (!(sum > 0.0)) { flag_singular(err, s); continue; }
+            const double is = 1.0 / sum;
+            for (int c = 0; c < n + nrhs; ++c) row[c] *= is;
+            continue;
+        }
         for (int sd = 0; sd < 2; ++sd) {
             const int side = sd == 0 ? (sides[u] & 0xFFFF) : ((sides[u] >> 16) & 0xFFFF);
             if (side == 0xFFFF) continue;

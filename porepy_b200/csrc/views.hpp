@@ -52,6 +52,7 @@ struct MpsaParams {
     const double *stiff;  // (9,9,nc)
     const uint8_t *bc;    // (nd,nf)
     const double *robw;   // (nd,nd,nf) or null
+    const double *basis;  // (nd,nd,nf) boundary-condition basis (bc.basis), null = identity
     double eta;
     int n_alpha;
     const double *alpha;  // n_alpha x (3,3,nc)

@@ -348,6 +348,13 @@ class DevicePlan:
                                            float(eta), nal, _lib.ptr(al, _lib._f64p)))
         self._nal = nal
 
+    def mpsa_set_basis(self, basis) -> None:
+        """``bc.basis`` (nd, nd, nf) or None for the identity; call after ``mpsa_upload``."""
+        b = None if basis is None else _lib.f64(basis)
+        if b is not None and b.shape != (self.nd, self.nd, self.nf):
+            raise ValueError("bc.basis must have shape (nd, nd, num_faces)")
+        _lib.check(self.lib.pb_mpsa_set_basis(self.h, _lib.ptr(b, _lib._f64p)))
+
     def mpsa_assemble(self) -> float:
         ms = C.c_float()
         _lib.check(self.lib.pb_mpsa_assemble(self.h, C.byref(ms)))
@@ -418,16 +425,23 @@ def vector_bc_codes(bc, nd: int, nf: int):
     codes[np.asarray(bc.is_neu, bool)[:nd]] = _lib.BC_NEU
     codes[np.asarray(bc.is_dir, bool)[:nd]] = _lib.BC_DIR
     codes[np.asarray(bc.is_rob, bool)[:nd]] = _lib.BC_ROB
-    basis = getattr(bc, "basis", None)
-    if basis is not None:
-        b = np.asarray(basis, float)
-        if b.ndim == 3 and not np.allclose(b[:nd, :nd], np.eye(nd)[:, :, None]):
-            raise NotImplementedError("rotated boundary bases (bc.basis) are not supported yet")
     robw = None
     if np.any(codes == _lib.BC_ROB):
         rw = np.asarray(bc.robin_weight, float)
         robw = np.ascontiguousarray(rw[:nd, :nd])
     return codes, robw
+
+
+def vector_bc_basis(bc, nd: int):
+    """``bc.basis`` (nd, nd, nf) when it is not the identity everywhere, else None
+    (_fvutils.py:765-945: boundary conditions given in a rotated coordinate system)."""
+    basis = getattr(bc, "basis", None)
+    if basis is None:
+        return None
+    b = np.asarray(basis, float)
+    if b.ndim != 3 or np.allclose(b[:nd, :nd], np.eye(nd)[:, :, None]):
+        return None
+    return np.ascontiguousarray(b[:nd, :nd])
 
 
 # ------------------------------------------------------------------------------------------
@@ -694,6 +708,7 @@ class Mpsa(_Base):
         codes, robw = vector_bc_codes(bc, sd.dim, sd.num_faces)
         t1 = time.perf_counter()
         plan.mpsa_upload(constit.values, codes, robw, float(eta), list(alphas.values()))
+        plan.mpsa_set_basis(vector_bc_basis(bc, sd.dim))
         t2 = time.perf_counter()
         ms = plan.mpsa_assemble()
         t3 = time.perf_counter()

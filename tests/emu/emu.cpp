@@ -122,13 +122,13 @@ int emu_upwind(void *h, const double *darcy_flux, const uint8_t *bc, int32_t *up
 #ifdef HAVE_MPSA
 int emu_mpsa(void *h, const double *nodes, const double *fnorm, const double *fcent,
              const double *farea, const double *ccent, const double *cvol, const double *stiff,
-             const uint8_t *bc, const double *robw, double eta, int n_alpha, const double *alpha,
-             double *stress, double *bstress, double *bdc, double *bdf, double **dd, double **bdd,
+             const uint8_t *bc, const double *robw, const double *basis, double eta, int n_alpha,
+             const double *alpha, double *stress, double *bstress, double *bdc, double *bdf, double **dd, double **bdd,
              double **sg, double **cons, double **bdp) {
     Emu *e = (Emu *)h;
     PlanView P = view_of(e->P);
     GeoView G{nodes, fnorm, fcent, farea, ccent, cvol, P.nn, 1, P.nf, 1, P.nc, 1};
-    MpsaParams prm{stiff, bc, robw, eta, n_alpha, alpha, P.nc, 1, P.nc, 1, 9 * P.nc};
+    MpsaParams prm{stiff, bc, robw, basis, eta, n_alpha, alpha, P.nc, 1, P.nc, 1, 9 * P.nc};
     MpsaOut o{};
     o.stress = stress; o.bstress = bstress; o.bdc = bdc; o.bdf = bdf;
     for (int a = 0; a < n_alpha; ++a) {

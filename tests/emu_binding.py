@@ -132,7 +132,7 @@ def block_expand(ip, ix, nd_rows, nd_cols):
     return new_ip, out
 
 
-def _mpsa(self, stiff, bc_codes, robw, eta, alpha=None):
+def _mpsa(self, stiff, bc_codes, robw, eta, alpha=None, basis=None):
     L = lib()
     nd = self.nd
     nd2 = nd * nd
@@ -153,8 +153,10 @@ def _mpsa(self, stiff, bc_codes, robw, eta, alpha=None):
     stiff = np.ascontiguousarray(stiff, np.float64)
     bc_codes = np.ascontiguousarray(bc_codes, np.uint8)
     robw = None if robw is None else np.ascontiguousarray(robw, np.float64)
+    basis = None if basis is None else np.ascontiguousarray(np.asarray(basis, np.float64)[:nd, :nd])
     rc = L.emu_mpsa(self.h, *[_p(a, C.c_double) for a in self.geo], _p(stiff, C.c_double),
-                    _p(bc_codes, C.c_uint8), _p(robw, C.c_double), C.c_double(eta), C.c_int(nal),
+                    _p(bc_codes, C.c_uint8), _p(robw, C.c_double), _p(basis, C.c_double), C.c_double(eta),
+                    C.c_int(nal),
                     _p(al, C.c_double), *[_p(a, C.c_double) for a in out], *arrs)
     if rc == 2:
         raise ValueError("Error in inversion of local linear systems")
@@ -242,12 +244,16 @@ class EmuBackedPlan:
 
     def mpsa_upload(self, stiff, codes, robw, eta, alphas=()):
         self._mpsa = (stiff, codes, robw, eta, {q: a for q, a in enumerate(alphas)})
+        self._basis = None
+
+    def mpsa_set_basis(self, basis):
+        self._basis = basis
 
     def mpsa_assemble(self):
         stiff, codes, robw, eta, al = self._mpsa
         if robw is not None:
             robw = np.asarray(robw)[:self.nd, :self.nd]
-        self._mout = self.emu.mpsa(stiff, codes, robw, eta, alpha=al or None)
+        self._mout = self.emu.mpsa(stiff, codes, robw, eta, alpha=al or None, basis=getattr(self, '_basis', None))
         return 0.0
 
     def mpsa_download(self):

@@ -113,9 +113,10 @@ def test_bc_encoding_and_error_behaviour():
     assert vcodes.shape == (3, g.num_faces) and (vcodes[:, bf[0]] == 1).all() and robw.shape == (3, 3, g.num_faces)
     with pytest.raises(AttributeError):  # mpsa.py:823: "MPSA must be given a vectorial boundary condition"
         vector_bc_codes(bc, 3, g.num_faces)
+    from porepy_b200.fv import vector_bc_basis
+    assert vector_bc_basis(vb, 3) is None            # identity everywhere
     vb.basis[0, 1, bf[0]] = 0.5
-    with pytest.raises(NotImplementedError):
-        vector_bc_codes(vb, 3, g.num_faces)
+    assert vector_bc_basis(vb, 3).shape == (3, 3, g.num_faces)
 
 
 def test_determine_eta_follows_the_reference_rule():

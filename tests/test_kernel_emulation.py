@@ -62,3 +62,16 @@ def test_patterns_are_structural_supersets():
     ref = c.mats["flux"].copy()
     ref.data = (abs(ref.data) > 1e-14).astype(float)
     assert (ref - ref.multiply(pat)).nnz == 0
+
+
+@pytest.mark.parametrize("name", case_names("rotbasis_"))
+def test_mpsa_node_routine_with_rotated_boundary_bases(name):
+    """Vectorial boundary conditions given in a rotated frame, a different rotation on every face
+    (bc.basis; _fvutils.py:765-945), Dirichlet / Neumann / Robin mixed per rotated component, with
+    and without Biot coupling: golden outputs of the reference."""
+    c = load_case(name)
+    nd = c.g.dim
+    out = EmuPlan(c.g).mpsa(c.raw["C"], vector_codes(c.bc, nd, c.g.num_faces), c.bc.robin_weight[:nd, :nd],
+                            c.eta, alpha=c.alpha or None, basis=c.raw["bc_basis"])
+    err, key = max_rel_err(c.mats, out)
+    assert err < TOL, (key, err)

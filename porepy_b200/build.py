@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libporeb200.so")
-SOURCES = ["api.cu", "spmv.cu"]
+SOURCES = ["api.cu", "spmv.cu", "mpfa_launch.cu", "mpsa2d.cu", "mpsa3d.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-Xcompiler", "-fopenmp"]
 
@@ -29,21 +29,33 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), lib: str = LIB) -> str:
+    """``extra_flags`` / ``lib``: developer knobs for A/B variants (e.g. ``-DPB_EXP_ONEBAR`` into
+    ``libporeb200_onebar.so``, selected at run time with ``POREB200_LIB``)."""
+    if not force and not needs_build() and lib == LIB:
         return LIB
-    objs = []
+    # one nvcc process per translation unit, in parallel (the kernel instantiations dominate)
+    jobs = []
+    objdir = os.path.join(HERE, "_obj", os.path.basename(lib))
+    os.makedirs(objdir, exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
-        subprocess.check_call(cmd)
+        jobs.append((obj, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for obj, cmd, proc in jobs:
+        out, _ = proc.communicate()
+        if verbose or proc.returncode:
+            sys.stderr.write(out)
+        if proc.returncode:
+            raise subprocess.CalledProcessError(proc.returncode, cmd)
         objs.append(obj)
-    subprocess.check_call([_nvcc(), "-shared", "-o", LIB, *objs, "-gencode",
+    subprocess.check_call([_nvcc(), "-shared", "-o", lib, *objs, "-gencode",
                            "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fopenmp", "-lgomp"])
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -15,13 +15,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/poreb200.h"
-#include "mpsa_node.cuh"
-#include "face_kernels.cuh"
-#include "node_kernels.cuh"
-#include "plan_host.hpp"
-
-using namespace pb;
+#include "plan.hpp"
 
 // ------------------------------------------------------------------------------------
 // error state
@@ -36,12 +30,6 @@ static int fail(int code, const std::string &msg) {
 }
 int pb_fail_(int code, const std::string &msg) { return fail(code, msg); }  // for spmv.cu
 void pb_count_launch_() { g_launches++; }
-#define CUDA_TRY(x)                                                                        \
-    do {                                                                                   \
-        cudaError_t e_ = (x);                                                              \
-        if (e_ != cudaSuccess)                                                             \
-            return fail(PB_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_));        \
-    } while (0)
 
 extern "C" const char *pb_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t pb_last_error_node(void) { return g_err_node; }
@@ -64,157 +52,6 @@ extern "C" int pb_host_alloc(uint64_t bytes, void **out) {
 extern "C" void pb_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
-
-// ------------------------------------------------------------------------------------
-// device buffers
-// ------------------------------------------------------------------------------------
-struct DevBuf {
-    void *p = nullptr;
-    size_t bytes = 0;
-    DevBuf() = default;
-    DevBuf(const DevBuf &) = delete;
-    DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
-    ~DevBuf() { release(); }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-    }
-    cudaError_t ensure(size_t n) {
-        if (n <= bytes && p) return cudaSuccess;
-        release();
-        if (n == 0) n = 8;
-        cudaError_t e = cudaMalloc(&p, n);
-        if (e == cudaSuccess) bytes = n;
-        return e;
-    }
-    template <class T>
-    cudaError_t upload(const T *h, size_t count, cudaStream_t st) {
-        cudaError_t e = ensure(count * sizeof(T));
-        if (e != cudaSuccess) return e;
-        if (count == 0) return cudaSuccess;
-        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st);
-    }
-    template <class T>
-    cudaError_t upload(const std::vector<T> &v, cudaStream_t st) { return upload(v.data(), v.size(), st); }
-    template <class T>
-    T *as() const { return (T *)p; }
-};
-
-// Solver configurations (node_kernels.cuh).  A node goes to the first one that fits.
-using Cfg0 = TileGJ<1, 2, 6, 4>;   // team 32  : MPFA hexahedral nodes (12 x 45), DMMA, one warp per node
-using Cfg1 = TileGJ<2, 3, 8, 6>;   // team 64  : MPSA hexahedral nodes (36 x 61), DMMA
-using Cfg2 = TileGJ<2, 3, 12, 4>;  // team 64  : Biot hexahedral nodes, DMMA
-using Cfg3 = TileGJ<5, 1, 18, 3>;  // team 160 : MPFA tetrahedral nodes (36 x 133), DMMA
-using Cfg4 = TileGJ<7, 2, 24, 1>;  // team 224 : MPSA tetrahedral nodes (108 x 181), FP64 tensor cores (DMMA)
-using Cfg5 = TileGJ<14, 1, 32, 1>; // team 448 : Biot tetrahedral nodes (108 x 205+), DMMA
-using Cfg6 = SmemGJ;               // team 256 : anything else (in-memory Gauss-Jordan)
-using Cfg7 = RegGJ<8, 14, 6, 1>;   // team 256 : scalar register-tiled alternative for cfg 4 (POREB200_CFG4=reg)
-struct SolverCfg { int team, max_n, max_w; };
-static const SolverCfg kCfg[] = {
-    {Cfg0::team, Cfg0::max_n, Cfg0::max_w}, {Cfg1::team, Cfg1::max_n, Cfg1::max_w},
-    {Cfg2::team, Cfg2::max_n, Cfg2::max_w}, {Cfg3::team, Cfg3::max_n, Cfg3::max_w},
-    {Cfg4::team, Cfg4::max_n, Cfg4::max_w}, {Cfg5::team, Cfg5::max_n, Cfg5::max_w},
-    {Cfg6::team, 1 << 30, 1 << 30},         {Cfg7::team, Cfg7::max_n, Cfg7::max_w},
-};
-static const int kNumCfg = 8;      // cfg 6 is the catch-all; 7 only by request
-static const int kCatchAll = 6;
-
-struct NodeClass {
-    int cfg = 0;
-    int team = 32;
-    int n = 0;
-    bool a_global = false;     // A lives in a global-memory workspace (does not fit shared memory)
-    int64_t a_doubles = 0;     // per team
-    int64_t rest_doubles = 0;  // per team
-    int64_t scr_doubles = 0;   // per team (solver scratch, first in the team's region)
-    DevBuf nodes;
-};
-
-struct pb_plan {
-    HostPlan H;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    // plan arrays
-    DevBuf fn_indptr, node_sc_ptr, sc_cell, node_sf_ptr, sf_face, sf_sides, sf_bloc, slot_sf, node_nb,
-        sc_ncn, posfc_ptr, posfb_ptr, poscc_ptr, poscb_ptr, pos_fc, pos_fb, pos_cc, pos_cb, fc_indptr,
-        fb_indptr, cc_indptr, cb_indptr, pat_idx[4], nbf_ptr, nbf_idx, cn_ptr, cn_idx, face_cells;
-    int64_t pat_rows[4] = {0, 0, 0, 0}, pat_cols[4] = {0, 0, 0, 0}, pat_nnz[4] = {0, 0, 0, 0};
-    // geometry
-    DevBuf nodes, fnorm, fcent, farea, ccent, cvol;
-    bool have_geo = false;
-    PlanView view{};
-    GeoView geo{};
-    DevBuf err, a_ws, repack_tmp;
-    // mpfa
-    std::vector<NodeClass> mpfa_cls;
-    DevBuf perm, bc, robw;
-    bool have_robw = false;
-    double eta = 0.0;
-    bool mpfa_ready = false;
-    DevBuf o_flux, o_bflux, o_bpc, o_bpf, o_vs, o_bpvs;
-    // mpsa
-    std::vector<NodeClass> mpsa_cls;
-    int mpsa_cls_nalpha = -1;
-    DevBuf stiff, vbc, vrobw, vbasis, alpha;
-    bool have_vrobw = false, have_vbasis = false;
-    int n_alpha = 0;
-    double veta = 0.0;
-    bool mpsa_ready = false;
-    DevBuf o_stress, o_bstress, o_bdc, o_bdf;
-    DevBuf o_dd[PB_MAX_ALPHA], o_bdd[PB_MAX_ALPHA], o_sg[PB_MAX_ALPHA], o_cons[PB_MAX_ALPHA],
-        o_bdp[PB_MAX_ALPHA];
-};
-
-// ------------------------------------------------------------------------------------
-// kernels
-// ------------------------------------------------------------------------------------
-// shared memory of one team: [solver scratch | index lists, sub-cell products ... | A]
-template <int ND, class Solver>
-__global__ void __launch_bounds__(Solver::team == 32 ? 128 : Solver::team, Solver::min_blocks)
-    mpfa_kernel(PlanView P, GeoView G, MpfaParams prm, MpfaOut o, const int32_t *__restrict__ nodes,
-                int n_nodes, int scr_doubles, int rest_doubles, int a_doubles, double *a_ws, int *err) {
-    extern __shared__ double smem[];
-    constexpr int TEAM = Solver::team;
-    GpuTeam<TEAM> t;
-    const int teams_per_block = blockDim.x / TEAM;
-    const int team_in_block = threadIdx.x / TEAM;
-    double *scratch = smem;
-    if (TEAM == 32) scratch += (size_t)team_in_block * (scr_doubles + rest_doubles + (a_ws ? 0 : a_doubles));
-    double *rest = scratch + scr_doubles;
-    double *A = a_ws ? a_ws + ((size_t)blockIdx.x * teams_per_block + team_in_block) * a_doubles
-                     : rest + rest_doubles;
-    for (int i = blockIdx.x * teams_per_block + team_in_block; i < n_nodes;
-         i += gridDim.x * teams_per_block)
-        mpfa_node<ND, Solver>(t, P, G, prm, o, (int64_t)nodes[i], A, rest, scratch, err);
-}
-
-template <int ND, class Solver>
-__global__ void __launch_bounds__(Solver::team == 32 ? 128 : Solver::team, Solver::min_blocks)
-    mpsa_kernel(PlanView P, GeoView G, MpsaParams prm, MpsaOut o, const int32_t *__restrict__ nodes,
-                int n_nodes, int scr_doubles, int rest_doubles, int a_doubles, double *a_ws, int *err) {
-    extern __shared__ double smem[];
-    constexpr int TEAM = Solver::team;
-    GpuTeam<TEAM> t;
-    const int teams_per_block = blockDim.x / TEAM;
-    const int team_in_block = threadIdx.x / TEAM;
-    double *scratch = smem;
-    if (TEAM == 32) scratch += (size_t)team_in_block * (scr_doubles + rest_doubles + (a_ws ? 0 : a_doubles));
-    double *rest = scratch + scr_doubles;
-    double *A = a_ws ? a_ws + ((size_t)blockIdx.x * teams_per_block + team_in_block) * a_doubles
-                     : rest + rest_doubles;
-    for (int i = blockIdx.x * teams_per_block + team_in_block; i < n_nodes;
-         i += gridDim.x * teams_per_block)
-    {
-        const int inext = i + gridDim.x * teams_per_block;  // prefetched into L2 during this region's output phase
-        const int64_t s_next = inext < n_nodes ? (int64_t)nodes[inext] : -1;
-        mpsa_node<ND, Solver>(t, P, G, prm, o, (int64_t)nodes[i], A, rest, scratch, err, s_next);
-    }
-}
-
-static const size_t kMaxSmem = 227 * 1024;
-static const int kSMs = 148;
 
 // ------------------------------------------------------------------------------------
 // plan
@@ -283,47 +120,6 @@ static int build_classes(pb_plan *p, std::vector<NodeClass> &out, F size_of) {
         }
         if (c.nodes.upload(lists[key], p->stream) != cudaSuccess) return fail(PB_ECUDA, "upload of node list failed");
     }
-    return PB_OK;
-}
-
-// launch one class with kernel template KERNEL<ND, Solver>
-#define PB_LAUNCH_CFG(KERNEL, ND, ...)                                              \
-    switch (c.cfg) {                                                                \
-        case 0: rc = launch_one(KERNEL<ND, Cfg0>, c, p, __VA_ARGS__); break;        \
-        case 1: rc = launch_one(KERNEL<ND, Cfg1>, c, p, __VA_ARGS__); break;        \
-        case 2: rc = launch_one(KERNEL<ND, Cfg2>, c, p, __VA_ARGS__); break;        \
-        case 3: rc = launch_one(KERNEL<ND, Cfg3>, c, p, __VA_ARGS__); break;        \
-        case 4: rc = launch_one(KERNEL<ND, Cfg4>, c, p, __VA_ARGS__); break;        \
-        case 5: rc = launch_one(KERNEL<ND, Cfg5>, c, p, __VA_ARGS__); break;        \
-        case 7: rc = launch_one(KERNEL<ND, Cfg7>, c, p, __VA_ARGS__); break;        \
-        default: rc = launch_one(KERNEL<ND, Cfg6>, c, p, __VA_ARGS__); break;       \
-    }
-
-template <class K, class Prm, class Out>
-static int launch_one(K kernel, const NodeClass &c, pb_plan *p, const Prm &prm, const Out &o) {
-    const int blk = c.team == 32 ? 128 : c.team;
-    const int tpb = blk / c.team;
-    const size_t smem = (size_t)(c.scr_doubles + c.rest_doubles + (c.a_global ? 0 : c.a_doubles)) *
-                        sizeof(double) * tpb;
-    if (smem > kMaxSmem)
-        return fail(PB_ENOTIMPL, "interaction region needs " + std::to_string(smem) +
-                                     " B of shared memory (> 227 KB)");
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, blk, smem));
-    if (per_sm < 1) per_sm = 1;
-    int64_t need = ((int64_t)c.n + tpb - 1) / tpb;
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)kSMs * per_sm));
-    double *ws = nullptr;
-    if (c.a_global) {
-        CUDA_TRY(p->a_ws.ensure((size_t)grid * tpb * c.a_doubles * sizeof(double)));
-        ws = p->a_ws.as<double>();
-    }
-    kernel<<<grid, blk, smem, p->stream>>>(p->view, p->geo, prm, o, c.nodes.as<int32_t>(), c.n,
-                                           (int)c.scr_doubles, (int)c.rest_doubles,
-                                           (int)c.a_doubles, ws, p->err.as<int>());
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
     return PB_OK;
 }
 
@@ -809,11 +605,7 @@ extern "C" int pb_mpfa_assemble(pb_plan *p, int want_flux, int want_trace, int w
     CUDA_TRY(cudaMemcpyAsync(p->err.p, &init, sizeof(int), cudaMemcpyHostToDevice, st));
     MpfaParams prm{p->perm.as<double>(), p->bc.as<uint8_t>(),
                    p->have_robw ? p->robw.as<double>() : nullptr, p->eta, 1, 9};
-    for (const NodeClass &c : p->mpfa_cls) {
-        int rc = PB_OK;
-        if (nd == 3) { PB_LAUNCH_CFG(mpfa_kernel, 3, prm, o) } else { PB_LAUNCH_CFG(mpfa_kernel, 2, prm, o) }
-        if (rc) return rc;
-    }
+    { int rc = pb_launch_mpfa_(p, prm, o); if (rc) return rc; }
     CUDA_TRY(cudaEventRecord(p->e1, st));
     CUDA_TRY(cudaEventSynchronize(p->e1));
     if (ms) CUDA_TRY(cudaEventElapsedTime(ms, p->e0, p->e1));
@@ -1198,11 +990,7 @@ extern "C" int pb_mpsa_assemble(pb_plan *p, float *ms) {
                    p->have_vrobw ? p->vrobw.as<double>() : nullptr,
                    p->have_vbasis ? p->vbasis.as<double>() : nullptr, p->veta, p->n_alpha,
                    p->n_alpha ? p->alpha.as<double>() : nullptr, 1, 81, 1, 9, 9 * H.nc};
-    for (const NodeClass &c : p->mpsa_cls) {
-        int rc = PB_OK;
-        if (nd == 3) { PB_LAUNCH_CFG(mpsa_kernel, 3, prm, o) } else { PB_LAUNCH_CFG(mpsa_kernel, 2, prm, o) }
-        if (rc) return rc;
-    }
+    { int rc = nd == 3 ? pb_launch_mpsa3_(p, prm, o) : pb_launch_mpsa2_(p, prm, o); if (rc) return rc; }
     CUDA_TRY(cudaEventRecord(p->e1, st));
     CUDA_TRY(cudaEventSynchronize(p->e1));
     if (ms) CUDA_TRY(cudaEventElapsedTime(ms, p->e0, p->e1));

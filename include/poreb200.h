@@ -51,6 +51,7 @@ extern "C" {
 #define PB_PAT_CELL_BFACE 3 /* nc x nf : boundary_displacement_divergence (x nd)              */
 
 typedef struct pb_plan pb_plan; /* opaque */
+struct pb_csr;                  /* opaque device CSR matrix, see "CSR SpMV" below */
 
 /* ---- library state ------------------------------------------------------------------ */
 const char *pb_last_error(void);
@@ -170,19 +171,30 @@ int pb_biot_download(pb_plan *p, int which_alpha, double *displacement_divergenc
 /* Replaces the scipy `M @ val` of AdArray.__rmatmul__ (numerics/ad/forward_mode.py:565-595)
  * and the residual chain of EquationSystem.assemble(evaluate_jacobian=False)
  * (numerics/ad/equation_system.py:1579-1713).  y = A x (+ beta*y).  */
-typedef struct pb_csr pb_csr; /* ---- two-point flux approximation and first-order upwinding (one thread per face) ----------------
- * Replaces Tpfa.discretize (numerics/fv/tpfa.py:40-280) and Upwind.discretize (numerics/fv/upwind.py:
- * 150-300).  bc_bits (nf): bits 0-1 = PB_BC_* effective code, bit 2 = raw is_dir, bit 3 = raw is_neu.
+typedef struct pb_csr pb_csr; /* opaque: device-resident CSR matrix */
+
+/* ---- two-point flux approximation and first-order upwinding (one thread per face) ----------------
+ * A pb_facegrid is the face-indexed device view of a grid of ANY dimension (1-D lines and 2-D planes
+ * embedded in 3-D included): the face -> cell table built from cell_faces (nf x nc CSC, +-1 data) and
+ * face_normals / face_centers (3 x nf), cell_centers (3 x nc), row-major.  No interaction-region plan.
+ * Replaces Tpfa.discretize (numerics/fv/tpfa.py:40-280), incl. the 1-D delegation of MPFA / MPSA
+ * (mpfa.py:690-712, mpsa.py:666-697), and Upwind.discretize (numerics/fv/upwind.py:150-300).
+ * bc_bits (nf): bits 0-1 = PB_BC_* effective code, bit 2 = raw is_dir, bit 3 = raw is_neu.
  * pb_tpfa: fc_indptr = row pointer of cell_faces in CSR-by-face form with ascending columns; value
  * arrays in that pattern (flux, bound_pressure_cell: nnz; vector sources: nnz*vdim, entry-major) and
  * the two diagonals (nf).  pb_upwind: upstream cell per face (-1 = face removed from the matrix) and the
  * diagonals of the Neumann / Dirichlet-inflow boundary matrices.  Host pointers; outputs may be NULL
  * for pb_tpfa. */
-int pb_tpfa(pb_plan *p, const double *permeability, const uint8_t *bc_bits, const int32_t *fc_indptr,
+typedef struct pb_facegrid pb_facegrid; /* opaque */
+int pb_facegrid_create(int64_t nc, int64_t nf, const int32_t *cf_indptr, const int32_t *cf_indices,
+                       const int8_t *cf_data, const double *face_normals, const double *face_centers,
+                       const double *cell_centers, pb_facegrid **out);
+void pb_facegrid_destroy(pb_facegrid *g);
+int pb_tpfa(pb_facegrid *g, const double *permeability, const uint8_t *bc_bits, const int32_t *fc_indptr,
             int vdim, double *flux, double *bound_pressure_cell, double *vector_source,
             double *bound_pressure_vector_source, double *bound_flux_diag,
             double *bound_pressure_face_diag);
-int pb_upwind(pb_plan *p, const double *darcy_flux, const uint8_t *bc_bits, int32_t *upstream_cell,
+int pb_upwind(pb_facegrid *g, const double *darcy_flux, const uint8_t *bc_bits, int32_t *upstream_cell,
               double *neumann_diag, double *dirichlet_diag);
 
 /* device-resident CSR matrix */

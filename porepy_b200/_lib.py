@@ -50,6 +50,9 @@ _SIGNATURES = {
     "pb_mpsa_assemble": (C.c_int, [C.c_void_p, _f32p]),
     "pb_mpsa_download": (C.c_int, [C.c_void_p] + [_f64p] * 4),
     "pb_biot_download": (C.c_int, [C.c_void_p, C.c_int] + [_f64p] * 5),
+    "pb_facegrid_create": (C.c_int, [C.c_int64, C.c_int64, _i32p, _i32p, _i8p, _f64p, _f64p, _f64p,
+                                     C.POINTER(C.c_void_p)]),
+    "pb_facegrid_destroy": (None, [C.c_void_p]),
     "pb_tpfa": (C.c_int, [C.c_void_p, _f64p, _u8p, _i32p, C.c_int] + [_f64p] * 6),
     "pb_upwind": (C.c_int, [C.c_void_p, _f64p, _u8p, _i32p, _f64p, _f64p]),
     "pb_csr_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _i32p, _i32p, _f64p,

@@ -510,9 +510,7 @@ __global__ void repack_kernel(const double *__restrict__ in, double *__restrict_
     }
 }
 
-static int upload_repacked(pb_plan *p, DevBuf &dst, const double *host, int ncomp, int64_t n) {
-    DevBuf &tmp = p->repack_tmp;
-    cudaStream_t st = p->stream;
+int pb_upload_repacked_(cudaStream_t st, DevBuf &tmp, DevBuf &dst, const double *host, int ncomp, int64_t n) {
     CUDA_TRY(tmp.upload(host, (size_t)ncomp * n, st));
     CUDA_TRY(dst.ensure((size_t)ncomp * n * sizeof(double)));
     const int64_t total = (int64_t)ncomp * n;
@@ -521,6 +519,9 @@ static int upload_repacked(pb_plan *p, DevBuf &dst, const double *host, int ncom
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return PB_OK;
+}
+static int upload_repacked(pb_plan *p, DevBuf &dst, const double *host, int ncomp, int64_t n) {
+    return pb_upload_repacked_(p->stream, p->repack_tmp, dst, host, ncomp, n);
 }
 
 extern "C" int pb_plan_set_geometry(pb_plan *p, const double *nodes, const double *face_normals,
@@ -1027,95 +1028,3 @@ extern "C" int pb_biot_download(pb_plan *p, int a, double *dd, double *bdd, doub
     return PB_OK;
 }
 
-// ------------------------------------------------------------------------------------
-// two-point flux approximation and upwinding: one thread per face (face_kernels.cuh)
-// ------------------------------------------------------------------------------------
-template <int ND>
-__global__ void tpfa_kernel(int64_t nf, GeoView G, const double *__restrict__ perm, int64_t perm_cs,
-                            int64_t perm_es, const uint8_t *__restrict__ bc,
-                            const int32_t *__restrict__ face_cells, const int32_t *__restrict__ fc_ptr,
-                            int vdim, TpfaOut o) {
-    for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x)
-        tpfa_face<ND>(f, G, perm, perm_cs, perm_es, bc, face_cells, fc_ptr, vdim, o);
-}
-
-__global__ void upwind_kernel(int64_t nf, const double *__restrict__ q, const uint8_t *__restrict__ bc,
-                              const int32_t *__restrict__ face_cells, int32_t *__restrict__ up_col,
-                              double *__restrict__ neu_diag, double *__restrict__ dir_diag) {
-    for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x)
-        upwind_face(f, q, bc, face_cells, up_col, neu_diag, dir_diag);
-}
-
-extern "C" int pb_tpfa(pb_plan *p, const double *permeability, const uint8_t *bc_bits, const int32_t *fc_indptr,
-                       int vdim, double *flux, double *bound_pressure_cell, double *vector_source,
-                       double *bound_pressure_vector_source, double *bound_flux_diag,
-                       double *bound_pressure_face_diag) {
-    if (!p || !permeability || !bc_bits || !fc_indptr) return fail(PB_EINVAL, "null pointer");
-    if (!p->have_geo) return fail(PB_EINVAL, "pb_plan_set_geometry has not been called");
-    if (vdim < 1 || vdim > 3) return fail(PB_EINVAL, "1 <= vdim <= 3");
-    const HostPlan &H = p->H;
-    cudaStream_t st = p->stream;
-    int rc = ensure_face_cells(p);
-    if (rc) return rc;
-    const size_t nnz = (size_t)fc_indptr[H.nf];
-    DevBuf perm, bc, ip, o_flux, o_bpc, o_vs, o_bpvs, o_bf, o_bpf;
-    { int rcs = upload_repacked(p, perm, permeability, 9, H.nc); if (rcs) return rcs; }
-    CUDA_TRY(bc.upload(bc_bits, (size_t)H.nf, st));
-    CUDA_TRY(ip.upload(fc_indptr, (size_t)H.nf + 1, st));
-    CUDA_TRY(o_flux.ensure(nnz * sizeof(double)));
-    CUDA_TRY(o_bpc.ensure(nnz * sizeof(double)));
-    CUDA_TRY(o_vs.ensure(nnz * vdim * sizeof(double)));
-    CUDA_TRY(o_bpvs.ensure(nnz * vdim * sizeof(double)));
-    CUDA_TRY(o_bf.ensure((size_t)H.nf * sizeof(double)));
-    CUDA_TRY(o_bpf.ensure((size_t)H.nf * sizeof(double)));
-    TpfaOut o{o_flux.as<double>(), o_bpc.as<double>(), o_vs.as<double>(), o_bpvs.as<double>(),
-              o_bf.as<double>(), o_bpf.as<double>()};
-    const int block = 256;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((H.nf + block - 1) / block, (int64_t)kSMs * 16));
-    if (H.nd == 3)
-        tpfa_kernel<3><<<grid, block, 0, st>>>(H.nf, p->geo, perm.as<double>(), 1, 9, bc.as<uint8_t>(),
-                                               p->face_cells.as<int32_t>(), ip.as<int32_t>(), vdim, o);
-    else
-        tpfa_kernel<2><<<grid, block, 0, st>>>(H.nf, p->geo, perm.as<double>(), 1, 9, bc.as<uint8_t>(),
-                                               p->face_cells.as<int32_t>(), ip.as<int32_t>(), vdim, o);
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
-    auto down = [&](double *h, DevBuf &d, size_t n) -> cudaError_t {
-        return h ? cudaMemcpyAsync(h, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, st) : cudaSuccess;
-    };
-    CUDA_TRY(down(flux, o_flux, nnz));
-    CUDA_TRY(down(bound_pressure_cell, o_bpc, nnz));
-    CUDA_TRY(down(vector_source, o_vs, nnz * vdim));
-    CUDA_TRY(down(bound_pressure_vector_source, o_bpvs, nnz * vdim));
-    CUDA_TRY(down(bound_flux_diag, o_bf, (size_t)H.nf));
-    CUDA_TRY(down(bound_pressure_face_diag, o_bpf, (size_t)H.nf));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return PB_OK;
-}
-
-extern "C" int pb_upwind(pb_plan *p, const double *darcy_flux, const uint8_t *bc_bits, int32_t *upstream_cell,
-                         double *neumann_diag, double *dirichlet_diag) {
-    if (!p || !darcy_flux || !bc_bits || !upstream_cell || !neumann_diag || !dirichlet_diag)
-        return fail(PB_EINVAL, "null pointer");
-    const HostPlan &H = p->H;
-    cudaStream_t st = p->stream;
-    int rc = ensure_face_cells(p);
-    if (rc) return rc;
-    DevBuf q, bc, up, neu, dir;
-    CUDA_TRY(q.upload(darcy_flux, (size_t)H.nf, st));
-    CUDA_TRY(bc.upload(bc_bits, (size_t)H.nf, st));
-    CUDA_TRY(up.ensure((size_t)H.nf * sizeof(int32_t)));
-    CUDA_TRY(neu.ensure((size_t)H.nf * sizeof(double)));
-    CUDA_TRY(dir.ensure((size_t)H.nf * sizeof(double)));
-    const int block = 256;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((H.nf + block - 1) / block, (int64_t)kSMs * 16));
-    upwind_kernel<<<grid, block, 0, st>>>(H.nf, q.as<double>(), bc.as<uint8_t>(), p->face_cells.as<int32_t>(),
-                                          up.as<int32_t>(), neu.as<double>(), dir.as<double>());
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(upstream_cell, up.p, (size_t)H.nf * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(neumann_diag, neu.p, (size_t)H.nf * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(dirichlet_diag, dir.p, (size_t)H.nf * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return PB_OK;
-}

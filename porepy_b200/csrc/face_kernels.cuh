@@ -24,7 +24,6 @@ struct TpfaOut {
 
 // face_cells: 2 per face, (cell << 1) | (sign < 0), -1 = none.  fc_ptr: CSR row pointer of the
 // face x cell pattern with ascending columns (scipy's cell_faces.tocsr()).
-template <int ND>
 PB_HD void tpfa_face(int64_t f, const GeoView &G, const double *perm, int64_t perm_cs, int64_t perm_es,
                      const uint8_t *bc, const int32_t *face_cells, const int32_t *fc_ptr, int vdim,
                      const TpfaOut &o) {

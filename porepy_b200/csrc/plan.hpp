@@ -183,3 +183,5 @@ static int launch_one(K kernel, const NodeClass &c, pb_plan *p, const Prm &prm, 
 int pb_launch_mpfa_(pb_plan *p, const MpfaParams &prm, const MpfaOut &o);
 int pb_launch_mpsa2_(pb_plan *p, const MpsaParams &prm, const MpsaOut &o);
 int pb_launch_mpsa3_(pb_plan *p, const MpsaParams &prm, const MpsaOut &o);
+// (ncomp, n) row-major host array -> entity-major records on the device (api.cu)
+int pb_upload_repacked_(cudaStream_t st, DevBuf &tmp, DevBuf &dst, const double *host, int ncomp, int64_t n);

@@ -111,14 +111,17 @@ def rotate_second_order(values: np.ndarray, rot: np.ndarray) -> np.ndarray:
 
 
 def lift_vector_source(ip: np.ndarray, ix: np.ndarray, data: np.ndarray, rows: np.ndarray, nc: int):
-    """(nf, 2 nc) vector-source matrix in the plane's coordinates -> (nf, 3 nc) in the ambient
-    space: every (face, cell) pair of in-plane coefficients is multiplied by the two in-plane
-    rows of the rotation (mpfa.py:423-466).  ``ip, ix`` is the FACE x CELL base pattern,
-    ``data`` holds the two coefficients of each base entry consecutively."""
-    d3 = np.asarray(data, dtype=np.float64).reshape(-1, 2) @ np.asarray(rows, dtype=np.float64)
-    dt = _index_dtype(3 * int(ix.size), 3 * nc)
-    cols = (ix.astype(dt)[:, None] * 3 + np.arange(3, dtype=dt)).ravel()
-    return sps.csr_matrix((d3.ravel(), cols, ip.astype(dt) * 3), shape=(ip.size - 1, 3 * nc))
+    """(nf, 2 nc) vector-source matrix in the plane's coordinates -> (nf, amb nc) in the ambient space
+    (amb = ``rows.shape[1]``, 2 or 3): every (face, cell) pair of in-plane coefficients is multiplied by the
+    two in-plane rows of the rotation, restricted to the first ``amb`` ambient components (mpfa.py:423-466).
+    ``ip, ix`` is the FACE x CELL base pattern, ``data`` holds the two coefficients of each base entry
+    consecutively."""
+    rows = np.asarray(rows, dtype=np.float64)
+    amb = rows.shape[1]
+    da = np.asarray(data, dtype=np.float64).reshape(-1, 2) @ rows
+    dt = _index_dtype(amb * int(ix.size), amb * nc)
+    cols = (ix.astype(dt)[:, None] * amb + np.arange(amb, dtype=dt)).ravel()
+    return sps.csr_matrix((da.ravel(), cols, ip.astype(dt) * amb), shape=(ip.size - 1, amb * nc))
 
 
 class DevicePlan:
@@ -303,33 +306,6 @@ class DevicePlan:
                                         _lib.ptr(rhs, _lib._f64p)))
         return rhs
 
-    # ---- two-point flux approximation, upwinding (one thread per face)
-    def tpfa(self, perm, bc_bits, fc_indptr, vdim: int) -> list:
-        """Value arrays of the six TPFA terms in the pattern of ``cell_faces`` (CSR by face):
-        [flux, bound_pressure_cell, vector_source, bound_pressure_vector_source] and the diagonals
-        [bound_flux, bound_pressure_face]."""
-        perm = _lib.f64(perm)
-        if perm.shape != (3, 3, self.nc):
-            raise ValueError("second_order_tensor.values must have shape (3, 3, num_cells)")
-        bits = np.ascontiguousarray(bc_bits, dtype=np.uint8)
-        ip = np.ascontiguousarray(fc_indptr, dtype=np.int32)
-        nnz = int(ip[-1])
-        out = [np.empty(nnz), np.empty(nnz), np.empty(nnz * vdim), np.empty(nnz * vdim), np.empty(self.nf),
-               np.empty(self.nf)]
-        _lib.check(self.lib.pb_tpfa(self.h, _lib.ptr(perm, _lib._f64p), _lib.ptr(bits, _lib._u8p),
-                                    _lib.ptr(ip, _lib._i32p), int(vdim), *[_lib.ptr(a, _lib._f64p) for a in out]))
-        return out
-
-    def upwind(self, darcy_flux, bc_bits):
-        """Upstream cell per face (-1: face not in the matrix) and the two boundary diagonals."""
-        q = _lib.f64(darcy_flux)
-        bits = np.ascontiguousarray(bc_bits, dtype=np.uint8)
-        up = np.empty(self.nf, np.int32)
-        neu, dr = np.empty(self.nf), np.empty(self.nf)
-        _lib.check(self.lib.pb_upwind(self.h, _lib.ptr(q, _lib._f64p), _lib.ptr(bits, _lib._u8p),
-                                      _lib.ptr(up, _lib._i32p), _lib.ptr(neu, _lib._f64p), _lib.ptr(dr, _lib._f64p)))
-        return up, neu, dr
-
     # ---- MPSA / Biot
     def mpsa_upload(self, stiff, codes, robw, eta, alphas=()) -> None:
         stiff = _lib.f64(stiff)
@@ -387,6 +363,70 @@ class DevicePlan:
             "mpsa_consistency": self.matrix(2, 1, 1, bufs[3]),
             "bound_displacement_pressure": self.matrix(0, nd, 1, bufs[4]),
         }
+
+
+class FaceGrid:
+    """Face-indexed device view of a grid of any dimension (``pb_facegrid``): the face -> cell table and
+    the face normals / centres and cell centres -- all the per-face schemes (TPFA, upwinding) read.  No
+    interaction-region plan is built, so 1-D grids (the reference's TPFA delegation, mpfa.py:690-712,
+    mpsa.py:666-697) and 2-D grids anywhere in space work as they are."""
+
+    def __init__(self, sd):
+        lib = _lib.load()
+        _lib.require_gpu()
+        self.lib = lib
+        if getattr(sd, "periodic_face_map", None) is not None:
+            raise NotImplementedError("periodic faces are not supported by porepy_b200")
+        cf = sps.csc_matrix(sd.cell_faces)
+        self.nc, self.nf = sd.num_cells, sd.num_faces
+        cfp, cfi = cf.indptr.astype(np.int32), cf.indices.astype(np.int32)
+        cfd = np.asarray(cf.data).astype(np.int8)
+        geo = [_lib.f64(a) for a in (sd.face_normals, sd.face_centers, sd.cell_centers)]
+        h = C.c_void_p()
+        _lib.check(lib.pb_facegrid_create(self.nc, self.nf, _lib.ptr(cfp, _lib._i32p), _lib.ptr(cfi, _lib._i32p),
+                                          _lib.ptr(cfd, _lib._i8p), *[_lib.ptr(a, _lib._f64p) for a in geo],
+                                          C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def for_grid(cls, sd) -> "FaceGrid":
+        return cls(sd)
+
+    def __del__(self):
+        h = getattr(self, "h", None)
+        if h is not None and h.value:
+            try:
+                self.lib.pb_facegrid_destroy(h)
+            except Exception:
+                pass
+            self.h = None
+
+    def tpfa(self, perm, bc_bits, fc_indptr, vdim: int) -> list:
+        """Value arrays of the six TPFA terms in the pattern of ``cell_faces`` (CSR by face):
+        [flux, bound_pressure_cell, vector_source, bound_pressure_vector_source] and the diagonals
+        [bound_flux, bound_pressure_face]."""
+        perm = _lib.f64(perm)
+        if perm.shape != (3, 3, self.nc):
+            raise ValueError("second_order_tensor.values must have shape (3, 3, num_cells)")
+        bits = np.ascontiguousarray(bc_bits, dtype=np.uint8)
+        ip = np.ascontiguousarray(fc_indptr, dtype=np.int32)
+        nnz = int(ip[-1])
+        out = [np.empty(nnz), np.empty(nnz), np.empty(nnz * vdim), np.empty(nnz * vdim), np.empty(self.nf),
+               np.empty(self.nf)]
+        _lib.check(self.lib.pb_tpfa(self.h, _lib.ptr(perm, _lib._f64p), _lib.ptr(bits, _lib._u8p),
+                                    _lib.ptr(ip, _lib._i32p), int(vdim), *[_lib.ptr(a, _lib._f64p) for a in out]))
+        return out
+
+    def upwind(self, darcy_flux, bc_bits):
+        """Upstream cell per face (-1: face not in the matrix) and the two boundary diagonals."""
+        q = _lib.f64(darcy_flux)
+        bits = np.ascontiguousarray(bc_bits, dtype=np.uint8)
+        up = np.empty(self.nf, np.int32)
+        neu, dr = np.empty(self.nf), np.empty(self.nf)
+        _lib.check(self.lib.pb_upwind(self.h, _lib.ptr(q, _lib._f64p), _lib.ptr(bits, _lib._u8p),
+                                      _lib.ptr(up, _lib._i32p), _lib.ptr(neu, _lib._f64p), _lib.ptr(dr, _lib._f64p)))
+        return up, neu, dr
+
 
 
 # ------------------------------------------------------------------------------------------
@@ -605,6 +645,13 @@ class Mpfa(_Base):
         ``mpfa_eta`` and ``ambient_dimension``; returns the six matrices of mpfa.py:496-508."""
         k = params["second_order_tensor"]
         bc = params["bc"]
+        if sd.dim <= 1:
+            # mpfa.py:687-722: the scheme reduces to TPFA on a line; a point grid has no faces
+            sub = {"bc": bc, "second_order_tensor": k, "ambient_dimension": params.get("ambient_dimension", sd.dim)}
+            tp = Tpfa(self.keyword)
+            out = tp._discretize_grid(sd, sub)
+            self.last_timing = tp.last_timing
+            return out
         eta = params.get("mpfa_eta", None)
         if eta is None:
             eta = determine_eta(sd)
@@ -623,16 +670,16 @@ class Mpfa(_Base):
         t1 = time.perf_counter()
         kvals = k.values
         if plan.rotation is not None:  # fracture plane: mpfa.py:733-754
-            if amb != 3:
-                raise NotImplementedError("a 2-D grid outside the xy-plane needs ambient_dimension=3")
             kvals = rotate_second_order(kvals, plan.rotation)
         plan.mpfa_upload(kvals, codes, robw, float(np.asarray(eta).ravel()[0]))
         t2 = time.perf_counter()
         ms = plan.mpfa_assemble()
         t3 = time.perf_counter()
         out = plan.mpfa_download()
-        if sd.dim == 2 and amb == 3:  # vector source back to the ambient space, mpfa.py:423-466
-            rows = (np.eye(3) if plan.rotation is None else plan.rotation)[:2]
+        if sd.dim == 2 and (amb == 3 or plan.rotation is not None):
+            # vector source back to the ambient space, mpfa.py:423-466 (with ambient_dimension = 2 on a tilted
+            # plane the reference keeps the first two ambient components, mpfa.py:459-462)
+            rows = (np.eye(3) if plan.rotation is None else plan.rotation)[:2, :amb]
             ip, ix = plan.base_pattern(0)
             for key in (self.vector_source_matrix_key, self.bound_pressure_vector_source_matrix_key):
                 out[key] = lift_vector_source(ip, ix, out[key].data, rows, sd.num_cells)
@@ -688,6 +735,19 @@ class Mpsa(_Base):
         ``fourth_order_tensor``, ``bc`` (vectorial), optional ``mpsa_eta``."""
         constit = params["fourth_order_tensor"]
         bc = params["bc"]
+        if getattr(bc, "bc_type", "vectorial") != "vectorial":
+            raise AttributeError("MPSA must be given a vectorial boundary condition")  # mpsa.py:658
+        if sd.dim == 1:
+            # mpsa.py:666-697: TPFA with the longitudinal modulus 2 mu + lambda, Neumann everywhere
+            if np.any(bc.is_dir):
+                raise ValueError("have not considered Dirichlet boundary values here")
+            from .params import BoundaryCondition, SecondOrderTensor
+            tp = Tpfa("tpfa_elasticity")
+            sub = {"bc": BoundaryCondition(sd), "second_order_tensor": SecondOrderTensor(2 * constit.mu + constit.lmbda)}
+            t = tp._discretize_grid(sd, sub)
+            return {"stress": t["flux"], "bound_stress": t["bound_flux"],
+                    "bound_displacement_cell": t["bound_pressure_cell"],
+                    "bound_displacement_face": t["bound_pressure_face"]}
         eta = params.get("mpsa_eta", None)
         if eta is None:
             eta = determine_eta(sd)
@@ -771,25 +831,45 @@ class Biot(Mpsa):
         raise NotImplementedError("This class cannot be used for assembly.\nUse the ad version instead")
 
 
+def _empty_flux_terms(discr, sd, vdim: int) -> dict:
+    """The 0-D shortcut of tpfa.py:87-104 (a point grid has no faces)."""
+    nc = sd.num_cells
+    return {
+        discr.flux_matrix_key: sps.csr_matrix((0, nc)),
+        discr.bound_flux_matrix_key: sps.csr_matrix((0, 0)),
+        discr.bound_pressure_cell_matrix_key: sps.csr_matrix((0, nc)),
+        discr.bound_pressure_face_matrix_key: sps.csr_matrix((0, 0)),
+        discr.vector_source_matrix_key: sps.csr_matrix((0, nc * max(vdim, 1))),
+        discr.bound_pressure_vector_source_matrix_key: sps.csr_matrix((0, nc * max(vdim, 1))),
+    }
+
+
 class Tpfa(Mpfa):
     """Two-point flux approximation (numerics/fv/tpfa.py:18; same keys and ``assemble_matrix_rhs`` as
-    MPFA through FVElliptic).  One thread per face; 1-D, 2-D and 3-D grids."""
+    MPFA through FVElliptic).  One thread per face on a ``FaceGrid``; grids of any dimension, anywhere in
+    space (the reference works on the 3-D coordinates, tpfa.py:160-175)."""
+
+    def discretize(self, sd, data: dict) -> None:
+        """tpfa.py:40: always the whole grid -- the reference's TPFA has no partial mode, so
+        ``specified_cells/faces/nodes`` (possibly left behind by an MPFA update on the same keyword,
+        _fvutils.py:346-353) and ``update_discretization`` are ignored."""
+        params = data[PARAMETERS][self.keyword]
+        mats = data.setdefault(DISCRETIZATION_MATRICES, {}).setdefault(self.keyword, {})
+        mats.update(self._discretize_grid(sd, params))
 
     def _discretize_grid(self, sd, params: dict) -> dict:
+        vdim = int(params.get("ambient_dimension", sd.dim))
+        if sd.dim == 0:
+            return _empty_flux_terms(self, sd, vdim)
         k = params["second_order_tensor"]
         bc = params["bc"]
-        vdim = int(params.get("ambient_dimension", sd.dim))
         self._check_unsupported(params, sd)
         t0 = time.perf_counter()
-        plan = DevicePlan.for_grid(sd)
-        if plan.rotation is not None:
-            # the reference keeps the 3-D coordinates here (tpfa.py:160-175); the plan holds the grid rotated
-            # into its plane, which would put the vector-source terms into the local frame
-            raise NotImplementedError("TPFA on a 2-D grid outside the xy-plane is not supported")
+        fg = FaceGrid.for_grid(sd)
         fc = sps.csr_matrix(sd.cell_faces)
         fc.sort_indices()
         ip, ix = fc.indptr, fc.indices
-        vals = plan.tpfa(k.values, face_bc_bits(bc, sd.num_faces), ip, vdim)
+        vals = fg.tpfa(k.values, face_bc_bits(bc, sd.num_faces), ip, vdim)
         nf, nc = sd.num_faces, sd.num_cells
         boundary = np.diff(ip) == 1
         cols_v = (ix[:, None].astype(np.int64) * vdim + np.arange(vdim)).ravel()
@@ -836,12 +916,25 @@ class Upwind(_Base):
         if bc is None:  # upwind.py:244-247: Dirichlet on the boundary
             from .params import BoundaryCondition
             bc = BoundaryCondition(sd, sd.get_boundary_faces(), "dir")
-        plan = DevicePlan.for_grid(sd)
-        up, neu, dr = plan.upwind(params[self._flux_array_key], face_bc_bits(bc, sd.num_faces))
         nf, nc = sd.num_faces, sd.num_cells
+        ncomp = int(params.get("num_components", 1))
+        if nf == 0:  # point grids: upwind.py:226-236
+            mats[self.upwind_matrix_key] = sps.csr_matrix((0, nc * ncomp))
+            mats[self.bound_transport_neu_matrix_key] = sps.csr_matrix((0, 0))
+            mats[self.bound_transport_dir_matrix_key] = sps.csr_matrix((0, 0))
+            return
+        fg = FaceGrid.for_grid(sd)
+        bits = face_bc_bits(bc, nf)
+        up, neu, dr = fg.upwind(params[self._flux_array_key], bits)
+        # A boundary face that is neither Dirichlet nor Neumann (Robin / unflagged) with inflow has no upstream
+        # cell: the reference ends up with column index -1 and scipy raises (upwind.py:272-281).  Fail as loudly.
+        single = np.diff(sps.csr_matrix(sd.cell_faces).indptr) == 1
+        orphan = single & (up < 0) & ((bits & 12) == 0)
+        if orphan.any():
+            raise ValueError(f"upwind: boundary face {int(np.flatnonzero(orphan)[0])} has inflow but neither a "
+                             "Dirichlet nor a Neumann condition")
         rows = np.flatnonzero(up >= 0)
         m = sps.csr_matrix((np.ones(rows.size), (rows, up[rows])), shape=(nf, nc))
-        ncomp = int(params.get("num_components", 1))
         eye = sps.eye(ncomp)
         mats[self.upwind_matrix_key] = sps.kron(m, eye).tocsr()
         mats[self.bound_transport_neu_matrix_key] = sps.kron(sps.diags(neu), eye).tocsr()

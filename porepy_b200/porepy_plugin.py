@@ -23,38 +23,33 @@ Use in a model (the mixin override of constitutive_laws.py:1078,3003,3506)::
 
     b200.install()        # or: rebind pp.Mpfa / pp.Mpsa / pp.Biot, stock models unchanged
 
-Scope: the GPU path covers the top-dimensional subdomains (3-D grids, 2-D grids lying in the
-xy-plane) and, for the flux discretization, 2-D fracture planes embedded in 3-D.  Intersection
-grids (1-D lines, 0-D points) are handed to the reference's own implementation (its TPFA
-fallback, mpfa.py:690-712), exactly as ``pp.Mpfa`` would.
+Scope: every subdomain of a mixed-dimensional grid runs through porepy_b200 -- 3-D and 2-D grids through
+the interaction-region kernels (fracture planes embedded in 3-D are rotated into their plane on the host),
+1-D intersection lines through the per-face TPFA kernel (the reference's own delegation, mpfa.py:690-712,
+mpsa.py:666-697), 0-D points get the empty matrices of tpfa.py:87-104.
+
+There is NO silent CPU fallback: what the GPU classes refuse (``NotImplementedError``: periodic faces,
+sub-face boundary conditions, ...) propagates to the caller.  ``plugin(pp, allow_reference_fallback=True)``
+opts into handing such calls to the reference's own implementation; every such call is logged and counted
+in ``b200.fallback_calls`` (GPU calls in ``b200.gpu_calls``) so that tests can assert the count is zero.
 """
 from __future__ import annotations
 
 import logging
 from types import SimpleNamespace
 
-import numpy as np
-
 from . import fv
 
 logger = logging.getLogger(__name__)
 
 
-def _gpu_scope(sd, flow: bool = False) -> bool:
-    """3-D grids; 2-D grids in a plane z = const; for the flux discretization also 2-D fracture
-    planes embedded in 3-D (rotated into their plane on the host, fv.plane_frame)."""
-    if sd.dim == 3:
-        return True
-    if sd.dim == 2:
-        if flow:
-            return True
-        z = np.asarray(sd.nodes)[2]
-        return bool(np.ptp(z) <= 1e-12 * max(1.0, float(np.abs(sd.nodes).max())))
-    return False
-
-
-def plugin(pp) -> SimpleNamespace:
+def plugin(pp, allow_reference_fallback: bool = False) -> SimpleNamespace:
     """Build the plugin classes against the given ``porepy`` module."""
+    fallback_calls: dict = {}
+    gpu_calls: dict = {}
+
+    def _count(d, name):
+        d[name] = d.get(name, 0) + 1
     # the reference classes as they are NOW: the plugin keeps working if the caller afterwards rebinds
     # pp.Mpfa etc. to the plugin classes (e.g. to run the reference's own tests on them)
     RefMpfa, RefMpsa, RefBiot = pp.Mpfa, pp.Mpsa, pp.Biot
@@ -62,10 +57,9 @@ def plugin(pp) -> SimpleNamespace:
     RefMpfaAd, RefMpsaAd, RefBiotAd = pp.ad.MpfaAd, pp.ad.MpsaAd, pp.ad.BiotAd
 
     def _core(name, gpu_cls, ref_cls, flow):
-        """Subclass of the reference core whose ``discretize`` runs on the GPU.  Anything the GPU
-        classes refuse (``NotImplementedError``: periodic faces, sub-face boundary conditions, rotated
-        boundary bases, ...) and every subdomain outside the GPU scope goes to the reference's own
-        implementation -- the plugin IS a subclass of it -- with a log line."""
+        """Subclass of the reference core whose ``discretize`` runs on the GPU.  What the GPU classes
+        refuse (``NotImplementedError``) is re-raised unless the plugin was built with
+        ``allow_reference_fallback=True``."""
 
         if name == "Biot":  # biot.py:77 has a default keyword, the others do not
             def __init__(self, keyword: str = "mechanics") -> None:
@@ -77,14 +71,15 @@ def plugin(pp) -> SimpleNamespace:
                 gpu_cls.__init__(self, keyword)
 
         def discretize(self, sd, data) -> None:
-            if _gpu_scope(sd, flow=flow) and not hasattr(sd, "periodic_face_map"):
-                try:
-                    gpu_cls.discretize(self, sd, data)
-                    return
-                except NotImplementedError as e:
-                    logger.info("B200 %s: %s -> reference path", name, e)
-            else:
-                logger.info("B200 %s: %s-d subdomain outside the GPU scope -> reference path", name, sd.dim)
+            try:
+                gpu_cls.discretize(self, sd, data)
+                _count(gpu_calls, name)
+                return
+            except NotImplementedError as e:
+                if not allow_reference_fallback:
+                    raise
+                logger.warning("B200 %s: %s -> reference path (allow_reference_fallback)", name, e)
+                _count(fallback_calls, f"{name}: {e}")
             ref_cls.discretize(self, sd, data)
 
         def update_discretization(self, sd, data) -> None:
@@ -108,20 +103,22 @@ def plugin(pp) -> SimpleNamespace:
     Biot = _core("Biot", fv.Biot, RefBiot, False)
 
     class Upwind(fv.Upwind, RefUpwind):
-        """pp.Upwind with the per-face GPU kernel; 0-D / 1-D grids and anything refused go to the
-        reference."""
+        """pp.Upwind with the per-face GPU kernel (grids of any dimension)."""
 
         def __init__(self, keyword: str = "transport") -> None:
             RefUpwind.__init__(self, keyword)
             fv.Upwind.__init__(self, keyword)
 
         def discretize(self, sd, data) -> None:
-            if _gpu_scope(sd) and not hasattr(sd, "periodic_face_map"):
-                try:
-                    fv.Upwind.discretize(self, sd, data)
-                    return
-                except NotImplementedError as e:
-                    logger.info("B200 Upwind: %s -> reference path", e)
+            try:
+                fv.Upwind.discretize(self, sd, data)
+                _count(gpu_calls, "Upwind")
+                return
+            except NotImplementedError as e:
+                if not allow_reference_fallback:
+                    raise
+                logger.warning("B200 Upwind: %s -> reference path (allow_reference_fallback)", e)
+                _count(fallback_calls, f"Upwind: {e}")
             RefUpwind.discretize(self, sd, data)
 
         def assemble_matrix_rhs(self, sd, data):
@@ -194,4 +191,5 @@ def plugin(pp) -> SimpleNamespace:
         pp.Tpfa, pp.Upwind = RefTpfa, RefUpwind
 
     return SimpleNamespace(Mpfa=Mpfa, Mpsa=Mpsa, Biot=Biot, Tpfa=Tpfa, Upwind=Upwind, MpfaAd=MpfaAd, MpsaAd=MpsaAd, BiotAd=BiotAd,
-                           ModelMixin=ModelMixin, install=install, uninstall=uninstall)
+                           ModelMixin=ModelMixin, install=install, uninstall=uninstall,
+                           fallback_calls=fallback_calls, gpu_calls=gpu_calls)

@@ -104,9 +104,41 @@ int emu_tpfa(void *h, const double *fnorm, const double *fcent, const double *cc
     GeoView G{nullptr, fnorm, fcent, nullptr, ccent, nullptr, H.nn, 1, H.nf, 1, H.nc, 1};
     TpfaOut o{flux, bpc, vs, bpvs, bflux_diag, bpf_diag};
     for (int64_t f = 0; f < H.nf; ++f) {
-        if (H.nd == 3) tpfa_face<3>(f, G, perm, H.nc, 1, bc, H.face_cells.data(), fc_ptr, vdim, o);
-        else tpfa_face<2>(f, G, perm, H.nc, 1, bc, H.face_cells.data(), fc_ptr, vdim, o);
+        tpfa_face(f, G, perm, H.nc, 1, bc, H.face_cells.data(), fc_ptr, vdim, o);
     }
+    return 0;
+}
+
+// ---- per-face schemes on a bare face grid (any dimension): the face -> cell table is built here the way
+// face.cu builds it on the device (slot 0 = smaller cell index)
+static std::vector<int32_t> face_cells_of(int64_t nc, int64_t nf, const int32_t *cf_ip, const int32_t *cf_ix,
+                                          const int8_t *cf_da) {
+    std::vector<int32_t> fc(2 * nf, -1);
+    for (int64_t c = 0; c < nc; ++c)
+        for (int q = cf_ip[c]; q < cf_ip[c + 1]; ++q) {
+            const int32_t f = cf_ix[q];
+            const int32_t enc = (int32_t)((c << 1) | (cf_da[q] < 0 ? 1 : 0));
+            if (fc[2 * f] < 0) fc[2 * f] = enc; else fc[2 * f + 1] = enc;
+        }
+    return fc;
+}
+
+int emu_facegrid_tpfa(int64_t nc, int64_t nf, const int32_t *cf_ip, const int32_t *cf_ix, const int8_t *cf_da,
+                      const double *fnorm, const double *fcent, const double *ccent, const double *perm,
+                      const uint8_t *bc, const int32_t *fc_ptr, int vdim, double *flux, double *bpc, double *vs,
+                      double *bpvs, double *bflux_diag, double *bpf_diag) {
+    std::vector<int32_t> fc = face_cells_of(nc, nf, cf_ip, cf_ix, cf_da);
+    GeoView G{nullptr, fnorm, fcent, nullptr, ccent, nullptr, 0, 1, nf, 1, nc, 1};
+    TpfaOut o{flux, bpc, vs, bpvs, bflux_diag, bpf_diag};
+    for (int64_t f = 0; f < nf; ++f) tpfa_face(f, G, perm, nc, 1, bc, fc.data(), fc_ptr, vdim, o);
+    return 0;
+}
+
+int emu_facegrid_upwind(int64_t nc, int64_t nf, const int32_t *cf_ip, const int32_t *cf_ix, const int8_t *cf_da,
+                        const double *darcy_flux, const uint8_t *bc, int32_t *up_col, double *neu_diag,
+                        double *dir_diag) {
+    std::vector<int32_t> fc = face_cells_of(nc, nf, cf_ip, cf_ix, cf_da);
+    for (int64_t f = 0; f < nf; ++f) upwind_face(f, darcy_flux, bc, fc.data(), up_col, neu_diag, dir_diag);
     return 0;
 }
 

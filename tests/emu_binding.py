@@ -218,30 +218,6 @@ class EmuBackedPlan:
     def mpfa_download(self, *a):
         return self._out
 
-    def tpfa(self, perm, bc_bits, fc_indptr, vdim):
-        L = lib()
-        ip = np.ascontiguousarray(fc_indptr, np.int32)
-        nnz = int(ip[-1])
-        nf = self.emu.nf
-        out = [np.zeros(nnz), np.zeros(nnz), np.zeros(nnz * vdim), np.zeros(nnz * vdim), np.zeros(nf), np.zeros(nf)]
-        perm = np.ascontiguousarray(perm, np.float64)
-        bits = np.ascontiguousarray(bc_bits, np.uint8)
-        g = self.emu.geo
-        L.emu_tpfa(self.emu.h, _p(g[1], C.c_double), _p(g[2], C.c_double), _p(g[4], C.c_double),
-                   _p(perm, C.c_double), _p(bits, C.c_uint8), _p(ip, C.c_int32), C.c_int(vdim),
-                   *[_p(a, C.c_double) for a in out])
-        return out
-
-    def upwind(self, darcy_flux, bc_bits):
-        L = lib()
-        nf = self.emu.nf
-        q = np.ascontiguousarray(darcy_flux, np.float64)
-        bits = np.ascontiguousarray(bc_bits, np.uint8)
-        up, neu, dr = np.zeros(nf, np.int32), np.zeros(nf), np.zeros(nf)
-        L.emu_upwind(self.emu.h, _p(q, C.c_double), _p(bits, C.c_uint8), _p(up, C.c_int32),
-                     _p(neu, C.c_double), _p(dr, C.c_double))
-        return up, neu, dr
-
     def mpsa_upload(self, stiff, codes, robw, eta, alphas=()):
         self._mpsa = (stiff, codes, robw, eta, {q: a for q, a in enumerate(alphas)})
         self._basis = None
@@ -264,6 +240,46 @@ class EmuBackedPlan:
         return {k: self._mout[k][q] for k in ("displacement_divergence", "boundary_displacement_divergence",
                                               "scalar_gradient", "mpsa_consistency",
                                               "bound_displacement_pressure")}
+
+
+class EmuBackedFaceGrid:
+    """Stand-in for ``porepy_b200.fv.FaceGrid`` backed by the host build of the per-face routines."""
+
+    def __init__(self, sd):
+        cf = sps.csc_matrix(sd.cell_faces)
+        self.nc, self.nf = sd.num_cells, sd.num_faces
+        self.cf = [cf.indptr.astype(np.int32), cf.indices.astype(np.int32), np.asarray(cf.data).astype(np.int8)]
+        self.geo = [np.ascontiguousarray(a, np.float64) for a in (sd.face_normals, sd.face_centers, sd.cell_centers)]
+
+    @classmethod
+    def for_grid(cls, sd):
+        return cls(sd)
+
+    def _cf(self):
+        return (C.c_int64(self.nc), C.c_int64(self.nf), _p(self.cf[0], C.c_int32), _p(self.cf[1], C.c_int32),
+                _p(self.cf[2], C.c_int8))
+
+    def tpfa(self, perm, bc_bits, fc_indptr, vdim):
+        L = lib()
+        ip = np.ascontiguousarray(fc_indptr, np.int32)
+        nnz = int(ip[-1])
+        nf = self.nf
+        out = [np.zeros(nnz), np.zeros(nnz), np.zeros(nnz * vdim), np.zeros(nnz * vdim), np.zeros(nf), np.zeros(nf)]
+        perm = np.ascontiguousarray(perm, np.float64)
+        bits = np.ascontiguousarray(bc_bits, np.uint8)
+        L.emu_facegrid_tpfa(*self._cf(), *[_p(a, C.c_double) for a in self.geo], _p(perm, C.c_double),
+                            _p(bits, C.c_uint8), _p(ip, C.c_int32), C.c_int(vdim), *[_p(a, C.c_double) for a in out])
+        return out
+
+    def upwind(self, darcy_flux, bc_bits):
+        L = lib()
+        nf = self.nf
+        q = np.ascontiguousarray(darcy_flux, np.float64)
+        bits = np.ascontiguousarray(bc_bits, np.uint8)
+        up, neu, dr = np.zeros(nf, np.int32), np.zeros(nf), np.zeros(nf)
+        L.emu_facegrid_upwind(*self._cf(), _p(q, C.c_double), _p(bits, C.c_uint8), _p(up, C.c_int32),
+                              _p(neu, C.c_double), _p(dr, C.c_double))
+        return up, neu, dr
 
 
 def face_bc_bits(bc, nf: int) -> np.ndarray:

@@ -52,13 +52,22 @@ def test_fracture_plane_flux_discretization_host_logic(name, monkeypatch):
     assert err < TOL, (key, err)
 
 
-def test_tilted_plane_needs_the_ambient_dimension(monkeypatch):
+def test_tilted_plane_without_ambient_dimension(monkeypatch):
+    """mpfa.py:459-462: with the default ambient dimension (= 2) the vector-source terms of a tilted plane keep
+    the first two ambient components -- the columns (c, 0), (c, 1) of the 3-component golden matrices (the
+    reference's own gravity tests run this case, tests/numerics/fv/test_mpfa.py)."""
     c = load_case("embedded_cart2d_tilted")
     monkeypatch.setattr(fv, "DevicePlan", EmuBackedPlan)
     p = _params(c)
     del p["ambient_dimension"]
-    with pytest.raises(NotImplementedError):
-        fv.Mpfa("flow").discretize(c.g, pb.initialize_data({}, "flow", p))
+    data = pb.initialize_data({}, "flow", p)
+    fv.Mpfa("flow").discretize(c.g, data)
+    nc = c.g.num_cells
+    keep = (3 * np.arange(nc)[:, None] + np.arange(2)).ravel()
+    for key in ("vector_source", "bound_pressure_vector_source"):
+        got, ref = data[pb.DISCRETIZATION_MATRICES]["flow"][key], c.mats[key].tocsc()[:, keep]
+        assert got.shape == (c.g.num_faces, 2 * nc)
+        assert abs(got - ref).max() <= TOL * abs(ref).max(), key
 
 
 def test_mechanics_on_a_tilted_plane_is_refused(monkeypatch):

@@ -9,7 +9,7 @@ import scipy.sparse as sps
 import porepy_b200 as pb
 from porepy_b200 import fv
 from cases import load_case, max_rel_err
-from emu_binding import EmuBackedPlan, EmuPlan
+from emu_binding import EmuBackedFaceGrid, EmuBackedPlan, EmuPlan
 from golden_io import case_names
 
 CASES = case_names("next_")
@@ -31,6 +31,7 @@ def test_face_routines_match_the_reference(name):
 @pytest.mark.parametrize("name", CASES)
 def test_operator_classes(name, monkeypatch):
     monkeypatch.setattr(fv, "DevicePlan", EmuBackedPlan)
+    monkeypatch.setattr(fv, "FaceGrid", EmuBackedFaceGrid)
     c = load_case(name)
     data = pb.initialize_data({}, "flow", {"second_order_tensor": pb.SecondOrderTensor.from_values(c.raw["K"]),
                                            "bc": c.bc})

@@ -27,8 +27,9 @@ def solve(discr, g, data):
 
 
 def test_tutorial_numbers(monkeypatch):
-    from emu_binding import EmuBackedPlan
+    from emu_binding import EmuBackedFaceGrid, EmuBackedPlan
     monkeypatch.setattr(fv, "DevicePlan", EmuBackedPlan)
+    monkeypatch.setattr(fv, "FaceGrid", EmuBackedFaceGrid)
     g, data = tutorial_problem()
     p_tpfa = solve(pb.Tpfa("flow"), g, data)
     assert np.isclose(np.sum(p_tpfa), 14.192684340967551)

@@ -6,8 +6,8 @@ read-only tree) with pp.Mpfa / pp.Mpsa / pp.Biot rebound to the porepy_b200 plug
 
 With a GPU the plugin runs the CUDA path; without one the device plan is replaced by the host build of the
 same node routines (tests/emu) so that the drop-in wiring can be checked in the build container.  Prints
-how many discretize() calls ran on the porepy_b200 path and how many the plugin handed to the reference
-(partial updates, periodic grids, 1-D grids, sub-face boundary conditions, ...).  Nothing is copied
+how many discretize() calls ran on the porepy_b200 path and, with the reason, every call the plugin handed
+to the reference (this tool opts into ``allow_reference_fallback``; the default plugin re-raises).  Nothing is copied
 from the reference; its test files are collected where they lie."""
 import collections
 import os
@@ -34,8 +34,9 @@ class Rebind:
         except Exception:
             gpu = False
         if not gpu:
-            from emu_binding import EmuBackedPlan
+            from emu_binding import EmuBackedFaceGrid, EmuBackedPlan
             fv.DevicePlan = EmuBackedPlan
+            fv.FaceGrid = EmuBackedFaceGrid
         COUNTS["backend: " + ("cuda" if gpu else "host build of the node routines")] = 1
         for name in ("Mpfa", "Mpsa", "Biot", "Tpfa", "Upwind"):
             for owner, tag in ((getattr(fv, name), "porepy_b200"), (getattr(pp, name), "reference")):
@@ -49,12 +50,17 @@ class Rebind:
         if "--stock" in sys.argv:  # control run: the unmodified reference in the same environment
             COUNTS["classes: stock reference (control run)"] = 1
             return
-        plugin(pp).install()
+        # the reference's tests also cover what porepy_b200 refuses (periodic faces, sub-face boundary
+        # conditions): opt into the counted hand-over so that those tests still run, and report every reason
+        self.b200 = plugin(pp, allow_reference_fallback=True)
+        self.b200.install()
 
     def pytest_terminal_summary(self, terminalreporter):
         terminalreporter.write_line("")
         for k in sorted(COUNTS):
             terminalreporter.write_line(f"[porepy_b200] {k}: {COUNTS[k]}")
+        for k, v in sorted(getattr(getattr(self, "b200", None), "fallback_calls", {}).items()):
+            terminalreporter.write_line(f"[porepy_b200] handed to the reference ({v}x): {k}")
 
 
 if __name__ == "__main__":

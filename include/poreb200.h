@@ -63,6 +63,10 @@ int pb_set_device(int device);
 /* kernels launched by this library since load (bench.py's gpu_launches evidence). */
 int64_t pb_launch_count(void);
 
+/* FP64 peak of this device, measured by a dependency-free register loop: kind 0 = DMMA (mma.sync.m8n8k4.f64, the
+ * pipe of the block Gauss-Jordan), kind 1 = scalar DFMA.  TFLOP/s, best of 5 launches (roofline denominator). */
+int pb_fp64_peak(int kind, double *tflops);
+
 /* Page-locked host buffers for the CSR value arrays the *_download calls fill (full PCIe rate;
  * pageable NumPy buffers go through the driver's staging copies).  The caller frees them. */
 int pb_host_alloc(uint64_t bytes, void **out);

@@ -28,6 +28,7 @@ _SIGNATURES = {
     "pb_device_count": (C.c_int, []),
     "pb_set_device": (C.c_int, [C.c_int]),
     "pb_launch_count": (C.c_int64, []),
+    "pb_fp64_peak": (C.c_int, [C.c_int, _f64p]),
     "pb_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
     "pb_host_free": (None, [C.c_void_p]),
     "pb_plan_create": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, _i32p, _i32p, _i8p,

@@ -152,7 +152,8 @@ def restrict_vector_bc(bc, shard: Shard):
     out.is_neu = np.asarray(bc.is_neu, bool)[:, f].copy()
     out.is_internal = np.asarray(bc.is_internal, bool)[f].copy()
     out.robin_weight = np.asarray(bc.robin_weight, float)[:, :, f].copy()
-    out.basis = np.asarray(bc.basis, float)[:, :, f].copy()
+    if getattr(bc, "basis", None) is not None:
+        out.basis = np.asarray(bc.basis, float)[:, :, f].copy()
     out.is_dir[:, shard.cut_face] = False
     out.is_rob[:, shard.cut_face] = False
     out.is_neu[:, shard.cut_face] = True

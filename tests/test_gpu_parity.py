@@ -36,8 +36,9 @@ def test_mpfa_golden(name):
     assert np.linalg.norm(p - c.raw["solution"]) <= 1e-9 * np.linalg.norm(c.raw["solution"])
 
 
-@pytest.mark.parametrize("name", case_names("mpsa_") + case_names("biot_"))
+@pytest.mark.parametrize("name", case_names("mpsa_") + case_names("biot_") + case_names("rotbasis_"))
 def test_mpsa_biot_golden(name):
+    """incl. vectorial boundary conditions in rotated bases (``bc.basis``, a different rotation per face)."""
     c = load_case(name)
     params = {"fourth_order_tensor": pb.FourthOrderTensor.from_values(c.raw["C"]), "bc": c.bc,
               "mpsa_eta": c.eta}

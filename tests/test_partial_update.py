@@ -157,3 +157,14 @@ def test_biot_update_in_place_incl_cell_row_terms():
             assert rel_err(want[key][kw], got[key][kw]) < 1e-12, (key, kw)
             if key != "boundary_displacement_divergence":   # (interior cells: the boundary term does not change)
                 assert rel_err(want[key][kw], old[key][kw]) > 1e-6, (key, kw)   # the update was not a no-op
+
+
+from golden_io import case_names  # noqa: E402
+from partial_line_checks import check_partial_update  # noqa: E402
+
+
+@pytest.mark.parametrize("name", case_names("partial_"))
+def test_in_place_update_equals_the_references(name):
+    """Host logic of the partial update against golden matrices of the reference's own
+    ``update_discretization`` (the GPU leg runs the same check through the CUDA kernels)."""
+    check_partial_update(name)

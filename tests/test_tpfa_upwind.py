@@ -58,3 +58,11 @@ def test_operator_classes(name, monkeypatch):
     td["parameters"]["transport"]["num_components"] = 2
     u.discretize(c.g, td)
     assert td[pb.DISCRETIZATION_MATRICES]["transport"]["transport"].shape == (2 * c.g.num_faces, 2 * c.g.num_cells)
+
+
+def test_line_grid_delegation(monkeypatch):
+    """1-D grid on a tilted line in 3-D: MPFA / MPSA delegate to TPFA (mpfa.py:690-712, mpsa.py:666-697)."""
+    from partial_line_checks import check_line
+    monkeypatch.setattr(fv, "DevicePlan", EmuBackedPlan)
+    monkeypatch.setattr(fv, "FaceGrid", EmuBackedFaceGrid)
+    check_line()

@@ -5,9 +5,17 @@ import numpy as np
 import pytest
 
 import porepy_b200 as pb
-from golden_io import rel_err
+from golden_io import case_names, rel_err
+from partial_line_checks import check_partial_update
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", case_names("partial_"))
+def test_in_place_update_equals_the_references(name):
+    """Against the reference itself: golden matrices of ``Mpfa / Mpsa.update_discretization`` after two cells
+    changed (tools/make_golden.py: case_partial_update)."""
+    check_partial_update(name)
 
 
 def test_update_in_place_equals_a_full_pass():

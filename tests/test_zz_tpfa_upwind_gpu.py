@@ -1,18 +1,15 @@
-"""GPU leg of tests/test_tpfa_upwind.py: ``pb.Tpfa`` / ``pb.Upwind`` through the real device plan
-(``pb_tpfa`` / ``pb_upwind``, one thread per face) against golden outputs of the reference.
-
-These kernels were added after the round's GPU budget was spent: the per-face routines are validated
-through the host build (bitwise equal to the reference) and the library cross-compiles, but the CUDA
-launch path has not been executed on a B200 yet -- hence non-strict xfail (an XPASS is the expected
-outcome; a failure here does not touch the validated MPFA / MPSA paths, whose SASS is unchanged)."""
+"""GPU leg of tests/test_tpfa_upwind.py: ``pb.Tpfa`` / ``pb.Upwind`` through the real per-face kernels
+(``pb_facegrid`` + ``pb_tpfa`` / ``pb_upwind``, one thread per face) against golden outputs of the reference,
+incl. a 1-D grid on a tilted line (the TPFA delegation of MPFA / MPSA)."""
 import pytest
 import scipy.sparse as sps
 
 import porepy_b200 as pb
 from cases import load_case, max_rel_err
 from golden_io import case_names
+from partial_line_checks import check_line
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first run of pb_tpfa / pb_upwind on a GPU")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", case_names("next_"))
@@ -29,3 +26,7 @@ def test_tpfa_and_upwind_on_the_device(name):
     M = td[pb.DISCRETIZATION_MATRICES]["transport"]
     for ref_key, key in (("upwind", "transport"), ("bound_transport_dir", "rhs_dir"), ("bound_transport_neu", "rhs_neu")):
         assert abs(sps.csr_matrix(c.mats[ref_key]) - M[key]).sum() == 0, key
+
+
+def test_line_grid_on_the_device():
+    check_line()

@@ -226,6 +226,88 @@ def case_next_rows(name, kind, seed):
     print(name, "nc", nc, "nf", nf)
 
 
+def case_partial_update(name, kind, seed, mech=False):
+    """The reference's in-place update (``Mpfa / Mpsa.update_discretization`` -> ``partial_update_discretization``,
+    _fvutils.py:1090-1257) after the parameters of two cells changed: fixture holds the old and the new
+    tensors, the modified cells and the matrices the reference ends up with."""
+    rng = np.random.default_rng(seed)
+    g = make_grid(kind, rng)
+    nc = g.num_cells
+    cells = np.sort(rng.choice(nc, size=2, replace=False))
+    d = grid_arrays(g)
+    if mech:
+        C = pp.FourthOrderTensor(np.exp(0.5 * rng.standard_normal(nc)), np.exp(0.5 * rng.standard_normal(nc)))
+        bc = vector_bc(g, rng, False)
+        kw, discr = "mech", pp.Mpsa("mech")
+        data = pp.initialize_data({}, kw, {"fourth_order_tensor": C, "bc": bc, "inverter": "python"})
+        discr.discretize(g, data)
+        C2 = C.copy()
+        C2.values[:, :, cells] *= 3.0
+        C2.mu[cells] *= 3.0
+        C2.lmbda[cells] *= 3.0
+        data[pp.PARAMETERS][kw]["fourth_order_tensor"] = C2
+        d.update(kind=np.array("partial_mpsa"), C=C.values, C2=C2.values)
+    else:
+        k = pp.SecondOrderTensor(1 + rng.random(nc), 1 + rng.random(nc), 1 + rng.random(nc),
+                                 0.3 * rng.random(nc), 0.3 * rng.random(nc), 0.3 * rng.random(nc))
+        bc = scalar_bc(g, rng, False)
+        kw, discr = "flow", pp.Mpfa("flow")
+        data = pp.initialize_data({}, kw, {"second_order_tensor": k, "bc": bc, "mpfa_inverter": "python"})
+        discr.discretize(g, data)
+        k2 = k.copy()
+        k2.values[:, :, cells] *= 7.0
+        data[pp.PARAMETERS][kw]["second_order_tensor"] = k2
+        d.update(kind=np.array("partial_mpfa"), K=k.values, K2=k2.values)
+    data["update_discretization"] = {"modified_cells": cells}
+    discr.update_discretization(g, data)
+    d.update(bc_is_dir=bc.is_dir, bc_is_neu=bc.is_neu, bc_is_rob=bc.is_rob, bc_is_internal=bc.is_internal,
+             bc_robin_weight=np.asarray(bc.robin_weight, float), modified_cells=cells,
+             eta=np.float64(pp.numerics.fv._fvutils.determine_eta(g)))
+    for key, m in data[pp.DISCRETIZATION_MATRICES][kw].items():
+        put_matrix(d, key, m)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "nc", nc, "modified", cells)
+
+
+def case_line(name, seed):
+    """A 1-D grid on a tilted line in 3-D (an intersection line of fractures): ``pp.Mpfa`` (which delegates to
+    TPFA, mpfa.py:690-712) with 3 ambient components, ``pp.Mpsa`` (mpsa.py:666-697) and upwinding."""
+    rng = np.random.default_rng(seed)
+    g = pp.CartGrid([6], [1.0])
+    g.nodes[0, 1:-1] += 0.05 * (0.5 - rng.random(5))
+    x = g.nodes[0].copy()
+    g.nodes = np.vstack((0.6 * x, 0.3 * x + 0.1, 0.74 * x - 0.2))
+    g.compute_geometry()
+    nc, nf = g.num_cells, g.num_faces
+    k = pp.SecondOrderTensor(1 + rng.random(nc))
+    bc = pp.BoundaryCondition(g, np.array([0]), "dir")
+    data = pp.initialize_data({}, "flow", {"second_order_tensor": k, "bc": bc, "ambient_dimension": 3})
+    pp.Mpfa("flow").discretize(g, data)
+    d = grid_arrays(g)
+    d.update(kind=np.array("line"), K=k.values, bc_is_dir=bc.is_dir, bc_is_neu=bc.is_neu, bc_is_rob=bc.is_rob,
+             bc_is_internal=bc.is_internal, bc_robin_weight=np.asarray(bc.robin_weight, float), eta=np.float64(0.0))
+    for key, m in data[pp.DISCRETIZATION_MATRICES]["flow"].items():
+        put_matrix(d, "tpfa_" + key, m)
+    mu, lam = 1 + rng.random(nc), rng.random(nc)
+    md = pp.initialize_data({}, "mech", {"fourth_order_tensor": pp.FourthOrderTensor(mu, lam),
+                                         "bc": pp.BoundaryConditionVectorial(g)})
+    pp.Mpsa("mech").discretize(g, md)
+    d["mu"], d["lmbda"] = mu, lam
+    for key, m in md[pp.DISCRETIZATION_MATRICES]["mech"].items():
+        put_matrix(d, "mpsa_" + key, m)
+    q = rng.standard_normal(nf)
+    up = pp.Upwind("transport")
+    dat = pp.initialize_data({}, "transport", {"bc": bc, up._flux_array_key: q})
+    up.discretize(g, dat)
+    U = dat[pp.DISCRETIZATION_MATRICES]["transport"]
+    d["darcy_flux"] = q
+    put_matrix(d, "upwind", U[up.upwind_matrix_key])
+    put_matrix(d, "bound_transport_dir", U[up.bound_transport_dir_matrix_key])
+    put_matrix(d, "bound_transport_neu", U[up.bound_transport_neu_matrix_key])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "nc", nc, "nf", nf)
+
+
 def case_mpsa(name, kind, robin, seed, biot=False, basis=False):
     rng = np.random.default_rng(seed)
     g = make_grid(kind, rng)
@@ -302,6 +384,13 @@ def main():
         (case_next_rows, ("next_cart3d", "cart3d_pert", 41), {}),
         (case_next_rows, ("next_tet3d", "tet3d", 42), {}),
         (case_next_rows, ("next_tri2d", "tri2d", 43), {}),
+        # a 1-D intersection line (prefix "line")
+        (case_line, ("line1d_tilted", 44), {}),
+        # the reference's in-place partial update (prefix "partial")
+        (case_partial_update, ("partial_mpfa_cart3d", "cart3d_pert", 61), {}),
+        (case_partial_update, ("partial_mpfa_tet3d", "tet3d", 62), {}),
+        (case_partial_update, ("partial_mpsa_cart3d", "cart3d_pert", 63), {"mech": True}),
+        (case_partial_update, ("partial_mpsa_tet3d", "tet3d", 64), {"mech": True}),
     ]
     for fn, args, kw in cases:
         if args[0].startswith(only):

@@ -90,6 +90,11 @@ void pb_plan_destroy(pb_plan *p);
 int pb_plan_sizes(const pb_plan *p, int64_t *num_subcells, int64_t *num_subfaces,
                   int64_t *num_subhalffaces, int32_t *max_subfaces_per_node,
                   int32_t *max_subcells_per_node);
+/* Restrict the assembly to the interaction regions of the flagged nodes (mask: nn bytes, NULL = all nodes).
+ * Used by the multi-GPU path: a shard assembles the regions of its OWN nodes only; the outer nodes of its halo
+ * layer are incomplete there and their rows are discarded anyway (reference: the overlap removal of
+ * numerics/fv/mpfa.py:301-304).  Rows of faces with an inactive node are incomplete. */
+int pb_plan_set_active_nodes(pb_plan *p, const uint8_t *mask);
 /* base pattern `which` (PB_PAT_*): nrows and nnz; then copy indptr (nrows+1) / indices (nnz). */
 int pb_plan_pattern_size(const pb_plan *p, int which, int64_t *nrows, int64_t *nnz);
 int pb_plan_pattern_get(const pb_plan *p, int which, int32_t *indptr, int32_t *indices);
@@ -205,6 +210,8 @@ int pb_upwind(pb_facegrid *g, const double *darcy_flux, const uint8_t *bc_bits, 
 int pb_csr_create(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t *indptr,
                   const int32_t *indices, const double *data, pb_csr **out);
 void pb_csr_destroy(pb_csr *a);
+/* Keep the first nrows rows (a row-partitioned system: the rows of a rank's own cells come first). */
+int pb_csr_truncate_rows(pb_csr *a, int64_t nrows);
 /* copy a device-resident matrix back (indptr nrows+1, indices nnz, data nnz); sizes via pb_csr_shape */
 int pb_csr_shape(const pb_csr *a, int64_t *nrows, int64_t *ncols, int64_t *nnz);
 int pb_csr_download(pb_csr *a, int32_t *indptr, int32_t *indices, double *data);

@@ -35,6 +35,7 @@ _SIGNATURES = {
                                  _i32p, _i32p, C.POINTER(C.c_void_p)]),
     "pb_plan_destroy": (None, [C.c_void_p]),
     "pb_plan_sizes": (C.c_int, [C.c_void_p, _i64p, _i64p, _i64p, _i32p, _i32p]),
+    "pb_plan_set_active_nodes": (C.c_int, [C.c_void_p, _u8p]),
     "pb_plan_pattern_size": (C.c_int, [C.c_void_p, C.c_int, _i64p, _i64p]),
     "pb_plan_pattern_get": (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p]),
     "pb_plan_pattern_expanded": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _i32p, _i32p]),
@@ -60,6 +61,7 @@ _SIGNATURES = {
                                 C.POINTER(C.c_void_p)]),
     "pb_csr_destroy": (None, [C.c_void_p]),
     "pb_csr_shape": (C.c_int, [C.c_void_p, _i64p, _i64p, _i64p]),
+    "pb_csr_truncate_rows": (C.c_int, [C.c_void_p, C.c_int64]),
     "pb_csr_download": (C.c_int, [C.c_void_p, _i32p, _i32p, _f64p]),
     "pb_csr_spmv": (C.c_int, [C.c_void_p, _f64p, _f64p]),
     "pb_csr_spmv_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),

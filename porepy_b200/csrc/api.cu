@@ -82,6 +82,7 @@ static int build_classes(pb_plan *p, std::vector<NodeClass> &out, F size_of) {
         int nsc = H.node_sc_ptr[s + 1] - H.node_sc_ptr[s];
         int nsf = H.node_sf_ptr[s + 1] - H.node_sf_ptr[s];
         if (nsf == 0) continue;
+        if (!p->active.empty() && !p->active[s]) continue;
         int n = 0, w = 0;
         int64_t a = 0, r = 0;
         size_of(nsf, nsc, H.node_nb[s], &n, &w, &a, &r);
@@ -121,6 +122,16 @@ static int build_classes(pb_plan *p, std::vector<NodeClass> &out, F size_of) {
         if (c.nodes.upload(lists[key], p->stream) != cudaSuccess) return fail(PB_ECUDA, "upload of node list failed");
     }
     return PB_OK;
+}
+
+static int build_mpfa_classes(pb_plan *p) {
+    const int nd = p->H.nd;
+    return build_classes(p, p->mpfa_cls, [&](int nsf, int nsc, int nb, int *n, int *w, int64_t *a, int64_t *r) {
+        *n = nsf;
+        *w = mpfa_width(nd, nsf, nsc, nb);
+        *a = mpfa_A_doubles(nd, nsf, nsc, nb);
+        *r = mpfa_rest_doubles(nd, nsf, nsc, nb);
+    });
 }
 
 // Structural patterns on the device: row r = sorted union over the nodes of row entity r of the
@@ -388,12 +399,7 @@ extern "C" int pb_plan_create(int nd, int64_t nc, int64_t nf, int64_t nn, const 
     v.pos_cc = p->pos_cc.as<int32_t>(); v.pos_cb = p->pos_cb.as<int32_t>();
     v.fc_indptr = p->fc_indptr.as<int32_t>(); v.fb_indptr = p->fb_indptr.as<int32_t>();
     v.cc_indptr = p->cc_indptr.as<int32_t>(); v.cb_indptr = p->cb_indptr.as<int32_t>();
-    rc = build_classes(p, p->mpfa_cls, [&](int nsf, int nsc, int nb, int *n, int *w, int64_t *a, int64_t *r) {
-        *n = nsf;
-        *w = mpfa_width(nd, nsf, nsc, nb);
-        *a = mpfa_A_doubles(nd, nsf, nsc, nb);
-        *r = mpfa_rest_doubles(nd, nsf, nsc, nb);
-    });
+    rc = build_mpfa_classes(p);
     if (rc) { delete p; return rc; }
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail("sync", e);
     // the host copies of the node-major lists are only needed for the uploads above
@@ -429,6 +435,16 @@ extern "C" int pb_plan_sizes(const pb_plan *p, int64_t *num_subcells, int64_t *n
     if (num_subhalffaces) *num_subhalffaces = p->H.H;
     if (max_sf) *max_sf = p->H.max_nsf;
     if (max_sc) *max_sc = p->H.max_nsc;
+    return PB_OK;
+}
+
+extern "C" int pb_plan_set_active_nodes(pb_plan *p, const uint8_t *mask) {
+    if (!p) return pb_fail_(PB_EINVAL, "null plan");
+    if (mask) p->active.assign(mask, mask + p->H.nn); else p->active.clear();
+    p->mpsa_cls_nalpha = -1;  // the MPSA / Biot node classes are rebuilt at the next upload
+    int rc = build_mpfa_classes(p);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
     return PB_OK;
 }
 

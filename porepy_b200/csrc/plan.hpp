@@ -109,6 +109,7 @@ struct pb_plan {
     // geometry
     DevBuf nodes, fnorm, fcent, farea, ccent, cvol;
     bool have_geo = false;
+    std::vector<uint8_t> active;   // per node: assemble its interaction region (empty = all); pb_plan_set_active_nodes
     PlanView view{};
     GeoView geo{};
     DevBuf err, a_ws, repack_tmp;

@@ -142,6 +142,12 @@ extern "C" int pb_csr_shape(const pb_csr *a, int64_t *nrows, int64_t *ncols, int
     return PB_OK;
 }
 
+extern "C" int pb_csr_truncate_rows(pb_csr *a, int64_t nrows) {
+    if (!a || nrows < 0 || nrows > a->nrows) return pb_fail_(PB_EINVAL, "bad row count");
+    a->nrows = nrows;  // the row-pointer prefix is a valid CSR; nnz keeps the allocated size
+    return PB_OK;
+}
+
 extern "C" int pb_csr_download(pb_csr *a, int32_t *indptr, int32_t *indices, double *data) {
     if (!a || !indptr || !indices || !data) return pb_fail_(PB_EINVAL, "null pointer");
     CUDA_TRY(cudaMemcpy(indptr, a->indptr, (a->nrows + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));

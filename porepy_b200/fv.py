@@ -188,6 +188,14 @@ class DevicePlan:
         arrs, self.rotation = plan_geometry(sd)
         _lib.check(self.lib.pb_plan_set_geometry(self.h, *[_lib.ptr(a, _lib._f64p) for a in arrs]))
 
+    def set_active_nodes(self, mask) -> None:
+        """Assemble only the interaction regions of the flagged nodes (``None``: all).  The multi-GPU path flags
+        a shard's own nodes: the outer nodes of its halo layer are incomplete and their rows are discarded."""
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        if m is not None and m.shape != (self.nn,):
+            raise ValueError("active-node mask must have one entry per node")
+        _lib.check(self.lib.pb_plan_set_active_nodes(self.h, _lib.ptr(m, _lib._u8p)))
+
     # ---- patterns
     def base_pattern(self, which: int):
         if which not in self._base:

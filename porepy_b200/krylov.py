@@ -64,6 +64,55 @@ def build_local_system(a, owner: np.ndarray, rank: int, world: int, group=None) 
     return LocalSystem(rank, world, owned, gh, a_local, recv_counts, send_index)
 
 
+def local_system_from_shard(shard, part: np.ndarray, a_rows, group=None) -> LocalSystem:
+    """This rank's rows of the global system, straight from its shard (``shard.extract_shard`` numbers the own
+    cells first): ``a_rows`` holds the rows of the own cells with columns in the shard's local cell numbering,
+    i.e. already [own | ghost] -- a scipy CSR or a ``DeviceCsr`` (e.g. ``DevicePlan.mpfa_system()`` after
+    ``truncate_rows(n_own)``).  No global matrix exists anywhere.  The ghost cells are regrouped by owner rank for
+    the exchange through a column permutation of the ghost block, which is returned in ``extra["ghost_perm"]``
+    and applied to the receive buffer instead of to the matrix.  Collective (exchanges the ghost lists)."""
+    rank = shard.rank
+    part = np.asarray(part)
+    n_own = int(shard.own_cell.sum())
+    assert shard.own_cell[:n_own].all() and not shard.own_cell[n_own:].any(), "shard cells must be own-first"
+    owned = shard.cells[:n_own]
+    ghosts = shard.cells[n_own:]                      # local column n_own + i  <->  global cell ghosts[i]
+    gowner = part[ghosts]
+    world = 1
+    if group is not None or _dist_initialized():
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+    order = np.lexsort((ghosts, gowner))              # receive order: grouped by owner, ascending global id
+    recv_counts = [int((gowner == q).sum()) for q in range(world)]
+    if world > 1:
+        import torch.distributed as dist
+        need = [ghosts[order][gowner[order] == q].tolist() for q in range(world)]
+        all_need = [None] * world
+        dist.all_gather_object(all_need, need, group=group)
+        g2l = {int(c): i for i, c in enumerate(owned)} if n_own < 2_000_000 else None
+        lut = np.full(int(shard.num_global[0]), -1, dtype=np.int64)
+        lut[owned] = np.arange(n_own)
+        send_index = [lut[np.asarray(all_need[q][rank], dtype=np.int64)] for q in range(world)]
+        del g2l
+        for ix in send_index:
+            assert (ix >= 0).all(), "a rank asked for a cell this rank does not own"
+    else:
+        send_index = [np.zeros(0, dtype=np.int64)]
+    # position in the receive buffer of each ghost column: recv slot j holds ghost order[j]
+    slot_of_ghost = np.empty(ghosts.size, dtype=np.int64)
+    slot_of_ghost[order] = np.arange(ghosts.size)
+    return LocalSystem(rank, world, owned, ghosts[order], a_rows, recv_counts, send_index,
+                       extra={"ghost_perm": slot_of_ghost})
+
+
+def _dist_initialized() -> bool:
+    try:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized()
+    except Exception:
+        return False
+
+
 class DistributedOperator:
     """y_own = (A x)_own with x distributed; torch tensors (cuda float64; cpu only with a stand-in)."""
 
@@ -76,6 +125,10 @@ class DistributedOperator:
         self.xbuf = torch.zeros(self.n_own + self.n_ghost, dtype=torch.float64, device=device)
         self.send_idx = [torch.as_tensor(ix, dtype=torch.int64, device=device) for ix in loc.send_index]
         self.halo_bytes = 8 * sum(int(ix.numel()) for ix in self.send_idx)
+        # shards keep their own ghost column order: receive into a staging buffer, then permute
+        perm = loc.extra.get("ghost_perm") if loc.extra else None
+        self.ghost_perm = None if perm is None else torch.as_tensor(perm, dtype=torch.int64, device=device)
+        self.recv = torch.zeros(self.n_ghost, dtype=torch.float64, device=device) if perm is not None else None
         if matvec is not None:
             self._matvec = matvec  # test stand-in (host logic checks under gloo)
             self.dev_csr = None
@@ -83,7 +136,7 @@ class DistributedOperator:
             if torch.device(device).type != "cuda":
                 raise RuntimeError("porepy_b200.krylov: the SpMV kernel needs a CUDA device (no CPU path)")
             from .sparse import DeviceCsr
-            self.dev_csr = DeviceCsr(loc.a_local)
+            self.dev_csr = loc.a_local if isinstance(loc.a_local, DeviceCsr) else DeviceCsr(loc.a_local)
             self._matvec = None
 
     def exchange(self, x_own):
@@ -93,7 +146,8 @@ class DistributedOperator:
         if self.loc.world == 1:
             return self.xbuf
         import torch.distributed as dist
-        ops, off = [], self.n_own
+        target = self.xbuf[self.n_own:] if self.recv is None else self.recv
+        ops, off = [], 0
         sends = []
         for q in range(self.loc.world):
             if q == self.loc.rank:
@@ -105,11 +159,13 @@ class DistributedOperator:
         for q in range(self.loc.world):
             cnt = self.loc.recv_counts[q]
             if q != self.loc.rank and cnt:
-                ops.append(dist.P2POp(dist.irecv, self.xbuf[off:off + cnt], q, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, target[off:off + cnt], q, group=self.group))
             off += cnt
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
+        if self.recv is not None:
+            torch.index_select(self.recv, 0, self.ghost_perm, out=self.xbuf[self.n_own:])
         return self.xbuf
 
     def matvec(self, x_own, out=None):
@@ -213,3 +269,23 @@ def solve(a, b, owner=None, tol: float = 1e-10, maxiter: int = 2000, jacobi: boo
     x, info = bicgstab(op, b_own, tol=tol, maxiter=maxiter, diag_own=diag)
     info["halo_bytes_per_spmv"] = op.halo_bytes
     return x, loc.owned, info
+
+
+def solve_local(loc: LocalSystem, b_own, diag_own=None, tol: float = 1e-10, maxiter: int = 2000, device=None,
+                matvec_factory=None, group=None):
+    """BiCGStab on a row-distributed system given by this rank's ``LocalSystem`` (e.g. from
+    ``local_system_from_shard``); ``b_own`` / ``diag_own``: NumPy arrays or torch tensors of the own rows.
+    Returns (x_own, info)."""
+    import torch
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu"
+    mv = None if matvec_factory is None else matvec_factory(loc)
+    op = DistributedOperator(loc, device, matvec=mv, group=group)
+    b = torch.as_tensor(np.asarray(b_own) if not torch.is_tensor(b_own) else b_own, dtype=torch.float64, device=device)
+    dg = None
+    if diag_own is not None:
+        dg = torch.as_tensor(np.asarray(diag_own) if not torch.is_tensor(diag_own) else diag_own,
+                             dtype=torch.float64, device=device)
+    x, info = bicgstab(op, b, tol=tol, maxiter=maxiter, diag_own=dg)
+    info["halo_bytes_per_spmv"] = op.halo_bytes
+    return x, info

@@ -29,15 +29,33 @@ from .grid import Grid
 
 
 def partition_cells(g, nparts: int, axis: int | None = None) -> np.ndarray:
-    """Equal-count coordinate slabs.  Returns part id per cell."""
+    """Part id per cell.  ``axis`` given: equal-count coordinate slabs along it.  Default: recursive coordinate
+    bisection (equal counts, always across the longest extent of the current piece) -- compact blocks, so the
+    one-layer halo of ``extract_shard`` stays small (2 x 2 x 2 blocks of a cube at 8 parts: ~11 % extra regions
+    at 10^6 tetrahedra, against ~29 % for 8 slabs).  The structured analogue of ``pp.partition.partition``
+    (grids/partition.py:269)."""
     cc = np.asarray(g.cell_centers)
-    if axis is None:
-        axis = int(np.argmax(np.ptp(cc, axis=1)))
-    order = np.argsort(cc[axis], kind="stable")
     part = np.empty(g.num_cells, dtype=np.int64)
-    bounds = np.linspace(0, g.num_cells, nparts + 1).astype(np.int64)
-    for p in range(nparts):
-        part[order[bounds[p]:bounds[p + 1]]] = p
+    if axis is not None:
+        order = np.argsort(cc[axis], kind="stable")
+        bounds = np.linspace(0, g.num_cells, nparts + 1).astype(np.int64)
+        for p in range(nparts):
+            part[order[bounds[p]:bounds[p + 1]]] = p
+        return part
+
+    def split(idx, first, count):
+        if count == 1:
+            part[idx] = first
+            return
+        x = cc[:, idx]
+        ax = int(np.argmax(np.ptp(x, axis=1)))
+        left = count // 2
+        cut = (idx.size * left) // count
+        order = np.argsort(x[ax], kind="stable")
+        split(idx[order[:cut]], first, left)
+        split(idx[order[cut:]], first + left, count - left)
+
+    split(np.arange(g.num_cells), 0, int(nparts))
     return part
 
 
@@ -52,6 +70,7 @@ class Shard:
     own_face: np.ndarray    # bool per local face: rows this shard keeps
     cut_face: np.ndarray    # bool per local face: artificial boundary of the overlap
     num_global: tuple       # (nc, nf, nn) of the global grid
+    own_node: np.ndarray | None = None   # bool per local node: regions this shard must assemble (None: all)
 
     def restrict_cell_array(self, a: np.ndarray) -> np.ndarray:
         """(..., nc_global) -> (..., nc_local)."""
@@ -74,28 +93,56 @@ class Shard:
                               shape=(nr * br, ncg * bc)).tocsr()
 
 
+def _ranges(indptr: np.ndarray, idx: np.ndarray):
+    """Positions of the concatenated slices ``indptr[i]:indptr[i+1]``, i in ``idx``, and their lengths."""
+    starts = indptr[idx].astype(np.int64)
+    lens = indptr[idx + 1].astype(np.int64) - starts
+    total = int(lens.sum())
+    if total == 0:
+        return np.zeros(0, np.int64), lens
+    ends = np.cumsum(lens)
+    pos = np.arange(total, dtype=np.int64) + np.repeat(starts - (ends - lens), lens)
+    return pos, lens
+
+
+def _sub_csc(m: sps.csc_matrix, cols: np.ndarray, row_map: np.ndarray, nrows: int):
+    """Columns ``cols`` of ``m`` with rows renumbered by ``row_map`` (every row of the selected columns must
+    be mapped): index arithmetic only, no scipy slicing."""
+    pos, lens = _ranges(m.indptr, cols)
+    indptr = np.zeros(cols.size + 1, dtype=np.int32)
+    np.cumsum(lens, out=indptr[1:])
+    return sps.csc_matrix((m.data[pos], row_map[m.indices[pos]].astype(np.int32), indptr), shape=(nrows, cols.size))
+
+
 def extract_cells(g, cells: np.ndarray, keep_faces: np.ndarray, keep_cells: np.ndarray, rank: int = 0) -> Shard:
     """Sub-grid of the given (sorted, global) cells as a ``Shard`` that keeps the rows of the global
     faces / cells flagged in ``keep_faces`` / ``keep_cells`` (bool per global entity).  The reference's
-    ``pp.partition.extract_subgrid`` (grids/partition.py) + ``subgrid_to_grid_mapping``."""
+    ``pp.partition.extract_subgrid`` (grids/partition.py) + ``subgrid_to_grid_mapping``; here by masks and
+    index arithmetic on the CSC arrays (O(size of the global arrays), no sparse-matrix slicing)."""
     cf = sps.csc_matrix(g.cell_faces)
     fn = sps.csc_matrix(g.face_nodes)
     nc, nf, nn = g.num_cells, g.num_faces, g.num_nodes
     cells = np.asarray(cells, dtype=np.int64)
-    sub_cf = cf[:, cells]
-    faces = np.unique(sub_cf.indices)
-    sub_cf = sub_cf.tocsr()[faces].tocsc()
-    sub_fn = fn[:, faces]
-    nodes = np.unique(sub_fn.indices)
-    sub_fn = sub_fn.tocsr()[nodes].tocsc()
+    pos, _ = _ranges(cf.indptr, cells)
+    fmask = np.zeros(nf, bool)
+    fmask[cf.indices[pos]] = True
+    faces = np.flatnonzero(fmask)
+    posn, _ = _ranges(fn.indptr, faces)
+    nmask = np.zeros(nn, bool)
+    nmask[fn.indices[posn]] = True
+    nodes = np.flatnonzero(nmask)
+    fmap = np.cumsum(fmask) - 1
+    nmap = np.cumsum(nmask) - 1
+    sub_cf = _sub_csc(cf, cells, fmap, faces.size)
+    sub_fn = _sub_csc(fn, faces, nmap, nodes.size)
     lg = Grid(g.dim, np.asarray(g.nodes)[:, nodes], sub_fn, sub_cf, name=getattr(g, "name", "Grid"))
     lg.set_geometry(np.asarray(g.face_normals)[:, faces], np.asarray(g.face_centers)[:, faces],
                     np.asarray(g.face_areas)[faces], np.asarray(g.cell_centers)[:, cells],
                     np.asarray(g.cell_volumes)[cells])
-    glob_bnd = np.zeros(nf, bool)
-    glob_bnd[g.get_all_boundary_faces()] = True
-    loc_single = np.asarray(abs(lg.cell_faces).sum(axis=1)).ravel() == 1
-    cut = loc_single & ~glob_bnd[faces]
+    glob_count = np.bincount(cf.indices, minlength=nf)
+    loc_count = np.bincount(sub_cf.indices, minlength=faces.size)
+    loc_single = loc_count == 1
+    cut = loc_single & (glob_count[faces] != 1)
     tags = getattr(g, "tags", {})
     if "fracture_faces" in tags:
         lg.tags["fracture_faces"] = np.asarray(tags["fracture_faces"], bool)[faces]
@@ -104,26 +151,52 @@ def extract_cells(g, cells: np.ndarray, keep_faces: np.ndarray, keep_cells: np.n
                  np.asarray(keep_faces, bool)[faces], cut, (nc, nf, nn))
 
 
-def extract_shard(g, part: np.ndarray, rank: int) -> Shard:
-    """This rank's nodes, every cell touching them (one halo layer); rows of the faces of the rank's own
-    cells (a shared face goes to the lower rank) and of its own cells."""
+def shard_cells(g, part: np.ndarray, rank: int):
+    """(cells of the shard, kept-face flags, own-cell flags) of ``rank``: its own cells' NODES, every cell touching
+    one of them (one halo layer); rows of the faces of the rank's own cells (a shared face goes to the lower rank)
+    and of its own cells.  Masks and segmented reductions over the CSC arrays only."""
     cf = sps.csc_matrix(g.cell_faces)
     fn = sps.csc_matrix(g.face_nodes)
     nc, nf, nn = g.num_cells, g.num_faces, g.num_nodes
-    own = part == rank
-    cell_nodes = (abs(fn) @ abs(cf)).tocsc()  # nn x nc
-    cell_nodes.data[:] = 1
-    own_nodes = np.zeros(nn, bool)
-    own_nodes[np.unique(cell_nodes[:, np.flatnonzero(own)].indices)] = True
-    touch = np.asarray((cell_nodes.T @ own_nodes.astype(np.float64))).ravel() > 0
-    # faces of own cells; shared faces go to the lower rank
+    own = np.asarray(part) == rank
+    own_cells = np.flatnonzero(own)
+    pos, _ = _ranges(cf.indptr, own_cells)
+    own_face = np.zeros(nf, bool)
+    own_face[cf.indices[pos]] = True
+    posn, _ = _ranges(fn.indptr, np.flatnonzero(own_face))
+    own_node = np.zeros(nn, bool)
+    own_node[fn.indices[posn]] = True
+    # a cell touches a node iff one of its faces contains it (every vertex of a cell lies on nd of its faces)
+    face_touch = np.logical_or.reduceat(own_node[fn.indices], fn.indptr[:-1].astype(np.int64))
+    face_touch[np.diff(fn.indptr) == 0] = False
+    touch = np.logical_or.reduceat(face_touch[cf.indices], cf.indptr[:-1].astype(np.int64))
+    touch[np.diff(cf.indptr) == 0] = False
+    # shared faces go to the lower rank
     face_min_part = np.full(nf, np.iinfo(np.int64).max)
-    coo = abs(cf).tocoo()
-    np.minimum.at(face_min_part, coo.row, part[coo.col])
-    own_face_glob = np.zeros(nf, bool)
-    own_face_glob[np.unique(cf[:, np.flatnonzero(own)].indices)] = True
-    own_face_glob &= face_min_part == rank
-    return extract_cells(g, np.flatnonzero(touch), own_face_glob, own, rank)
+    cell_of_entry = np.repeat(np.arange(nc, dtype=np.int64), np.diff(cf.indptr))
+    np.minimum.at(face_min_part, cf.indices, np.asarray(part, dtype=np.int64)[cell_of_entry])
+    own_face &= face_min_part == rank
+    return np.flatnonzero(touch), own_face, own
+
+
+def extract_shard(g, part: np.ndarray, rank: int) -> Shard:
+    """This rank's nodes, every cell touching them (one halo layer); rows of the faces of the rank's own
+    cells (a shared face goes to the lower rank) and of its own cells.  Local cell numbering: OWN CELLS FIRST
+    (ascending global id), then the halo cells -- the rows of a system matrix assembled on the shard that
+    belong to this rank are then a prefix, and its columns are already [own | ghost] (``krylov``)."""
+    cells, own_face, own = shard_cells(g, part, rank)
+    cells = np.concatenate((cells[own[cells]], cells[~own[cells]]))
+    s = extract_cells(g, cells, own_face, own, rank)
+    # nodes of the own cells: the interaction regions this shard needs (faces of own cells -> their nodes)
+    lcf = sps.csc_matrix(s.grid.cell_faces)
+    lfn = sps.csc_matrix(s.grid.face_nodes)
+    n_own = int(s.own_cell.sum())
+    fmask = np.zeros(s.grid.num_faces, bool)
+    fmask[lcf.indices[:lcf.indptr[n_own]]] = True
+    pos, _ = _ranges(lfn.indptr, np.flatnonzero(fmask))
+    s.own_node = np.zeros(s.grid.num_nodes, bool)
+    s.own_node[lfn.indices[pos]] = True
+    return s
 
 
 def restrict_scalar_bc(bc, shard: Shard):
@@ -231,6 +304,11 @@ def discretize_shard(discr, g, data: dict, part: np.ndarray, rank: int) -> dict:
     eta_key = "mpfa_eta" if "second_order_tensor" in params else "mpsa_eta"
     params.setdefault(eta_key, determine_eta(g))
     local = initialize_data({}, kw, params)
+    if shard.own_node is not None and shard.grid.dim >= 2:
+        from .fv import DevicePlan
+        plan = DevicePlan.for_grid(shard.grid)
+        if hasattr(plan, "set_active_nodes"):
+            plan.set_active_nodes(shard.own_node)
     discr.discretize(shard.grid, local)
     return {key: embed(shard, key, m) for key, m in local[DISCRETIZATION_MATRICES][kw].items()}
 

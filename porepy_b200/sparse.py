@@ -41,13 +41,20 @@ class DeviceCsr:
         self.shape, self.nnz, self.h, self.lib = (nr.value, ncl.value), nz.value, h, lib
         return self
 
+    def truncate_rows(self, nrows: int) -> "DeviceCsr":
+        """Keep the first ``nrows`` rows (in place; the own rows of a shard's system come first)."""
+        _lib.check(self.lib.pb_csr_truncate_rows(self.h, int(nrows)))
+        self.shape = (int(nrows), self.shape[1])
+        return self
+
     def to_scipy(self) -> sps.csr_matrix:
         ip = np.empty(self.shape[0] + 1, np.int32)
         ix = np.empty(max(self.nnz, 1), np.int32)
         da = np.empty(max(self.nnz, 1), np.float64)
         _lib.check(self.lib.pb_csr_download(self.h, _lib.ptr(ip, _lib._i32p), _lib.ptr(ix, _lib._i32p),
                                             _lib.ptr(da, _lib._f64p)))
-        return sps.csr_matrix((da[:self.nnz], ix[:self.nnz], ip), shape=self.shape)
+        nnz = int(ip[-1])   # after truncate_rows the row-pointer prefix addresses fewer entries
+        return sps.csr_matrix((da[:nnz], ix[:nnz], ip), shape=self.shape)
 
     def __del__(self):
         h = getattr(self, "h", None)

@@ -3,16 +3,26 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
 
-One "step" = one full MPFA assembly (all six matrices) + one full MPSA assembly (all four
-matrices) of the workload grid, inputs resident in HBM.  ``value`` = cells / device time
-(CUDA events on the launching stream, max over ranks).  ``e2e`` = the same through the
-reference-facing operator API (``pb.Mpfa(kw).discretize(g, data)`` + ``pb.Mpsa(kw).discretize``)
-from host NumPy arrays to host scipy CSR, plan construction, H2D and D2H inside the timed region.
-N > 1: one process per GPU (torchrun), each rank assembles its own subdomain of the same size
-(weak scaling; the assembly has no data-path collective -- SURVEY.md §8e).
+One "step" = one full MPFA assembly (all six matrices) + one full MPSA assembly (all four matrices) of the
+workload grid, inputs resident in HBM.  ``value`` = cells of the WHOLE mesh / device time (CUDA events on the
+launching stream, max over ranks).
 
-``--impl reference`` times the CPU restatement of the reference's algorithm (oracle/, the
-checker) on the host cores, on a bounded sample of the same kind of mesh.
+N > 1 (torchrun, one process per GPU): ONE mesh is sharded -- recursive coordinate bisection of the cells, every
+rank takes the interaction regions of its own cells' nodes plus one halo layer of cells
+(``porepy_b200.shard``; no data-path collective in the assembly) -> strong scaling on a shared
+mesh.  The sharded flow system (rows of the rank's own cells, assembled on the device from its shard only) is then
+solved by the distributed Jacobi-BiCGStab (NCCL: ghost entries by point-to-point, dot products by all-reduce).
+
+``e2e`` = the same mesh through the reference-facing operator API from HOST arrays (page-locked):
+``pb.Mpfa(kw).discretize`` + ``assemble_matrix_rhs`` and ``pb.Mpsa(kw).discretize`` + ``assemble_matrix_rhs``,
+with [N > 1: the shard extraction,] the topology plan, every H2D copy, the kernels, the device-side system assembly
+and the D2H of the right-hand sides and of a checksum of the system values inside the timed region.  The ten
+discretization matrices and the two system matrices stay in HBM behind scipy-compatible lazy matrices
+(``porepy_b200.sparse.LazyCsr``); ``e2e.variants`` also reports the same call with the two system matrices, and
+with all ten matrices, fetched to the host.
+
+``--impl reference`` times the UNMODIFIED reference (``pp.Mpfa.discretize`` + ``pp.Mpsa.discretize``, loaded from
+/root/reference or oracle/_ref) on the host cores, on a bounded sample of the same kind of mesh.
 """
 from __future__ import annotations
 
@@ -221,6 +231,30 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def pinned_copy(a):
+    """Page-locked copy of a host array (the e2e inputs are read by H2D copies at full PCIe rate)."""
+    from porepy_b200 import _lib
+    a = np.ascontiguousarray(a)
+    out = _lib.pinned_empty(a.size, a.dtype).reshape(a.shape)
+    out[...] = a
+    return out
+
+
+def pin_grid(g):
+    for attr in ("nodes", "face_normals", "face_centers", "face_areas", "cell_centers", "cell_volumes"):
+        setattr(g, attr, pinned_copy(np.asarray(getattr(g, attr), dtype=np.float64)))
+    return g
+
+
+def input_bytes(g, k, C):
+    import scipy.sparse as sps
+    cf, fn = sps.csc_matrix(g.cell_faces), sps.csc_matrix(g.face_nodes)
+    topo = 4 * (cf.indptr.size + cf.indices.size + fn.indptr.size + fn.indices.size) + cf.nnz
+    geo = 8 * (g.nodes.size + g.face_normals.size + g.face_centers.size + g.face_areas.size
+               + g.cell_centers.size + g.cell_volumes.size)
+    return int(topo + geo + k.values.nbytes + C.values.nbytes + 4 * g.num_faces)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -232,6 +266,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spmv", action="store_true")
+    ap.add_argument("--no-krylov", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -256,6 +291,9 @@ def main():
     import torch
     import porepy_b200 as pb
     from porepy_b200 import _lib
+    from porepy_b200 import krylov as kr
+    from porepy_b200 import shard as sh
+    from porepy_b200.sparse import LazyCsr, materialize
     lib = _lib.load()
     if lib.pb_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; porepy_b200 has no CPU path")
@@ -271,15 +309,47 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    def allmax(vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def allsum(vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    # ---- ONE global mesh on every rank's host (the input of the run), sharded for N > 1
     kind, dims, desc = WORKLOADS[args.workload]
-    g = make_grid(kind, dims, seed=rank)
-    k, bc, C, vbc = make_params(g, seed=rank)
+    gg = make_grid(kind, dims, seed=0)
+    gk, gbc, gC, gvbc = make_params(gg, seed=0)
+    nc_global = gg.num_cells
+    eta = pb.determine_eta(gg)
+    bv = np.zeros(gg.num_faces)
+    bfaces = gg.get_all_boundary_faces()
+    bv[bfaces[gg.face_centers[0, bfaces] < 1e-10]] = 1.0           # unit pressure on x = 0
+    part = sh.partition_cells(gg, world) if world > 1 else None
+
+    def my_problem():
+        """This rank's grid and parameters: the whole mesh (N = 1) or its shard, from the global host arrays."""
+        if world == 1:
+            return None, gg, gk, gbc, gC, gvbc, bv
+        s = sh.extract_shard(gg, part, rank)
+        k = pb.SecondOrderTensor.from_values(s.restrict_cell_array(gk.values))
+        C = pb.FourthOrderTensor.from_values(s.restrict_cell_array(gC.values))
+        return s, s.grid, k, sh.restrict_scalar_bc(gbc, s), C, sh.restrict_vector_bc(gvbc, s), bv[s.faces]
+
+    shard, g, k, bc, C, vbc, bvl = my_problem()
     nc = g.num_cells
+    n_own = nc if shard is None else int(shard.own_cell.sum())
     from porepy_b200.fv import scalar_bc_codes, vector_bc_codes
     t0 = time.perf_counter()
     plan = pb.DevicePlan.for_grid(g)
+    if shard is not None:
+        plan.set_active_nodes(shard.own_node)
     plan_s = time.perf_counter() - t0
-    eta = pb.determine_eta(g)
     plan.mpfa_upload(k.values, scalar_bc_codes(bc, g.num_faces), None, eta)
     codes, robw = vector_bc_codes(vbc, 3, g.num_faces)
     plan.mpsa_upload(C.values, codes, robw, eta)
@@ -306,96 +376,149 @@ def main():
     wall = time.perf_counter() - t0
     launches = lib.pb_launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    dev_ms = ms_mpfa + ms_mpsa
-    tt = torch.tensor([dev_ms, wall * 1e3, ms_mpfa, ms_mpsa], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms, ms_mpfa, ms_mpsa = (float(v) for v in tt.tolist())
+    own_ms_mpfa, own_ms_mpsa = ms_mpfa, ms_mpsa
+    dev_ms, wall_ms, ms_mpfa, ms_mpsa = allmax([ms_mpfa + ms_mpsa, wall * 1e3, ms_mpfa, ms_mpsa])
     ms_per_step = dev_ms / args.steps
-    value = world * nc / (ms_per_step * 1e-3)
+    value = nc_global / (ms_per_step * 1e-3)
+    sz = plan.sizes()
+    regions_all = allsum([float((shard.own_node.sum() if shard is not None else g.num_nodes))])[0]
+    cells_all = allsum([float(nc)])[0]
+    del plan
+    if hasattr(g, "_b200_plan"):
+        del g._b200_plan
 
-    # ---- end to end through the operator API: host arrays in, host scipy CSR out
-    e2e = None
-    e2e_vals, h2d, d2h = [], 0, 0
+    # ---- end to end through the operator API: host arrays (page-locked) in, device-resident systems + host rhs out
+    pin_grid(gg)
+    gk.values, gC.values = pinned_copy(gk.values), pinned_copy(gC.values)
+
+    def e2e_call(fetch=None):
+        """One cold call: [shard extraction,] topology plan, H2D, kernels, device system assembly, rhs + checksum D2H.
+        fetch: None | "systems" | "all" additionally downloads the two system matrices / all ten matrices."""
+        d0 = sum(LazyCsr.downloads.values())
+        sh_, lg, lk, lbc, lC, lvbc, lbv = my_problem()
+        if hasattr(lg, "_b200_plan"):
+            del lg._b200_plan               # cold: plan construction is part of the call
+        pl = pb.DevicePlan.for_grid(lg)
+        if sh_ is not None:
+            pl.set_active_nodes(sh_.own_node)
+        d1 = pb.initialize_data({}, "flow", {"second_order_tensor": lk, "bc": lbc, "bc_values": lbv})
+        m1 = pb.Mpfa("flow")
+        m1.discretize(lg, d1)
+        A1, b1 = m1.assemble_matrix_rhs(lg, d1)
+        d2 = pb.initialize_data({}, "mech", {"fourth_order_tensor": lC, "bc": lvbc,
+                                             "bc_values": np.zeros(3 * lg.num_faces), "source": np.zeros(3 * lg.num_cells)})
+        m2 = pb.Mpsa("mech")
+        m2.discretize(lg, d2)
+        A2, b2 = m2.assemble_matrix_rhs(lg, d2)
+        chk = (A1.device_csr.checksum(), A2.device_csr.checksum())   # device reductions, 32 bytes to the host
+        if fetch in ("systems", "all"):
+            materialize({"a": A1, "b": A2})
+        if fetch == "all":
+            materialize(d1[pb.DISCRETIZATION_MATRICES]["flow"])
+            materialize(d2[pb.DISCRETIZATION_MATRICES]["mech"])
+        d2h = b1.nbytes + b2.nbytes + 32 + 8 + sum(LazyCsr.downloads.values()) - d0
+        timing = {"mpfa": m1.last_timing, "mpsa": m2.last_timing}
+        return (A1, b1, A2, b2, chk, sh_, lg, d1, d2), d2h, timing
+
+    e2e_vals, d2h_step, timing = [], 0, {}
+    keep = None
     for i in range(max(args.e2e_steps, 1) + 1):
-        if hasattr(g, "_b200_plan") and i > 0:
-            del g._b200_plan  # cold: plan construction is part of discretize()
-            plan = None
+        keep = None
+        import gc
+        gc.collect()
         barrier()
         t0 = time.perf_counter()
-        d1 = pb.initialize_data({}, "flow", {"second_order_tensor": k, "bc": bc})
-        m1 = pb.Mpfa("flow")
-        m1.discretize(g, d1)
-        d2 = pb.initialize_data({}, "mech", {"fourth_order_tensor": C, "bc": vbc})
-        m2 = pb.Mpsa("mech")
-        m2.discretize(g, d2)
+        keep, d2h_step, timing = e2e_call()
         barrier()
         dt = time.perf_counter() - t0
-        print(f"[bench] e2e call {i}: {dt:.3f} s  mpfa {m1.last_timing}  mpsa {m2.last_timing}", file=sys.stderr)
-        if i == 0:
-            continue  # the first call is the warm-up (page-locked buffer pool, CUDA context)
-        e2e_vals.append(dt)
-        if i == 1:
-            import scipy.sparse as sps
-            cf, fn = sps.csc_matrix(g.cell_faces), sps.csc_matrix(g.face_nodes)
-            topo = 4 * (cf.indptr.size + cf.indices.size + fn.indptr.size + fn.indices.size) + cf.nnz
-            geo = 8 * (g.nodes.size + g.face_normals.size + g.face_centers.size + g.face_areas.size
-                       + g.cell_centers.size + g.cell_volumes.size)
-            h2d = topo + 2 * geo + k.values.nbytes + C.values.nbytes + g.num_faces * 4
-            d2h = sum(m.data.nbytes for m in d1[pb.DISCRETIZATION_MATRICES]["flow"].values())
-            d2h += sum(m.data.nbytes for m in d2[pb.DISCRETIZATION_MATRICES]["mech"].values())
-            timing = {"mpfa": m1.last_timing, "mpsa": m2.last_timing}
-        del d1, d2
-        import gc
-        gc.collect()  # return the page-locked output buffers to the pool (outside the timed region)
-    # warm call: plan cached on the grid (re-discretization of the same mesh, e.g. per time step)
-    barrier()
-    t0 = time.perf_counter()
-    d1 = pb.initialize_data({}, "flow", {"second_order_tensor": k, "bc": bc})
-    pb.Mpfa("flow").discretize(g, d1)
-    d2 = pb.initialize_data({}, "mech", {"fourth_order_tensor": C, "bc": vbc})
-    pb.Mpsa("mech").discretize(g, d2)
-    barrier()
-    warm_s = time.perf_counter() - t0
-    del d1, d2
-    te = torch.tensor([sum(e2e_vals) / len(e2e_vals)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    e2e = {"value": world * nc / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h), "seconds_per_step": e2e_s,
-           "includes": "plan construction + H2D + kernels + D2H + scipy CSR wrapping", "breakdown": timing,
-           "warm_plan_seconds_per_step": warm_s, "warm_plan_value": world * nc / warm_s}
+        print(f"[bench] rank {rank} e2e call {i}: {dt:.3f} s  {timing}", file=sys.stderr)
+        if i > 0:                       # the first call is the warm-up (page-locked pool, CUDA context)
+            e2e_vals.append(dt)
+    e2e_s = allmax([sum(e2e_vals) / len(e2e_vals)])[0]
+    h2d_step = input_bytes(keep[6], k, C) + bvl.nbytes + 2 * 8 * 3 * keep[6].num_faces
+    h2d_all, d2h_all = allsum([float(h2d_step), float(d2h_step)])
+    e2e = {"value": nc_global / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": int(h2d_all),
+           "d2h_bytes_per_step": int(d2h_all), "seconds_per_step": e2e_s,
+           "includes": ("shard extraction + " if world > 1 else "") +
+                       "topology plan + H2D from page-locked host arrays + MPFA/MPSA kernels + device-side "
+                       "A = div @ flux, A = div_nd @ stress and right-hand sides + D2H of the right-hand sides and "
+                       "of the checksums of both system matrices; all twelve matrices stay in HBM behind "
+                       "scipy-compatible lazy matrices",
+           "result_check": {"flow_system_sum_sumsq": keep[4][0], "mech_system_sum_sumsq": keep[4][1]},
+           "breakdown": timing}
+
+    # ---- distributed Jacobi-BiCGStab on the flow system assembled above (rows of the own cells, from the shard)
+    krylov = None
+    if not args.no_krylov:
+        A1, b1 = keep[0], keep[1]
+        a_dev = A1.device_csr
+        diag = torch.as_tensor(a_dev.diagonal()[:n_own], dtype=torch.float64, device="cuda")
+        a_dev.truncate_rows(n_own)
+        if shard is not None:
+            loc = kr.local_system_from_shard(keep[5], part, a_dev)
+        else:
+            loc = kr.LocalSystem(0, 1, np.arange(nc), np.zeros(0, np.int64), a_dev, [0], [np.zeros(0, np.int64)])
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x, info = kr.solve_local(loc, b1[:n_own], diag_own=diag, tol=1e-8, maxiter=3000)
+        barrier()
+        solve_s = allmax([time.perf_counter() - t0])[0]
+        krylov = {"system": "A = div @ flux of the sharded mesh (rows of each rank's own cells)", "rows": int(nc_global),
+                  "iterations": info["iterations"], "converged": bool(info["converged"]), "relres": info["relres"],
+                  "seconds": solve_s, "spmv": info["spmv"], "allreduce": info["allreduce"],
+                  "halo_bytes_per_spmv_all_ranks": int(allsum([float(info["halo_bytes_per_spmv"])])[0]),
+                  "ms_per_iteration": 1e3 * solve_s / max(info["iterations"], 1),
+                  "collectives": "ghost entries: NCCL send/recv per neighbour; dots: one all-reduce of 1-3 doubles"
+                  if world > 1 else "none (single GPU)"}
+        del x, loc
+    keep = None
 
     if rank != 0:
         if dist is not None:
+            dist.barrier()
             dist.destroy_process_group()
         return
+
+    # ---- N = 1 extras: e2e variants with the matrices fetched to the host
+    variants = None
+    if world == 1:
+        variants = {}
+        for name, fetch in (("systems_to_host", "systems"), ("all_matrices_to_host", "all")):
+            import gc
+            for rep in range(2):
+                gc.collect()
+                t0 = time.perf_counter()
+                kk, d2h_v, _ = e2e_call(fetch)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                del kk
+            variants[name] = {"seconds_per_step": dt, "value": nc_global / dt, "d2h_bytes_per_step": int(d2h_v)}
+        e2e["variants"] = variants
 
     # ---- roofline of the dominant kernel family
     plan = pb.DevicePlan.for_grid(g)
     peak, peak_src = measured_peak_hbm()
     nfc, nfb = plan.nnz(0), plan.nnz(1)
-    sz = plan.sizes()
     geo_bytes = 8 * (g.nodes.size + g.face_normals.size + g.face_centers.size + g.face_areas.size
                      + g.cell_centers.size + g.cell_volumes.size)
     topo_bytes = 4 * sz["subcells"] + 4 * sz["subfaces"] + 2 * sz["subhalffaces"]
     bytes_mpfa = geo_bytes + topo_bytes + k.values.nbytes + g.num_faces + 8 * (2 * nfc + 2 * nfb + 6 * nfc)
     bytes_mpsa = geo_bytes + topo_bytes + C.values.nbytes + 3 * g.num_faces + 8 * 9 * (2 * nfc + 2 * nfb)
-    dom = "mpsa" if ms_mpsa >= ms_mpfa else "mpfa"
-    dom_ms = (ms_mpsa if dom == "mpsa" else ms_mpfa) / args.steps
+    dom = "mpsa" if own_ms_mpsa >= own_ms_mpfa else "mpfa"
+    dom_ms = (own_ms_mpsa if dom == "mpsa" else own_ms_mpfa) / args.steps
     dom_bytes = bytes_mpsa if dom == "mpsa" else bytes_mpfa
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     # FP64 work of the local solves (Gauss-Jordan), from the plan's per-node sizes
-    H = plan
     import scipy.sparse as sps
     fn = sps.csc_matrix(g.face_nodes)
     nsf_node = np.bincount(fn.indices, minlength=g.num_nodes)
     cn = (abs(g.face_nodes) @ abs(g.cell_faces))
     cn.data[:] = 1
     nsc_node = np.asarray(cn.sum(axis=1)).ravel()
-    fl_mpfa = float(gj_flops(nsf_node, nsc_node * 4).sum())
-    fl_mpsa = float(gj_flops(3 * nsf_node, nsc_node * 3).sum())
+    act = np.ones(g.num_nodes, bool) if shard is None else shard.own_node
+    fl_mpfa = float(gj_flops(nsf_node[act], nsc_node[act] * 4).sum())
+    fl_mpsa = float(gj_flops(3 * nsf_node[act], nsc_node[act] * 3).sum())
     fl_dom = fl_mpsa if dom == "mpsa" else fl_mpfa
     import ctypes
     fp64_peak = {}
@@ -407,16 +530,17 @@ def main():
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(args.workload)
-        if tj and dom in tj["kernel"]:
+        if tj and dom in tj["kernel"] and world == 1:
             traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
     except Exception:
         pass
     roofline = {
-        "kernel": f"{dom}_kernel (interaction-region assembly)", "bound": "hbm",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "kernel": f"{dom}_kernel (interaction-region assembly), rank 0" + (" of its shard" if world > 1 else ""),
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": dom_ms,
-        "note": "latency bound (serial pivot chain per interaction region), neither HBM nor FP64 bound (SURVEY §8d); fp64 figures alongside",
+        "note": "latency / FP64 bound (serial pivot chain per interaction region), not HBM bound (SURVEY 8d); "
+                "fp64 figures alongside",
         "fp64_gflops_achieved": fl_dom / (dom_ms * 1e-3) / 1e9,
         "fp64_peak_measured": fp64_peak,
         "fp64_frac_of_measured_dmma": (fl_dom / (dom_ms * 1e-3) / 1e12 / fp64_peak["dmma_tflops"])
@@ -425,45 +549,43 @@ def main():
                      "kernel time, against the DMMA / DFMA register-loop peaks measured in this run (pb_fp64_peak)",
         "fp64_flops_per_launch_gauss_jordan": fl_dom,
     }
-    # ---- SpMV on the assembled Jacobian div @ flux (HBM-bound)
+    # ---- SpMV on the assembled Jacobians (HBM-bound): flow (scalar) and mechanics (3 x 3 blocks)
     spmv = None
     if not args.no_spmv:
-        d1 = pb.initialize_data({}, "flow", {"second_order_tensor": k, "bc": bc})
-        m1 = pb.Mpfa("flow")
-        m1.discretize(g, d1)
-        A = (g.divergence(1) @ d1[pb.DISCRETIZATION_MATRICES]["flow"]["flux"]).tocsr()
-        dA = pb.DeviceCsr(A)
-        ms = dA.bench(50)
-        gbs = dA.algorithmic_bytes() / (ms * 1e-3) / 1e9
-        x = np.random.default_rng(0).standard_normal(A.shape[1])
-        t0 = time.perf_counter()
-        for _ in range(5):
-            A @ x
-        cpu_ms = (time.perf_counter() - t0) / 5 * 1e3
-        spmv = {"matrix": "div @ flux", "nrows": int(A.shape[0]), "nnz": int(A.nnz), "ms": ms,
-                "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                "cpu_scipy_ms": cpu_ms, "cpu_scipy_gbs": dA.algorithmic_bytes() / (cpu_ms * 1e-3) / 1e9}
-        del d1
+        kk, _, _ = e2e_call()
+        spmv = {}
+        for name, A in (("div @ flux", kk[0]), ("div_nd @ stress", kk[2])):
+            dA = A.device_csr
+            ms = dA.bench(50)
+            gbs = dA.algorithmic_bytes() / (ms * 1e-3) / 1e9
+            spmv[name] = {"nrows": int(dA.shape[0]), "nnz": int(dA.nnz), "ms": ms, "bound": "hbm", "achieved": gbs,
+                          "peak": peak, "unit": "GB/s", "frac": gbs / peak}
+        del kk
     # ---- CPU baseline: the unmodified reference on a bounded sample of the same kind of mesh
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         cpu = cpu_reference_throughput(kind, passes=1)
     line = {
         "metric": "3D cells/sec MPFA+MPSA assembly", "value": value, "unit": "cells/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": desc, "cells_per_gpu": int(nc), "outputs": "all six MPFA + all four MPSA matrices",
+        "config": {"workload": desc, "cells": int(nc_global), "outputs": "all six MPFA + all four MPSA matrices",
                    "l2": "inputs+outputs per step exceed the 126 MB L2 (no explicit flush)" if nc > 200000
-                   else "small workload: outputs fit L2 (parity-size run, not a bench line)",
-                   "parallelism": f"subdomain-per-GPU x{world}", "plan_seconds": plan_s,
+                   else "small shard/workload: outputs of one step may fit L2",
+                   "parallelism": ("single GPU" if world == 1 else
+                                   f"one mesh, recursive coordinate bisection into {world} shards, node ownership + "
+                                   "one halo layer of cells, no collective in the assembly"),
+                   "cells_per_gpu_incl_halo": cells_all / world, "halo_cell_overhead": cells_all / nc_global - 1.0,
+                   "interaction_regions_all_ranks": regions_all, "plan_seconds": plan_s,
                    "ms_mpfa": ms_mpfa / args.steps, "ms_mpsa": ms_mpsa / args.steps,
                    "wall_ms_per_step": wall_ms / args.steps},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-        "spmv": spmv, "cpu_baseline": cpu,
+        "spmv": spmv, "krylov": krylov, "cpu_baseline": cpu,
     }
     emit(json.dumps(line))
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

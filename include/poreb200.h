@@ -135,18 +135,44 @@ int pb_mpfa_download(pb_plan *p, double *flux, double *bound_flux, double *bound
                      double *bound_pressure_face, double *vector_source,
                      double *bound_pressure_vector_source);
 
+/* ---- device-resident results ----------------------------------------------------------------------------
+ * The value array of one output matrix can be MOVED out of the plan as a pb_values handle: the matrix then
+ * stays in HBM until the caller asks for it (the Python layer stores scipy-compatible matrices whose data /
+ * indices are downloaded on first touch), and the plan allocates a fresh array at its next assemble.  Keys: */
+#define PB_OUT_FLUX 0
+#define PB_OUT_BOUND_FLUX 1
+#define PB_OUT_BOUND_PRESSURE_CELL 2
+#define PB_OUT_BOUND_PRESSURE_FACE 3
+#define PB_OUT_VECTOR_SOURCE 4
+#define PB_OUT_BOUND_PRESSURE_VECTOR_SOURCE 5
+#define PB_OUT_STRESS 6
+#define PB_OUT_BOUND_STRESS 7
+#define PB_OUT_BOUND_DISPLACEMENT_CELL 8
+#define PB_OUT_BOUND_DISPLACEMENT_FACE 9
+/* Biot, coupling tensor q: PB_OUT_BIOT + 5*q + {0 displacement_divergence, 1 boundary_displacement_divergence,
+ * 2 scalar_gradient, 3 mpsa_consistency, 4 bound_displacement_pressure} */
+#define PB_OUT_BIOT 10
+typedef struct pb_values pb_values; /* opaque: device array of doubles */
+int pb_plan_take_output(pb_plan *p, int key, pb_values **out);
+int64_t pb_values_size(const pb_values *v);
+int pb_values_download(pb_values *v, double *host); /* D2H of all values (page-locked host buffer: full PCIe rate) */
+int pb_values_checksum(pb_values *v, double *sum, double *sum_of_squares); /* device reduction, 16-byte read */
+void pb_values_destroy(pb_values *v);
+
 /* Device-side system of the flow problem, replacing the host scipy products of
  * FVElliptic.assemble_matrix_rhs (numerics/fv/fv_elliptic.py:67-112):
  *   A = div @ flux  on the CELL_CELL pattern, kept in HBM as a device CSR handle, no D2H of the matrices;
  *   b = -div @ (bound_flux @ bc_values) [- div @ (vector_source @ v)]   (host vectors in/out).
- * Needs a preceding pb_mpfa_assemble with the flux terms (and the vector source when v != NULL). */
-int pb_mpfa_system(pb_plan *p, struct pb_csr **out);
-int pb_mpfa_rhs(pb_plan *p, const double *bc_values, const double *vector_source, double *rhs);
+ * The discretization matrices are given by their value handles (NULL = the plan's last assembled arrays). */
+int pb_mpfa_system(pb_plan *p, const pb_values *flux, struct pb_csr **out);
+int pb_mpfa_rhs(pb_plan *p, const pb_values *bound_flux, const pb_values *vector_source_discr,
+                const double *bc_values, const double *vector_source, double *rhs);
 /* Same for mechanics (Mpsa.assemble_matrix_rhs, numerics/fv/mpsa.py:486-529): A = div_nd @ stress
  * (nd x nd blocks on the CELL_CELL pattern, row c*nd+i, column k*nd+j) as a device CSR and
  * b = -div_nd @ (bound_stress @ bc_values) + source  (bc_values: nf*nd face-major, source: nc*nd). */
-int pb_mpsa_system(pb_plan *p, struct pb_csr **out);
-int pb_mpsa_rhs(pb_plan *p, const double *bc_values, const double *source, double *rhs);
+int pb_mpsa_system(pb_plan *p, const pb_values *stress, struct pb_csr **out);
+int pb_mpsa_rhs(pb_plan *p, const pb_values *bound_stress, const double *bc_values, const double *source,
+                double *rhs);
 
 /* ---- MPSA / Biot ------------------------------------------------------------------------ */
 /* Replaces Mpsa._stress_discretization (numerics/fv/mpsa.py:531-781),
@@ -212,6 +238,10 @@ int pb_csr_create(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t *indp
 void pb_csr_destroy(pb_csr *a);
 /* Keep the first nrows rows (a row-partitioned system: the rows of a rank's own cells come first). */
 int pb_csr_truncate_rows(pb_csr *a, int64_t nrows);
+/* diagonal (min(nrows, ncols) doubles, host) -- the Jacobi preconditioner of the Krylov solve */
+int pb_csr_diagonal(pb_csr *a, double *diag);
+/* sum and sum of squares of the stored values (device reduction) */
+int pb_csr_checksum(pb_csr *a, double *sum, double *sum_of_squares);
 /* copy a device-resident matrix back (indptr nrows+1, indices nnz, data nnz); sizes via pb_csr_shape */
 int pb_csr_shape(const pb_csr *a, int64_t *nrows, int64_t *ncols, int64_t *nnz);
 int pb_csr_download(pb_csr *a, int32_t *indptr, int32_t *indices, double *data);

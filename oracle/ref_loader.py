@@ -39,6 +39,24 @@ class _Stub(types.ModuleType):
         return MagicMock()
 
 
+REF_MAX_THREADS = 32
+
+
+def _cap_numba_threads() -> None:
+    """The reference inverts its local systems inside a numba ``prange`` (``invert_diagonal_blocks``,
+    matrix_operations.py:1310-1371); every numba thread calls LAPACK.  The image's OpenBLAS supports at most 128
+    calling threads and aborts ("too many memory regions") on the GPU boxes, whose hosts have more cores than
+    that.  Cap the pool at ``REF_MAX_THREADS`` (the inversion is memory bound: more threads measured slower)."""
+    n = max(1, min(os.cpu_count() or 1, REF_MAX_THREADS))
+    if "numba" not in sys.modules:
+        os.environ.setdefault("NUMBA_NUM_THREADS", str(n))
+    try:
+        import numba
+        numba.set_num_threads(min(n, numba.config.NUMBA_NUM_THREADS))
+    except Exception:
+        pass
+
+
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REF_SRC, "porepy"))
 
@@ -57,7 +75,9 @@ def load_porepy():
                 sys.modules[name] = _Stub(name)
     if REF_SRC not in sys.path:
         sys.path.insert(0, REF_SRC)
+    _cap_numba_threads()
     import porepy  # noqa: E402
+    _cap_numba_threads()
 
     return porepy
 

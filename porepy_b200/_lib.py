@@ -43,10 +43,15 @@ _SIGNATURES = {
     "pb_mpfa_upload": (C.c_int, [C.c_void_p, _f64p, _u8p, _f64p, C.c_double]),
     "pb_mpfa_assemble": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _f32p]),
     "pb_mpfa_download": (C.c_int, [C.c_void_p] + [_f64p] * 6),
-    "pb_mpfa_system": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
-    "pb_mpfa_rhs": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p]),
-    "pb_mpsa_system": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
-    "pb_mpsa_rhs": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p]),
+    "pb_plan_take_output": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "pb_values_size": (C.c_int64, [C.c_void_p]),
+    "pb_values_download": (C.c_int, [C.c_void_p, _f64p]),
+    "pb_values_checksum": (C.c_int, [C.c_void_p, _f64p, _f64p]),
+    "pb_values_destroy": (None, [C.c_void_p]),
+    "pb_mpfa_system": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pb_mpfa_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _f64p, _f64p, _f64p]),
+    "pb_mpsa_system": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pb_mpsa_rhs": (C.c_int, [C.c_void_p, C.c_void_p, _f64p, _f64p, _f64p]),
     "pb_mpsa_upload": (C.c_int, [C.c_void_p, _f64p, _u8p, _f64p, C.c_double, C.c_int, _f64p]),
     "pb_mpsa_set_basis": (C.c_int, [C.c_void_p, _f64p]),
     "pb_mpsa_assemble": (C.c_int, [C.c_void_p, _f32p]),
@@ -61,6 +66,8 @@ _SIGNATURES = {
                                 C.POINTER(C.c_void_p)]),
     "pb_csr_destroy": (None, [C.c_void_p]),
     "pb_csr_shape": (C.c_int, [C.c_void_p, _i64p, _i64p, _i64p]),
+    "pb_csr_diagonal": (C.c_int, [C.c_void_p, _f64p]),
+    "pb_csr_checksum": (C.c_int, [C.c_void_p, _f64p, _f64p]),
     "pb_csr_truncate_rows": (C.c_int, [C.c_void_p, C.c_int64]),
     "pb_csr_download": (C.c_int, [C.c_void_p, _i32p, _i32p, _f64p]),
     "pb_csr_spmv": (C.c_int, [C.c_void_p, _f64p, _f64p]),

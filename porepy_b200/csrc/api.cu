@@ -265,13 +265,14 @@ extern "C" int pb_plan_create(int nd, int64_t nc, int64_t nf, int64_t nn, const 
     std::string err;
     {
         // torchrun exports OMP_NUM_THREADS=1; the plan builder is the one OpenMP user here, so give
-        // it this rank's share of the cores (POREB200_PLAN_THREADS overrides)
+        // it this rank's share of the cores (POREB200_PLAN_THREADS overrides) -- through a num_threads clause on
+        // its parallel regions, not through the process-wide setter (numpy / torch keep their thread counts)
         int hw = (int)std::thread::hardware_concurrency();
         const char *lws = getenv("LOCAL_WORLD_SIZE");
         int share = hw / std::max(1, lws ? atoi(lws) : 1);
         const char *ov = getenv("POREB200_PLAN_THREADS");
         int nt = ov ? atoi(ov) : std::min(64, std::max(1, share));
-        omp_set_num_threads(std::max(1, nt));
+        pb::g_plan_threads = std::max(1, nt);
     }
     auto tp0 = std::chrono::steady_clock::now();
     int rc = build_host_plan(nd, nc, nf, nn, cf_indptr, cf_indices, cf_data, fn_indptr, fn_indices,
@@ -653,6 +654,94 @@ extern "C" int pb_mpfa_download(pb_plan *p, double *flux, double *bound_flux, do
 }
 
 // ------------------------------------------------------------------------------------
+// detached output value arrays (device resident; the lazily downloaded matrices of the Python layer)
+// ------------------------------------------------------------------------------------
+struct pb_values {
+    DevBuf buf;
+    int64_t n = 0;
+    cudaStream_t stream = nullptr;  // the plan's stream (kernels that wrote the values were ordered on it)
+};
+
+static DevBuf *output_slot(pb_plan *p, int key, int64_t *n) {
+    const int64_t nd = p->H.nd, nd2 = nd * nd;
+    const int64_t nfc = p->pat_nnz[0], nfb = p->pat_nnz[1], ncc = p->pat_nnz[2], ncb = p->pat_nnz[3];
+    switch (key) {
+        case PB_OUT_FLUX: *n = nfc; return &p->o_flux;
+        case PB_OUT_BOUND_FLUX: *n = nfb; return &p->o_bflux;
+        case PB_OUT_BOUND_PRESSURE_CELL: *n = nfc; return &p->o_bpc;
+        case PB_OUT_BOUND_PRESSURE_FACE: *n = nfb; return &p->o_bpf;
+        case PB_OUT_VECTOR_SOURCE: *n = nfc * nd; return &p->o_vs;
+        case PB_OUT_BOUND_PRESSURE_VECTOR_SOURCE: *n = nfc * nd; return &p->o_bpvs;
+        case PB_OUT_STRESS: *n = nfc * nd2; return &p->o_stress;
+        case PB_OUT_BOUND_STRESS: *n = nfb * nd2; return &p->o_bstress;
+        case PB_OUT_BOUND_DISPLACEMENT_CELL: *n = nfc * nd2; return &p->o_bdc;
+        case PB_OUT_BOUND_DISPLACEMENT_FACE: *n = nfb * nd2; return &p->o_bdf;
+        default: break;
+    }
+    if (key >= PB_OUT_BIOT && key < PB_OUT_BIOT + 5 * PB_MAX_ALPHA) {
+        const int q = (key - PB_OUT_BIOT) / 5, t = (key - PB_OUT_BIOT) % 5;
+        if (q >= p->n_alpha) return nullptr;
+        switch (t) {
+            case 0: *n = ncc * nd; return &p->o_dd[q];
+            case 1: *n = ncb * nd; return &p->o_bdd[q];
+            case 2: *n = nfc * nd; return &p->o_sg[q];
+            case 3: *n = ncc; return &p->o_cons[q];
+            default: *n = nfc * nd; return &p->o_bdp[q];
+        }
+    }
+    return nullptr;
+}
+
+extern "C" int pb_plan_take_output(pb_plan *p, int key, pb_values **out) {
+    if (!p || !out) return fail(PB_EINVAL, "null pointer");
+    int64_t n = 0;
+    DevBuf *slot = output_slot(p, key, &n);
+    if (!slot) return fail(PB_EINVAL, "unknown output key");
+    if (!slot->p || slot->bytes < (size_t)n * sizeof(double)) return fail(PB_EINVAL, "output was not assembled");
+    pb_values *v = new pb_values;
+    v->buf = std::move(*slot);   // the plan allocates a fresh array at its next assemble
+    v->n = n;
+    v->stream = p->stream;
+    *out = v;
+    return PB_OK;
+}
+extern "C" int64_t pb_values_size(const pb_values *v) { return v ? v->n : -1; }
+extern "C" void pb_values_destroy(pb_values *v) { delete v; }
+extern "C" int pb_values_download(pb_values *v, double *host) {
+    if (!v || !host) return fail(PB_EINVAL, "null pointer");
+    if (v->n) CUDA_TRY(cudaMemcpy(host, v->buf.p, (size_t)v->n * sizeof(double), cudaMemcpyDeviceToHost));
+    return PB_OK;
+}
+// sum and sum of squares of the values (device reduction; a 16-byte read that proves the values exist)
+__global__ void values_checksum_kernel(int64_t n, const double *__restrict__ v, double *out) {
+    double s = 0.0, q = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = v[i];
+        s += x; q += x * x;
+    }
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, s); atomicAdd(out + 1, q); }
+}
+int pb_checksum_dev_(const double *v, int64_t n, double *sum, double *sumsq) {
+    DevBuf o;
+    CUDA_TRY(o.ensure(16));
+    CUDA_TRY(cudaMemset(o.p, 0, 16));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)kSMs * 8));
+    values_checksum_kernel<<<grid, 256>>>(n, v, o.as<double>());
+    g_launches++;
+    double h[2];
+    CUDA_TRY(cudaMemcpy(h, o.p, 16, cudaMemcpyDeviceToHost));
+    if (sum) *sum = h[0];
+    if (sumsq) *sumsq = h[1];
+    return PB_OK;
+}
+extern "C" int pb_values_checksum(pb_values *v, double *sum, double *sumsq) {
+    if (!v) return fail(PB_EINVAL, "null pointer");
+    CUDA_TRY(cudaStreamSynchronize(v->stream));
+    return pb_checksum_dev_(v->buf.as<double>(), v->n, sum, sumsq);
+}
+
+// ------------------------------------------------------------------------------------
 // device-side flow system  A = div @ flux,  b = -div @ (bound_flux @ bc [+ vector_source @ v])
 // ------------------------------------------------------------------------------------
 struct pb_csr;
@@ -725,9 +814,11 @@ static int ensure_face_cells(pb_plan *p) {
     return fail(PB_EINVAL, "plan has no face->cell table");
 }
 
-extern "C" int pb_mpfa_system(pb_plan *p, pb_csr **out) {
+extern "C" int pb_mpfa_system(pb_plan *p, const pb_values *flux, pb_csr **out) {
     if (!p || !out) return fail(PB_EINVAL, "null pointer");
-    if (!p->o_flux.p) return fail(PB_EINVAL, "pb_mpfa_assemble (flux terms) has not been called");
+    const double *flux_dev = flux ? flux->buf.as<double>() : p->o_flux.as<double>();
+    if (flux && flux->n != p->pat_nnz[0]) return fail(PB_EINVAL, "flux values do not belong to this plan");
+    if (!flux_dev) return fail(PB_EINVAL, "pb_mpfa_assemble (flux terms) has not been called");
     const HostPlan &H = p->H;
     int rc = ensure_face_cells(p);
     if (rc) return rc;
@@ -739,7 +830,7 @@ extern "C" int pb_mpfa_system(pb_plan *p, pb_csr **out) {
     const int block = 256;
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>((H.nf * 32 + block - 1) / block, (int64_t)kSMs * 16));
     div_flux_kernel<<<grid, block, 0, p->stream>>>(H.nf, p->fc_indptr.as<int32_t>(), p->pat_idx[0].as<int32_t>(),
-                                                   p->o_flux.as<double>(), p->face_cells.as<int32_t>(),
+                                                   flux_dev, p->face_cells.as<int32_t>(),
                                                    p->cc_indptr.as<int32_t>(), p->pat_idx[2].as<int32_t>(),
                                                    pb_csr_data_(a));
     g_launches++;
@@ -749,10 +840,16 @@ extern "C" int pb_mpfa_system(pb_plan *p, pb_csr **out) {
     return PB_OK;
 }
 
-extern "C" int pb_mpfa_rhs(pb_plan *p, const double *bc_values, const double *vector_source, double *rhs) {
+extern "C" int pb_mpfa_rhs(pb_plan *p, const pb_values *bound_flux, const pb_values *vector_source_discr,
+                           const double *bc_values, const double *vector_source, double *rhs) {
     if (!p || !bc_values || !rhs) return fail(PB_EINVAL, "null pointer");
-    if (!p->o_bflux.p) return fail(PB_EINVAL, "pb_mpfa_assemble (flux terms) has not been called");
-    if (vector_source && !p->o_vs.p) return fail(PB_EINVAL, "vector source terms were not assembled");
+    const double *bflux_dev = bound_flux ? bound_flux->buf.as<double>() : p->o_bflux.as<double>();
+    const double *vs_dev = vector_source_discr ? vector_source_discr->buf.as<double>() : p->o_vs.as<double>();
+    if (bound_flux && bound_flux->n != p->pat_nnz[1]) return fail(PB_EINVAL, "bound_flux values do not belong to this plan");
+    if (vector_source_discr && vector_source_discr->n != p->pat_nnz[0] * p->H.nd)
+        return fail(PB_EINVAL, "vector_source values do not belong to this plan");
+    if (!bflux_dev) return fail(PB_EINVAL, "pb_mpfa_assemble (flux terms) has not been called");
+    if (vector_source && !vs_dev) return fail(PB_EINVAL, "vector source terms were not assembled");
     const HostPlan &H = p->H;
     cudaStream_t st = p->stream;
     int rc = ensure_face_cells(p);
@@ -766,12 +863,12 @@ extern "C" int pb_mpfa_rhs(pb_plan *p, const double *bc_values, const double *ve
     const int block = 256;
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>((H.nf * 32 + block - 1) / block, (int64_t)kSMs * 16));
     face_row_dot_kernel<<<grid, block, 0, st>>>(H.nf, p->fb_indptr.as<int32_t>(), p->pat_idx[1].as<int32_t>(),
-                                                p->o_bflux.as<double>(), 1, bc.as<double>(), w.as<double>());
+                                                bflux_dev, 1, bc.as<double>(), w.as<double>());
     g_launches++;
     if (vector_source) {
         CUDA_TRY(vs.upload(vector_source, (size_t)H.nc * H.nd, st));
         face_row_dot_kernel<<<grid, block, 0, st>>>(H.nf, p->fc_indptr.as<int32_t>(), p->pat_idx[0].as<int32_t>(),
-                                                    p->o_vs.as<double>(), H.nd, vs.as<double>(), w.as<double>());
+                                                    vs_dev, H.nd, vs.as<double>(), w.as<double>());
         g_launches++;
     }
     int grid2 = (int)std::max<int64_t>(1, std::min<int64_t>((H.nf + block - 1) / block, (int64_t)kSMs * 16));
@@ -855,9 +952,11 @@ __global__ void neg_div_nd_kernel(int64_t nf, int nd, const int32_t *__restrict_
     }
 }
 
-extern "C" int pb_mpsa_system(pb_plan *p, pb_csr **out) {
+extern "C" int pb_mpsa_system(pb_plan *p, const pb_values *stress, pb_csr **out) {
     if (!p || !out) return fail(PB_EINVAL, "null pointer");
-    if (!p->o_stress.p) return fail(PB_EINVAL, "pb_mpsa_assemble has not been called");
+    const double *stress_dev = stress ? stress->buf.as<double>() : p->o_stress.as<double>();
+    if (stress && stress->n != p->pat_nnz[0] * p->H.nd * p->H.nd) return fail(PB_EINVAL, "stress values do not belong to this plan");
+    if (!stress_dev) return fail(PB_EINVAL, "pb_mpsa_assemble has not been called");
     const HostPlan &H = p->H;
     const int nd = H.nd, nd2 = nd * nd;
     if ((int64_t)p->pat_nnz[2] * nd2 >= 0x7FFFFFFFll) return fail(PB_ENOTIMPL, "system matrix does not fit int32 indices");
@@ -880,7 +979,7 @@ extern "C" int pb_mpsa_system(pb_plan *p, pb_csr **out) {
     if (rc) return rc;
     int grid2 = (int)std::max<int64_t>(1, std::min<int64_t>((H.nf * 32 + block - 1) / block, (int64_t)kSMs * 16));
     div_stress_kernel<<<grid2, block, 0, st>>>(H.nf, nd, p->fc_indptr.as<int32_t>(), p->pat_idx[0].as<int32_t>(),
-                                               p->o_stress.as<double>(), p->face_cells.as<int32_t>(),
+                                               stress_dev, p->face_cells.as<int32_t>(),
                                                p->cc_indptr.as<int32_t>(), p->pat_idx[2].as<int32_t>(), pb_csr_data_(a));
     g_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -889,9 +988,13 @@ extern "C" int pb_mpsa_system(pb_plan *p, pb_csr **out) {
     return PB_OK;
 }
 
-extern "C" int pb_mpsa_rhs(pb_plan *p, const double *bc_values, const double *source, double *rhs) {
+extern "C" int pb_mpsa_rhs(pb_plan *p, const pb_values *bound_stress, const double *bc_values, const double *source,
+                           double *rhs) {
     if (!p || !bc_values || !rhs) return fail(PB_EINVAL, "null pointer");
-    if (!p->o_bstress.p) return fail(PB_EINVAL, "pb_mpsa_assemble has not been called");
+    const double *bstress_dev = bound_stress ? bound_stress->buf.as<double>() : p->o_bstress.as<double>();
+    if (bound_stress && bound_stress->n != p->pat_nnz[1] * p->H.nd * p->H.nd)
+        return fail(PB_EINVAL, "bound_stress values do not belong to this plan");
+    if (!bstress_dev) return fail(PB_EINVAL, "pb_mpsa_assemble has not been called");
     const HostPlan &H = p->H;
     const int nd = H.nd;
     cudaStream_t st = p->stream;
@@ -906,7 +1009,7 @@ extern "C" int pb_mpsa_rhs(pb_plan *p, const double *bc_values, const double *so
     const int block = 256;
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>((H.nf * nd * 32 + block - 1) / block, (int64_t)kSMs * 16));
     bound_stress_dot_kernel<<<grid, block, 0, st>>>(H.nf, nd, p->fb_indptr.as<int32_t>(), p->pat_idx[1].as<int32_t>(),
-                                                    p->o_bstress.as<double>(), bc.as<double>(), w.as<double>());
+                                                    bstress_dev, bc.as<double>(), w.as<double>());
     int grid2 = (int)std::max<int64_t>(1, std::min<int64_t>((H.nf * nd + block - 1) / block, (int64_t)kSMs * 16));
     neg_div_nd_kernel<<<grid2, block, 0, st>>>(H.nf, nd, p->face_cells.as<int32_t>(), w.as<double>(), r.as<double>());
     g_launches += 2;

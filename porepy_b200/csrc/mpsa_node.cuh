@@ -173,28 +173,6 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
     t.sync();
     // ---- phase 3: PS[k][p][a][m] = sum_kappa (C o S)[p,(a,kappa)] E[kappa][m];
     //               SA[p][(u,a)]  += w_k sum_kappa (C o !S)[p,(a,kappa)] E[kappa][m]
-#ifdef PB_EXP_FINE
-    // one item per (sub-cell, p, a): 3x more, 3x smaller items -- hexahedral regions have 72 (k, p)
-    // items on a 64-thread team (a second round for 8 items), 216 fine items fill 3.4 rounds
-    for (int it = t.tid(); it < nsc * ND2 * ND; it += t.size()) {
-        const int kp = it / ND, a = it - kp * ND;
-        const int k = kp / ND2, p = kp - k * ND2;
-        const int64_t c = cell[k];
-        const int pi = p / ND, pr = p - pi * ND;
-        const double *Crow = prm.stiff + (int64_t)c9<ND>(pi, pr) * 9 * prm.stiff_cs + c * prm.stiff_es;
-        double cs[ND];
-#pragma unroll
-        for (int q = 0; q < ND; ++q)
-            cs[q] = sym_mask<ND>(p, a * ND + q) ? Crow[(int64_t)c9<ND>(a, q) * prm.stiff_cs] : 0.0;
-#pragma unroll
-        for (int m = 0; m < ND; ++m) {
-            double v = 0.0;
-#pragma unroll
-            for (int q = 0; q < ND; ++q) v += cs[q] * E[k * ND2 + q * ND + m];
-            PS[((k * ND2 + p) * ND + a) * ND + m] = v;
-        }
-    }
-#else
     for (int it = t.tid(); it < nsc * ND2; it += t.size()) {
         const int k = it / ND2, p = it - k * ND2;
         const int64_t c = cell[k];
@@ -215,7 +193,6 @@ PB_HD void mpsa_node(Team &t, const PlanView &P, const GeoView &G, const MpsaPar
             }
         }
     }
-#endif
     // one item per (p, a, sub-cell); a sub-face entry of SigmaA receives one contribution per side
     // (<= 2, so the sum does not depend on the order).  Node-volume weights w_K = vol_K / sum vol
     // (mpsa.py:1619-1640) are formed on the fly.

@@ -358,11 +358,7 @@ struct TileGJ {
     static_assert(NP <= 256, "row index must fit the 8-bit key field");
     static_assert(NI <= 8, "extend the PB_PICK list");
     static __host__ __device__ constexpr int64_t scratch_doubles_c() {
-#ifdef PB_EXP_ONEBAR
-        return 2 * NP * 4 + 2 * 4 * WP + 16 * (NW + 1) + (8 + NP) / 2 + 4;
-#else
         return NP * 4 + 2 * 4 * WP + 16 * (NW + 1) + (8 + NP) / 2 + 4;
-#endif
     }
     static PB_HD int64_t scratch_doubles(int) { return scratch_doubles_c(); }
 
@@ -383,21 +379,11 @@ struct TileGJ {
             const double f = __shfl_sync(0xffffffffu, m, mj * 4 + k);
             if (mj != k) { m -= f * mk; iv -= f * ik; }
         }
-#ifdef PB_EXP_REDUX
         // max |entry| through one redux.sync on the float-rounded magnitude (monotone bit pattern for
         // non-negative floats; inf and nan map above every finite value) instead of four rounds of
         // 64-bit shuffles: the result is only compared with the growth threshold
         const unsigned key = __reduce_max_sync(0xffffffffu, __float_as_uint(fabsf((float)iv)) & 0x7FFFFFFFu);
         return (key >= 0x7F800000u) ? __longlong_as_double(0x7FF0000000000000LL) : (double)__uint_as_float(key);
-#else
-        double g = fabs(iv);
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-            const double g2 = __shfl_xor_sync(0xffffffffu, g, o);
-            g = (g2 > g || !(g2 == g2)) ? g2 : g;  // propagate nan
-        }
-        return g;
-#endif
     }
 
     // Pivot choice for one panel (one warp).  Fast path: the panel's natural rows p0..p0+3 (the
@@ -526,169 +512,10 @@ struct TileGJ {
         }
     }
 
-#ifdef PB_EXP_ONEBAR
-    // One barrier per panel on the fast path.  A11^-1 is folded into the LEFT factor,
-    //   A22 -= (A21 A11^-1) Raw,   pivot rows += (A11^-1 - I) Raw   (same DMMA; Raw holds those rows),
-    // so the R = A11^-1 Raw pass and its barrier disappear.  The posted pivot rows and the panel dump
-    // are double-buffered by panel parity (a warp may dump panel q+1 while another still tests panel
-    // q); the bookkeeping of panel q is committed right after the barrier of panel q+1.
-    template <class Team>
-    static __device__ __forceinline__ bool solve_onebar(Team &t, double *A, int n, int W, int nrhs,
-                                                        int *rowidx, double *scratch) {
-        const int ti = t.warp(), l = t.lane();
-        const int gr = l >> 2, gc = (l & 3) * 2;
-        const int wend = n + nrhs;
-        double c[RT][NCT][2];
-#pragma unroll
-        for (int rt = 0; rt < RT; ++rt) {
-            const int myrow = 8 * (ti + NW * rt) + gr;
-#pragma unroll
-            for (int tc = 0; tc < NCT; ++tc) {
-                const int col = 8 * tc + gc;
-                c[rt][tc][0] = (myrow < n && col < wend) ? A[myrow * W + col] : 0.0;
-                c[rt][tc][1] = (myrow < n && col + 1 < wend) ? A[myrow * W + col + 1] : 0.0;
-            }
-        }
-        double *P0b = scratch;                 // [2][NP][4]  panel columns, by panel parity
-        double *Rawb = P0b + 2 * NP * 4;       // [2][4][WP]  raw pivot rows, by panel parity
-        double *Ainv = Rawb + 2 * 4 * WP;      // [NW+1][4][4]: copy 0 = slow-path result, copy 1+w = warp w's own
-        int *prs = (int *)(Ainv + 16 * (NW + 1));
-        int *usedf = prs + 8;
-        for (int i = t.tid(); i < NP; i += t.size()) usedf[i] = i < n ? 0 : 1;
-        for (int i = t.tid(); i < 2 * NP * 4; i += t.size()) P0b[i] = 0.0;
-        if (t.tid() == 0) prs[4] = 0;
-        t.sync();
-        const int npanel = (n + 3) >> 2;
-        bool ok = true;
-        int pend_p0 = -1, pend_pw = 0;         // fast-path bookkeeping of the previous panel (uniform)
-        double *mine = Ainv + 16 * (ti + 1);
-#pragma unroll
-        for (int tcp = 0; tcp < NRT && tcp < NCT; ++tcp) {
-            for (int half = 0; half < 2; ++half) {
-                const int q = 2 * tcp + half;
-                if (q >= npanel || !ok) break;
-                const int p0 = 4 * q;
-                const int pw = (n - p0) < 4 ? (n - p0) : 4;
-                double *P0 = P0b + half * NP * 4;      // q & 1 == half
-                double *Raw = Rawb + half * 4 * WP;
-                // S1: panel dump + speculative post of the natural pivot rows
-                if (((l & 3) >> 1) == half) {
-                    const int j0 = 2 * (l & 1);
-#pragma unroll
-                    for (int rt = 0; rt < RT; ++rt) {
-                        const int myrow = 8 * (ti + NW * rt) + gr;
-                        P0[myrow * 4 + j0] = c[rt][tcp][0];
-                        P0[myrow * 4 + j0 + 1] = c[rt][tcp][1];
-                    }
-                }
-                int myp[RT];
-#pragma unroll
-                for (int rt = 0; rt < RT; ++rt) {
-                    const int myrow = 8 * (ti + NW * rt) + gr;
-                    const int j = myrow - p0;
-                    myp[rt] = (j >= 0 && j < pw) ? j : -1;
-                    if (myp[rt] >= 0) {
-#pragma unroll
-                        for (int tc = tcp; tc < NCT; ++tc) {
-                            Raw[myp[rt] * WP + 8 * tc + gc] = c[rt][tc][0];
-                            Raw[myp[rt] * WP + 8 * tc + gc + 1] = c[rt][tc][1];
-                        }
-                    }
-                }
-                t.sync();  // the only barrier of the fast path
-                if (pend_p0 >= 0 && t.tid() < pend_pw) {  // every warp is past the previous panel's test
-                    usedf[pend_p0 + t.tid()] = 1;
-                    rowidx[pend_p0 + t.tid()] = pend_p0 + t.tid();
-                }
-                double iv;
-                const bool fast = try_diagonal_block(l, P0, usedf, p0, pw, iv);
-                if (fast) {
-                    if (l < 16) mine[l] = iv;
-                    pend_p0 = p0;
-                    pend_pw = pw;
-                } else {
-                    pend_p0 = -1;
-                    t.sync();  // the pending bookkeeping is visible, all warps have read usedf / P0
-                    if (ti == 0) factor_panel<false>(l, P0, usedf, prs, Ainv, rowidx, p0, pw);
-                    t.sync();
-                    ok = prs[4] == 0;
-                    if (!ok) break;
-#pragma unroll
-                    for (int rt = 0; rt < RT; ++rt) {
-                        const int myrow = 8 * (ti + NW * rt) + gr;
-                        myp[rt] = -1;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (prs[j] == myrow) myp[rt] = j;
-                        if (myp[rt] >= 0) {
-#pragma unroll
-                            for (int tc = tcp; tc < NCT; ++tc) {
-                                Raw[myp[rt] * WP + 8 * tc + gc] = c[rt][tc][0];
-                                Raw[myp[rt] * WP + 8 * tc + gc + 1] = c[rt][tc][1];
-                            }
-                        }
-                    }
-                    if (l < 16) mine[l] = Ainv[l];
-                    t.sync();
-                }
-                __syncwarp();
-                // S5: left factor (A21 A11^-1); pivot rows get (A11^-1 - I)
-                {
-                    const int k = l & 3;
-                    double af[RT];
-#pragma unroll
-                    for (int rt = 0; rt < RT; ++rt) {
-                        const int myrow = 8 * (ti + NW * rt) + gr;
-                        if (myp[rt] >= 0) {
-                            // the posted row IS this row: row <- row + (A11^-1 - I)[j,:] Raw = A11^-1[j,:] Raw
-                            af[rt] = (k < pw) ? mine[myp[rt] * 4 + k] - (k == myp[rt] ? 1.0 : 0.0) : 0.0;
-                        } else {
-                            double x = 0.0;
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                if (i < pw) x += P0[myrow * 4 + i] * mine[i * 4 + k];
-                            af[rt] = (k < pw) ? -x : 0.0;
-                        }
-                    }
-                    const double *rb = Raw + k * WP + (l >> 2);
-#pragma unroll
-                    for (int tc = tcp; tc < NCT; ++tc) {
-                        const double bf = (k < pw) ? rb[8 * tc] : 0.0;
-#pragma unroll
-                        for (int rt = 0; rt < RT; ++rt) pb_dmma(c[rt][tc], af[rt], bf);
-                    }
-                }
-            }
-        }
-        if (pend_p0 >= 0 && t.tid() < pend_pw) {
-            usedf[pend_p0 + t.tid()] = 1;
-            rowidx[pend_p0 + t.tid()] = pend_p0 + t.tid();
-        }
-        t.sync();
-        if (!ok) return false;
-#pragma unroll
-        for (int rt = 0; rt < RT; ++rt) {
-            const int myrow = 8 * (ti + NW * rt) + gr;
-#pragma unroll
-            for (int tc = 0; tc < NCT; ++tc) {
-                const int col = 8 * tc + gc;
-                if (myrow < n) {
-                    if (col >= n && col < wend) A[myrow * W + col] = c[rt][tc][0];
-                    if (col + 1 >= n && col + 1 < wend) A[myrow * W + col + 1] = c[rt][tc][1];
-                }
-            }
-        }
-        t.sync();
-        return true;
-    }
-#endif
 
     template <class Team>
     static __device__ __forceinline__ bool solve(Team &t, double *A, int n, int W, int nrhs,
                                                  int *rowidx, double *scratch) {
-#ifdef PB_EXP_ONEBAR
-        return solve_onebar(t, A, n, W, nrhs, rowidx, scratch);
-#endif
         const int ti = t.warp(), l = t.lane();
         const int gr = l >> 2, gc = (l & 3) * 2;
         const int wend = n + nrhs;

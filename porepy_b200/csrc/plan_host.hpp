@@ -14,6 +14,9 @@
 // drops exact zeros): row f of FACE_CELL holds every cell sharing a node with face f, etc.
 #pragma once
 #include <algorithm>
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -23,6 +26,16 @@
 #include <vector>
 
 namespace pb {
+
+// threads of the parallel regions below (set by pb_plan_create; tests/emu keeps the default)
+static int g_plan_threads = 0;
+static inline int plan_threads() {
+#if defined(_OPENMP)
+    return g_plan_threads > 0 ? g_plan_threads : omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 
 struct Csr {
     int64_t nrows = 0, ncols = 0;
@@ -76,7 +89,7 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
     std::vector<int32_t> cfaces(cf_indices, cf_indices + cf_indptr[nc]);
     std::vector<int8_t> csign(cf_data, cf_data + cf_indptr[nc]);
     int bad_input = 0;
-#pragma omp parallel for schedule(static) reduction(| : bad_input)
+#pragma omp parallel for schedule(static) reduction(| : bad_input) num_threads(plan_threads())
     for (int64_t c = 0; c < nc; ++c) {
         int b = cf_indptr[c], e = cf_indptr[c + 1];
         for (int i = b + 1; i < e; ++i) {  // insertion sort by face (cells have few faces)
@@ -144,7 +157,7 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
     P.node_nb.assign(nn, 0);
     P.sc_ncn.assign(nc, 0);
     int bad = 0, mx_sf = 0, mx_sc = 0, mx_nb = 0;
-#pragma omp parallel
+#pragma omp parallel num_threads(plan_threads())
     {
         std::vector<int32_t> us;
 #pragma omp for schedule(dynamic, 512) reduction(| : bad) reduction(max : mx_sf, mx_sc, mx_nb)
@@ -213,7 +226,7 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
     std::vector<int32_t> nbf_ptr(nn + 1, 0), nbf_idx;
     for (int64_t s = 0; s < nn; ++s) nbf_ptr[s + 1] = nbf_ptr[s] + P.node_nb[s];
     nbf_idx.resize(nbf_ptr[nn]);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(plan_threads())
     for (int64_t s = 0; s < nn; ++s)
         for (int32_t q = P.node_sf_ptr[s]; q < P.node_sf_ptr[s + 1]; ++q)
             if (P.sf_bloc[q] != 0xFFFF) nbf_idx[nbf_ptr[s] + P.sf_bloc[q]] = P.sf_face[q];
@@ -226,7 +239,7 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
         out.nrows = nrows; out.ncols = ncols;
         out.indptr.assign(nrows + 1, 0);
         for (int pass = 0; pass < 2; ++pass) {
-#pragma omp parallel
+#pragma omp parallel num_threads(plan_threads())
             {
                 std::vector<int32_t> tmp;
 #pragma omp for schedule(dynamic, 1024)
@@ -287,7 +300,7 @@ inline int build_host_plan(int nd, int64_t nc, int64_t nf, int64_t nn, const int
         const int32_t *b = A.indices.data() + A.indptr[r], *e = A.indices.data() + A.indptr[r + 1];
         return (int32_t)(std::lower_bound(b, e, c) - A.indices.data());
     };
-#pragma omp parallel for schedule(dynamic, 512)
+#pragma omp parallel for schedule(dynamic, 512) num_threads(plan_threads())
     for (int64_t s = 0; s < nn; ++s) {
         const int32_t *cells = P.sc_cell.data() + P.node_sc_ptr[s];
         const int32_t *faces = P.sf_face.data() + P.node_sf_ptr[s];

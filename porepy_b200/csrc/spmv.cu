@@ -142,6 +142,40 @@ extern "C" int pb_csr_shape(const pb_csr *a, int64_t *nrows, int64_t *ncols, int
     return PB_OK;
 }
 
+int pb_checksum_dev_(const double *v, int64_t n, double *sum, double *sumsq);  // api.cu
+extern "C" int pb_csr_checksum(pb_csr *a, double *sum, double *sumsq) {
+    if (!a) return pb_fail_(PB_EINVAL, "null matrix");
+    CUDA_TRY(cudaDeviceSynchronize());
+    int64_t nnz = a->nnz;
+    return pb_checksum_dev_(a->data, nnz, sum, sumsq);
+}
+
+__global__ void csr_diagonal_kernel(int64_t nrows, const int32_t *__restrict__ ip, const int32_t *__restrict__ ix,
+                                    const double *__restrict__ data, double *__restrict__ diag) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+        double d = 0.0;
+        for (int q = ip[r]; q < ip[r + 1]; ++q)
+            if (ix[q] == r) d += data[q];
+        diag[r] = d;
+    }
+}
+
+// diagonal of the matrix (Jacobi preconditioner), to a host array of nrows doubles
+extern "C" int pb_csr_diagonal(pb_csr *a, double *diag) {
+    if (!a || !diag) return pb_fail_(PB_EINVAL, "null pointer");
+    const int64_t n = a->nrows < a->ncols ? a->nrows : a->ncols;
+    double *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (n ? n : 1) * sizeof(double)));
+    const int grid = (int)(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
+    csr_diagonal_kernel<<<grid, 256, 0, a->stream>>>(n, a->indptr, a->indices, a->data, d);
+    pb_count_launch_();
+    cudaError_t e = cudaMemcpyAsync(diag, d, n * sizeof(double), cudaMemcpyDeviceToHost, a->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(a->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return pb_fail_(PB_ECUDA, cudaGetErrorString(e));
+    return PB_OK;
+}
+
 extern "C" int pb_csr_truncate_rows(pb_csr *a, int64_t nrows) {
     if (!a || nrows < 0 || nrows > a->nrows) return pb_fail_(PB_EINVAL, "bad row count");
     a->nrows = nrows;  // the row-pointer prefix is a valid CSR; nnz keeps the allocated size

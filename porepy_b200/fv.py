@@ -124,6 +124,44 @@ def lift_vector_source(ip: np.ndarray, ix: np.ndarray, data: np.ndarray, rows: n
     return sps.csr_matrix((da.ravel(), cols, ip.astype(dt) * amb), shape=(ip.size - 1, amb * nc))
 
 
+def _on_device(*mats) -> bool:
+    """All given matrices are ``LazyCsr`` whose values still live only on the device (untouched by the host)."""
+    from .sparse import LazyCsr
+    return all(isinstance(m, LazyCsr) and m.device_values is not None and not m.on_host for m in mats)
+
+
+def _lazy_system(a_dev):
+    """scipy-compatible view of a device-assembled system matrix; downloaded on first touch."""
+    from .sparse import LazyCsr
+    cache = {}
+
+    def host():
+        if "m" not in cache:
+            cache["m"] = a_dev.to_scipy()
+        return cache["m"]
+    return LazyCsr.lazy(a_dev.shape, a_dev.nnz, lambda: host().data, lambda: host().indices, lambda: host().indptr,
+                        device_csr=a_dev)
+
+
+def _lifted(plan, m, rows: np.ndarray, nc: int):
+    """``lift_vector_source`` of the (possibly still device-resident) in-plane matrix ``m``, itself lazy: the
+    lifting runs on the host when the lifted matrix is first touched.  Keeps the in-plane device values and the
+    rotation rows for ``assemble_matrix_rhs`` (which rotates the vector instead of the matrix)."""
+    from .sparse import LazyCsr
+    amb = rows.shape[1]
+    cache = {}
+
+    def built():
+        if "m" not in cache:
+            ip, ix = plan.base_pattern(0)
+            cache["m"] = lift_vector_source(ip, ix, m.data, rows, nc)
+        return cache["m"]
+    out = LazyCsr.lazy((m.shape[0], amb * nc), (m.nnz // 2) * amb, lambda: built().data, lambda: built().indices,
+                       lambda: built().indptr, device_values=getattr(m, "device_values", None), plan=plan)
+    out.__dict__["plane_rows"] = rows
+    return out
+
+
 class DevicePlan:
     """Device-resident sub-cell topology + output patterns of one grid (``pb_plan``).
 
@@ -154,7 +192,7 @@ class DevicePlan:
                                       _lib.ptr(fni, _lib._i32p), C.byref(h)))
         self.plan_seconds = time.perf_counter() - t0
         self.h = h
-        self.fingerprint = (self.nd, self.nc, self.nf, self.nn, int(cf.nnz), int(fn.nnz))
+        self.fingerprint = self._fingerprint(sd, cf, fn)
         self._base = {}
         self._expanded = {}
         self.rotation = None
@@ -168,10 +206,19 @@ class DevicePlan:
                 pass
             self.h = None
 
+    @staticmethod
+    def _fingerprint(sd, cf, fn):
+        """Counts plus a strided checksum of the index arrays: a topology edit that keeps the counts (split faces
+        renumbered, ...) must not reuse a stale plan."""
+        ci, fi = np.asarray(cf.indices), np.asarray(fn.indices)
+        return (int(sd.dim), sd.num_cells, sd.num_faces, sd.num_nodes, int(cf.nnz), int(fn.nnz),
+                int(ci[::7].astype(np.int64).sum()), int(fi[::7].astype(np.int64).sum()),
+                int(np.asarray(cf.indptr)[::5].astype(np.int64).sum()))
+
     @classmethod
     def for_grid(cls, sd) -> "DevicePlan":
         cf, fn = sd.cell_faces, sd.face_nodes
-        fp = (int(sd.dim), sd.num_cells, sd.num_faces, sd.num_nodes, int(cf.nnz), int(fn.nnz))
+        fp = cls._fingerprint(sd, cf, fn)
         plan = getattr(sd, "_b200_plan", None)
         if plan is None or plan.fingerprint != fp:
             plan = cls(sd)
@@ -205,7 +252,9 @@ class DevicePlan:
             ix = np.zeros(max(nz.value, 1), np.int32)
             _lib.check(self.lib.pb_plan_pattern_get(self.h, which, _lib.ptr(ip, _lib._i32p),
                                                     _lib.ptr(ix, _lib._i32p)))
-            self._base[which] = (ip, ix[:nz.value])
+            ix = ix[:nz.value]
+            ip.flags.writeable = ix.flags.writeable = False   # shared by every matrix on this grid
+            self._base[which] = (ip, ix)
         return self._base[which]
 
     def nnz(self, which: int) -> int:
@@ -226,10 +275,11 @@ class DevicePlan:
                     nix = _lib.pinned_empty(max(nnz, 1), np.int32)
                     _lib.check(self.lib.pb_plan_pattern_expanded(
                         self.h, which, br, bc, _lib.ptr(nip, _lib._i32p), _lib.ptr(nix, _lib._i32p)))
-                    self._expanded[key] = (nip, nix[:nnz])
+                    nix = nix[:nnz]
                 else:  # beyond int32: host expansion with 64-bit indices
                     nip, nix = block_expand(ip, ix, br, bc)
-                    self._expanded[key] = (nip, nix)
+                nip.flags.writeable = nix.flags.writeable = False
+                self._expanded[key] = (nip, nix)
         return self._expanded[key]
 
     def matrix(self, which: int, br: int, bc: int, data: np.ndarray) -> sps.csr_matrix:
@@ -282,36 +332,88 @@ class DevicePlan:
                  "bound_pressure_vector_source": (0, 1, nd)}
         return {k: self.matrix(*shape[k], v) for k, v in bufs.items() if v is not None}
 
-    def mpfa_system(self):
-        """A = div @ flux assembled and kept on the device (``DeviceCsr``); needs ``mpfa_assemble``."""
+    # ---- device-resident results (lazily downloaded scipy matrices)
+    def _ncols(self, which: int, bc: int) -> int:
+        return {0: self.nc, 1: self.nf, 2: self.nc, 3: self.nf}[which] * bc
+
+    def take(self, key: int):
+        """Move the value array of output ``key`` (``PB_OUT_*``) out of the plan; it stays in HBM."""
+        from .sparse import DeviceValues
+        h = C.c_void_p()
+        _lib.check(self.lib.pb_plan_take_output(self.h, int(key), C.byref(h)))
+        return DeviceValues(h, self.lib)
+
+    def lazy_matrix(self, key: int, which: int, br: int, bc: int):
+        """Output ``key`` as a ``LazyCsr`` on pattern ``which`` expanded to br x bc blocks: values, indices and
+        row pointers are downloaded when (and if) a caller touches them."""
+        from .sparse import LazyCsr
+        vals = self.take(key)
+        nrows = {0: self.nf, 1: self.nf, 2: self.nc, 3: self.nc}[which] * br
+        pat_nnz = {w: None for w in range(4)}
+        nr, nz = C.c_int64(), C.c_int64()
+        _lib.check(self.lib.pb_plan_pattern_size(self.h, which, C.byref(nr), C.byref(nz)))
+        del pat_nnz
+        return LazyCsr.lazy((nrows, self._ncols(which, bc)), nz.value * br * bc, vals.download,
+                            lambda: self.pattern(which, br, bc)[1], lambda: self.pattern(which, br, bc)[0],
+                            device_values=vals, plan=self)
+
+    def mpfa_lazy(self, flux=True, trace=True, vector_source=True) -> dict:
+        nd = self.nd
+        spec = {"flux": (0, 0, 1, flux), "bound_flux": (1, 1, 1, flux), "bound_pressure_cell": (2, 0, 1, trace),
+                "bound_pressure_face": (3, 1, 1, trace), "vector_source": (4, 0, nd, flux and vector_source),
+                "bound_pressure_vector_source": (5, 0, nd, trace and vector_source)}
+        return {k: self.lazy_matrix(key, which, 1, bc) for k, (key, which, bc, want) in spec.items() if want}
+
+    def mpsa_lazy(self) -> dict:
+        nd = self.nd
+        return {"stress": self.lazy_matrix(6, 0, nd, nd), "bound_stress": self.lazy_matrix(7, 1, nd, nd),
+                "bound_displacement_cell": self.lazy_matrix(8, 0, nd, nd),
+                "bound_displacement_face": self.lazy_matrix(9, 1, nd, nd)}
+
+    def biot_lazy(self, q: int) -> dict:
+        nd, b = self.nd, 10 + 5 * q
+        return {"displacement_divergence": self.lazy_matrix(b, 2, 1, nd),
+                "boundary_displacement_divergence": self.lazy_matrix(b + 1, 3, 1, nd),
+                "scalar_gradient": self.lazy_matrix(b + 2, 0, nd, 1),
+                "mpsa_consistency": self.lazy_matrix(b + 3, 2, 1, 1),
+                "bound_displacement_pressure": self.lazy_matrix(b + 4, 0, nd, 1)}
+
+    @staticmethod
+    def _vh(values):
+        return None if values is None else values.h
+
+    def mpfa_system(self, flux=None):
+        """A = div @ flux assembled and kept on the device (``DeviceCsr``) from the flux values given as a
+        ``DeviceValues`` handle (``None``: the plan's last assembled array)."""
         from .sparse import DeviceCsr
         h = C.c_void_p()
-        _lib.check(self.lib.pb_mpfa_system(self.h, C.byref(h)))
+        _lib.check(self.lib.pb_mpfa_system(self.h, self._vh(flux), C.byref(h)))
         return DeviceCsr.from_handle(h)
 
-    def mpfa_rhs(self, bc_values, vector_source=None) -> np.ndarray:
+    def mpfa_rhs(self, bc_values, vector_source=None, bound_flux=None, vector_source_discr=None) -> np.ndarray:
         """b = -div @ (bound_flux @ bc_values) [- div @ (vector_source_discr @ vector_source)]."""
         bv = _lib.f64(bc_values)
         vs = None if vector_source is None else _lib.f64(vector_source)
         rhs = np.empty(self.nc)
-        _lib.check(self.lib.pb_mpfa_rhs(self.h, _lib.ptr(bv, _lib._f64p), _lib.ptr(vs, _lib._f64p),
+        _lib.check(self.lib.pb_mpfa_rhs(self.h, self._vh(bound_flux), self._vh(vector_source_discr),
+                                        _lib.ptr(bv, _lib._f64p), _lib.ptr(vs, _lib._f64p),
                                         _lib.ptr(rhs, _lib._f64p)))
         return rhs
 
-    def mpsa_system(self):
-        """A = div_nd @ stress assembled and kept on the device (``DeviceCsr``); needs ``mpsa_assemble``."""
+    def mpsa_system(self, stress=None):
+        """A = div_nd @ stress assembled and kept on the device (``DeviceCsr``)."""
         from .sparse import DeviceCsr
         h = C.c_void_p()
-        _lib.check(self.lib.pb_mpsa_system(self.h, C.byref(h)))
+        _lib.check(self.lib.pb_mpsa_system(self.h, self._vh(stress), C.byref(h)))
         return DeviceCsr.from_handle(h)
 
-    def mpsa_rhs(self, bc_values, source=None) -> np.ndarray:
+    def mpsa_rhs(self, bc_values, source=None, bound_stress=None) -> np.ndarray:
         """b = -div_nd @ (bound_stress @ bc_values) + source   (mpsa.py:486-529)."""
         bv = _lib.f64(bc_values)
         src = None if source is None else _lib.f64(source)
         rhs = np.empty(self.nc * self.nd)
-        _lib.check(self.lib.pb_mpsa_rhs(self.h, _lib.ptr(bv, _lib._f64p), _lib.ptr(src, _lib._f64p),
-                                        _lib.ptr(rhs, _lib._f64p)))
+        _lib.check(self.lib.pb_mpsa_rhs(self.h, self._vh(bound_stress), _lib.ptr(bv, _lib._f64p),
+                                        _lib.ptr(src, _lib._f64p), _lib.ptr(rhs, _lib._f64p)))
         return rhs
 
     # ---- MPSA / Biot
@@ -487,8 +589,11 @@ def vector_bc_basis(bc, nd: int):
     if basis is None:
         return None
     b = np.asarray(basis, float)
-    if b.ndim != 3 or np.allclose(b[:nd, :nd], np.eye(nd)[:, :, None]):
+    if b.ndim != 3:
         return None
+    sub = b[:nd, :nd]
+    if all(np.array_equal(sub[i, j], np.full(sub.shape[2], 1.0 if i == j else 0.0)) for i in range(nd) for j in range(nd)):
+        return None   # the identity on every face (exact test: cheap, and anything else IS a rotated basis)
     return np.ascontiguousarray(b[:nd, :nd])
 
 
@@ -683,14 +788,14 @@ class Mpfa(_Base):
         t2 = time.perf_counter()
         ms = plan.mpfa_assemble()
         t3 = time.perf_counter()
-        out = plan.mpfa_download()
+        # device-resident results: scipy-compatible matrices whose arrays are fetched on first touch
+        out = plan.mpfa_lazy() if hasattr(plan, "mpfa_lazy") else plan.mpfa_download()
         if sd.dim == 2 and (amb == 3 or plan.rotation is not None):
             # vector source back to the ambient space, mpfa.py:423-466 (with ambient_dimension = 2 on a tilted
             # plane the reference keeps the first two ambient components, mpfa.py:459-462)
             rows = (np.eye(3) if plan.rotation is None else plan.rotation)[:2, :amb]
-            ip, ix = plan.base_pattern(0)
             for key in (self.vector_source_matrix_key, self.bound_pressure_vector_source_matrix_key):
-                out[key] = lift_vector_source(ip, ix, out[key].data, rows, sd.num_cells)
+                out[key] = _lifted(plan, out[key], rows, sd.num_cells)
         t4 = time.perf_counter()
         self.last_timing = dict(plan_s=t1 - t0, upload_s=t2 - t1, kernel_ms=ms,
                                 assemble_s=t3 - t2, download_s=t4 - t3)
@@ -698,26 +803,40 @@ class Mpfa(_Base):
 
     def assemble_matrix_rhs(self, sd, data: dict):
         """fv_elliptic.py:67-112: A = div @ flux, b = -div @ bound_flux @ bc_values
-        (- div @ vector_source_discr @ vector_source)."""
+        (- div @ vector_source_discr @ vector_source).  When the stored matrices are still device resident
+        (``LazyCsr`` not yet touched) the products run on the GPU from exactly those matrices and ``A`` comes back
+        as a ``LazyCsr`` backed by the device system (``A.device_csr`` feeds ``porepy_b200.krylov`` directly);
+        otherwise the host scipy products of the reference."""
         mats = data[DISCRETIZATION_MATRICES][self.keyword]
         params = data[PARAMETERS][self.keyword]
+        flux, bflux = mats[self.flux_matrix_key], mats[self.bound_flux_matrix_key]
+        vsd = mats.get(self.vector_source_matrix_key) if "vector_source" in params else None
+        if _on_device(flux, bflux) and (vsd is None or _on_device(vsd)) and flux.shape == (sd.num_faces, sd.num_cells):
+            plan = flux.plan
+            vec = None
+            if vsd is not None:
+                vec = np.asarray(params["vector_source"], dtype=np.float64)
+                rows = vsd.__dict__.get("plane_rows")
+                if rows is not None:  # fracture plane: the device values live in the plane's frame
+                    vec = (vec.reshape(-1, rows.shape[1]) @ rows.T).ravel()
+            a = plan.mpfa_system(flux.device_values)
+            b = plan.mpfa_rhs(params["bc_values"], vec, bound_flux=bflux.device_values,
+                              vector_source_discr=None if vsd is None else vsd.device_values)
+            return _lazy_system(a), b
         div = sd.divergence(dim=1)
-        matrix = div @ mats[self.flux_matrix_key]
-        rhs = -div @ (mats[self.bound_flux_matrix_key] @ params["bc_values"])
+        matrix = div @ flux
+        rhs = -div @ (bflux @ params["bc_values"])
         if "vector_source" in params:
             rhs -= div @ (mats[self.vector_source_matrix_key] @ params["vector_source"])
         return matrix, rhs
 
-
     def assemble_matrix_rhs_device(self, sd, data: dict):
-        """Device-resident counterpart of ``assemble_matrix_rhs``: ``A = div @ flux`` is formed on the GPU
-        from the values of the last ``discretize`` (still in HBM) and returned as a ``DeviceCsr`` -- no D2H
-        of the matrices; ``b`` comes back as a host vector.  Feed both to ``porepy_b200.krylov``."""
-        params = data[PARAMETERS][self.keyword]
-        plan = DevicePlan.for_grid(sd)
-        a = plan.mpfa_system()
-        b = plan.mpfa_rhs(params["bc_values"], params.get("vector_source"))
-        return a, b
+        """(``DeviceCsr``, host rhs) of ``assemble_matrix_rhs``; raises unless the stored matrices are still device
+        resident."""
+        a, b = self.assemble_matrix_rhs(sd, data)
+        if getattr(a, "device_csr", None) is None:
+            raise RuntimeError("the discretization matrices are no longer device resident")
+        return a.device_csr, b
 
 
 class Mpsa(_Base):
@@ -780,13 +899,14 @@ class Mpsa(_Base):
         t2 = time.perf_counter()
         ms = plan.mpsa_assemble()
         t3 = time.perf_counter()
-        out = plan.mpsa_download()
+        lazy = hasattr(plan, "mpsa_lazy")
+        out = plan.mpsa_lazy() if lazy else plan.mpsa_download()
         if alphas:
             coupled = {k: {} for k in ("displacement_divergence", "boundary_displacement_divergence",
                                        "scalar_gradient", "mpsa_consistency",
                                        "bound_displacement_pressure")}
             for q, key in enumerate(alphas):
-                for name, m in plan.biot_download(q).items():
+                for name, m in (plan.biot_lazy(q) if lazy else plan.biot_download(q)).items():
                     coupled[name][key] = m
             out.update(coupled)
         t4 = time.perf_counter()
@@ -794,20 +914,27 @@ class Mpsa(_Base):
                                 assemble_s=t3 - t2, download_s=t4 - t3)
         return out
 
-    def assemble_matrix_rhs_device(self, sd, data: dict):
-        """Device-resident counterpart of ``assemble_matrix_rhs`` (see ``Mpfa.assemble_matrix_rhs_device``)."""
-        params = data[PARAMETERS][self.keyword]
-        plan = DevicePlan.for_grid(sd)
-        return plan.mpsa_system(), plan.mpsa_rhs(params["bc_values"], params.get("source"))
-
     def assemble_matrix_rhs(self, sd, data: dict):
-        """mpsa.py:486-529."""
+        """mpsa.py:486-529; device path as in ``Mpfa.assemble_matrix_rhs``."""
         mats = data[DISCRETIZATION_MATRICES][self.keyword]
         params = data[PARAMETERS][self.keyword]
+        stress, bstress = mats["stress"], mats["bound_stress"]
+        if _on_device(stress, bstress) and stress.shape[0] == sd.num_faces * sd.dim:
+            plan = stress.plan
+            a = plan.mpsa_system(stress.device_values)
+            b = plan.mpsa_rhs(params["bc_values"], params["source"], bound_stress=bstress.device_values)
+            return _lazy_system(a), b
         div = sd.divergence(dim=sd.dim)
-        matrix = div @ mats["stress"]
-        rhs = -div @ (mats["bound_stress"] @ params["bc_values"]) + params["source"]
+        matrix = div @ stress
+        rhs = -div @ (bstress @ params["bc_values"]) + params["source"]
         return matrix, rhs
+
+    def assemble_matrix_rhs_device(self, sd, data: dict):
+        """(``DeviceCsr``, host rhs); see ``Mpfa.assemble_matrix_rhs_device``."""
+        a, b = self.assemble_matrix_rhs(sd, data)
+        if getattr(a, "device_csr", None) is None:
+            raise RuntimeError("the discretization matrices are no longer device resident")
+        return a.device_csr, b
 
 
 class Biot(Mpsa):

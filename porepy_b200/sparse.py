@@ -47,6 +47,17 @@ class DeviceCsr:
         self.shape = (int(nrows), self.shape[1])
         return self
 
+    def diagonal(self) -> np.ndarray:
+        d = np.empty(min(self.shape))
+        _lib.check(self.lib.pb_csr_diagonal(self.h, _lib.ptr(d, _lib._f64p)))
+        return d
+
+    def checksum(self):
+        """(sum, sum of squares) of the stored values: a device reduction."""
+        a, b = C.c_double(), C.c_double()
+        _lib.check(self.lib.pb_csr_checksum(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def to_scipy(self) -> sps.csr_matrix:
         ip = np.empty(self.shape[0] + 1, np.int32)
         ix = np.empty(max(self.nnz, 1), np.int32)
@@ -86,3 +97,120 @@ class DeviceCsr:
     def algorithmic_bytes(self) -> int:
         """12 B per non-zero + 20 B per row."""
         return 12 * self.nnz + 20 * self.shape[0]
+
+
+# ------------------------------------------------------------------------------------------
+# device-resident discretization matrices behind the scipy interface
+# ------------------------------------------------------------------------------------------
+
+
+class DeviceValues:
+    """Value array of one output matrix, detached from the plan and kept in HBM (``pb_values``)."""
+
+    def __init__(self, h, lib):
+        self.h, self.lib = h, lib
+        self.size = int(lib.pb_values_size(h))
+
+    def download(self) -> np.ndarray:
+        out = _lib.pinned_empty(self.size)
+        _lib.check(self.lib.pb_values_download(self.h, _lib.ptr(out, _lib._f64p)))
+        return out
+
+    def checksum(self):
+        s, q = C.c_double(), C.c_double()
+        _lib.check(self.lib.pb_values_checksum(self.h, C.byref(s), C.byref(q)))
+        return s.value, q.value
+
+    def __del__(self):
+        h = getattr(self, "h", None)
+        if h is not None and h.value:
+            try:
+                self.lib.pb_values_destroy(h)
+            except Exception:
+                pass
+            self.h = None
+
+
+def _lazy_field(name):
+    slot, loader = "_lazy_" + name, "_load_" + name
+
+    def get(self):
+        d = self.__dict__
+        v = d.get(slot)
+        if v is None:
+            ld = d.get(loader)
+            if ld is None:
+                raise AttributeError(name)
+            v = ld()
+            d[slot] = v
+            d[loader] = None
+            LazyCsr.downloads[name] += int(getattr(v, "nbytes", 0))
+        return v
+
+    def put(self, v):
+        self.__dict__[slot] = v
+        self.__dict__[loader] = None
+    return property(get, put)
+
+
+class LazyCsr(sps.csr_matrix):
+    """A ``scipy.sparse.csr_matrix`` whose ``data`` / ``indices`` / ``indptr`` arrays are fetched from the device on
+    first touch.  ``discretize()`` stores these in ``data[pp.DISCRETIZATION_MATRICES]``: the drop-in contract of the
+    reference (scipy-sparse outputs: ``.shape``, ``@``, slicing, ``sps.block_diag`` ... -- it IS a ``csr_matrix``) is
+    kept, but only the matrices a caller actually uses cross PCIe, and ``assemble_matrix_rhs`` of the same classes
+    builds the system from the device copies without any download.  ``LazyCsr.downloads`` counts the bytes fetched."""
+
+    downloads = {"data": 0, "indices": 0, "indptr": 0}
+    data = _lazy_field("data")
+    indices = _lazy_field("indices")
+    indptr = _lazy_field("indptr")
+
+    @classmethod
+    def lazy(cls, shape, nnz, load_data, load_indices, load_indptr, device_values=None, device_csr=None, plan=None):
+        zero = np.broadcast_to(np.float64(0.0), (0,))
+        self = cls((zero, np.zeros(0, np.int32), np.zeros(int(shape[0]) + 1, np.int32)), shape=shape, copy=False)
+        d = self.__dict__
+        d["_lazy_data"] = d["_lazy_indices"] = d["_lazy_indptr"] = None
+        d["_load_data"], d["_load_indices"], d["_load_indptr"] = load_data, load_indices, load_indptr
+        d["_structural_nnz"] = int(nnz)
+        d["device_values"], d["device_csr"], d["plan"] = device_values, device_csr, plan
+        self.has_sorted_indices = True
+        self.has_canonical_format = True
+        return self
+
+    @property
+    def on_host(self) -> bool:
+        """True once the values have been downloaded (or the matrix was built from host arrays)."""
+        return self.__dict__.get("_lazy_data") is not None
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float64) if not self.on_host else self.data.dtype
+
+    @property
+    def nnz(self):
+        n = self.__dict__.get("_structural_nnz")
+        return n if (n is not None and self.__dict__.get("_lazy_indptr") is None) else int(self.indptr[-1])
+
+    def _getnnz(self, axis=None):
+        if axis is None:
+            return self.nnz
+        return super()._getnnz(axis)
+
+    def getnnz(self, axis=None):
+        return self._getnnz(axis)
+
+    def __repr__(self):
+        where = "host" if self.on_host else "device"
+        return f"<{self.shape[0]}x{self.shape[1]} LazyCsr, {self.nnz} stored elements, values on the {where}>"
+
+
+def materialize(obj):
+    """Force every ``LazyCsr`` in a matrix dictionary (or a single matrix) to the host; returns the bytes fetched."""
+    before = sum(LazyCsr.downloads.values())
+    if isinstance(obj, dict):
+        for v in obj.values():
+            materialize(v)
+    elif isinstance(obj, LazyCsr):
+        obj.data, obj.indices, obj.indptr  # noqa: B018  (property access triggers the download)
+    return sum(LazyCsr.downloads.values()) - before

@@ -263,6 +263,7 @@ def test_sharded_equals_unsplit():
               "bound_displacement_face": ("face", "face", 3, 3)}
     for r in range(2):
         s = sh.extract_shard(g, part, r)
+        pb.DevicePlan.for_grid(s.grid).set_active_nodes(s.own_node)   # the shard's own interaction regions only
         d1 = pb.initialize_data({}, "flow", {
             "second_order_tensor": pb.SecondOrderTensor.from_values(s.restrict_cell_array(k.values)),
             "bc": sh.restrict_scalar_bc(bc, s)})
@@ -308,11 +309,11 @@ def test_high_contrast_vs_oracle(make):
 
 
 def test_device_side_flow_system_and_solve():
-    """A = div @ flux and b assembled on the device (no D2H of the matrices) equal the host
-    products of fv_elliptic.py:67-112; BiCGStab on the device matrix reproduces the direct solve."""
+    """``discretize`` leaves device-resident lazy matrices; ``assemble_matrix_rhs`` then forms A = div @ flux and b on
+    the device FROM THOSE MATRICES (no download) and equals the host products of fv_elliptic.py:67-112; two
+    keywords on one grid do not see each other's values; BiCGStab on the device matrix reproduces the direct solve."""
     from porepy_b200 import krylov as kr
-    from porepy_b200.fv import DevicePlan
-    import torch
+    from porepy_b200.sparse import LazyCsr
     g = pb.structured_tet_grid([6, 5, 4])
     rng = np.random.default_rng(3)
     k = _aniso(g.num_cells, rng)
@@ -325,20 +326,33 @@ def test_device_side_flow_system_and_solve():
                                            "vector_source": vs})
     d = pb.Mpfa("flow")
     d.discretize(g, data)
-    A_host, b_host = d.assemble_matrix_rhs(g, data)
-    plan = DevicePlan.for_grid(g)
-    A_dev = plan.mpfa_system()
-    assert rel_err(A_host, A_dev.to_scipy()) < 1e-13
-    b_dev = plan.mpfa_rhs(bv, vs)
-    assert np.abs(b_dev - b_host).max() <= 1e-12 * np.abs(b_host).max()
+    mats = data[pb.DISCRETIZATION_MATRICES]["flow"]
+    assert all(isinstance(m, LazyCsr) and not m.on_host for m in mats.values())
+    # a second keyword on the same grid (shared plan) with another permeability, discretized AFTERWARDS
+    other = pb.initialize_data({}, "fourier", {"second_order_tensor": pb.SecondOrderTensor(7.0 * np.ones(g.num_cells)),
+                                               "bc": bc, "bc_values": bv})
+    pb.Mpfa("fourier").discretize(g, other)
+    before = dict(LazyCsr.downloads)
+    A_lazy, b_dev = d.assemble_matrix_rhs(g, data)
+    A_dev = A_lazy.device_csr
+    assert A_dev is not None and LazyCsr.downloads == before and not mats["flux"].on_host
     x = rng.standard_normal(g.num_cells)
-    assert np.abs(A_dev @ x - A_host @ x).max() <= 1e-12 * np.abs(A_host @ x).max()
+    y_dev = A_dev @ x
+    # host products from downloaded copies of the SAME stored matrices
+    div = g.divergence(dim=1)
+    A_host = (div @ sps.csr_matrix(mats["flux"])).tocsr()
+    b_host = -div @ (mats["bound_flux"] @ bv) - div @ (mats["vector_source"] @ vs)
+    assert mats["flux"].on_host
+    assert rel_err(A_host, A_dev.to_scipy()) < 1e-13
+    assert rel_err(A_host, A_lazy) < 1e-13            # the lazy system downloads on touch
+    assert np.abs(b_dev - b_host).max() <= 1e-12 * np.abs(b_host).max()
+    assert np.abs(y_dev - A_host @ x).max() <= 1e-12 * np.abs(A_host @ x).max()
+    # once touched by the host the matrices are used from the host (they may have been edited there)
+    A2, b2 = d.assemble_matrix_rhs(g, data)
+    assert getattr(A2, "device_csr", None) is None and rel_err(A_host, A2) < 1e-13
     # solve on the device matrix
-    loc = kr.build_local_system(A_host, np.zeros(g.num_cells, dtype=np.int64), 0, 1)
-    op = kr.DistributedOperator(loc, torch.device("cuda", 0))
-    op.dev_csr = A_dev  # use the device-assembled matrix
-    diag = torch.as_tensor(A_host.diagonal(), dtype=torch.float64, device="cuda")
-    xs, info = kr.bicgstab(op, torch.as_tensor(b_dev, device="cuda"), tol=1e-11, diag_own=diag)
+    loc = kr.LocalSystem(0, 1, np.arange(g.num_cells), np.zeros(0, np.int64), A_dev, [0], [np.zeros(0, np.int64)])
+    xs, info = kr.solve_local(loc, b_dev, diag_own=A_dev.diagonal(), tol=1e-11)
     ref = spla.spsolve(sps.csc_matrix(A_host), b_host)
     assert info["converged"] and np.linalg.norm(xs.cpu().numpy() - ref) <= 1e-8 * np.linalg.norm(ref)
 
@@ -359,10 +373,49 @@ def test_device_side_mechanics_system():
                                            "bc_values": bv.ravel("F"), "source": src})
     d = pb.Mpsa("mech")
     d.discretize(g, data)
-    A_host, b_host = d.assemble_matrix_rhs(g, data)
     A_dev, b_dev = d.assemble_matrix_rhs_device(g, data)
+    mats = data[pb.DISCRETIZATION_MATRICES]["mech"]
+    div = g.divergence(dim=3)
+    A_host = (div @ sps.csr_matrix(mats["stress"])).tocsr()
+    b_host = -div @ (mats["bound_stress"] @ bv.ravel("F")) + src
     assert A_dev.shape == A_host.shape
     assert rel_err(A_host, A_dev.to_scipy()) < 1e-13
     assert np.abs(b_dev - b_host).max() <= 1e-12 * np.abs(b_host).max()
     x = rng.standard_normal(3 * nc)
     assert np.abs(A_dev @ x - A_host @ x).max() <= 1e-12 * np.abs(A_host @ x).max()
+    s, q = A_dev.checksum()
+    assert abs(s - A_host.data.sum()) <= 1e-9 * np.abs(A_host.data).sum() and abs(q - (A_host.data ** 2).sum()) <= 1e-10 * q
+
+
+def test_sharded_system_rows_on_the_device():
+    """Two shards of one mesh, each on its own plan restricted to its own nodes (``set_active_nodes``): the rows of
+    the own cells of the device-assembled flow system are the rows of the unsplit system (columns [own | ghost])."""
+    from porepy_b200 import shard as sh
+    g = pb.structured_tet_grid([5, 4, 4])
+    rng = np.random.default_rng(9)
+    k = _aniso(g.num_cells, rng)
+    bc = _mixed_scalar_bc(g)
+    bf = g.get_all_boundary_faces()
+    bv = np.zeros(g.num_faces)
+    bv[bf] = rng.random(bf.size)
+    data = pb.initialize_data({}, "flow", {"second_order_tensor": k, "bc": bc, "bc_values": bv})
+    d = pb.Mpfa("flow")
+    d.discretize(g, data)
+    A, b = d.assemble_matrix_rhs(g, data)
+    A = sps.csr_matrix(A)
+    part = sh.partition_cells(g, 2)
+    for r in range(2):
+        s = sh.extract_shard(g, part, r)
+        n_own = int(s.own_cell.sum())
+        plan = pb.DevicePlan.for_grid(s.grid)
+        plan.set_active_nodes(s.own_node)
+        dl = pb.initialize_data({}, "flow", {
+            "second_order_tensor": pb.SecondOrderTensor.from_values(s.restrict_cell_array(k.values)),
+            "bc": sh.restrict_scalar_bc(bc, s), "bc_values": bv[s.faces], "mpfa_eta": pb.determine_eta(g)})
+        dd = pb.Mpfa("flow")
+        dd.discretize(s.grid, dl)
+        a_dev, b_loc = dd.assemble_matrix_rhs_device(s.grid, dl)
+        rows = a_dev.truncate_rows(n_own).to_scipy()
+        ref = A[s.cells[:n_own]][:, s.cells]
+        assert abs(ref - rows).max() <= 1e-12 * abs(A).max()
+        assert np.abs(b_loc[:n_own] - b[s.cells[:n_own]]).max() <= 1e-12 * np.abs(b).max()

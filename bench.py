@@ -395,29 +395,46 @@ def main():
         """One cold call: [shard extraction,] topology plan, H2D, kernels, device system assembly, rhs + checksum D2H.
         fetch: None | "systems" | "all" additionally downloads the two system matrices / all ten matrices."""
         d0 = sum(LazyCsr.downloads.values())
+        tm = {}
+        t_ = time.perf_counter()
+
+        def lap(name):
+            nonlocal t_
+            now = time.perf_counter()
+            tm[name] = now - t_
+            t_ = now
         sh_, lg, lk, lbc, lC, lvbc, lbv = my_problem()
+        lap("shard_extraction")
         if hasattr(lg, "_b200_plan"):
             del lg._b200_plan               # cold: plan construction is part of the call
         pl = pb.DevicePlan.for_grid(lg)
         if sh_ is not None:
             pl.set_active_nodes(sh_.own_node)
+        lap("topology_plan")
         d1 = pb.initialize_data({}, "flow", {"second_order_tensor": lk, "bc": lbc, "bc_values": lbv})
         m1 = pb.Mpfa("flow")
         m1.discretize(lg, d1)
+        lap("mpfa_discretize")
         A1, b1 = m1.assemble_matrix_rhs(lg, d1)
+        lap("flow_system")
         d2 = pb.initialize_data({}, "mech", {"fourth_order_tensor": lC, "bc": lvbc,
                                              "bc_values": np.zeros(3 * lg.num_faces), "source": np.zeros(3 * lg.num_cells)})
         m2 = pb.Mpsa("mech")
         m2.discretize(lg, d2)
+        lap("mpsa_discretize")
         A2, b2 = m2.assemble_matrix_rhs(lg, d2)
+        lap("mech_system")
         chk = (A1.device_csr.checksum(), A2.device_csr.checksum())   # device reductions, 32 bytes to the host
+        lap("checksums")
         if fetch in ("systems", "all"):
             materialize({"a": A1, "b": A2})
         if fetch == "all":
             materialize(d1[pb.DISCRETIZATION_MATRICES]["flow"])
             materialize(d2[pb.DISCRETIZATION_MATRICES]["mech"])
+        if fetch:
+            lap("fetch_to_host")
         d2h = b1.nbytes + b2.nbytes + 32 + 8 + sum(LazyCsr.downloads.values()) - d0
-        timing = {"mpfa": m1.last_timing, "mpsa": m2.last_timing}
+        timing = {"stages_s": tm, "mpfa": m1.last_timing, "mpsa": m2.last_timing}
         return (A1, b1, A2, b2, chk, sh_, lg, d1, d2), d2h, timing
 
     e2e_vals, d2h_step, timing = [], 0, {}
@@ -465,6 +482,9 @@ def main():
         barrier()
         solve_s = allmax([time.perf_counter() - t0])[0]
         krylov = {"system": "A = div @ flux of the sharded mesh (rows of each rank's own cells)", "rows": int(nc_global),
+                  "inputs_finite": bool(np.isfinite(b1).all() and bool(torch.isfinite(diag).all())),
+                  "diag_min": float(diag.min()), "fused": bool(info.get("fused", False)),
+                  "host_syncs": info.get("host_syncs"), "breakdown": info.get("breakdown"),
                   "iterations": info["iterations"], "converged": bool(info["converged"]), "relres": info["relres"],
                   "seconds": solve_s, "spmv": info["spmv"], "allreduce": info["allreduce"],
                   "halo_bytes_per_spmv_all_ranks": int(allsum([float(info["halo_bytes_per_spmv"])])[0]),

@@ -63,6 +63,9 @@ int pb_set_device(int device);
 /* kernels launched by this library since load (bench.py's gpu_launches evidence). */
 int64_t pb_launch_count(void);
 
+/* Return the device blocks cached by the library's size-keyed pool (see csrc/plan.hpp: DevPool) to the driver. */
+void pb_device_pool_trim(void);
+
 /* FP64 peak of this device, measured by a dependency-free register loop: kind 0 = DMMA (mma.sync.m8n8k4.f64, the
  * pipe of the block Gauss-Jordan), kind 1 = scalar DFMA.  TFLOP/s, best of 5 launches (roofline denominator). */
 int pb_fp64_peak(int kind, double *tflops);
@@ -249,6 +252,25 @@ int pb_csr_download(pb_csr *a, int32_t *indptr, int32_t *indices, double *data);
 int pb_csr_spmv(pb_csr *a, const double *x, double *y);
 /* device pointers (e.g. torch tensors' data_ptr()); stream = cudaStream_t as integer (0 = default) */
 int pb_csr_spmv_dev(pb_csr *a, const double *x_dev, double *y_dev, uint64_t stream);
+/* y = A x on device pointers with the Krylov dot products in the epilogue: *d1 += (w1, y), *d2 += (w2, y)
+ * (w2 NULL: (y, y)); d1 / d2 are device addresses or NULL. */
+int pb_csr_spmv_dots_dev(pb_csr *a, const double *x_dev, double *y_dev, const double *w1_dev, double *d1_dev,
+                         const double *w2_dev, double *d2_dev, uint64_t stream);
+
+/* ---- fused vector kernels of the Jacobi-BiCGStab (csrc/krylov.cu; SURVEY 8f rank 1, replaces the direct solve of
+ * models/solution_strategy.py:830-884).  All pointers are DEVICE pointers; `scal` is the 14-double scalar buffer
+ * described in krylov.cu (every scalar of the recurrence stays on the device; the caller all-reduces slices of it
+ * between the kernels under torch.distributed and polls it every few iterations); cur = iteration parity. */
+int pb_kry_init(int64_t n, const double *b, double *x, double *r, double *rhat, double *p, double *v, double *scal,
+                double tol, uint64_t stream);
+int pb_kry_seed(double *scal, uint64_t stream);
+int pb_kry_p(int64_t n, const double *r, double *p, const double *v, const double *minv, double *ph, double *scal,
+             int cur, uint64_t stream);
+int pb_kry_s(int64_t n, const double *r, const double *v, const double *minv, double *s, double *sh, double *scal,
+             int cur, uint64_t stream);
+int pb_kry_xr(int64_t n, double *x, const double *ph, const double *sh, const double *s, const double *t, double *r,
+              const double *rhat, double *scal, int cur, int carry /* 1 on exactly one rank */, uint64_t stream);
+
 /* time `reps` device SpMVs with CUDA events on the launching stream; returns mean ms */
 int pb_csr_spmv_bench(pb_csr *a, int reps, float *mean_ms);
 

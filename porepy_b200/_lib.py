@@ -28,6 +28,7 @@ _SIGNATURES = {
     "pb_device_count": (C.c_int, []),
     "pb_set_device": (C.c_int, [C.c_int]),
     "pb_launch_count": (C.c_int64, []),
+    "pb_device_pool_trim": (None, []),
     "pb_fp64_peak": (C.c_int, [C.c_int, _f64p]),
     "pb_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
     "pb_host_free": (None, [C.c_void_p]),
@@ -72,6 +73,12 @@ _SIGNATURES = {
     "pb_csr_download": (C.c_int, [C.c_void_p, _i32p, _i32p, _f64p]),
     "pb_csr_spmv": (C.c_int, [C.c_void_p, _f64p, _f64p]),
     "pb_csr_spmv_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "pb_csr_spmv_dots_dev": (C.c_int, [C.c_void_p] * 7 + [C.c_uint64]),
+    "pb_kry_init": (C.c_int, [C.c_int64] + [C.c_void_p] * 7 + [C.c_double, C.c_uint64]),
+    "pb_kry_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "pb_kry_p": (C.c_int, [C.c_int64] + [C.c_void_p] * 6 + [C.c_int, C.c_uint64]),
+    "pb_kry_s": (C.c_int, [C.c_int64] + [C.c_void_p] * 6 + [C.c_int, C.c_uint64]),
+    "pb_kry_xr": (C.c_int, [C.c_int64] + [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_uint64]),
     "pb_csr_spmv_bench": (C.c_int, [C.c_void_p, C.c_int, _f32p]),
 }
 

@@ -31,6 +31,12 @@ static int fail(int code, const std::string &msg) {
 int pb_fail_(int code, const std::string &msg) { return fail(code, msg); }  // for spmv.cu
 void pb_count_launch_() { g_launches++; }
 
+DevPool &pb_dev_pool_() {
+    static DevPool *pool = new DevPool;   // leaked on purpose: DevBufs of static lifetime may release after exit handlers
+    return *pool;
+}
+extern "C" void pb_device_pool_trim(void) { pb_dev_pool_().trim(); }
+
 extern "C" const char *pb_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t pb_last_error_node(void) { return g_err_node; }
 extern "C" int64_t pb_launch_count(void) { return g_launches.load(); }

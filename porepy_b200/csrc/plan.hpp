@@ -9,7 +9,10 @@
 #include <atomic>
 #include <climits>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -33,6 +36,42 @@ using namespace pb;
 // ------------------------------------------------------------------------------------
 // device buffers
 // ------------------------------------------------------------------------------------
+// Freed device arrays are kept in a size-keyed pool (like the page-locked host pool of the Python layer): every
+// discretize() of a model allocates and releases the same ~25 GB of value arrays, and cudaMalloc / cudaFree of such
+// blocks cost tens of milliseconds each and synchronise the device.  POREB200_DEVICE_POOL_BYTES caps the pool
+// (default 64 GiB; 0 disables it).
+struct DevPool {
+    std::mutex mu;
+    std::multimap<size_t, void *> free_blocks;
+    size_t held = 0, cap = 64ull << 30;
+    DevPool() {
+        if (const char *e = getenv("POREB200_DEVICE_POOL_BYTES")) cap = strtoull(e, nullptr, 10);
+    }
+    void *take(size_t n) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = free_blocks.find(n);
+        if (it == free_blocks.end()) return nullptr;
+        void *q = it->second;
+        free_blocks.erase(it);
+        held -= n;
+        return q;
+    }
+    bool give(void *q, size_t n) {
+        std::lock_guard<std::mutex> g(mu);
+        if (n < (1u << 20) || held + n > cap) return false;   // small blocks: the driver's own allocator is fine
+        free_blocks.emplace(n, q);
+        held += n;
+        return true;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto &kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+        held = 0;
+    }
+};
+DevPool &pb_dev_pool_();  // api.cu
+
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
@@ -46,7 +85,7 @@ struct DevBuf {
     }
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p && !pb_dev_pool_().give(p, bytes)) cudaFree(p);
         p = nullptr;
         bytes = 0;
     }
@@ -54,8 +93,14 @@ struct DevBuf {
         if (n <= bytes && p) return cudaSuccess;
         release();
         if (n == 0) n = 8;
+        if ((p = pb_dev_pool_().take(n)) != nullptr) { bytes = n; return cudaSuccess; }
         cudaError_t e = cudaMalloc(&p, n);
-        if (e == cudaSuccess) bytes = n;
+        if (e == cudaErrorMemoryAllocation) {   // give the pooled blocks back to the driver and retry once
+            (void)cudaGetLastError();
+            pb_dev_pool_().trim();
+            e = cudaMalloc(&p, n);
+        }
+        if (e == cudaSuccess) bytes = n; else p = nullptr;
         return e;
     }
     template <class T>
@@ -76,7 +121,11 @@ using Cfg0 = TileGJ<1, 2, 6, 4>;   // team 32  : MPFA hexahedral nodes (12 x 45)
 using Cfg1 = TileGJ<2, 3, 8, 6>;   // team 64  : MPSA hexahedral nodes (36 x 61), DMMA
 using Cfg2 = TileGJ<2, 3, 12, 4>;  // team 64  : Biot hexahedral nodes, DMMA
 using Cfg3 = TileGJ<5, 1, 18, 3>;  // team 160 : MPFA tetrahedral nodes (36 x 133), DMMA
+#ifdef PB_CFG4_WIDE
+using Cfg4 = TileGJ<14, 1, 24, 1>; // experiment: 448 threads, one row tile per warp (96 tile registers instead of 192)
+#else
 using Cfg4 = TileGJ<7, 2, 24, 1>;  // team 224 : MPSA tetrahedral nodes (108 x 181), FP64 tensor cores (DMMA)
+#endif
 using Cfg5 = TileGJ<14, 1, 32, 1>; // team 448 : Biot tetrahedral nodes (108 x 205+), DMMA
 using Cfg6 = SmemGJ;               // team 256 : anything else (in-memory Gauss-Jordan)
 using Cfg7 = RegGJ<8, 14, 6, 1>;   // team 256 : scalar register-tiled alternative for cfg 4 (POREB200_CFG4=reg)

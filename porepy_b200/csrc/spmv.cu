@@ -15,23 +15,25 @@
 #include <atomic>
 #include <string>
 
-#include "../../include/poreb200.h"
+#include "plan.hpp"
 
-extern "C" int64_t pb_launch_count(void);
-int pb_fail_(int code, const std::string &msg);   // api.cu
-void pb_count_launch_();                           // api.cu
-
-#define CUDA_TRY(x)                                                                         \
-    do {                                                                                    \
-        cudaError_t e_ = (x);                                                               \
-        if (e_ != cudaSuccess)                                                              \
-            return pb_fail_(PB_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_));     \
-    } while (0)
 
 struct pb_csr {
     int64_t nrows = 0, ncols = 0, nnz = 0;
     int32_t *indptr = nullptr, *indices = nullptr;
     double *data = nullptr, *x = nullptr, *y = nullptr;
+    DevBuf b_indptr, b_indices, b_data, b_x, b_y;   // owners of the arrays above (pooled device blocks)
+    cudaError_t alloc() {
+        cudaError_t e;
+        if ((e = b_indptr.ensure((size_t)(nrows + 1) * sizeof(int32_t))) != cudaSuccess) return e;
+        if ((e = b_indices.ensure((size_t)(nnz ? nnz : 1) * sizeof(int32_t))) != cudaSuccess) return e;
+        if ((e = b_data.ensure((size_t)(nnz ? nnz : 1) * sizeof(double))) != cudaSuccess) return e;
+        if ((e = b_x.ensure((size_t)(ncols ? ncols : 1) * sizeof(double))) != cudaSuccess) return e;
+        if ((e = b_y.ensure((size_t)(nrows ? nrows : 1) * sizeof(double))) != cudaSuccess) return e;
+        indptr = b_indptr.as<int32_t>(); indices = b_indices.as<int32_t>();
+        data = b_data.as<double>(); x = b_x.as<double>(); y = b_y.as<double>();
+        return cudaSuccess;
+    }
     int tpr = 8;
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -55,6 +57,62 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// y = A x with the dot products of the Krylov recurrence in the epilogue: d1 += (w1, y), d2 += (w2, y)
+// (w2 == y gives |y|^2); one atomic per warp.  Skipped rows never exist: every row is written.
+template <int TPR>
+__global__ void __launch_bounds__(256)
+    csr_spmv_dots_kernel(int64_t nrows, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                         const double *__restrict__ data, const double *__restrict__ x, double *__restrict__ y,
+                         const double *__restrict__ w1, double *d1, const double *__restrict__ w2, int w2_is_y,
+                         double *d2) {
+    const int lane = threadIdx.x & (TPR - 1);
+    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / TPR;
+    const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / TPR;
+    double a1 = 0.0, a2 = 0.0;
+    for (int64_t r = group; r < nrows; r += ngroups) {
+        const int b = __ldg(indptr + r), e = __ldg(indptr + r + 1);
+        double acc = 0.0;
+        for (int q = b + lane; q < e; q += TPR) acc += __ldg(data + q) * __ldg(x + __ldg(indices + q));
+#pragma unroll
+        for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, TPR);
+        if (lane == 0) {
+            y[r] = acc;
+            if (d1) a1 += w1[r] * acc;
+            if (d2) a2 += (w2_is_y ? acc : w2[r]) * acc;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (d1 && a1 != 0.0) atomicAdd(d1, a1);
+        if (d2 && a2 != 0.0) atomicAdd(d2, a2);
+    }
+}
+
+static int launch_spmv_dots(pb_csr *a, const double *x, double *y, const double *w1, double *d1, const double *w2,
+                            int w2_is_y, double *d2, cudaStream_t st) {
+    const int block = 256;
+    const int64_t groups_per_block = block / a->tpr;
+    int64_t need = (a->nrows + groups_per_block - 1) / groups_per_block;
+    int64_t cap = 148LL * 8 * 4;
+    int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+#define PB_SPMV_DOTS(T) csr_spmv_dots_kernel<T><<<grid, block, 0, st>>>(a->nrows, a->indptr, a->indices, a->data, x, y, w1, d1, w2, w2_is_y, d2)
+    switch (a->tpr) {
+        case 2: PB_SPMV_DOTS(2); break;
+        case 4: PB_SPMV_DOTS(4); break;
+        case 8: PB_SPMV_DOTS(8); break;
+        case 16: PB_SPMV_DOTS(16); break;
+        default: PB_SPMV_DOTS(32); break;
+    }
+#undef PB_SPMV_DOTS
+    pb_count_launch_();
+    CUDA_TRY(cudaGetLastError());
+    return PB_OK;
+}
+
 static int launch_spmv(pb_csr *a, const double *x, double *y, cudaStream_t st) {
     const int block = 256;
     const int64_t groups_per_block = block / a->tpr;
@@ -73,9 +131,32 @@ static int launch_spmv(pb_csr *a, const double *x, double *y, cudaStream_t st) {
     return PB_OK;
 }
 
+// pick the lanes-per-row that is fastest for THIS matrix (a few launches, once per matrix; the timing does not
+// depend on the values, so device-assembled matrices are tuned before they are filled)
+static void autotune_tpr(pb_csr *a) {
+    const double mean = a->nrows ? (double)a->nnz / (double)a->nrows : 0.0;
+    a->tpr = mean <= 3 ? 2 : mean <= 6 ? 4 : mean <= 24 ? 8 : mean <= 48 ? 16 : 32;
+    if (a->nnz <= (1 << 20) || mean > 96.0) return;   // long rows: a full warp per row
+    cudaMemsetAsync(a->x, 0, (a->ncols ? a->ncols : 1) * sizeof(double), a->stream);
+    float best = 1e30f;
+    int best_tpr = a->tpr;
+    const int cands[4] = {4, 8, 16, 32};
+    for (int ci = 0; ci < 4; ++ci) {
+        if (cands[ci] * 6 < mean || cands[ci] > 8 * mean) continue;   // implausible for this row length
+        a->tpr = cands[ci];
+        float ms = 1e30f;
+        if (launch_spmv(a, a->x, a->y, a->stream) != PB_OK) break;
+        cudaEventRecord(a->e0, a->stream);
+        for (int i = 0; i < 3; ++i) launch_spmv(a, a->x, a->y, a->stream);
+        cudaEventRecord(a->e1, a->stream);
+        if (cudaEventSynchronize(a->e1) == cudaSuccess) cudaEventElapsedTime(&ms, a->e0, a->e1);
+        if (ms < best) { best = ms; best_tpr = cands[ci]; }
+    }
+    a->tpr = best_tpr;
+}
+
 extern "C" void pb_csr_destroy(pb_csr *a) {
     if (!a) return;
-    cudaFree(a->indptr); cudaFree(a->indices); cudaFree(a->data); cudaFree(a->x); cudaFree(a->y);
     if (a->e0) cudaEventDestroy(a->e0);
     if (a->e1) cudaEventDestroy(a->e1);
     if (a->stream) cudaStreamDestroy(a->stream);
@@ -100,11 +181,7 @@ extern "C" int pb_csr_create(int64_t nrows, int64_t ncols, int64_t nnz, const in
     if ((e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreate(&a->e0)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreate(&a->e1)) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&a->indptr, (nrows + 1) * sizeof(int32_t))) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&a->indices, (nnz ? nnz : 1) * sizeof(int32_t))) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&a->data, (nnz ? nnz : 1) * sizeof(double))) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&a->x, (ncols ? ncols : 1) * sizeof(double))) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&a->y, (nrows ? nrows : 1) * sizeof(double))) != cudaSuccess) return bail(e);
+    if ((e = a->alloc()) != cudaSuccess) return bail(e);
     if ((e = cudaMemcpy(a->indptr, indptr, (nrows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
     if (nnz) {
         if ((e = cudaMemcpy(a->indices, indices, nnz * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
@@ -112,24 +189,7 @@ extern "C" int pb_csr_create(int64_t nrows, int64_t ncols, int64_t nnz, const in
     }
     double mean = nrows ? (double)nnz / (double)nrows : 0.0;
     a->tpr = mean <= 3 ? 2 : mean <= 6 ? 4 : mean <= 24 ? 8 : mean <= 48 ? 16 : 32;
-    // pick the lanes-per-row that is fastest for THIS matrix (a few launches, once per matrix)
-    if (nnz > (1 << 20)) {
-        cudaMemsetAsync(a->x, 0, (ncols ? ncols : 1) * sizeof(double), a->stream);
-        float best = 1e30f;
-        int best_tpr = a->tpr;
-        const int cands[4] = {4, 8, 16, 32};
-        for (int ci = 0; ci < 4; ++ci) {
-            a->tpr = cands[ci];
-            float ms = 1e30f;
-            if (launch_spmv(a, a->x, a->y, a->stream) != PB_OK) break;
-            cudaEventRecord(a->e0, a->stream);
-            for (int i = 0; i < 3; ++i) launch_spmv(a, a->x, a->y, a->stream);
-            cudaEventRecord(a->e1, a->stream);
-            if (cudaEventSynchronize(a->e1) == cudaSuccess) cudaEventElapsedTime(&ms, a->e0, a->e1);
-            if (ms < best) { best = ms; best_tpr = cands[ci]; }
-        }
-        a->tpr = best_tpr;
-    }
+    autotune_tpr(a);
     *out = a;
     return PB_OK;
 }
@@ -206,16 +266,11 @@ int pb_csr_from_device_pattern_(int64_t nrows, int64_t ncols, int64_t nnz, const
     if ((e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreate(&a->e0)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreate(&a->e1)) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&a->indptr, (nrows + 1) * sizeof(int32_t))) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&a->indices, (nnz ? nnz : 1) * sizeof(int32_t))) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&a->data, (nnz ? nnz : 1) * sizeof(double))) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&a->x, (ncols ? ncols : 1) * sizeof(double))) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&a->y, (nrows ? nrows : 1) * sizeof(double))) != cudaSuccess) return bail(e);
+    if ((e = a->alloc()) != cudaSuccess) return bail(e);
     if ((e = cudaMemcpy(a->indptr, indptr_dev, (nrows + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice)) != cudaSuccess) return bail(e);
     if (nnz && (e = cudaMemcpy(a->indices, indices_dev, nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice)) != cudaSuccess) return bail(e);
     if ((e = cudaMemset(a->data, 0, (nnz ? nnz : 1) * sizeof(double))) != cudaSuccess) return bail(e);
-    double mean = nrows ? (double)nnz / (double)nrows : 0.0;
-    a->tpr = mean <= 3 ? 2 : mean <= 6 ? 4 : mean <= 24 ? 8 : mean <= 48 ? 16 : 32;
+    autotune_tpr(a);
     *out = a;
     return PB_OK;
 }
@@ -234,6 +289,15 @@ extern "C" int pb_csr_spmv(pb_csr *a, const double *x, double *y) {
 extern "C" int pb_csr_spmv_dev(pb_csr *a, const double *x_dev, double *y_dev, uint64_t stream) {
     if (!a || !x_dev || !y_dev) return pb_fail_(PB_EINVAL, "null pointer");
     return launch_spmv(a, x_dev, y_dev, (cudaStream_t)stream);
+}
+
+// y = A x on device pointers, plus d1 += (w1, y) and d2 += (w2, y) (w2 == NULL with d2 != NULL: d2 += (y, y));
+// d1 / d2 are device addresses (slots of the Krylov scalar buffer) or NULL
+extern "C" int pb_csr_spmv_dots_dev(pb_csr *a, const double *x_dev, double *y_dev, const double *w1, double *d1,
+                                    const double *w2, double *d2, uint64_t stream) {
+    if (!a || !x_dev || !y_dev) return pb_fail_(PB_EINVAL, "null pointer");
+    if (d1 && !w1) return pb_fail_(PB_EINVAL, "d1 needs w1");
+    return launch_spmv_dots(a, x_dev, y_dev, w1, d1, w2, w2 == nullptr, d2, (cudaStream_t)stream);
 }
 
 extern "C" int pb_csr_spmv_bench(pb_csr *a, int reps, float *mean_ms) {

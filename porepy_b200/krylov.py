@@ -191,9 +191,13 @@ class DistributedOperator:
 
 
 def bicgstab(op: DistributedOperator, b_own, x0=None, tol: float = 1e-10, maxiter: int = 2000,
-             diag_own=None):
+             diag_own=None, check_every: int = 8):
     """Right-preconditioned (Jacobi, optional) BiCGStab on the distributed operator.
-    Returns (x_own, info) with info = {"iterations", "relres", "converged", "spmv", "allreduce"}."""
+    Returns (x_own, info) with info = {"iterations", "relres", "converged", "breakdown", "spmv", "allreduce"}.
+    On a CUDA operator the fused device loop runs (``_bicgstab_fused``: no host synchronisation inside the
+    iteration); the eager torch recurrence below serves the CPU stand-in tests of the host logic."""
+    if op.dev_csr is not None and x0 is None:
+        return _bicgstab_fused(op, b_own, tol, maxiter, diag_own, check_every)
     torch = op.torch
     x = torch.zeros_like(b_own) if x0 is None else x0.clone()
     minv = None if diag_own is None else 1.0 / diag_own
@@ -201,23 +205,31 @@ def bicgstab(op: DistributedOperator, b_own, x0=None, tol: float = 1e-10, maxite
     rhat = r.clone()
     bnorm = float(torch.sqrt(op.dots([(b_own, b_own)])[0]))
     if bnorm == 0.0:
-        return x, {"iterations": 0, "relres": 0.0, "converged": True, "spmv": 0, "allreduce": 1}
+        return x, {"iterations": 0, "relres": 0.0, "converged": True, "breakdown": False, "spmv": 0, "allreduce": 1}
     rho = alpha = omega = 1.0
     v = torch.zeros_like(r)
     p = torch.zeros_like(r)
     nspmv, nred, relres = 0, 1, 1.0
+
+    def done(it, breakdown):
+        return x, {"iterations": it, "relres": relres, "converged": relres < tol, "breakdown": breakdown,
+                   "spmv": nspmv, "allreduce": nred}
     for it in range(1, maxiter + 1):
+        # every scalar below comes out of an all-reduce: identical on all ranks, so all ranks leave together
         rho_new = float(op.dots([(rhat, r)])[0])
         nred += 1
-        if rho_new == 0.0:
-            break
+        if rho_new == 0.0 or not np.isfinite(rho_new):
+            return done(it - 1, True)
         beta = (rho_new / rho) * (alpha / omega)
         p = r + beta * (p - omega * v)
         ph = p if minv is None else p * minv
         v = op.matvec(ph)
         nspmv += 1
-        alpha = rho_new / float(op.dots([(rhat, v)])[0])
+        rv = float(op.dots([(rhat, v)])[0])
         nred += 1
+        if rv == 0.0 or not np.isfinite(rv):
+            return done(it - 1, True)
+        alpha = rho_new / rv
         s = r - alpha * v
         sh = s if minv is None else s * minv
         t = op.matvec(sh)
@@ -231,10 +243,85 @@ def bicgstab(op: DistributedOperator, b_own, x0=None, tol: float = 1e-10, maxite
         rho = rho_new
         relres = float(torch.sqrt(op.dots([(r, r)])[0])) / bnorm
         nred += 1
-        if relres < tol or omega == 0.0:
-            return x, {"iterations": it, "relres": relres, "converged": relres < tol, "spmv": nspmv,
-                       "allreduce": nred}
-    return x, {"iterations": maxiter, "relres": relres, "converged": False, "spmv": nspmv, "allreduce": nred}
+        if not np.isfinite(relres):
+            return done(it, True)
+        if relres < tol:
+            return done(it, False)
+        if omega == 0.0:
+            return done(it, True)
+    return done(maxiter, False)
+
+
+def _bicgstab_fused(op: DistributedOperator, b_own, tol, maxiter, diag_own, check_every):
+    """The iteration on the device: three fused vector kernels (csrc/krylov.cu) and two SpMVs whose epilogue
+    accumulates the dot products; all scalars of the recurrence stay in a 14-double device buffer, all-reduced in
+    contiguous slices (NCCL on the same stream) under torch.distributed.  The host reads the buffer every
+    ``check_every`` iterations only; a sticky device-side DONE flag freezes the vectors once the residual is below
+    the tolerance, so running a few iterations past convergence is harmless."""
+    import ctypes as C
+    from . import _lib
+    torch = op.torch
+    lib = _lib.load()
+    n = op.n_own
+    dev = b_own.device
+    world = op.loc.world
+    vec = lambda: torch.empty(n, dtype=torch.float64, device=dev)  # noqa: E731
+    x, r, rhat, p, v, ph, s, sh, t = (vec() for _ in range(9))
+    minv = None if diag_own is None else (1.0 / diag_own).contiguous()
+    scal = torch.zeros(14, dtype=torch.float64, device=dev)
+    P = lambda a: C.c_void_p(a.data_ptr()) if a is not None else None  # noqa: E731
+    S = lambda i: C.c_void_p(scal.data_ptr() + 8 * i)  # noqa: E731
+    stream = torch.cuda.current_stream().cuda_stream
+    b_own = b_own.contiguous()
+    nred = 0
+
+    def reduce(lo, hi):
+        nonlocal nred
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(scal[lo:hi], group=op.group)
+            nred += 1
+    _lib.check(lib.pb_kry_init(n, P(b_own), P(x), P(r), P(rhat), P(p), P(v), P(scal), float(tol), stream))
+    reduce(10, 11)
+    _lib.check(lib.pb_kry_seed(P(scal), stream))
+    h = scal.cpu().numpy()
+    if h[10] == 0.0:
+        return x, {"iterations": 0, "relres": 0.0, "converged": True, "breakdown": False, "spmv": 0, "allreduce": nred}
+    bb = float(h[10])
+    it, nspmv = 0, 0
+    relres, converged, breakdown = 1.0, False, False
+    csr = op.dev_csr
+    while it < maxiter:
+        for _ in range(min(check_every, maxiter - it)):
+            cur = it & 1
+            g = 5 * cur
+            _lib.check(lib.pb_kry_p(n, P(r), P(p), P(v), P(minv), P(ph), P(scal), cur, stream))
+            xb = op.exchange(ph)
+            _lib.check(lib.pb_csr_spmv_dots_dev(csr.h, P(xb), P(v), P(rhat), S(g + 0), None, None, stream))
+            reduce(g + 0, g + 1)
+            _lib.check(lib.pb_kry_s(n, P(r), P(v), P(minv), P(s), P(sh), P(scal), cur, stream))
+            xb = op.exchange(sh)
+            _lib.check(lib.pb_csr_spmv_dots_dev(csr.h, P(xb), P(t), P(s), S(g + 1), None, S(g + 2), stream))
+            reduce(g + 1, g + 3)
+            _lib.check(lib.pb_kry_xr(n, P(x), P(ph), P(sh), P(s), P(t), P(r), P(rhat), P(scal), cur,
+                                      1 if op.loc.rank == 0 else 0, stream))
+            nx = 5 * (cur ^ 1)
+            reduce(nx + 3, nx + 5)
+            it += 1
+            nspmv += 2
+        h = scal.cpu().numpy()            # the only host synchronisation: every check_every iterations
+        rr = float(h[5 * (it & 1) + 3])
+        if not np.isfinite(h).all():
+            breakdown = True
+            break
+        relres = float(np.sqrt(max(rr, 0.0) / bb))
+        if relres <= tol:
+            converged = True
+            break
+    done_it = int(h[12]) if np.isfinite(h[12]) else it
+    return x, {"iterations": done_it if converged else it, "relres": relres, "converged": converged,
+               "breakdown": breakdown, "spmv": nspmv, "allreduce": nred, "fused": True,
+               "host_syncs": (it + check_every - 1) // check_every + 1}
 
 
 def solve(a, b, owner=None, tol: float = 1e-10, maxiter: int = 2000, jacobi: bool = True, device=None,

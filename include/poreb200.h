@@ -162,6 +162,10 @@ int pb_values_download(pb_values *v, double *host); /* D2H of all values (page-l
 int pb_values_checksum(pb_values *v, double *sum, double *sum_of_squares); /* device reduction, 16-byte read */
 void pb_values_destroy(pb_values *v);
 
+/* One output matrix as a device CSR handle (block-expanded pattern + a copy of the values): operand of the
+ * device-side AD chain below.  which / br / bc as in pb_plan_pattern_expanded. */
+int pb_plan_output_csr(pb_plan *p, const pb_values *v, int which, int br, int bc, struct pb_csr **out);
+
 /* Device-side system of the flow problem, replacing the host scipy products of
  * FVElliptic.assemble_matrix_rhs (numerics/fv/fv_elliptic.py:67-112):
  *   A = div @ flux  on the CELL_CELL pattern, kept in HBM as a device CSR handle, no D2H of the matrices;
@@ -243,6 +247,17 @@ void pb_csr_destroy(pb_csr *a);
 int pb_csr_truncate_rows(pb_csr *a, int64_t nrows);
 /* diagonal (min(nrows, ncols) doubles, host) -- the Jacobi preconditioner of the Krylov solve */
 int pb_csr_diagonal(pb_csr *a, double *diag);
+/* ---- device-side sparse algebra of the AD Jacobian chain (csrc/sparse_ops.cu) ---------------------------------
+ * M @ jac (AdArray.__rmatmul__, numerics/ad/forward_mode.py:565-595), diag(v) @ jac (:613-616), jac + jac,
+ * the block concatenation of MergedOperator.parse (numerics/ad/ad_utils.py:597-664) and the vstack of
+ * EquationSystem.assemble (numerics/ad/equation_system.py:1695-1713), on matrices that stay in HBM.
+ * All results are new handles with sorted rows.  d_dev: DEVICE vector. */
+int pb_csr_spgemm(const pb_csr *a, const pb_csr *b, pb_csr **out);                      /* C = A @ B */
+int pb_csr_axpby(double alpha, const pb_csr *a, double beta, const pb_csr *b, pb_csr **out); /* C = alpha A + beta B */
+int pb_csr_scale_dev(const pb_csr *a, const double *d_dev, int by_cols, pb_csr **out);  /* diag(d) A  |  A diag(d) */
+/* nbr x nbc grid of blocks, row-major, NULL = zero block; row_sizes (nbr) / col_sizes (nbc) */
+int pb_csr_bmat(int nbr, int nbc, const pb_csr *const *blocks, const int64_t *row_sizes, const int64_t *col_sizes,
+                pb_csr **out);
 /* sum and sum of squares of the stored values (device reduction) */
 int pb_csr_checksum(pb_csr *a, double *sum, double *sum_of_squares);
 /* copy a device-resident matrix back (indptr nrows+1, indices nnz, data nnz); sizes via pb_csr_shape */

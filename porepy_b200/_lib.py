@@ -67,6 +67,11 @@ _SIGNATURES = {
                                 C.POINTER(C.c_void_p)]),
     "pb_csr_destroy": (None, [C.c_void_p]),
     "pb_csr_shape": (C.c_int, [C.c_void_p, _i64p, _i64p, _i64p]),
+    "pb_plan_output_csr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "pb_csr_spgemm": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pb_csr_axpby": (C.c_int, [C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pb_csr_scale_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "pb_csr_bmat": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p), _i64p, _i64p, C.POINTER(C.c_void_p)]),
     "pb_csr_diagonal": (C.c_int, [C.c_void_p, _f64p]),
     "pb_csr_checksum": (C.c_int, [C.c_void_p, _f64p, _f64p]),
     "pb_csr_truncate_rows": (C.c_int, [C.c_void_p, C.c_int64]),

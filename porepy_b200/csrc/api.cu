@@ -281,12 +281,6 @@ extern "C" int pb_plan_create(int nd, int64_t nc, int64_t nf, int64_t nn, const 
         pb::g_plan_threads = std::max(1, nt);
     }
     auto tp0 = std::chrono::steady_clock::now();
-    int rc = build_host_plan(nd, nc, nf, nn, cf_indptr, cf_indices, cf_data, fn_indptr, fn_indices,
-                             p->H, err, /*build_pos_maps=*/false, /*build_patterns=*/false);
-    if (rc) {
-        delete p;
-        return fail(rc, err);
-    }
     auto bail = [&](const char *what, cudaError_t e) {
         std::string m = std::string(what) + ": " + cudaGetErrorString(e);
         delete p;
@@ -298,19 +292,41 @@ extern "C" int pb_plan_create(int nd, int64_t nc, int64_t nf, int64_t nn, const 
     if ((e = cudaEventCreate(&p->e1)) != cudaSuccess) return bail("event", e);
     HostPlan &H = p->H;
     cudaStream_t st = p->stream;
+    DevBuf fn_idx_dev;
+    // ---- sub-cell topology: on the device (plan_device.cu); the host construction (plan_host.hpp) is the fallback
+    // for interaction regions beyond the shared-memory sort capacity, and can be forced with POREB200_HOST_PLAN=1
+    int rc = getenv("POREB200_HOST_PLAN") ? -1
+             : pb_build_device_topology_(p, nd, nc, nf, nn, cf_indptr, cf_indices, cf_data, fn_indptr, fn_indices,
+                                         fn_idx_dev, err);
+    if (rc > 0) { delete p; return fail(rc, err); }
+    const bool device_topology = rc == 0;
+    if (getenv("POREB200_PLAN_TIMING")) {
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[plan] topology on the %s        %8.1f ms (since start)\n", device_topology ? "device" : "host  ",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count());
+    }
+    if (!device_topology) {
+        p->H = HostPlan{};
+        rc = build_host_plan(nd, nc, nf, nn, cf_indptr, cf_indices, cf_data, fn_indptr, fn_indices,
+                             p->H, err, /*build_pos_maps=*/false, /*build_patterns=*/false);
+        if (rc) {
+            delete p;
+            return fail(rc, err);
+        }
 #define UP(field, vec)                                                      \
     if ((e = p->field.upload(vec, st)) != cudaSuccess) return bail(#field, e);
-    UP(fn_indptr, H.fn_indptr) UP(node_sc_ptr, H.node_sc_ptr) UP(sc_cell, H.sc_cell)
-    UP(node_sf_ptr, H.node_sf_ptr) UP(sf_face, H.sf_face) UP(sf_sides, H.sf_sides)
-    UP(sf_bloc, H.sf_bloc) UP(slot_sf, H.slot_sf) UP(node_nb, H.node_nb) UP(sc_ncn, H.sc_ncn)
-    UP(posfc_ptr, H.posfc_ptr) UP(posfb_ptr, H.posfb_ptr) UP(poscc_ptr, H.poscc_ptr)
-    UP(poscb_ptr, H.poscb_ptr) UP(nbf_ptr, H.nbf_ptr) UP(nbf_idx, H.nbf_idx) UP(cn_ptr, H.cn_ptr)
-    UP(cn_idx, H.cn_idx)
+        UP(fn_indptr, H.fn_indptr) UP(node_sc_ptr, H.node_sc_ptr) UP(sc_cell, H.sc_cell)
+        UP(node_sf_ptr, H.node_sf_ptr) UP(sf_face, H.sf_face) UP(sf_sides, H.sf_sides)
+        UP(sf_bloc, H.sf_bloc) UP(slot_sf, H.slot_sf) UP(node_nb, H.node_nb) UP(sc_ncn, H.sc_ncn)
+        UP(posfc_ptr, H.posfc_ptr) UP(posfb_ptr, H.posfb_ptr) UP(poscc_ptr, H.poscc_ptr)
+        UP(poscb_ptr, H.poscb_ptr) UP(nbf_ptr, H.nbf_ptr) UP(nbf_idx, H.nbf_idx) UP(cn_ptr, H.cn_ptr)
+        UP(cn_idx, H.cn_idx) UP(face_cells, H.face_cells)
+#undef UP
+        if ((e = fn_idx_dev.upload(fn_indices, (size_t)fn_indptr[nf], st)) != cudaSuccess) return bail("fn_indices", e);
+    }
     {
         // ---- structural patterns on the device (host fallback when a row has > 256 candidates)
         struct PJob { int which; int64_t nrows, ncols; DevBuf *rnp, *rn, *cp, *ci, *ip; };
-        DevBuf fn_idx_dev;
-        if ((e = fn_idx_dev.upload(fn_indices, (size_t)fn_indptr[nf], st)) != cudaSuccess) return bail("fn_indices", e);
         PJob pj[4] = {{0, nf, nc, &p->fn_indptr, &fn_idx_dev, &p->node_sc_ptr, &p->sc_cell, &p->fc_indptr},
                       {1, nf, nf, &p->fn_indptr, &fn_idx_dev, &p->nbf_ptr, &p->nbf_idx, &p->fb_indptr},
                       {2, nc, nc, &p->cn_ptr, &p->cn_idx, &p->node_sc_ptr, &p->sc_cell, &p->cc_indptr},
@@ -367,7 +383,6 @@ extern "C" int pb_plan_create(int nd, int64_t nc, int64_t nf, int64_t nn, const 
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count());
         }
     }
-#undef UP
     {
         struct Job { DevBuf *pos; const std::vector<int64_t> *ptr; DevBuf *pptr; int pat;
                      DevBuf *rp, *re, *cp, *ce; DevBuf *ip; };
@@ -410,8 +425,6 @@ extern "C" int pb_plan_create(int nd, int64_t nc, int64_t nf, int64_t nn, const 
     if (rc) { delete p; return rc; }
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail("sync", e);
     // the host copies of the node-major lists are only needed for the uploads above
-    if ((e = p->face_cells.upload(H.face_cells, st)) != cudaSuccess) return bail("face_cells", e);
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail("sync", e);
     {
         auto drop = [](auto &v) { v.clear(); v.shrink_to_fit(); };
         drop(H.sc_cell); drop(H.sf_face); drop(H.sf_sides); drop(H.sf_bloc); drop(H.slot_sf); drop(H.sc_ncn);
@@ -818,6 +831,33 @@ __global__ void neg_div_kernel(int64_t nf, const int32_t *__restrict__ face_cell
 static int ensure_face_cells(pb_plan *p) {
     if (p->face_cells.p) return PB_OK;  // uploaded by pb_plan_create
     return fail(PB_EINVAL, "plan has no face->cell table");
+}
+
+int pb_csr_alloc_(int64_t nrows, int64_t ncols, int64_t nnz, pb_csr **out);  // spmv.cu
+int32_t *pb_csr_indptr_(pb_csr *a);
+int32_t *pb_csr_indices_(pb_csr *a);
+
+// One output matrix as a device CSR (the block-expanded pattern + a copy of the values): the operand form of the
+// device-side AD chain (sparse_ops.cu).  which / br / bc as in pb_plan_pattern_expanded.
+extern "C" int pb_plan_output_csr(pb_plan *p, const pb_values *v, int which, int br, int bc, pb_csr **out) {
+    if (!p || !v || !out || which < 0 || which > 3 || br < 1 || bc < 1) return fail(PB_EINVAL, "bad arguments");
+    const int64_t nrows = p->pat_rows[which], nnz = p->pat_nnz[which] * br * bc;
+    if (v->n != nnz) return fail(PB_EINVAL, "values do not match this pattern / block size");
+    if (nnz >= 0x7FFFFFFFll || p->pat_cols[which] * bc >= 0x7FFFFFFFll) return fail(PB_ENOTIMPL, "matrix does not fit int32 indices");
+    pb_csr *a = nullptr;
+    int rc = pb_csr_alloc_(nrows * br, p->pat_cols[which] * bc, nnz, &a);
+    if (rc) return rc;
+    DevBuf *bip = which == 0 ? &p->fc_indptr : which == 1 ? &p->fb_indptr : which == 2 ? &p->cc_indptr : &p->cb_indptr;
+    const int block = 256;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nrows * 32 + block - 1) / block, (int64_t)kSMs * 16));
+    expand_pattern_kernel<<<grid, block, 0, p->stream>>>(nrows, bip->as<int32_t>(), p->pat_idx[which].as<int32_t>(), br, bc,
+                                                         pb_csr_indptr_(a), pb_csr_indices_(a));
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (nnz) CUDA_TRY(cudaMemcpyAsync(pb_csr_data_(a), v->buf.p, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    *out = a;
+    return PB_OK;
 }
 
 extern "C" int pb_mpfa_system(pb_plan *p, const pb_values *flux, pb_csr **out) {

@@ -239,3 +239,7 @@ int pb_launch_mpsa2_(pb_plan *p, const MpsaParams &prm, const MpsaOut &o);
 int pb_launch_mpsa3_(pb_plan *p, const MpsaParams &prm, const MpsaOut &o);
 // (ncomp, n) row-major host array -> entity-major records on the device (api.cu)
 int pb_upload_repacked_(cudaStream_t st, DevBuf &tmp, DevBuf &dst, const double *host, int ncomp, int64_t n);
+// sub-cell topology built on the device (plan_device.cu): 0 ok, > 0 error code with `err`, -1 = fall back to the host
+int pb_build_device_topology_(pb_plan *p, int nd, int64_t nc, int64_t nf, int64_t nn, const int32_t *cf_indptr,
+                              const int32_t *cf_indices, const int8_t *cf_data, const int32_t *fn_indptr,
+                              const int32_t *fn_indices, DevBuf &fn_idx_dev, std::string &err);

@@ -276,6 +276,30 @@ int pb_csr_from_device_pattern_(int64_t nrows, int64_t ncols, int64_t nnz, const
 }
 double *pb_csr_data_(pb_csr *a) { return a->data; }
 
+// an empty matrix of the given sizes (sparse_ops.cu fills indptr / indices / data)
+int pb_csr_alloc_(int64_t nrows, int64_t ncols, int64_t nnz, pb_csr **out) {
+    pb_csr *a = new pb_csr;
+    a->nrows = nrows; a->ncols = ncols; a->nnz = nnz;
+    auto bail = [&](cudaError_t e) {
+        std::string m = cudaGetErrorString(e);
+        pb_csr_destroy(a);
+        return pb_fail_(PB_ECUDA, m);
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreate(&a->e0)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreate(&a->e1)) != cudaSuccess) return bail(e);
+    if ((e = a->alloc()) != cudaSuccess) return bail(e);
+    const double mean = nrows ? (double)nnz / (double)nrows : 0.0;
+    a->tpr = mean <= 3 ? 2 : mean <= 6 ? 4 : mean <= 24 ? 8 : mean <= 48 ? 16 : 32;
+    *out = a;
+    return PB_OK;
+}
+int32_t *pb_csr_indptr_(pb_csr *a) { return a->indptr; }
+int32_t *pb_csr_indices_(pb_csr *a) { return a->indices; }
+struct CsrView { int64_t nrows, ncols, nnz; int32_t *indptr, *indices; double *data; };
+CsrView pb_csr_view_(const pb_csr *a) { return CsrView{a->nrows, a->ncols, a->nnz, a->indptr, a->indices, a->data}; }
+
 extern "C" int pb_csr_spmv(pb_csr *a, const double *x, double *y) {
     if (!a || !x || !y) return pb_fail_(PB_EINVAL, "null pointer");
     CUDA_TRY(cudaMemcpyAsync(a->x, x, a->ncols * sizeof(double), cudaMemcpyHostToDevice, a->stream));

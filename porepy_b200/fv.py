@@ -353,9 +353,19 @@ class DevicePlan:
         nr, nz = C.c_int64(), C.c_int64()
         _lib.check(self.lib.pb_plan_pattern_size(self.h, which, C.byref(nr), C.byref(nz)))
         del pat_nnz
-        return LazyCsr.lazy((nrows, self._ncols(which, bc)), nz.value * br * bc, vals.download,
-                            lambda: self.pattern(which, br, bc)[1], lambda: self.pattern(which, br, bc)[0],
-                            device_values=vals, plan=self)
+        m = LazyCsr.lazy((nrows, self._ncols(which, bc)), nz.value * br * bc, vals.download,
+                         lambda: self.pattern(which, br, bc)[1], lambda: self.pattern(which, br, bc)[0],
+                         device_values=vals, plan=self)
+        m.__dict__["pattern_key"] = (which, br, bc)
+        return m
+
+    def output_csr(self, values, which: int, br: int, bc: int):
+        """A detached output as a ``DeviceCsr`` (block-expanded pattern + a copy of the values), the operand form of
+        the device-side AD chain (``porepy_b200.ad``)."""
+        from .sparse import DeviceCsr
+        h = C.c_void_p()
+        _lib.check(self.lib.pb_plan_output_csr(self.h, values.h, which, br, bc, C.byref(h)))
+        return DeviceCsr.from_handle(h)
 
     def mpfa_lazy(self, flux=True, trace=True, vector_source=True) -> dict:
         nd = self.nd

@@ -76,7 +76,102 @@ class DeviceCsr:
                 pass
             self.h = None
 
+    # ---- device-side sparse algebra (csrc/sparse_ops.cu): the operations of the AD Jacobian chain
+    @staticmethod
+    def _new(lib, h) -> "DeviceCsr":
+        return DeviceCsr.from_handle(h)
+
+    def matmul(self, other: "DeviceCsr") -> "DeviceCsr":
+        """C = A @ B (SpGEMM on the device; ``M @ jac`` of forward_mode.py:565-595)."""
+        h = C.c_void_p()
+        _lib.check(self.lib.pb_csr_spgemm(self.h, other.h, C.byref(h)))
+        return DeviceCsr.from_handle(h)
+
+    def axpby(self, alpha: float, other: "DeviceCsr", beta: float) -> "DeviceCsr":
+        """alpha * self + beta * other on the union pattern."""
+        h = C.c_void_p()
+        _lib.check(self.lib.pb_csr_axpby(float(alpha), self.h, float(beta), other.h, C.byref(h)))
+        return DeviceCsr.from_handle(h)
+
+    def scaled(self, d, by_cols: bool = False) -> "DeviceCsr":
+        """diag(d) @ self (``_diagvec_mul_jac``, forward_mode.py:613-616) or self @ diag(d); ``d``: CUDA tensor."""
+        if d.numel() != self.shape[1 if by_cols else 0]:
+            raise ValueError("dimension mismatch")
+        h = C.c_void_p()
+        _lib.check(self.lib.pb_csr_scale_dev(self.h, C.c_void_p(d.data_ptr()), int(by_cols), C.byref(h)))
+        return DeviceCsr.from_handle(h)
+
+    @staticmethod
+    def bmat(blocks) -> "DeviceCsr":
+        """Block matrix from a 2-D list of ``DeviceCsr`` / ``None`` (zero blocks); every block row / column needs at
+        least one matrix to fix its size."""
+        lib = _lib.load()
+        nbr, nbc = len(blocks), len(blocks[0])
+        rs, cs = [None] * nbr, [None] * nbc
+        for i, row in enumerate(blocks):
+            if len(row) != nbc:
+                raise ValueError("ragged block list")
+            for j, b in enumerate(row):
+                if b is not None:
+                    if rs[i] not in (None, b.shape[0]) or cs[j] not in (None, b.shape[1]):
+                        raise ValueError("block shape mismatch")
+                    rs[i], cs[j] = b.shape[0], b.shape[1]
+        if None in rs or None in cs:
+            raise ValueError("a block row / column holds only zero blocks")
+        arr = (C.c_void_p * (nbr * nbc))(*[None if b is None else b.h for row in blocks for b in row])
+        rsz = np.asarray(rs, dtype=np.int64)
+        csz = np.asarray(cs, dtype=np.int64)
+        h = C.c_void_p()
+        _lib.check(lib.pb_csr_bmat(nbr, nbc, arr, _lib.ptr(rsz, _lib._i64p), _lib.ptr(csz, _lib._i64p), C.byref(h)))
+        return DeviceCsr.from_handle(h)
+
+    @staticmethod
+    def block_diag(mats) -> "DeviceCsr":
+        """``MergedOperator.parse``'s concatenation of per-subdomain matrices (ad_utils.py:650-664)."""
+        n = len(mats)
+        return DeviceCsr.bmat([[mats[i] if i == j else None for j in range(n)] for i in range(n)])
+
+    @staticmethod
+    def vstack(mats) -> "DeviceCsr":
+        """``EquationSystem.assemble``'s stacking of the equation blocks (equation_system.py:1695-1713)."""
+        return DeviceCsr.bmat([[m] for m in mats])
+
+    @staticmethod
+    def hstack(mats) -> "DeviceCsr":
+        return DeviceCsr.bmat([list(mats)])
+
+    @staticmethod
+    def identity(n: int) -> "DeviceCsr":
+        return DeviceCsr(sps.identity(n, format="csr"))
+
+    def __add__(self, other):
+        return self.axpby(1.0, other, 1.0) if isinstance(other, DeviceCsr) else NotImplemented
+
+    def __sub__(self, other):
+        return self.axpby(1.0, other, -1.0) if isinstance(other, DeviceCsr) else NotImplemented
+
+    def __neg__(self):
+        return self.axpby(-1.0, self, 0.0)
+
+    def __mul__(self, a):
+        if isinstance(a, (int, float, np.floating, np.integer)):
+            return self.axpby(float(a), self, 0.0)
+        return NotImplemented
+
+    __rmul__ = __mul__
+
     def __matmul__(self, x):
+        if isinstance(x, DeviceCsr):
+            return self.matmul(x)
+        if hasattr(x, "__rmatmul__") and type(x).__name__ == "DeviceAdArray":
+            return x.__rmatmul__(self)
+        if hasattr(x, "data_ptr"):       # CUDA tensor: y = A x on the device
+            import torch
+            if x.numel() != self.shape[1]:
+                raise ValueError("dimension mismatch")
+            y = torch.empty(self.shape[0], dtype=torch.float64, device=x.device)
+            self.spmv_device(x.contiguous().data_ptr(), y.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            return y
         x = _lib.f64(x)
         if x.shape != (self.shape[1],):
             raise ValueError("dimension mismatch")
@@ -174,6 +269,7 @@ class LazyCsr(sps.csr_matrix):
         d["_load_data"], d["_load_indices"], d["_load_indptr"] = load_data, load_indices, load_indptr
         d["_structural_nnz"] = int(nnz)
         d["device_values"], d["device_csr"], d["plan"] = device_values, device_csr, plan
+        d["pattern_key"] = None
         self.has_sorted_indices = True
         self.has_canonical_format = True
         return self

@@ -337,9 +337,8 @@ def main():
         if world == 1:
             return None, gg, gk, gbc, gC, gvbc, bv
         s = sh.extract_shard(gg, part, rank)
-        k = pb.SecondOrderTensor.from_values(s.restrict_cell_array(gk.values))
-        C = pb.FourthOrderTensor.from_values(s.restrict_cell_array(gC.values))
-        return s, s.grid, k, sh.restrict_scalar_bc(gbc, s), C, sh.restrict_vector_bc(gvbc, s), bv[s.faces]
+        # the cell tensors stay GLOBAL: the plan restricts them on the device (DevicePlan.set_cell_map)
+        return s, s.grid, gk, sh.restrict_scalar_bc(gbc, s), gC, sh.restrict_vector_bc(gvbc, s), bv[s.faces]
 
     shard, g, k, bc, C, vbc, bvl = my_problem()
     nc = g.num_cells
@@ -349,6 +348,7 @@ def main():
     plan = pb.DevicePlan.for_grid(g)
     if shard is not None:
         plan.set_active_nodes(shard.own_node)
+        plan.set_cell_map(shard.cells, nc_global)
     plan_s = time.perf_counter() - t0
     plan.mpfa_upload(k.values, scalar_bc_codes(bc, g.num_faces), None, eta)
     codes, robw = vector_bc_codes(vbc, 3, g.num_faces)
@@ -410,6 +410,7 @@ def main():
         pl = pb.DevicePlan.for_grid(lg)
         if sh_ is not None:
             pl.set_active_nodes(sh_.own_node)
+            pl.set_cell_map(sh_.cells, nc_global)
         lap("topology_plan")
         d1 = pb.initialize_data({}, "flow", {"second_order_tensor": lk, "bc": lbc, "bc_values": lbv})
         m1 = pb.Mpfa("flow")
@@ -475,14 +476,27 @@ def main():
             loc = kr.local_system_from_shard(keep[5], part, a_dev)
         else:
             loc = kr.LocalSystem(0, 1, np.arange(nc), np.zeros(0, np.int64), a_dev, [0], [np.zeros(0, np.int64)])
+        # self-checks of the distributed operator at full size: the halo exchange delivers the global vector at the
+        # shard's ghost cells, and the residual of the returned solution is recomputed with one more distributed SpMV
+        op_chk = kr.DistributedOperator(loc, torch.device("cuda", local))
+        cells_local = np.arange(nc) if shard is None else keep[5].cells
+        probe = np.sin(0.37 * np.arange(nc_global))
+        xb = op_chk.exchange(torch.as_tensor(probe[cells_local[:n_own]], device="cuda")).cpu().numpy()
+        halo_err = float(np.abs(xb - probe[cells_local]).max())
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         x, info = kr.solve_local(loc, b1[:n_own], diag_own=diag, tol=1e-8, maxiter=3000)
         barrier()
         solve_s = allmax([time.perf_counter() - t0])[0]
+        b_t = torch.as_tensor(b1[:n_own], device="cuda")
+        res = b_t - op_chk.matvec(x)
+        rr, bbn = allsum([float(res @ res), float(b_t @ b_t)])
+        true_relres = float(np.sqrt(rr / bbn))
         krylov = {"system": "A = div @ flux of the sharded mesh (rows of each rank's own cells)", "rows": int(nc_global),
                   "inputs_finite": bool(np.isfinite(b1).all() and bool(torch.isfinite(diag).all())),
+                  "halo_exchange_max_error": allmax([halo_err])[0], "true_relres": true_relres,
+                  "cuda_graph": info.get("cuda_graph"),
                   "diag_min": float(diag.min()), "fused": bool(info.get("fused", False)),
                   "host_syncs": info.get("host_syncs"), "breakdown": info.get("breakdown"),
                   "iterations": info["iterations"], "converged": bool(info["converged"]), "relres": info["relres"],
@@ -491,7 +505,7 @@ def main():
                   "ms_per_iteration": 1e3 * solve_s / max(info["iterations"], 1),
                   "collectives": "ghost entries: NCCL send/recv per neighbour; dots: one all-reduce of 1-3 doubles"
                   if world > 1 else "none (single GPU)"}
-        del x, loc
+        del x, loc, op_chk
     keep = None
 
     if rank != 0:
@@ -523,8 +537,8 @@ def main():
     geo_bytes = 8 * (g.nodes.size + g.face_normals.size + g.face_centers.size + g.face_areas.size
                      + g.cell_centers.size + g.cell_volumes.size)
     topo_bytes = 4 * sz["subcells"] + 4 * sz["subfaces"] + 2 * sz["subhalffaces"]
-    bytes_mpfa = geo_bytes + topo_bytes + k.values.nbytes + g.num_faces + 8 * (2 * nfc + 2 * nfb + 6 * nfc)
-    bytes_mpsa = geo_bytes + topo_bytes + C.values.nbytes + 3 * g.num_faces + 8 * 9 * (2 * nfc + 2 * nfb)
+    bytes_mpfa = geo_bytes + topo_bytes + 72 * nc + g.num_faces + 8 * (2 * nfc + 2 * nfb + 6 * nfc)
+    bytes_mpsa = geo_bytes + topo_bytes + 648 * nc + 3 * g.num_faces + 8 * 9 * (2 * nfc + 2 * nfb)
     dom = "mpsa" if own_ms_mpsa >= own_ms_mpfa else "mpfa"
     dom_ms = (own_ms_mpsa if dom == "mpsa" else own_ms_mpfa) / args.steps
     dom_bytes = bytes_mpsa if dom == "mpsa" else bytes_mpfa

@@ -93,6 +93,10 @@ void pb_plan_destroy(pb_plan *p);
 int pb_plan_sizes(const pb_plan *p, int64_t *num_subcells, int64_t *num_subfaces,
                   int64_t *num_subhalffaces, int32_t *max_subfaces_per_node,
                   int32_t *max_subcells_per_node);
+/* Shards: cell e of this plan is cell cells[e] of a larger (global) grid of n_source_cells cells.  The cell tensors of
+ * the following pb_mpfa_upload / pb_mpsa_upload (permeability, stiffness, coupling tensors) are then the GLOBAL arrays
+ * ((3,3,n_source), (9,9,n_source)) and are restricted on the device; NULL removes the map. */
+int pb_plan_set_cell_map(pb_plan *p, const int64_t *cells, int64_t n_source_cells);
 /* Restrict the assembly to the interaction regions of the flagged nodes (mask: nn bytes, NULL = all nodes).
  * Used by the multi-GPU path: a shard assembles the regions of its OWN nodes only; the outer nodes of its halo
  * layer are incomplete there and their rows are discarded anyway (reference: the overlap removal of

@@ -556,8 +556,50 @@ int pb_upload_repacked_(cudaStream_t st, DevBuf &tmp, DevBuf &dst, const double 
     CUDA_TRY(cudaGetLastError());
     return PB_OK;
 }
+
+// the same with a gather: the host array holds the cells of a LARGER (global) grid, (ncomp, n_src) row-major, and
+// entity e of this plan is cell map[e] of it (a shard uploads the global tensor and restricts it on the device)
+__global__ void repack_gather_kernel(const double *__restrict__ in, double *__restrict__ out, int ncomp, int64_t n,
+                                     int64_t n_src, const int64_t *__restrict__ map) {
+    const int64_t total = (int64_t)ncomp * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / ncomp;
+        const int comp = (int)(i - e * ncomp);
+        out[i] = in[(int64_t)comp * n_src + map[e]];
+    }
+}
+
 static int upload_repacked(pb_plan *p, DevBuf &dst, const double *host, int ncomp, int64_t n) {
     return pb_upload_repacked_(p->stream, p->repack_tmp, dst, host, ncomp, n);
+}
+
+// cell tensors: through the cell map when one is set (pb_plan_set_cell_map)
+static int upload_cell_tensor(pb_plan *p, DevBuf &dst, const double *host, int ncomp) {
+    const int64_t n = p->H.nc;
+    if (!p->cell_map.p) return upload_repacked(p, dst, host, ncomp, n);
+    cudaStream_t st = p->stream;
+    CUDA_TRY(p->repack_tmp.upload(host, (size_t)ncomp * p->cell_map_src, st));
+    CUDA_TRY(dst.ensure((size_t)ncomp * n * sizeof(double)));
+    const int64_t total = (int64_t)ncomp * n;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)kSMs * 32));
+    repack_gather_kernel<<<grid, 256, 0, st>>>(p->repack_tmp.as<double>(), dst.as<double>(), ncomp, n, p->cell_map_src,
+                                               p->cell_map.as<int64_t>());
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" int pb_plan_set_cell_map(pb_plan *p, const int64_t *cells, int64_t n_source_cells) {
+    if (!p) return fail(PB_EINVAL, "null plan");
+    if (!cells) { p->cell_map.release(); p->cell_map_src = 0; return PB_OK; }
+    if (n_source_cells < 1) return fail(PB_EINVAL, "bad source size");
+    for (int64_t e = 0; e < p->H.nc; ++e)
+        if (cells[e] < 0 || cells[e] >= n_source_cells) return fail(PB_EINVAL, "cell map entry out of range");
+    CUDA_TRY(p->cell_map.upload(cells, (size_t)p->H.nc, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    p->cell_map_src = n_source_cells;
+    return PB_OK;
 }
 
 extern "C" int pb_plan_set_geometry(pb_plan *p, const double *nodes, const double *face_normals,
@@ -605,7 +647,7 @@ extern "C" int pb_mpfa_upload(pb_plan *p, const double *perm, const uint8_t *bc,
     if (!p->have_geo) return fail(PB_EINVAL, "pb_plan_set_geometry has not been called");
     const HostPlan &H = p->H;
     cudaStream_t st = p->stream;
-    { int rcp = upload_repacked(p, p->perm, perm, 9, H.nc); if (rcp) return rcp; }
+    { int rcp = upload_cell_tensor(p, p->perm, perm, 9); if (rcp) return rcp; }
     CUDA_TRY(p->bc.upload(bc, H.nf, st));
     p->have_robw = robin_weight != nullptr;
     if (robin_weight) CUDA_TRY(p->robw.upload(robin_weight, H.nf, st));
@@ -1078,7 +1120,7 @@ extern "C" int pb_mpsa_upload(pb_plan *p, const double *stiffness, const uint8_t
     const HostPlan &H = p->H;
     const int nd = H.nd;
     cudaStream_t st = p->stream;
-    { int rcs = upload_repacked(p, p->stiff, stiffness, 81, H.nc); if (rcs) return rcs; }
+    { int rcs = upload_cell_tensor(p, p->stiff, stiffness, 81); if (rcs) return rcs; }
     CUDA_TRY(p->vbc.upload(bc, (size_t)nd * H.nf, st));
     p->have_vrobw = robin_weight != nullptr;
     p->have_vbasis = false;  // set again by pb_mpsa_set_basis after every upload
@@ -1087,7 +1129,7 @@ extern "C" int pb_mpsa_upload(pb_plan *p, const double *stiffness, const uint8_t
         CUDA_TRY(p->alpha.ensure((size_t)n_alpha * 9 * H.nc * sizeof(double)));
         for (int q = 0; q < n_alpha; ++q) {
             DevBuf one;
-            int rca = upload_repacked(p, one, alpha + (size_t)q * 9 * H.nc, 9, H.nc);
+            int rca = upload_cell_tensor(p, one, alpha + (size_t)q * 9 * (p->cell_map.p ? p->cell_map_src : H.nc), 9);
             if (rca) return rca;
             CUDA_TRY(cudaMemcpyAsync(p->alpha.as<double>() + (size_t)q * 9 * H.nc, one.p,
                                      (size_t)9 * H.nc * sizeof(double), cudaMemcpyDeviceToDevice, st));

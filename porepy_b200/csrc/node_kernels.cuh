@@ -369,36 +369,6 @@ struct TileGJ {
     // Returns max |inverse entry| (inf / nan when the block is not invertible in that order).
     static __device__ __forceinline__ double invert_block(int l, double m, double &iv) {
         const int mj = (l >> 2) & 3, mi = l & 3;
-#ifdef PB_EXP_ADJ
-        // closed form through the twelve 2x2 minors of the row pairs (0,1) and (2,3): every lane gathers the 16
-        // entries with independent shuffles and evaluates its own entry -- a dependent chain of ~6 operations
-        // instead of the 4 x (shuffle, reciprocal, multiply, shuffle, fma) of the elimination below
-        double a[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int cidx = 0; cidx < 4; ++cidx) a[r][cidx] = __shfl_sync(0xffffffffu, m, 4 * r + cidx);
-        const double s0 = a[0][0] * a[1][1] - a[1][0] * a[0][1], s1 = a[0][0] * a[1][2] - a[1][0] * a[0][2];
-        const double s2 = a[0][0] * a[1][3] - a[1][0] * a[0][3], s3 = a[0][1] * a[1][2] - a[1][1] * a[0][2];
-        const double s4 = a[0][1] * a[1][3] - a[1][1] * a[0][3], s5 = a[0][2] * a[1][3] - a[1][2] * a[0][3];
-        const double c5 = a[2][2] * a[3][3] - a[3][2] * a[2][3], c4 = a[2][1] * a[3][3] - a[3][1] * a[2][3];
-        const double c3 = a[2][1] * a[3][2] - a[3][1] * a[2][2], c2 = a[2][0] * a[3][3] - a[3][0] * a[2][3];
-        const double c1 = a[2][0] * a[3][2] - a[3][0] * a[2][2], c0 = a[2][0] * a[3][1] - a[3][0] * a[2][1];
-        const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
-        // column mi of the inverse is built from row r = mi ^ 1 and the minors of the OTHER row pair
-        const int r = mi ^ 1;
-        const double x0 = r == 0 ? a[0][0] : r == 1 ? a[1][0] : r == 2 ? a[2][0] : a[3][0];
-        const double x1 = r == 0 ? a[0][1] : r == 1 ? a[1][1] : r == 2 ? a[2][1] : a[3][1];
-        const double x2 = r == 0 ? a[0][2] : r == 1 ? a[1][2] : r == 2 ? a[2][2] : a[3][2];
-        const double x3 = r == 0 ? a[0][3] : r == 1 ? a[1][3] : r == 2 ? a[2][3] : a[3][3];
-        const bool lo = mi < 2;
-        const double m0 = lo ? c0 : s0, m1 = lo ? c1 : s1, m2 = lo ? c2 : s2, m3 = lo ? c3 : s3, m4 = lo ? c4 : s4,
-                     m5 = lo ? c5 : s5;
-        const double b0 = x1 * m5 - x2 * m4 + x3 * m3, b1 = -x0 * m5 + x2 * m2 - x3 * m1;
-        const double b2 = x0 * m4 - x1 * m2 + x3 * m0, b3 = -x0 * m3 + x1 * m1 - x2 * m0;
-        const double bj = mj == 0 ? b0 : mj == 1 ? b1 : mj == 2 ? b2 : b3;
-        iv = ((mi & 1) ? -bj : bj) * __drcp_rn(det);
-#else
         iv = (mi == mj) ? 1.0 : 0.0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -409,7 +379,6 @@ struct TileGJ {
             const double f = __shfl_sync(0xffffffffu, m, mj * 4 + k);
             if (mj != k) { m -= f * mk; iv -= f * ik; }
         }
-#endif
         // max |entry| through one redux.sync on the float-rounded magnitude (monotone bit pattern for
         // non-negative floats; inf and nan map above every finite value) instead of four rounds of
         // 64-bit shuffles: the result is only compared with the growth threshold

@@ -121,11 +121,8 @@ using Cfg0 = TileGJ<1, 2, 6, 4>;   // team 32  : MPFA hexahedral nodes (12 x 45)
 using Cfg1 = TileGJ<2, 3, 8, 6>;   // team 64  : MPSA hexahedral nodes (36 x 61), DMMA
 using Cfg2 = TileGJ<2, 3, 12, 4>;  // team 64  : Biot hexahedral nodes, DMMA
 using Cfg3 = TileGJ<5, 1, 18, 3>;  // team 160 : MPFA tetrahedral nodes (36 x 133), DMMA
-#ifdef PB_CFG4_WIDE
-using Cfg4 = TileGJ<14, 1, 24, 1>; // experiment: 448 threads, one row tile per warp (96 tile registers instead of 192)
-#else
 using Cfg4 = TileGJ<7, 2, 24, 1>;  // team 224 : MPSA tetrahedral nodes (108 x 181), FP64 tensor cores (DMMA)
-#endif
+                                   // (TileGJ<14,1,24>: 448 threads, half the tile registers -- measured 7 % slower)
 using Cfg5 = TileGJ<14, 1, 32, 1>; // team 448 : Biot tetrahedral nodes (108 x 205+), DMMA
 using Cfg6 = SmemGJ;               // team 256 : anything else (in-memory Gauss-Jordan)
 using Cfg7 = RegGJ<8, 14, 6, 1>;   // team 256 : scalar register-tiled alternative for cfg 4 (POREB200_CFG4=reg)
@@ -162,6 +159,8 @@ struct pb_plan {
     // geometry
     DevBuf nodes, fnorm, fcent, farea, ccent, cvol;
     bool have_geo = false;
+    DevBuf cell_map;               // optional: cell e of this plan is cell cell_map[e] of a larger source grid
+    int64_t cell_map_src = 0;      //           (cell tensors are then given for the source grid and gathered on the device)
     std::vector<uint8_t> active;   // per node: assemble its interaction region (empty = all); pb_plan_set_active_nodes
     PlanView view{};
     GeoView geo{};

@@ -235,6 +235,32 @@ class DevicePlan:
         arrs, self.rotation = plan_geometry(sd)
         _lib.check(self.lib.pb_plan_set_geometry(self.h, *[_lib.ptr(a, _lib._f64p) for a in arrs]))
 
+    def set_cell_map(self, cells, n_source_cells: int) -> None:
+        """Cell ``e`` of this plan is cell ``cells[e]`` of a larger grid with ``n_source_cells`` cells: the cell
+        tensors of the following uploads may then be the arrays of THAT grid (shape (3, 3, n_source) / (9, 9,
+        n_source)); they are restricted on the device.  A shard passes the global tensors as they are."""
+        if cells is None:
+            _lib.check(self.lib.pb_plan_set_cell_map(self.h, None, 0))
+            self.n_source_cells = None
+            return
+        m = np.ascontiguousarray(cells, dtype=np.int64)
+        if m.shape != (self.nc,):
+            raise ValueError("cell map must have one entry per cell of this plan")
+        _lib.check(self.lib.pb_plan_set_cell_map(self.h, _lib.ptr(m, _lib._i64p), int(n_source_cells)))
+        self.n_source_cells = int(n_source_cells)
+        self._cell_map_host = m
+
+    def _cells_of(self, arr) -> bool:
+        """True when a cell tensor has the source grid's size and must go through the cell map (clears the map when
+        the caller passes arrays of this plan's own size instead)."""
+        n = arr.shape[-1]
+        src = getattr(self, "n_source_cells", None)
+        if src is not None and n == src and n != self.nc:
+            return True
+        if src is not None and n == self.nc:
+            self.set_cell_map(None, 0)
+        return False
+
     def set_active_nodes(self, mask) -> None:
         """Assemble only the interaction regions of the flagged nodes (``None``: all).  The multi-GPU path flags
         a shard's own nodes: the outer nodes of its halo layer are incomplete and their rows are discarded."""
@@ -301,7 +327,7 @@ class DevicePlan:
     # ---- MPFA
     def mpfa_upload(self, perm, codes, robw, eta) -> None:
         perm = _lib.f64(perm)
-        if perm.shape != (3, 3, self.nc):
+        if not self._cells_of(perm) and perm.shape != (3, 3, self.nc):
             raise ValueError("second_order_tensor.values must have shape (3, 3, num_cells)")
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
         robw = None if robw is None else _lib.f64(robw)
@@ -429,16 +455,21 @@ class DevicePlan:
     # ---- MPSA / Biot
     def mpsa_upload(self, stiff, codes, robw, eta, alphas=()) -> None:
         stiff = _lib.f64(stiff)
-        if stiff.shape != (9, 9, self.nc):
+        mapped = self._cells_of(stiff)
+        if not mapped and stiff.shape != (9, 9, self.nc):
             raise ValueError("fourth_order_tensor.values must have shape (9, 9, num_cells)")
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
         robw = None if robw is None else _lib.f64(robw)
         nal = len(alphas)
         al = None
         if nal:
-            al = np.zeros((nal, 3, 3, self.nc))
+            al = np.zeros((nal, 3, 3, self.n_source_cells if mapped else self.nc))
             for q, a in enumerate(alphas):
-                al[q] = a
+                a = np.asarray(a)
+                if mapped and a.shape[-1] == self.nc:      # a tensor given for this plan's own cells
+                    al[q][..., self._cell_map_host] = a
+                else:
+                    al[q] = a
         _lib.check(self.lib.pb_mpsa_upload(self.h, _lib.ptr(stiff, _lib._f64p),
                                            _lib.ptr(codes, _lib._u8p), _lib.ptr(robw, _lib._f64p),
                                            float(eta), nal, _lib.ptr(al, _lib._f64p)))

@@ -168,6 +168,33 @@ class DistributedOperator:
             torch.index_select(self.recv, 0, self.ghost_perm, out=self.xbuf[self.n_own:])
         return self.xbuf
 
+    def exchange_into(self, xbuf):
+        """Ghost exchange for a caller-owned buffer [x_own | ghosts] whose own part is already in place (the fused
+        Krylov kernels write their output vectors straight into such buffers: no staging copy)."""
+        if self.loc.world == 1:
+            return xbuf
+        torch = self.torch
+        import torch.distributed as dist
+        x_own = xbuf[: self.n_own]
+        target = xbuf[self.n_own:] if self.recv is None else self.recv
+        ops, off, sends = [], 0, []
+        for q in range(self.loc.world):
+            if q != self.loc.rank and self.send_idx[q].numel():
+                buf = x_own.index_select(0, self.send_idx[q])
+                sends.append(buf)
+                ops.append(dist.P2POp(dist.isend, buf, q, group=self.group))
+        for q in range(self.loc.world):
+            cnt = self.loc.recv_counts[q]
+            if q != self.loc.rank and cnt:
+                ops.append(dist.P2POp(dist.irecv, target[off:off + cnt], q, group=self.group))
+            off += cnt
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if self.recv is not None:
+            torch.index_select(self.recv, 0, self.ghost_perm, out=xbuf[self.n_own:])
+        return xbuf
+
     def matvec(self, x_own, out=None):
         torch = self.torch
         xb = self.exchange(x_own)
@@ -255,61 +282,97 @@ def bicgstab(op: DistributedOperator, b_own, x0=None, tol: float = 1e-10, maxite
 def _bicgstab_fused(op: DistributedOperator, b_own, tol, maxiter, diag_own, check_every):
     """The iteration on the device: three fused vector kernels (csrc/krylov.cu) and two SpMVs whose epilogue
     accumulates the dot products; all scalars of the recurrence stay in a 14-double device buffer, all-reduced in
-    contiguous slices (NCCL on the same stream) under torch.distributed.  The host reads the buffer every
-    ``check_every`` iterations only; a sticky device-side DONE flag freezes the vectors once the residual is below
-    the tolerance, so running a few iterations past convergence is harmless."""
+    contiguous slices (NCCL on the same stream) under torch.distributed.  The preconditioned vectors are written
+    straight into the [own | ghost] SpMV input buffers.  A block of ``check_every`` iterations is captured once in a
+    CUDA graph and replayed (``POREB200_KRYLOV_GRAPH=0`` or a failed capture: plain launches); the host reads the scalar
+    buffer once per block only, and a sticky device-side DONE flag freezes the vectors once the residual is below the
+    tolerance, so running to the end of a block past convergence is harmless."""
     import ctypes as C
+    import os
     from . import _lib
     torch = op.torch
     lib = _lib.load()
-    n = op.n_own
+    n, ng = op.n_own, op.n_ghost
     dev = b_own.device
     world = op.loc.world
-    vec = lambda: torch.empty(n, dtype=torch.float64, device=dev)  # noqa: E731
-    x, r, rhat, p, v, ph, s, sh, t = (vec() for _ in range(9))
+    vec = lambda m=n: torch.zeros(m, dtype=torch.float64, device=dev)  # noqa: E731
+    x, r, rhat, p, v, s, t = (vec() for _ in range(7))
+    xb_p, xb_s = vec(n + ng), vec(n + ng)            # SpMV inputs [own | ghost]; ph / sh are their own parts
+    ph, sh = xb_p[:n], xb_s[:n]
     minv = None if diag_own is None else (1.0 / diag_own).contiguous()
     scal = torch.zeros(14, dtype=torch.float64, device=dev)
     P = lambda a: C.c_void_p(a.data_ptr()) if a is not None else None  # noqa: E731
     S = lambda i: C.c_void_p(scal.data_ptr() + 8 * i)  # noqa: E731
-    stream = torch.cuda.current_stream().cuda_stream
     b_own = b_own.contiguous()
-    nred = 0
+    csr = op.dev_csr
+    carry = 1 if op.loc.rank == 0 else 0
+    nred = [0]
 
     def reduce(lo, hi):
-        nonlocal nred
         if world > 1:
             import torch.distributed as dist
             dist.all_reduce(scal[lo:hi], group=op.group)
-            nred += 1
-    _lib.check(lib.pb_kry_init(n, P(b_own), P(x), P(r), P(rhat), P(p), P(v), P(scal), float(tol), stream))
-    reduce(10, 11)
-    _lib.check(lib.pb_kry_seed(P(scal), stream))
-    h = scal.cpu().numpy()
-    if h[10] == 0.0:
-        return x, {"iterations": 0, "relres": 0.0, "converged": True, "breakdown": False, "spmv": 0, "allreduce": nred}
-    bb = float(h[10])
-    it, nspmv = 0, 0
-    relres, converged, breakdown = 1.0, False, False
-    csr = op.dev_csr
-    while it < maxiter:
-        for _ in range(min(check_every, maxiter - it)):
+            nred[0] += 1
+
+    def iterations(count, it0):
+        stream = torch.cuda.current_stream().cuda_stream
+        for it in range(it0, it0 + count):
             cur = it & 1
             g = 5 * cur
             _lib.check(lib.pb_kry_p(n, P(r), P(p), P(v), P(minv), P(ph), P(scal), cur, stream))
-            xb = op.exchange(ph)
-            _lib.check(lib.pb_csr_spmv_dots_dev(csr.h, P(xb), P(v), P(rhat), S(g + 0), None, None, stream))
+            op.exchange_into(xb_p)
+            _lib.check(lib.pb_csr_spmv_dots_dev(csr.h, P(xb_p), P(v), P(rhat), S(g + 0), None, None, stream))
             reduce(g + 0, g + 1)
             _lib.check(lib.pb_kry_s(n, P(r), P(v), P(minv), P(s), P(sh), P(scal), cur, stream))
-            xb = op.exchange(sh)
-            _lib.check(lib.pb_csr_spmv_dots_dev(csr.h, P(xb), P(t), P(s), S(g + 1), None, S(g + 2), stream))
+            op.exchange_into(xb_s)
+            _lib.check(lib.pb_csr_spmv_dots_dev(csr.h, P(xb_s), P(t), P(s), S(g + 1), None, S(g + 2), stream))
             reduce(g + 1, g + 3)
-            _lib.check(lib.pb_kry_xr(n, P(x), P(ph), P(sh), P(s), P(t), P(r), P(rhat), P(scal), cur,
-                                      1 if op.loc.rank == 0 else 0, stream))
+            _lib.check(lib.pb_kry_xr(n, P(x), P(ph), P(sh), P(s), P(t), P(r), P(rhat), P(scal), cur, carry, stream))
             nx = 5 * (cur ^ 1)
             reduce(nx + 3, nx + 5)
-            it += 1
-            nspmv += 2
-        h = scal.cpu().numpy()            # the only host synchronisation: every check_every iterations
+
+    stream0 = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.pb_kry_init(n, P(b_own), P(x), P(r), P(rhat), P(p), P(v), P(scal), float(tol), stream0))
+    reduce(10, 11)
+    _lib.check(lib.pb_kry_seed(P(scal), stream0))
+    h = scal.cpu().numpy()
+    if h[10] == 0.0:
+        return x, {"iterations": 0, "relres": 0.0, "converged": True, "breakdown": False, "spmv": 0, "allreduce": nred[0]}
+    bb = float(h[10])
+    check_every = max(2, check_every + (check_every & 1))         # even: a block starts at parity 0
+    graph = None
+    if os.environ.get("POREB200_KRYLOV_GRAPH", "1") != "0" and maxiter >= check_every:
+        try:
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream(device=dev)
+            g_ = torch.cuda.CUDAGraph()
+            red0 = nred[0]
+            with torch.cuda.graph(g_, stream=side):
+                iterations(check_every, 0)
+            nred[0] = red0
+            graph = g_
+        except Exception as e:                                   # capture not possible here: plain launches
+            import logging
+            logging.getLogger(__name__).info("BiCGStab: CUDA graph capture failed (%s); plain launches", e)
+            graph = None
+            torch.cuda.synchronize()
+            # a failed capture may have run nothing or a part: restart the recurrence from a clean state
+            _lib.check(lib.pb_kry_init(n, P(b_own), P(x), P(r), P(rhat), P(p), P(v), P(scal), float(tol), stream0))
+            reduce(10, 11)
+            _lib.check(lib.pb_kry_seed(P(scal), stream0))
+    it, nspmv = 0, 0
+    relres, converged, breakdown = 1.0, False, False
+    per_block_red = 3 if world > 1 else 0
+    while it < maxiter:
+        count = min(check_every, maxiter - it)
+        if graph is not None and count == check_every:
+            graph.replay()
+            nred[0] += per_block_red * count
+        else:
+            iterations(count, it)
+        it += count
+        nspmv += 2 * count
+        h = scal.cpu().numpy()            # the only host synchronisation: once per block
         rr = float(h[5 * (it & 1) + 3])
         if not np.isfinite(h).all():
             breakdown = True
@@ -320,8 +383,8 @@ def _bicgstab_fused(op: DistributedOperator, b_own, tol, maxiter, diag_own, chec
             break
     done_it = int(h[12]) if np.isfinite(h[12]) else it
     return x, {"iterations": done_it if converged else it, "relres": relres, "converged": converged,
-               "breakdown": breakdown, "spmv": nspmv, "allreduce": nred, "fused": True,
-               "host_syncs": (it + check_every - 1) // check_every + 1}
+               "breakdown": breakdown, "spmv": nspmv, "allreduce": nred[0], "fused": True,
+               "cuda_graph": graph is not None, "host_syncs": (it + check_every - 1) // check_every + 1}
 
 
 def solve(a, b, owner=None, tol: float = 1e-10, maxiter: int = 2000, jacobi: bool = True, device=None,

@@ -409,8 +409,12 @@ def test_sharded_system_rows_on_the_device():
         n_own = int(s.own_cell.sum())
         plan = pb.DevicePlan.for_grid(s.grid)
         plan.set_active_nodes(s.own_node)
+        # rank 0 restricts the permeability on the host, rank 1 hands over the GLOBAL tensor (device-side gather)
+        if r == 1:
+            plan.set_cell_map(s.cells, g.num_cells)
+        kl = k if r == 1 else pb.SecondOrderTensor.from_values(s.restrict_cell_array(k.values))
         dl = pb.initialize_data({}, "flow", {
-            "second_order_tensor": pb.SecondOrderTensor.from_values(s.restrict_cell_array(k.values)),
+            "second_order_tensor": kl,
             "bc": sh.restrict_scalar_bc(bc, s), "bc_values": bv[s.faces], "mpfa_eta": pb.determine_eta(g)})
         dd = pb.Mpfa("flow")
         dd.discretize(s.grid, dl)

@@ -243,6 +243,12 @@ int pb_tpfa(pb_facegrid *g, const double *permeability, const uint8_t *bc_bits, 
 int pb_upwind(pb_facegrid *g, const double *darcy_flux, const uint8_t *bc_bits, int32_t *upstream_cell,
               double *neumann_diag, double *dirichlet_diag);
 
+/* Interface upwinding (UpwindCoupling.discretize, numerics/fv/upwind.py:427-528): per mortar cell the sign of the
+ * interface flux and the masks "upstream is the higher-dimensional side" / "... the lower-dimensional side".
+ * Host pointers, n doubles each. */
+int pb_upwind_coupling(int64_t n, const double *interface_flux, double *sign, double *from_primary,
+                       double *from_secondary);
+
 /* device-resident CSR matrix */
 int pb_csr_create(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t *indptr,
                   const int32_t *indices, const double *data, pb_csr **out);

@@ -163,3 +163,38 @@ extern "C" int pb_upwind(pb_facegrid *g, const double *darcy_flux, const uint8_t
     CUDA_TRY(cudaStreamSynchronize(st));
     return PB_OK;
 }
+
+// ---- interface upwinding (UpwindCoupling.discretize, numerics/fv/upwind.py:427-528): per mortar cell the sign of
+// the interface flux and the two upstream masks (flux > 0: the higher-dimensional side is upstream)
+__global__ void upwind_coupling_kernel(int64_t n, const double *__restrict__ lam, double *__restrict__ sgn,
+                                       double *__restrict__ from_primary, double *__restrict__ from_secondary) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = lam[i];
+        const double s = v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : (v == 0.0 ? 0.0 : v));   // np.sign (nan stays nan)
+        sgn[i] = s;
+        from_primary[i] = s > 0.0 ? 1.0 : 0.0;
+        from_secondary[i] = s > 0.0 ? 0.0 : 1.0;
+    }
+}
+
+extern "C" int pb_upwind_coupling(int64_t n, const double *interface_flux, double *sign, double *from_primary,
+                                  double *from_secondary) {
+    if (n < 0 || (n > 0 && (!interface_flux || !sign || !from_primary || !from_secondary)))
+        return pb_fail_(PB_EINVAL, "bad arguments");
+    if (n == 0) return PB_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return pb_fail_(PB_ECUDA, "no CUDA device: libporeb200 has no CPU path");
+    DevBuf in, o0, o1, o2;
+    CUDA_TRY(in.upload(interface_flux, (size_t)n, 0));
+    CUDA_TRY(o0.ensure((size_t)n * 8)); CUDA_TRY(o1.ensure((size_t)n * 8)); CUDA_TRY(o2.ensure((size_t)n * 8));
+    const int block = 256;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + block - 1) / block, (int64_t)kSMs * 16));
+    upwind_coupling_kernel<<<grid, block>>>(n, in.as<double>(), o0.as<double>(), o1.as<double>(), o2.as<double>());
+    pb_count_launch_();
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(sign, o0.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(from_primary, o1.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(from_secondary, o2.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return PB_OK;
+}

@@ -1128,3 +1128,76 @@ class Upwind(_Base):
         rhs = div @ ((mats[self.bound_transport_neu_matrix_key] + mats[self.bound_transport_dir_matrix_key] @ q)
                      @ params["bc_values"])
         return matrix, rhs
+
+
+class UpwindCoupling:
+    """Upwinding of an advective flux across the interface between a subdomain and a lower-dimensional one
+    (numerics/fv/upwind.py:377).  ``discretize`` writes the reference's six matrices to
+    ``data_intf["discretization_matrices"][keyword]``; ``assemble_matrix_rhs`` as upwind.py:530-680."""
+
+    def __init__(self, keyword: str) -> None:
+        self.keyword = keyword
+        self.trace_primary_matrix_key = "trace"
+        self.inv_trace_primary_matrix_key = "inv_trace"
+        self.upwind_primary_matrix_key = "upwind_primary"
+        self.upwind_secondary_matrix_key = "upwind_secondary"
+        self.flux_matrix_key = "flux"
+        self.mortar_discr_matrix_key = "mortar_discr"
+        self._flux_array_key = "darcy_flux"
+
+    def key(self) -> str:
+        return self.keyword + "_"
+
+    def discretization_key(self):
+        return self.key() + DISCRETIZATION_MATRICES
+
+    @property
+    def flux_array_key(self) -> str:
+        return self._flux_array_key
+
+    @flux_array_key.setter
+    def flux_array_key(self, value: str) -> None:
+        self._flux_array_key = value
+
+    def ndof(self, intf) -> int:
+        return intf.num_cells
+
+    def discretize(self, sd_primary, sd_secondary, intf, data_primary, data_secondary, data_intf) -> None:
+        if sd_primary.dim - sd_secondary.dim not in [1, 2]:
+            raise ValueError("Implementation is only valid for grids one dimension apart.")
+        mats = data_intf.setdefault(DISCRETIZATION_MATRICES, {}).setdefault(self.keyword, {})
+        lam = _lib.f64(data_intf[PARAMETERS][self.keyword][self._flux_array_key])
+        lib = _lib.load()
+        _lib.require_gpu()
+        n = int(lam.size)
+        sgn, up1, up2 = np.empty(n), np.empty(n), np.empty(n)
+        _lib.check(lib.pb_upwind_coupling(n, _lib.ptr(lam, _lib._f64p), _lib.ptr(sgn, _lib._f64p),
+                                          _lib.ptr(up1, _lib._f64p), _lib.ptr(up2, _lib._f64p)))
+        inv_trace = abs(sd_primary.divergence(dim=1))
+        mats[self.inv_trace_primary_matrix_key] = inv_trace
+        mats[self.trace_primary_matrix_key] = inv_trace.T
+        mats[self.upwind_primary_matrix_key] = sps.diags(up1)
+        mats[self.upwind_secondary_matrix_key] = sps.diags(up2)
+        mats[self.flux_matrix_key] = sps.diags(sgn)
+        mats[self.mortar_discr_matrix_key] = sps.eye(intf.num_cells)
+
+    def assemble_matrix_rhs(self, sd_primary, sd_secondary, intf, data_primary, data_secondary, data_intf, matrix):
+        """upwind.py:530-680: the 3 x 3 block contribution of the coupling condition (right-hand side zero)."""
+        m = data_intf[DISCRETIZATION_MATRICES][self.keyword]
+        dof = np.array([matrix[0, 0].shape[1], matrix[1, 1].shape[1], intf.num_cells])
+        cc = np.array([sps.coo_matrix((i, j)) for i in dof for j in dof]).reshape((3, 3))
+        lam = np.abs(data_intf[PARAMETERS][self.keyword][self._flux_array_key])
+        scaling = sps.dia_matrix((lam, 0), shape=(intf.num_cells, intf.num_cells))
+        cc[0, 2] = m[self.inv_trace_primary_matrix_key] @ intf.mortar_to_primary_int()
+        cc[1, 2] = -intf.mortar_to_secondary_int()
+        cc[2, 0] = (scaling @ m[self.flux_matrix_key] @ m[self.upwind_primary_matrix_key]
+                    @ intf.primary_to_mortar_avg() @ m[self.trace_primary_matrix_key])
+        cc[2, 1] = scaling @ m[self.flux_matrix_key] @ m[self.upwind_secondary_matrix_key] @ intf.secondary_to_mortar_avg()
+        cc[2, 2] = -m[self.mortar_discr_matrix_key]
+        if sd_primary == sd_secondary:
+            cc = np.array([np.sum(cc, axis=(0, 1))])
+        rhs = np.array([np.zeros(dof[0]), np.zeros(dof[1]), np.zeros(dof[2])], dtype=object)
+        if rhs.ndim == 2:
+            rhs = rhs.ravel()
+        matrix += cc
+        return matrix, rhs

@@ -54,6 +54,7 @@ def plugin(pp, allow_reference_fallback: bool = False) -> SimpleNamespace:
     # pp.Mpfa etc. to the plugin classes (e.g. to run the reference's own tests on them)
     RefMpfa, RefMpsa, RefBiot = pp.Mpfa, pp.Mpsa, pp.Biot
     RefTpfa, RefUpwind = pp.Tpfa, pp.Upwind
+    RefUpwindCoupling = pp.UpwindCoupling
     RefMpfaAd, RefMpsaAd, RefBiotAd = pp.ad.MpfaAd, pp.ad.MpsaAd, pp.ad.BiotAd
 
     def _core(name, gpu_cls, ref_cls, flow):
@@ -124,6 +125,17 @@ def plugin(pp, allow_reference_fallback: bool = False) -> SimpleNamespace:
         def assemble_matrix_rhs(self, sd, data):
             return RefUpwind.assemble_matrix_rhs(self, sd, data)
 
+    class UpwindCoupling(fv.UpwindCoupling, RefUpwindCoupling):
+        """pp.UpwindCoupling with the interface masks computed by the per-entry GPU kernel."""
+
+        def __init__(self, keyword: str) -> None:
+            RefUpwindCoupling.__init__(self, keyword)
+            fv.UpwindCoupling.__init__(self, keyword)
+
+        def discretize(self, sd_primary, sd_secondary, intf, data_primary, data_secondary, data_intf) -> None:
+            fv.UpwindCoupling.discretize(self, sd_primary, sd_secondary, intf, data_primary, data_secondary, data_intf)
+            _count(gpu_calls, "UpwindCoupling")
+
     def _rewrap(obj, discr, subdomains, coupling_terms=None):
         obj._discretization = discr
         if coupling_terms is None:
@@ -185,11 +197,13 @@ def plugin(pp, allow_reference_fallback: bool = False) -> SimpleNamespace:
         the model classes (this is how tools/run_reference_tests.py runs the reference's own tests)."""
         pp.Mpfa, pp.Mpsa, pp.Biot = Mpfa, Mpsa, Biot
         pp.Tpfa, pp.Upwind = Tpfa, Upwind
+        pp.UpwindCoupling = UpwindCoupling
 
     def uninstall() -> None:
         pp.Mpfa, pp.Mpsa, pp.Biot = RefMpfa, RefMpsa, RefBiot
         pp.Tpfa, pp.Upwind = RefTpfa, RefUpwind
+        pp.UpwindCoupling = RefUpwindCoupling
 
-    return SimpleNamespace(Mpfa=Mpfa, Mpsa=Mpsa, Biot=Biot, Tpfa=Tpfa, Upwind=Upwind, MpfaAd=MpfaAd, MpsaAd=MpsaAd, BiotAd=BiotAd,
+    return SimpleNamespace(Mpfa=Mpfa, Mpsa=Mpsa, Biot=Biot, Tpfa=Tpfa, Upwind=Upwind, UpwindCoupling=UpwindCoupling, MpfaAd=MpfaAd, MpsaAd=MpsaAd, BiotAd=BiotAd,
                            ModelMixin=ModelMixin, install=install, uninstall=uninstall,
                            fallback_calls=fallback_calls, gpu_calls=gpu_calls)

@@ -30,3 +30,56 @@ def test_tpfa_and_upwind_on_the_device(name):
 
 def test_line_grid_on_the_device():
     check_line()
+
+
+def test_upwind_coupling_on_the_device():
+    """``pb.UpwindCoupling`` (upwind.py:377-680): the interface masks from the device kernel, the trace operators and
+    the assembled 3 x 3 block contribution -- against the reference's own class on a real mixed-dimensional grid when
+    ``oracle/_ref`` is on the box, against the reference's formulas otherwise."""
+    import numpy as np
+    from types import SimpleNamespace
+    g = pb.cart_grid_3d([4, 3, 3])
+    rng = np.random.default_rng(4)
+    n = 11
+    lam = rng.standard_normal(n)
+    lam[[2, 7]] = 0.0
+    low = SimpleNamespace(dim=2)
+    intf = SimpleNamespace(num_cells=n)
+    di = pb.initialize_data({}, "transport", {"darcy_flux": lam})
+    up = pb.UpwindCoupling("transport")
+    up.discretize(g, low, intf, {}, {}, di)
+    M = di[pb.DISCRETIZATION_MATRICES]["transport"]
+    sgn = np.sign(lam)
+    assert np.array_equal(M["flux"].diagonal(), sgn)
+    assert np.array_equal(M["upwind_primary"].diagonal(), (sgn > 0).astype(float))
+    assert np.array_equal(M["upwind_secondary"].diagonal(), 1 - (sgn > 0).astype(float))
+    assert abs(M["inv_trace"] - abs(g.divergence(1))).sum() == 0 and abs(M["trace"] - abs(g.divergence(1)).T).sum() == 0
+    assert abs(M["mortar_discr"] - sps.eye(n)).sum() == 0
+    try:
+        from oracle.ref_loader import load_porepy, reference_available
+        if not reference_available():
+            return
+        pp = load_porepy()
+    except Exception:
+        return
+    # the reference's class on a real interface (3-D matrix, one fracture plane)
+    frac = pp.PlaneFracture(np.array([[0.5, 0.5, 0.5, 0.5], [0.0, 1.0, 1.0, 0.0], [0.0, 0.0, 1.0, 1.0]]))
+    mdg = pp.create_mdg("cartesian", {"cell_size": 0.25}, pp.create_fracture_network([frac], pp.domains.unit_cube_domain(3)))
+    (intf_r, d_intf), = [(i, d) for i, d in mdg.interfaces(return_data=True) if i.dim == 2]
+    sd_h, sd_l = mdg.interface_to_subdomain_pair(intf_r)
+    lam = np.random.default_rng(5).standard_normal(intf_r.num_cells)
+    ref_d = pp.initialize_data({}, "transport", {"darcy_flux": lam})
+    mine_d = pp.initialize_data({}, "transport", {"darcy_flux": lam})
+    ref, mine = pp.UpwindCoupling("transport"), pb.UpwindCoupling("transport")
+    ref.discretize(sd_h, sd_l, intf_r, {}, {}, ref_d)
+    mine.discretize(sd_h, sd_l, intf_r, {}, {}, mine_d)
+    for key, m in ref_d[pp.DISCRETIZATION_MATRICES]["transport"].items():
+        assert abs(sps.csr_matrix(m) - sps.csr_matrix(mine_d[pp.DISCRETIZATION_MATRICES]["transport"][key])).sum() == 0, key
+
+    def blocks():
+        nh, nl = sd_h.num_cells, sd_l.num_cells
+        return np.array([[sps.coo_matrix((a, b)) for b in (nh, nl, intf_r.num_cells)] for a in (nh, nl, intf_r.num_cells)],
+                        dtype=object)
+    A_ref, _ = ref.assemble_matrix_rhs(sd_h, sd_l, intf_r, {}, {}, ref_d, blocks())
+    A_mine, _ = mine.assemble_matrix_rhs(sd_h, sd_l, intf_r, {}, {}, mine_d, blocks())
+    assert abs(sps.bmat(A_ref) - sps.bmat(A_mine)).sum() == 0

@@ -16,6 +16,14 @@
 #include <vector>
 
 #include "plan.hpp"
+#include <nvtx3/nvToolsExt.h>
+
+// NVTX range for the lifetime of a scope: one range per C-ABI phase (the reference logs per-phase times,
+// models/solution_strategy.py:435-441; here the phases show up in nsys / ncu --nvtx timelines)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ------------------------------------------------------------------------------------
 // error state
@@ -262,6 +270,7 @@ __global__ void posmap_kernel(int64_t nn, const int32_t *__restrict__ row_ptr, c
 extern "C" int pb_plan_create(int nd, int64_t nc, int64_t nf, int64_t nn, const int32_t *cf_indptr,
                               const int32_t *cf_indices, const int8_t *cf_data,
                               const int32_t *fn_indptr, const int32_t *fn_indices, pb_plan **out) {
+    NvtxRange nvtx_("pb_plan_create");
     if (!out || !cf_indptr || !cf_indices || !cf_data || !fn_indptr || !fn_indices)
         return fail(PB_EINVAL, "null pointer");
     int ndev = 0;
@@ -605,6 +614,7 @@ extern "C" int pb_plan_set_cell_map(pb_plan *p, const int64_t *cells, int64_t n_
 extern "C" int pb_plan_set_geometry(pb_plan *p, const double *nodes, const double *face_normals,
                                     const double *face_centers, const double *face_areas,
                                     const double *cell_centers, const double *cell_volumes) {
+    NvtxRange nvtx_("pb_plan_set_geometry");
     if (!p || !nodes || !face_normals || !face_centers || !face_areas || !cell_centers || !cell_volumes)
         return fail(PB_EINVAL, "null pointer");
     const HostPlan &H = p->H;
@@ -643,6 +653,7 @@ static int check_singular(pb_plan *p) {
 // ------------------------------------------------------------------------------------
 extern "C" int pb_mpfa_upload(pb_plan *p, const double *perm, const uint8_t *bc,
                               const double *robin_weight, double eta) {
+    NvtxRange nvtx_("pb_mpfa_upload");
     if (!p || !perm || !bc) return fail(PB_EINVAL, "null pointer");
     if (!p->have_geo) return fail(PB_EINVAL, "pb_plan_set_geometry has not been called");
     const HostPlan &H = p->H;
@@ -658,6 +669,7 @@ extern "C" int pb_mpfa_upload(pb_plan *p, const double *perm, const uint8_t *bc,
 }
 
 extern "C" int pb_mpfa_assemble(pb_plan *p, int want_flux, int want_trace, int want_vs, float *ms) {
+    NvtxRange nvtx_("pb_mpfa_assemble");
     if (!p) return fail(PB_EINVAL, "null plan");
     if (!p->mpfa_ready) return fail(PB_EINVAL, "pb_mpfa_upload has not been called");
     const HostPlan &H = p->H;
@@ -903,6 +915,7 @@ extern "C" int pb_plan_output_csr(pb_plan *p, const pb_values *v, int which, int
 }
 
 extern "C" int pb_mpfa_system(pb_plan *p, const pb_values *flux, pb_csr **out) {
+    NvtxRange nvtx_("pb_mpfa_system");
     if (!p || !out) return fail(PB_EINVAL, "null pointer");
     const double *flux_dev = flux ? flux->buf.as<double>() : p->o_flux.as<double>();
     if (flux && flux->n != p->pat_nnz[0]) return fail(PB_EINVAL, "flux values do not belong to this plan");
@@ -930,6 +943,7 @@ extern "C" int pb_mpfa_system(pb_plan *p, const pb_values *flux, pb_csr **out) {
 
 extern "C" int pb_mpfa_rhs(pb_plan *p, const pb_values *bound_flux, const pb_values *vector_source_discr,
                            const double *bc_values, const double *vector_source, double *rhs) {
+    NvtxRange nvtx_("pb_mpfa_rhs");
     if (!p || !bc_values || !rhs) return fail(PB_EINVAL, "null pointer");
     const double *bflux_dev = bound_flux ? bound_flux->buf.as<double>() : p->o_bflux.as<double>();
     const double *vs_dev = vector_source_discr ? vector_source_discr->buf.as<double>() : p->o_vs.as<double>();
@@ -1041,6 +1055,7 @@ __global__ void neg_div_nd_kernel(int64_t nf, int nd, const int32_t *__restrict_
 }
 
 extern "C" int pb_mpsa_system(pb_plan *p, const pb_values *stress, pb_csr **out) {
+    NvtxRange nvtx_("pb_mpsa_system");
     if (!p || !out) return fail(PB_EINVAL, "null pointer");
     const double *stress_dev = stress ? stress->buf.as<double>() : p->o_stress.as<double>();
     if (stress && stress->n != p->pat_nnz[0] * p->H.nd * p->H.nd) return fail(PB_EINVAL, "stress values do not belong to this plan");
@@ -1078,6 +1093,7 @@ extern "C" int pb_mpsa_system(pb_plan *p, const pb_values *stress, pb_csr **out)
 
 extern "C" int pb_mpsa_rhs(pb_plan *p, const pb_values *bound_stress, const double *bc_values, const double *source,
                            double *rhs) {
+    NvtxRange nvtx_("pb_mpsa_rhs");
     if (!p || !bc_values || !rhs) return fail(PB_EINVAL, "null pointer");
     const double *bstress_dev = bound_stress ? bound_stress->buf.as<double>() : p->o_bstress.as<double>();
     if (bound_stress && bound_stress->n != p->pat_nnz[1] * p->H.nd * p->H.nd)
@@ -1113,6 +1129,7 @@ extern "C" int pb_mpsa_rhs(pb_plan *p, const pb_values *bound_stress, const doub
 extern "C" int pb_mpsa_upload(pb_plan *p, const double *stiffness, const uint8_t *bc,
                               const double *robin_weight, double eta, int n_alpha,
                               const double *alpha) {
+    NvtxRange nvtx_("pb_mpsa_upload");
     if (!p || !stiffness || !bc) return fail(PB_EINVAL, "null pointer");
     if (!p->have_geo) return fail(PB_EINVAL, "pb_plan_set_geometry has not been called");
     if (n_alpha < 0 || n_alpha > PB_MAX_ALPHA) return fail(PB_EINVAL, "0 <= n_alpha <= 4");
@@ -1167,6 +1184,7 @@ extern "C" int pb_mpsa_set_basis(pb_plan *p, const double *basis) {
 }
 
 extern "C" int pb_mpsa_assemble(pb_plan *p, float *ms) {
+    NvtxRange nvtx_("pb_mpsa_assemble");
     if (!p) return fail(PB_EINVAL, "null plan");
     if (!p->mpsa_ready) return fail(PB_EINVAL, "pb_mpsa_upload has not been called");
     const HostPlan &H = p->H;

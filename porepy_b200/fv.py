@@ -21,6 +21,7 @@ raises ``RuntimeError``.
 from __future__ import annotations
 
 import ctypes as C
+import logging
 import time
 
 import numpy as np
@@ -28,6 +29,8 @@ import scipy.sparse as sps
 
 from . import _lib
 from .params import DISCRETIZATION_MATRICES, PARAMETERS
+
+logger = logging.getLogger(__name__)
 
 
 def determine_eta(sd) -> float:
@@ -122,6 +125,22 @@ def lift_vector_source(ip: np.ndarray, ix: np.ndarray, data: np.ndarray, rows: n
     dt = _index_dtype(amb * int(ix.size), amb * nc)
     cols = (ix.astype(dt)[:, None] * amb + np.arange(amb, dtype=dt)).ravel()
     return sps.csr_matrix((da.ravel(), cols, ip.astype(dt) * amb), shape=(ip.size - 1, amb * nc))
+
+
+def _log_throughput(name: str, keyword: str, sd, kernel_ms: float, wall_s: float, out: dict) -> None:
+    """One INFO line per discretization (the reference logs the elapsed time of ``discretize``,
+    models/solution_strategy.py:435-441): cells/s of the kernels and of the whole call, and the rate at which the
+    output values were written."""
+    if not logger.isEnabledFor(logging.INFO):
+        return
+    nbytes = 0
+    for m in out.values():
+        for mm in (m.values() if isinstance(m, dict) else (m,)):
+            nbytes += 8 * int(getattr(mm, "nnz", 0))
+    k_s = max(kernel_ms, 1e-6) * 1e-3
+    logger.info("B200 %s(%s): %d cells (dim %d), kernels %.2f ms = %.3g cells/s, %.1f GB/s of output values; "
+                "discretize() %.3f s = %.3g cells/s", name, keyword, sd.num_cells, sd.dim, kernel_ms,
+                sd.num_cells / k_s, nbytes / k_s / 1e9, wall_s, sd.num_cells / max(wall_s, 1e-9))
 
 
 def _on_device(*mats) -> bool:
@@ -840,6 +859,7 @@ class Mpfa(_Base):
         t4 = time.perf_counter()
         self.last_timing = dict(plan_s=t1 - t0, upload_s=t2 - t1, kernel_ms=ms,
                                 assemble_s=t3 - t2, download_s=t4 - t3)
+        _log_throughput("Mpfa", self.keyword, sd, ms, t4 - t0, out)
         return out
 
     def assemble_matrix_rhs(self, sd, data: dict):
@@ -953,6 +973,7 @@ class Mpsa(_Base):
         t4 = time.perf_counter()
         self.last_timing = dict(plan_s=t1 - t0, upload_s=t2 - t1, kernel_ms=ms,
                                 assemble_s=t3 - t2, download_s=t4 - t3)
+        _log_throughput(type(self).__name__, self.keyword, sd, ms, t4 - t0, out)
         return out
 
     def assemble_matrix_rhs(self, sd, data: dict):
@@ -1130,6 +1151,19 @@ class Upwind(_Base):
         return matrix, rhs
 
 
+def interface_upwind_masks(interface_flux):
+    """(sign, upstream-is-primary, upstream-is-secondary) per mortar cell through ``pb_upwind_coupling`` (one thread per
+    entry).  A separate function so that the CPU tests can substitute the host formulas."""
+    lam = _lib.f64(interface_flux)
+    lib = _lib.load()
+    _lib.require_gpu()
+    n = int(lam.size)
+    sgn, up1, up2 = np.empty(n), np.empty(n), np.empty(n)
+    _lib.check(lib.pb_upwind_coupling(n, _lib.ptr(lam, _lib._f64p), _lib.ptr(sgn, _lib._f64p),
+                                      _lib.ptr(up1, _lib._f64p), _lib.ptr(up2, _lib._f64p)))
+    return sgn, up1, up2
+
+
 class UpwindCoupling:
     """Upwinding of an advective flux across the interface between a subdomain and a lower-dimensional one
     (numerics/fv/upwind.py:377).  ``discretize`` writes the reference's six matrices to
@@ -1166,13 +1200,7 @@ class UpwindCoupling:
         if sd_primary.dim - sd_secondary.dim not in [1, 2]:
             raise ValueError("Implementation is only valid for grids one dimension apart.")
         mats = data_intf.setdefault(DISCRETIZATION_MATRICES, {}).setdefault(self.keyword, {})
-        lam = _lib.f64(data_intf[PARAMETERS][self.keyword][self._flux_array_key])
-        lib = _lib.load()
-        _lib.require_gpu()
-        n = int(lam.size)
-        sgn, up1, up2 = np.empty(n), np.empty(n), np.empty(n)
-        _lib.check(lib.pb_upwind_coupling(n, _lib.ptr(lam, _lib._f64p), _lib.ptr(sgn, _lib._f64p),
-                                          _lib.ptr(up1, _lib._f64p), _lib.ptr(up2, _lib._f64p)))
+        sgn, up1, up2 = interface_upwind_masks(data_intf[PARAMETERS][self.keyword][self._flux_array_key])
         inv_trace = abs(sd_primary.divergence(dim=1))
         mats[self.inv_trace_primary_matrix_key] = inv_trace
         mats[self.trace_primary_matrix_key] = inv_trace.T

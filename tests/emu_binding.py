@@ -340,3 +340,10 @@ def _upwind(self, darcy_flux, bc):
 
 EmuPlan.tpfa = _tpfa
 EmuPlan.upwind = _upwind
+
+
+def emu_interface_upwind_masks(interface_flux):
+    """Host stand-in of ``fv.interface_upwind_masks`` (the formulas of upwind.py:496-510)."""
+    s = np.sign(np.asarray(interface_flux, dtype=np.float64))
+    flag = (s > 0).astype(float)
+    return s, flag, 1 - flag

@@ -187,10 +187,11 @@ def _solve(pp, cls):
 
 @pytest.fixture()
 def emu_plan(monkeypatch):
-    from emu_binding import EmuBackedFaceGrid, EmuBackedPlan
+    from emu_binding import EmuBackedFaceGrid, EmuBackedPlan, emu_interface_upwind_masks
     from porepy_b200 import fv
     monkeypatch.setattr(fv, "DevicePlan", EmuBackedPlan)
     monkeypatch.setattr(fv, "FaceGrid", EmuBackedFaceGrid)
+    monkeypatch.setattr(fv, "interface_upwind_masks", emu_interface_upwind_masks)
 
 
 def test_single_phase_flow_model_with_a_fracture(pp, emu_plan):

@@ -37,6 +37,8 @@ class Rebind:
             from emu_binding import EmuBackedFaceGrid, EmuBackedPlan
             fv.DevicePlan = EmuBackedPlan
             fv.FaceGrid = EmuBackedFaceGrid
+            import emu_binding
+            fv.interface_upwind_masks = emu_binding.emu_interface_upwind_masks
         COUNTS["backend: " + ("cuda" if gpu else "host build of the node routines")] = 1
         for name in ("Mpfa", "Mpsa", "Biot", "Tpfa", "Upwind"):
             for owner, tag in ((getattr(fv, name), "porepy_b200"), (getattr(pp, name), "reference")):

@@ -133,6 +133,14 @@ static int build_classes(pb_plan *p, std::vector<NodeClass> &out, F size_of) {
             const int tpb = c.team == 32 ? 4 : 1;
             if ((size_t)(c.a_doubles + c.rest_doubles + c.scr_doubles) * 8 * tpb > kMaxSmem) c.a_global = true;
         }
+        // Launch order = a space-filling (Morton) order of the node coordinates when the geometry is known: the <= m_f
+        // nodes of a face are then processed close in time, so the scatter-adds into one face row meet in L2 instead
+        // of each paying a DRAM read-modify-write (index order puts the neighbours in the 2nd / 3rd grid direction
+        // thousands of regions apart; ncu: 2.9x the algorithmic DRAM traffic).  POREB200_NODE_ORDER=index disables it.
+        if (!p->node_key.empty()) {
+            const std::vector<uint32_t> &nk = p->node_key;
+            std::stable_sort(lists[key].begin(), lists[key].end(), [&](int32_t x, int32_t y) { return nk[x] < nk[y]; });
+        }
         if (c.nodes.upload(lists[key], p->stream) != cudaSuccess) return fail(PB_ECUDA, "upload of node list failed");
     }
     return PB_OK;
@@ -620,6 +628,38 @@ extern "C" int pb_plan_set_geometry(pb_plan *p, const double *nodes, const doubl
     const HostPlan &H = p->H;
     cudaStream_t st = p->stream;
     int rc;
+    {   // Morton keys of the nodes (10 bits per axis over the bounding box) and re-ordered class lists
+        const char *ord = getenv("POREB200_NODE_ORDER");
+        const bool morton = !(ord && strcmp(ord, "index") == 0);
+        const bool had = !p->node_key.empty();
+        p->node_key.clear();
+        if (morton) {
+            double lo[3], hi[3];
+            for (int d = 0; d < 3; ++d) {
+                lo[d] = 1e300; hi[d] = -1e300;
+                for (int64_t s = 0; s < H.nn; ++s) { const double v = nodes[d * H.nn + s]; lo[d] = std::min(lo[d], v); hi[d] = std::max(hi[d], v); }
+            }
+            auto spread = [](uint32_t v) {   // 10 bits -> every third bit
+                v &= 0x3ff;
+                v = (v | (v << 16)) & 0x30000ff; v = (v | (v << 8)) & 0x300f00f;
+                v = (v | (v << 4)) & 0x30c30c3;  v = (v | (v << 2)) & 0x9249249;
+                return v;
+            };
+            p->node_key.resize(H.nn);
+            for (int64_t s = 0; s < H.nn; ++s) {
+                uint32_t q[3];
+                for (int d = 0; d < 3; ++d) {
+                    const double ext = hi[d] - lo[d];
+                    q[d] = ext > 0 ? (uint32_t)std::min(1023.0, (nodes[d * H.nn + s] - lo[d]) / ext * 1024.0) : 0u;
+                }
+                p->node_key[s] = spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2);
+            }
+        }
+        if (morton || had) {
+            if ((rc = build_mpfa_classes(p))) return rc;
+            p->mpsa_cls_nalpha = -1;   // MPSA / Biot classes are rebuilt (and ordered) at the next upload
+        }
+    }
     if ((rc = upload_repacked(p, p->nodes, nodes, 3, H.nn))) return rc;
     if ((rc = upload_repacked(p, p->fnorm, face_normals, 3, H.nf))) return rc;
     if ((rc = upload_repacked(p, p->fcent, face_centers, 3, H.nf))) return rc;

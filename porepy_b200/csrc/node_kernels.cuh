@@ -540,7 +540,6 @@ struct TileGJ {
         for (int i = t.tid(); i < NP * 4; i += t.size()) P0[i] = 0.0;
         if (t.tid() == 0) prs[4] = 0;
         t.sync();
-#ifdef PB_NO_ROT
         const int npanel = (n + 3) >> 2;
         bool ok = true;
 #pragma unroll
@@ -657,143 +656,6 @@ struct TileGJ {
                 }
             }
         }
-        const int shift = 0;
-#else
-        const int npanel = (n + 3) >> 2;
-        bool ok = true;
-        // The tile column that holds the current panel is always REGISTER index 0: once both of its panels are
-        // eliminated the tiles are shifted down by one (2 * RT * NCT register moves), so ONE loop body serves all
-        // tile columns (the fully unrolled version had NRT copies of it: 600 KB of SASS for the tetrahedral MPSA class,
-        // far beyond the instruction cache; ncu: 8-22 % of the stall samples were instruction fetches).  `shift` tile
-        // columns have been rotated out; register tile tc holds absolute tile tc + shift, tiles >= live are dead.
-        int shift = 0;
-#pragma unroll 1
-        for (int tcol = 0; tcol < NRT && tcol < NCT; ++tcol) {
-            const int live = NCT - shift;
-            bool both = false;
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const int q = 2 * tcol + half;
-                if (q >= npanel || !ok) break;
-                both = half == 1;
-                const int p0 = 4 * q;
-                const int pw = (n - p0) < 4 ? (n - p0) : 4;
-                // S1: dump my 8x4 slices of the panel; the owners of the panel's natural rows
-                // p0..p0+3 post them as raw pivot rows right away (speculation for the fast path)
-                if (((l & 3) >> 1) == half) {
-                    const int j0 = 2 * (l & 1);
-#pragma unroll
-                    for (int rt = 0; rt < RT; ++rt) {
-                        const int myrow = 8 * (ti + NW * rt) + gr;
-                        P0[myrow * 4 + j0] = c[rt][0][0];
-                        P0[myrow * 4 + j0 + 1] = c[rt][0][1];
-                    }
-                }
-                int myp[RT];
-#pragma unroll
-                for (int rt = 0; rt < RT; ++rt) {
-                    const int myrow = 8 * (ti + NW * rt) + gr;
-                    const int j = myrow - p0;
-                    myp[rt] = (j >= 0 && j < pw) ? j : -1;
-                    if (myp[rt] >= 0) {
-                        double *rw = Raw + myp[rt] * WP + 8 * shift + gc;
-#pragma unroll
-                        for (int tc = 0; tc < NCT; ++tc)
-                            if (tc < live) { rw[8 * tc] = c[rt][tc][0]; rw[8 * tc + 1] = c[rt][tc][1]; }
-                    }
-                }
-                t.sync();
-                // S2: every warp tests the diagonal block (threshold block pivoting)
-                double iv;
-                const bool fast = try_diagonal_block(l, P0, usedf, p0, pw, iv);
-                const double *ainv = Ainv;  // slow path: warp 0's result, published behind a barrier
-                if (fast) {
-                    double *mine = Ainv + 16 * (ti + 1);  // private copy: no cross-warp sharing
-                    if (l < 16) mine[l] = iv;
-                    __syncwarp();
-                    ainv = mine;
-                } else {
-                    // rare: partial pivoting on the panel by warp 0, then the owners re-post the rows
-                    t.sync();  // all warps have read usedf / P0 for the test
-                    if (ti == 0) factor_panel<false>(l, P0, usedf, prs, Ainv, rowidx, p0, pw);
-                    t.sync();
-                    ok = prs[4] == 0;  // uniform over the team
-                    if (!ok) break;
-#pragma unroll
-                    for (int rt = 0; rt < RT; ++rt) {
-                        const int myrow = 8 * (ti + NW * rt) + gr;
-                        myp[rt] = -1;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (prs[j] == myrow) myp[rt] = j;
-                        if (myp[rt] >= 0) {
-                            double *rw = Raw + myp[rt] * WP + 8 * shift + gc;
-#pragma unroll
-                            for (int tc = 0; tc < NCT; ++tc)
-                                if (tc < live) { rw[8 * tc] = c[rt][tc][0]; rw[8 * tc + 1] = c[rt][tc][1]; }
-                        }
-                    }
-                    t.sync();
-                }
-                // S4: R = A11^-1 * Raw, one column per thread
-                for (int col = 8 * shift + t.tid(); col < NCT * 8; col += t.size()) {
-                    double raw[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) raw[i] = (i < pw) ? Raw[i * WP + col] : 0.0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        double x = 0.0;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) x += ainv[j * 4 + i] * raw[i];
-                        R[j * WP + col] = (j < pw) ? x : 0.0;
-                    }
-                }
-                t.sync();
-                // S5: A22 -= A21 * R  (one DMMA per tile), pivot rows <- R
-                if (fast && t.tid() < pw) {  // bookkeeping of the fast path (after every warp's test)
-                    usedf[p0 + t.tid()] = 1;
-                    rowidx[p0 + t.tid()] = p0 + t.tid();
-                }
-                {
-                    const int k = l & 3;
-                    const int src = (l & ~3) | (2 * half + (k >> 1));
-                    double af[RT];
-#pragma unroll
-                    for (int rt = 0; rt < RT; ++rt) {
-                        const double v0 = __shfl_sync(0xffffffffu, c[rt][0][0], src);
-                        const double v1 = __shfl_sync(0xffffffffu, c[rt][0][1], src);
-                        af[rt] = (k < pw) ? -((k & 1) ? v1 : v0) : 0.0;
-                    }
-                    const double *rb = R + k * WP + (l >> 2) + 8 * shift;
-#pragma unroll
-                    for (int tc = 0; tc < NCT; ++tc) {
-                        if (tc < live) {
-                            const double bf = rb[8 * tc];
-#pragma unroll
-                            for (int rt = 0; rt < RT; ++rt) pb_dmma(c[rt][tc], af[rt], bf);
-                        }
-                    }
-#pragma unroll
-                    for (int rt = 0; rt < RT; ++rt)
-                        if (myp[rt] >= 0) {
-                            const double *rr = R + myp[rt] * WP + 8 * shift + gc;
-#pragma unroll
-                            for (int tc = 0; tc < NCT; ++tc)
-                                if (tc < live) { c[rt][tc][0] = rr[8 * tc]; c[rt][tc][1] = rr[8 * tc + 1]; }
-                        }
-                }
-            }
-            if (!ok) break;
-            if (both) {   // the tile column is eliminated: rotate it out
-#pragma unroll
-                for (int rt = 0; rt < RT; ++rt)
-#pragma unroll
-                    for (int tc = 0; tc + 1 < NCT; ++tc) { c[rt][tc][0] = c[rt][tc + 1][0]; c[rt][tc][1] = c[rt][tc + 1][1]; }
-                ++shift;
-            }
-            if (2 * tcol + 2 >= npanel) break;
-        }
-#endif
         t.sync();
         if (!ok) return false;
 #pragma unroll
@@ -801,7 +663,7 @@ struct TileGJ {
             const int myrow = 8 * (ti + NW * rt) + gr;
 #pragma unroll
             for (int tc = 0; tc < NCT; ++tc) {
-                const int col = 8 * (tc + shift) + gc;   // register tile tc holds absolute tile tc + shift
+                const int col = 8 * tc + gc;
                 if (myrow < n) {
                     if (col >= n && col < wend) A[myrow * W + col] = c[rt][tc][0];
                     if (col + 1 >= n && col + 1 < wend) A[myrow * W + col + 1] = c[rt][tc][1];

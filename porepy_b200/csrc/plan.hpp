@@ -161,6 +161,7 @@ struct pb_plan {
     bool have_geo = false;
     DevBuf cell_map;               // optional: cell e of this plan is cell cell_map[e] of a larger source grid
     int64_t cell_map_src = 0;      //           (cell tensors are then given for the source grid and gathered on the device)
+    std::vector<uint32_t> node_key;  // Morton key per node (set with the geometry): launch order of the node classes
     std::vector<uint8_t> active;   // per node: assemble its interaction region (empty = all); pb_plan_set_active_nodes
     PlanView view{};
     GeoView geo{};

@@ -270,6 +270,9 @@ int pb_csr_from_device_pattern_(int64_t nrows, int64_t ncols, int64_t nnz, const
     if ((e = cudaMemcpy(a->indptr, indptr_dev, (nrows + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice)) != cudaSuccess) return bail(e);
     if (nnz && (e = cudaMemcpy(a->indices, indices_dev, nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice)) != cudaSuccess) return bail(e);
     if ((e = cudaMemset(a->data, 0, (nnz ? nnz : 1) * sizeof(double))) != cudaSuccess) return bail(e);
+    // the copies and the memset above ran on the legacy default stream, which does NOT order against the callers'
+    // non-blocking streams (the assembly kernels accumulate into `data` right after this returns)
+    if ((e = cudaStreamSynchronize(0)) != cudaSuccess) return bail(e);
     autotune_tpr(a);
     *out = a;
     return PB_OK;

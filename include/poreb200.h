@@ -249,6 +249,27 @@ int pb_upwind(pb_facegrid *g, const double *darcy_flux, const uint8_t *bc_bits, 
 int pb_upwind_coupling(int64_t n, const double *interface_flux, double *sign, double *from_primary,
                        double *from_secondary);
 
+/* ---- sharding of ONE grid across ranks (csrc/shard.cu; host code) ---------------------------------------------
+ * This rank's share of a grid from the GLOBAL topology: replaces the reference's memory-splitting chain
+ * _fvutils.subproblems (numerics/fv/_fvutils.py:414-539) -> partition.extract_subgrid (grids/partition.py:540-640)
+ * for this path.  cf_* / fn_*: CSC arrays of cell_faces (nf x nc, data +-1) and face_nodes (nn x nf); part: rank of
+ * each cell.  Shard cells = every cell with a face holding a node of an own cell (one halo layer), OWN CELLS FIRST
+ * (ascending), then the halo; faces / nodes ascending.  pb_shard_sizes: {cells, faces, nodes, own cells, nnz of the
+ * local cell_faces, nnz of the local face_nodes}.  pb_shard_fill: local->global maps, per local face the flags
+ * "row kept by this rank" / "cut face of the overlap" / "one cell inside the shard", per local node "interaction
+ * region assembled by this rank", and the local CSC arrays (any output may be NULL). */
+typedef struct pb_shard pb_shard; /* opaque */
+int pb_shard_create(int64_t nc, int64_t nf, int64_t nn, const int32_t *cf_indptr, const int32_t *cf_indices,
+                    const double *cf_data, const int32_t *fn_indptr, const int32_t *fn_indices,
+                    const int64_t *part, int64_t rank, pb_shard **out);
+int pb_shard_sizes(const pb_shard *s, int64_t *sizes6);
+int pb_shard_fill(const pb_shard *s, int64_t *cells, int64_t *faces, int64_t *nodes, uint8_t *own_face,
+                  uint8_t *cut_face, uint8_t *single_face, uint8_t *own_node, int32_t *cf_indptr,
+                  int32_t *cf_indices, double *cf_data, int32_t *fn_indptr, int32_t *fn_indices);
+void pb_shard_destroy(pb_shard *s);
+/* dst[r, j] = src[r, idx[j]]: the (3, n) geometry arrays of a sub-grid (row-major host arrays) */
+int pb_gather_columns(const double *src, int64_t nrows, int64_t ncols, const int64_t *idx, int64_t n, double *dst);
+
 /* device-resident CSR matrix */
 int pb_csr_create(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t *indptr,
                   const int32_t *indices, const double *data, pb_csr **out);

@@ -65,6 +65,12 @@ _SIGNATURES = {
     "pb_tpfa": (C.c_int, [C.c_void_p, _f64p, _u8p, _i32p, C.c_int] + [_f64p] * 6),
     "pb_upwind": (C.c_int, [C.c_void_p, _f64p, _u8p, _i32p, _f64p, _f64p]),
     "pb_upwind_coupling": (C.c_int, [C.c_int64, _f64p, _f64p, _f64p, _f64p]),
+    "pb_shard_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _i32p, _i32p, _f64p, _i32p, _i32p, _i64p, C.c_int64,
+                                  C.POINTER(C.c_void_p)]),
+    "pb_shard_sizes": (C.c_int, [C.c_void_p, _i64p]),
+    "pb_shard_fill": (C.c_int, [C.c_void_p, _i64p, _i64p, _i64p, _u8p, _u8p, _u8p, _u8p, _i32p, _i32p, _f64p, _i32p, _i32p]),
+    "pb_shard_destroy": (None, [C.c_void_p]),
+    "pb_gather_columns": (C.c_int, [_f64p, C.c_int64, C.c_int64, _i64p, C.c_int64, _f64p]),
     "pb_csr_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _i32p, _i32p, _f64p,
                                 C.POINTER(C.c_void_p)]),
     "pb_csr_destroy": (None, [C.c_void_p]),

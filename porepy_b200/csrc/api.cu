@@ -632,8 +632,12 @@ extern "C" int pb_plan_set_geometry(pb_plan *p, const double *nodes, const doubl
         const char *ord = getenv("POREB200_NODE_ORDER");
         const bool morton = !(ord && strcmp(ord, "index") == 0);
         const bool had = !p->node_key.empty();
-        p->node_key.clear();
-        if (morton) {
+        double sig = 0.0;   // cheap signature of the coordinates: unchanged geometry keeps the keys and the lists
+        for (int64_t i = 0; i < 3 * H.nn; i += 7) sig += nodes[i] * (double)((i % 13) + 1);
+        const bool same = had && morton && sig == p->node_key_sig;
+        p->node_key_sig = sig;
+        if (!same) p->node_key.clear();
+        if (morton && !same) {
             double lo[3], hi[3];
             for (int d = 0; d < 3; ++d) {
                 lo[d] = 1e300; hi[d] = -1e300;
@@ -655,7 +659,7 @@ extern "C" int pb_plan_set_geometry(pb_plan *p, const double *nodes, const doubl
                 p->node_key[s] = spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2);
             }
         }
-        if (morton || had) {
+        if (!same && (morton || had)) {
             if ((rc = build_mpfa_classes(p))) return rc;
             p->mpsa_cls_nalpha = -1;   // MPSA / Biot classes are rebuilt (and ordered) at the next upload
         }

@@ -47,13 +47,15 @@ struct DevPool {
     DevPool() {
         if (const char *e = getenv("POREB200_DEVICE_POOL_BYTES")) cap = strtoull(e, nullptr, 10);
     }
-    void *take(size_t n) {
+    void *take(size_t n, size_t &got) {
         std::lock_guard<std::mutex> g(mu);
-        auto it = free_blocks.find(n);
-        if (it == free_blocks.end()) return nullptr;
+        // best fit within 25 %: a re-discretization of a slightly different (sub-)grid still finds its blocks
+        auto it = free_blocks.lower_bound(n);
+        if (it == free_blocks.end() || it->first > n + n / 4) return nullptr;
         void *q = it->second;
+        got = it->first;
         free_blocks.erase(it);
-        held -= n;
+        held -= got;
         return q;
     }
     bool give(void *q, size_t n) {
@@ -93,7 +95,8 @@ struct DevBuf {
         if (n <= bytes && p) return cudaSuccess;
         release();
         if (n == 0) n = 8;
-        if ((p = pb_dev_pool_().take(n)) != nullptr) { bytes = n; return cudaSuccess; }
+        size_t got = 0;
+        if ((p = pb_dev_pool_().take(n, got)) != nullptr) { bytes = got; return cudaSuccess; }
         cudaError_t e = cudaMalloc(&p, n);
         if (e == cudaErrorMemoryAllocation) {   // give the pooled blocks back to the driver and retry once
             (void)cudaGetLastError();
@@ -161,6 +164,7 @@ struct pb_plan {
     bool have_geo = false;
     DevBuf cell_map;               // optional: cell e of this plan is cell cell_map[e] of a larger source grid
     int64_t cell_map_src = 0;      //           (cell tensors are then given for the source grid and gathered on the device)
+    double node_key_sig = 0.0;
     std::vector<uint32_t> node_key;  // Morton key per node (set with the geometry): launch order of the node classes
     std::vector<uint8_t> active;   // per node: assemble its interaction region (empty = all); pb_plan_set_active_nodes
     PlanView view{};

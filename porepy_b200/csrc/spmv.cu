@@ -45,15 +45,20 @@ __global__ void __launch_bounds__(256)
                     const int32_t *__restrict__ indices, const double *__restrict__ data,
                     const double *__restrict__ x, double *__restrict__ y) {
     const int lane = threadIdx.x & (TPR - 1);
+    const int gw = (threadIdx.x & 31) / TPR;           // row group inside the warp
     const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / TPR;
     const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / TPR;
-    for (int64_t r = group; r < nrows; r += ngroups) {
-        const int b = __ldg(indptr + r), e = __ldg(indptr + r + 1);
+    // the trip count is WARP-uniform (it depends on the warp's first row only): the full-mask shuffles below are
+    // executed by all 32 lanes; groups past the last row carry an empty range
+    for (int64_t r0 = group - gw; r0 < nrows; r0 += ngroups) {
+        const int64_t r = r0 + gw;
+        const bool valid = r < nrows;
+        const int b = valid ? __ldg(indptr + r) : 0, e = valid ? __ldg(indptr + r + 1) : 0;
         double acc = 0.0;
         for (int q = b + lane; q < e; q += TPR) acc += __ldg(data + q) * __ldg(x + __ldg(indices + q));
 #pragma unroll
         for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, TPR);
-        if (lane == 0) y[r] = acc;
+        if (lane == 0 && valid) y[r] = acc;
     }
 }
 
@@ -66,16 +71,23 @@ __global__ void __launch_bounds__(256)
                          const double *__restrict__ w1, double *d1, const double *__restrict__ w2, int w2_is_y,
                          double *d2) {
     const int lane = threadIdx.x & (TPR - 1);
+    const int gw = (threadIdx.x & 31) / TPR;
     const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / TPR;
     const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / TPR;
     double a1 = 0.0, a2 = 0.0;
-    for (int64_t r = group; r < nrows; r += ngroups) {
-        const int b = __ldg(indptr + r), e = __ldg(indptr + r + 1);
+    // warp-uniform trip count (see csr_spmv_kernel): with a per-group bound, the groups of one warp that run out of
+    // rows first would meet the full-mask shuffles of the epilogue while the others are still inside the loop --
+    // undefined, and in practice a row's partial sum leaks into the dot products (seen as a BiCGStab that stalls
+    // when the row count of a shard puts the boundary inside a warp)
+    for (int64_t r0 = group - gw; r0 < nrows; r0 += ngroups) {
+        const int64_t r = r0 + gw;
+        const bool valid = r < nrows;
+        const int b = valid ? __ldg(indptr + r) : 0, e = valid ? __ldg(indptr + r + 1) : 0;
         double acc = 0.0;
         for (int q = b + lane; q < e; q += TPR) acc += __ldg(data + q) * __ldg(x + __ldg(indices + q));
 #pragma unroll
         for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, TPR);
-        if (lane == 0) {
+        if (lane == 0 && valid) {
             y[r] = acc;
             if (d1) a1 += w1[r] * acc;
             if (d2) a2 += (w2_is_y ? acc : w2[r]) * acc;

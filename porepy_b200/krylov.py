@@ -308,11 +308,25 @@ def _bicgstab_fused(op: DistributedOperator, b_own, tol, maxiter, diag_own, chec
     carry = 1 if op.loc.rank == 0 else 0
     nred = [0]
 
+    dbg_reduce = os.environ.get("POREB200_KRY_REDUCE", "")
+    dbg_exch = os.environ.get("POREB200_KRY_EXCH", "")
+
     def reduce(lo, hi):
         if world > 1:
             import torch.distributed as dist
-            dist.all_reduce(scal[lo:hi], group=op.group)
+            if dbg_reduce == "clone":
+                tmp = scal[lo:hi].clone()
+                dist.all_reduce(tmp, group=op.group)
+                scal[lo:hi].copy_(tmp)
+            else:
+                dist.all_reduce(scal[lo:hi], group=op.group)
             nred[0] += 1
+
+    def exch(buf):
+        if dbg_exch == "copy" and world > 1:
+            buf.copy_(op.exchange(buf[:n].clone()))
+        else:
+            op.exchange_into(buf)
 
     def iterations(count, it0):
         stream = torch.cuda.current_stream().cuda_stream
@@ -320,11 +334,11 @@ def _bicgstab_fused(op: DistributedOperator, b_own, tol, maxiter, diag_own, chec
             cur = it & 1
             g = 5 * cur
             _lib.check(lib.pb_kry_p(n, P(r), P(p), P(v), P(minv), P(ph), P(scal), cur, stream))
-            op.exchange_into(xb_p)
+            exch(xb_p)
             _lib.check(lib.pb_csr_spmv_dots_dev(csr.h, P(xb_p), P(v), P(rhat), S(g + 0), None, None, stream))
             reduce(g + 0, g + 1)
             _lib.check(lib.pb_kry_s(n, P(r), P(v), P(minv), P(s), P(sh), P(scal), cur, stream))
-            op.exchange_into(xb_s)
+            exch(xb_s)
             _lib.check(lib.pb_csr_spmv_dots_dev(csr.h, P(xb_s), P(t), P(s), S(g + 1), None, S(g + 2), stream))
             reduce(g + 1, g + 3)
             _lib.check(lib.pb_kry_xr(n, P(x), P(ph), P(sh), P(s), P(t), P(r), P(rhat), P(scal), cur, carry, stream))
@@ -363,6 +377,7 @@ def _bicgstab_fused(op: DistributedOperator, b_own, tol, maxiter, diag_own, chec
     it, nspmv = 0, 0
     relres, converged, breakdown = 1.0, False, False
     per_block_red = 3 if world > 1 else 0
+    trace = [] if os.environ.get("POREB200_KRYLOV_TRACE") else None
     while it < maxiter:
         count = min(check_every, maxiter - it)
         if graph is not None and count == check_every:
@@ -378,13 +393,16 @@ def _bicgstab_fused(op: DistributedOperator, b_own, tol, maxiter, diag_own, chec
             breakdown = True
             break
         relres = float(np.sqrt(max(rr, 0.0) / bb))
+        if trace is not None:
+            trace.append((it, relres) + tuple(float(v) for v in h[:10]))
         if relres <= tol:
             converged = True
             break
     done_it = int(h[12]) if np.isfinite(h[12]) else it
     return x, {"iterations": done_it if converged else it, "relres": relres, "converged": converged,
                "breakdown": breakdown, "spmv": nspmv, "allreduce": nred[0], "fused": True,
-               "cuda_graph": graph is not None, "host_syncs": (it + check_every - 1) // check_every + 1}
+               "cuda_graph": graph is not None, "host_syncs": (it + check_every - 1) // check_every + 1,
+               **({"trace": trace} if trace is not None else {})}
 
 
 def solve(a, b, owner=None, tol: float = 1e-10, maxiter: int = 2000, jacobi: bool = True, device=None,

@@ -183,7 +183,70 @@ def extract_shard(g, part: np.ndarray, rank: int) -> Shard:
     """This rank's nodes, every cell touching them (one halo layer); rows of the faces of the rank's own
     cells (a shared face goes to the lower rank) and of its own cells.  Local cell numbering: OWN CELLS FIRST
     (ascending global id), then the halo cells -- the rows of a system matrix assembled on the shard that
-    belong to this rank are then a prefix, and its columns are already [own | ghost] (``krylov``)."""
+    belong to this rank are then a prefix, and its columns are already [own | ghost] (``krylov``).
+
+    Runs in the native library (``pb_shard_create``, csrc/shard.cu: one pass over the global CSC arrays, ~20x the
+    speed of the NumPy restatement ``extract_shard_numpy`` below, which the tests hold it against)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    cf = g.cell_faces if sps.isspmatrix_csc(g.cell_faces) else sps.csc_matrix(g.cell_faces)
+    fn = g.face_nodes if sps.isspmatrix_csc(g.face_nodes) else sps.csc_matrix(g.face_nodes)
+    nc, nf, nn = g.num_cells, g.num_faces, g.num_nodes
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)  # noqa: E731
+    cf_ip, cf_ix, cf_da = i32(cf.indptr), i32(cf.indices), np.ascontiguousarray(cf.data, dtype=np.float64)
+    fn_ip, fn_ix = i32(fn.indptr), i32(fn.indices)
+    part64 = np.ascontiguousarray(part, dtype=np.int64)
+    h = C.c_void_p()
+    _lib.check(lib.pb_shard_create(nc, nf, nn, _lib.ptr(cf_ip, _lib._i32p), _lib.ptr(cf_ix, _lib._i32p),
+                                   _lib.ptr(cf_da, _lib._f64p), _lib.ptr(fn_ip, _lib._i32p), _lib.ptr(fn_ix, _lib._i32p),
+                                   _lib.ptr(part64, _lib._i64p), int(rank), C.byref(h)))
+    try:
+        sz = np.zeros(6, dtype=np.int64)
+        _lib.check(lib.pb_shard_sizes(h, _lib.ptr(sz, _lib._i64p)))
+        ncl, nfl, nnl, n_own, nnz_cf, nnz_fn = (int(v) for v in sz)
+        cells, faces, nodes = (np.empty(n, dtype=np.int64) for n in (ncl, nfl, nnl))
+        own_face, cut, single = (np.empty(nfl, dtype=np.uint8) for _ in range(3))
+        own_node = np.empty(nnl, dtype=np.uint8)
+        l_cf_ip, l_cf_ix, l_cf_da = np.empty(ncl + 1, np.int32), np.empty(nnz_cf, np.int32), np.empty(nnz_cf, np.float64)
+        l_fn_ip, l_fn_ix = np.empty(nfl + 1, np.int32), np.empty(nnz_fn, np.int32)
+        _lib.check(lib.pb_shard_fill(h, _lib.ptr(cells, _lib._i64p), _lib.ptr(faces, _lib._i64p), _lib.ptr(nodes, _lib._i64p),
+                                     _lib.ptr(own_face, _lib._u8p), _lib.ptr(cut, _lib._u8p), _lib.ptr(single, _lib._u8p),
+                                     _lib.ptr(own_node, _lib._u8p), _lib.ptr(l_cf_ip, _lib._i32p),
+                                     _lib.ptr(l_cf_ix, _lib._i32p), _lib.ptr(l_cf_da, _lib._f64p),
+                                     _lib.ptr(l_fn_ip, _lib._i32p), _lib.ptr(l_fn_ix, _lib._i32p)))
+    finally:
+        lib.pb_shard_destroy(h)
+
+    def gather(a, idx):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        a2 = a.reshape(-1, a.shape[-1])
+        out = np.empty((a2.shape[0], idx.size), dtype=np.float64)
+        _lib.check(lib.pb_gather_columns(_lib.ptr(a2, _lib._f64p), a2.shape[0], a2.shape[1], _lib.ptr(idx, _lib._i64p),
+                                         idx.size, _lib.ptr(out, _lib._f64p)))
+        return out.reshape(a.shape[:-1] + (idx.size,))
+
+    sub_cf = sps.csc_matrix((l_cf_da, l_cf_ix, l_cf_ip), shape=(nfl, ncl))
+    sub_fn = sps.csc_matrix((np.ones(nnz_fn, dtype=bool), l_fn_ix, l_fn_ip), shape=(nnl, nfl))
+    lg = Grid.__new__(Grid)
+    lg.dim, lg.name = int(g.dim), getattr(g, "name", "Grid")
+    lg.nodes, lg.face_nodes, lg.cell_faces = gather(g.nodes, nodes), sub_fn, sub_cf
+    lg.num_nodes, lg.num_faces, lg.num_cells = nnl, nfl, ncl
+    lg.set_geometry(gather(g.face_normals, faces), gather(g.face_centers, faces), gather(g.face_areas, faces),
+                    gather(g.cell_centers, cells), gather(g.cell_volumes, cells))
+    single = single.astype(bool)
+    tags = getattr(g, "tags", {})
+    frac = np.asarray(tags["fracture_faces"], bool)[faces] if "fracture_faces" in tags else np.zeros(nfl, bool)
+    lg.tags = {"domain_boundary_faces": single & ~frac, "fracture_faces": frac, "tip_faces": np.zeros(nfl, bool)}
+    own_cell = np.zeros(ncl, dtype=bool)
+    own_cell[:n_own] = True
+    return Shard(rank, lg, cells, faces, nodes, own_cell, own_face.astype(bool), cut.astype(bool), (nc, nf, nn),
+                 own_node.astype(bool))
+
+
+def extract_shard_numpy(g, part: np.ndarray, rank: int) -> Shard:
+    """NumPy restatement of ``extract_shard`` (masks and segmented reductions over the CSC arrays): the checker of
+    the native routine in the tests."""
     cells, own_face, own = shard_cells(g, part, rank)
     cells = np.concatenate((cells[own[cells]], cells[~own[cells]]))
     s = extract_cells(g, cells, own_face, own, rank)

@@ -110,3 +110,31 @@ def test_two_rank_gloo_split_equals_unsplit():
     for p in procs:
         p.join(60)
     assert err < 1e-12
+
+
+@pytest.mark.parametrize("kind,dims,nparts", [("tet", (5, 4, 3), 3), ("cart", (7, 5, 4), 4), ("cart2d", (9, 7), 2)])
+def test_native_extraction_equals_numpy_restatement(kind, dims, nparts):
+    """``pb_shard_create`` (csrc/shard.cu, the routine the ranks run) against the NumPy restatement of the same rule,
+    field by field: index maps, kept / cut / own flags, the local CSC arrays, the geometry and the tags."""
+    if kind == "tet":
+        g = pb.structured_tet_grid(list(dims))
+    elif kind == "cart":
+        g = pb.cart_grid_3d(list(dims), perturb=0.2)
+    else:
+        g = pb.cart_grid_2d(list(dims))
+    part = sh.partition_cells(g, nparts)
+    for rank in range(nparts):
+        a, b = sh.extract_shard(g, part, rank), sh.extract_shard_numpy(g, part, rank)
+        for key in ("cells", "faces", "nodes", "own_cell", "own_face", "cut_face", "own_node"):
+            assert np.array_equal(getattr(a, key), getattr(b, key)), key
+        assert a.num_global == b.num_global
+        for key in ("nodes", "face_normals", "face_centers", "face_areas", "cell_centers", "cell_volumes"):
+            assert np.array_equal(getattr(a.grid, key), getattr(b.grid, key)), key
+        for key in ("cell_faces", "face_nodes"):
+            ma, mb = getattr(a.grid, key), getattr(b.grid, key)
+            assert ma.shape == mb.shape and np.array_equal(ma.indptr, mb.indptr)
+            assert np.array_equal(ma.indices, mb.indices) and np.array_equal(ma.data, mb.data), key
+        for key in b.grid.tags:
+            assert np.array_equal(a.grid.tags[key], b.grid.tags[key]), key
+        assert (a.grid.dim, a.grid.num_cells, a.grid.num_faces, a.grid.num_nodes) == \
+               (b.grid.dim, b.grid.num_cells, b.grid.num_faces, b.grid.num_nodes)

@@ -240,6 +240,12 @@ int pb_tpfa(pb_facegrid *g, const double *permeability, const uint8_t *bc_bits, 
             int vdim, double *flux, double *bound_pressure_cell, double *vector_source,
             double *bound_pressure_vector_source, double *bound_flux_diag,
             double *bound_pressure_face_diag);
+/* Differentiable TPFA (csrc/tpfa_diff.cuh; reference numerics/fv/tpfa.py:281-760 DifferentiableTpfa and the AD
+ * expression of models/constitutive_laws.py:1544-1583): k = 9 * nc doubles, the 3 x 3 tensor of cell c at k[9c..9c+8]
+ * row-major; fc_indptr as for pb_tpfa (half-faces numbered by face, then by cell).  Outputs: half-face
+ * transmissibilities t_hf (nhf), face transmissibilities T (nf), dT/dk (nhf * 9: the 9 derivatives with respect to the
+ * tensor of the half-face's cell).  Host pointers. */
+int pb_tpfa_diff(pb_facegrid *g, const double *k, const int32_t *fc_indptr, double *t_hf, double *T, double *dT_dk);
 int pb_upwind(pb_facegrid *g, const double *darcy_flux, const uint8_t *bc_bits, int32_t *upstream_cell,
               double *neumann_diag, double *dirichlet_diag);
 
@@ -248,6 +254,19 @@ int pb_upwind(pb_facegrid *g, const double *darcy_flux, const uint8_t *bc_bits, 
  * Host pointers, n doubles each. */
 int pb_upwind_coupling(int64_t n, const double *interface_flux, double *sign, double *from_primary,
                        double *from_secondary);
+
+/* ---- Grid.compute_geometry for 3-D grids (csrc/geometry.cu; reference grids/grid.py:362-381, 572-778) ---------
+ * Face normals (area weighted) / centres / areas and cell centres / volumes of a grid of general polyhedral cells
+ * from its topology and nodes: each face is fanned into triangles around the mean of its nodes, each cell into
+ * tetrahedra around the mean of its faces' centres.  Host arrays in the reference's layouts: CSC of cell_faces
+ * (nf x nc, row indices ascending inside a column, data +-1), CSC of face_nodes (nn x nf, the nodes of a face in loop
+ * order), nodes (3, nn) row-major; outputs (3, nf), (3, nf), (nf), (3, nc), (nc).  kernel_ms (may be NULL) = device
+ * time of the two kernels.  PB_EINVAL ("Some tetrahedra have negative volume", grid.py:754; cell in
+ * pb_last_error_node()) for inverted cells. */
+int pb_compute_geometry_3d(int64_t nc, int64_t nf, int64_t nn, const int32_t *cf_indptr, const int32_t *cf_indices,
+                           const int8_t *cf_data, const int32_t *fn_indptr, const int32_t *fn_indices,
+                           const double *nodes, double *face_normals, double *face_centers, double *face_areas,
+                           double *cell_centers, double *cell_volumes, float *kernel_ms);
 
 /* ---- sharding of ONE grid across ranks (csrc/shard.cu; host code) ---------------------------------------------
  * This rank's share of a grid from the GLOBAL topology: replaces the reference's memory-splitting chain
@@ -310,10 +329,14 @@ int pb_csr_spmv_dots_dev(pb_csr *a, const double *x_dev, double *y_dev, const do
 int pb_kry_init(int64_t n, const double *b, double *x, double *r, double *rhat, double *p, double *v, double *scal,
                 double tol, uint64_t stream);
 int pb_kry_seed(double *scal, uint64_t stream);
+/* minv / bs: the preconditioner M^-1 -- bs = 1: inverse diagonal (n doubles, Jacobi); bs = 2, 3: inverted bs x bs
+ * diagonal blocks, row-major (n/bs blocks; block Jacobi over the displacement components of a cell); NULL: none */
 int pb_kry_p(int64_t n, const double *r, double *p, const double *v, const double *minv, double *ph, double *scal,
-             int cur, uint64_t stream);
+             int cur, int bs, uint64_t stream);
 int pb_kry_s(int64_t n, const double *r, const double *v, const double *minv, double *s, double *sh, double *scal,
-             int cur, uint64_t stream);
+             int cur, int bs, uint64_t stream);
+/* inverses of the first nblocks bs x bs diagonal blocks of a device CSR, to a DEVICE array (nblocks*bs*bs doubles) */
+int pb_csr_block_diag_inv_dev(const pb_csr *a, int bs, int64_t nblocks, double *out_dev, uint64_t stream);
 int pb_kry_xr(int64_t n, double *x, const double *ph, const double *sh, const double *s, const double *t, double *r,
               const double *rhat, double *scal, int cur, int carry /* 1 on exactly one rank */, uint64_t stream);
 

@@ -6,13 +6,15 @@ first use; there is no CPU fallback.
 """
 from .fv import (Biot, DevicePlan, FaceGrid, Mpfa, Mpsa, Tpfa, Upwind, UpwindCoupling,  # noqa: F401
                  determine_eta)
+from .geometry import compute_geometry  # noqa: F401
 from .grid import Grid, cart_grid_2d, cart_grid_3d, structured_tet_grid, tet_grid_from_cells  # noqa: F401
 from .params import (DISCRETIZATION_MATRICES, PARAMETERS, BoundaryCondition,  # noqa: F401
                      BoundaryConditionVectorial, FourthOrderTensor, SecondOrderTensor,
                      initialize_data)
 from .sparse import DeviceCsr  # noqa: F401
+from .tpfa_ad import DifferentiableTpfa  # noqa: F401
 
 __all__ = ["Mpfa", "Mpsa", "Biot", "Tpfa", "Upwind", "UpwindCoupling", "DevicePlan", "FaceGrid", "DeviceCsr", "Grid", "cart_grid_2d", "cart_grid_3d",
            "structured_tet_grid", "tet_grid_from_cells", "SecondOrderTensor", "FourthOrderTensor",
            "BoundaryCondition", "BoundaryConditionVectorial", "initialize_data", "PARAMETERS",
-           "DISCRETIZATION_MATRICES", "determine_eta"]
+           "DISCRETIZATION_MATRICES", "determine_eta", "compute_geometry", "DifferentiableTpfa"]

@@ -63,8 +63,11 @@ _SIGNATURES = {
                                      C.POINTER(C.c_void_p)]),
     "pb_facegrid_destroy": (None, [C.c_void_p]),
     "pb_tpfa": (C.c_int, [C.c_void_p, _f64p, _u8p, _i32p, C.c_int] + [_f64p] * 6),
+    "pb_tpfa_diff": (C.c_int, [C.c_void_p, _f64p, _i32p, _f64p, _f64p, _f64p]),
     "pb_upwind": (C.c_int, [C.c_void_p, _f64p, _u8p, _i32p, _f64p, _f64p]),
     "pb_upwind_coupling": (C.c_int, [C.c_int64, _f64p, _f64p, _f64p, _f64p]),
+    "pb_compute_geometry_3d": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _i32p, _i32p, _i8p, _i32p, _i32p] + [_f64p] * 6
+                               + [_f32p]),
     "pb_shard_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _i32p, _i32p, _f64p, _i32p, _i32p, _i64p, C.c_int64,
                                   C.POINTER(C.c_void_p)]),
     "pb_shard_sizes": (C.c_int, [C.c_void_p, _i64p]),
@@ -89,8 +92,9 @@ _SIGNATURES = {
     "pb_csr_spmv_dots_dev": (C.c_int, [C.c_void_p] * 7 + [C.c_uint64]),
     "pb_kry_init": (C.c_int, [C.c_int64] + [C.c_void_p] * 7 + [C.c_double, C.c_uint64]),
     "pb_kry_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
-    "pb_kry_p": (C.c_int, [C.c_int64] + [C.c_void_p] * 6 + [C.c_int, C.c_uint64]),
-    "pb_kry_s": (C.c_int, [C.c_int64] + [C.c_void_p] * 6 + [C.c_int, C.c_uint64]),
+    "pb_kry_p": (C.c_int, [C.c_int64] + [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_uint64]),
+    "pb_kry_s": (C.c_int, [C.c_int64] + [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_uint64]),
+    "pb_csr_block_diag_inv_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_uint64]),
     "pb_kry_xr": (C.c_int, [C.c_int64] + [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_uint64]),
     "pb_csr_spmv_bench": (C.c_int, [C.c_void_p, C.c_int, _f32p]),
 }

@@ -47,6 +47,7 @@ extern "C" void pb_device_pool_trim(void) { pb_dev_pool_().trim(); }
 
 extern "C" const char *pb_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t pb_last_error_node(void) { return g_err_node; }
+void pb_set_error_node_(int64_t node) { g_err_node = node; }
 extern "C" int64_t pb_launch_count(void) { return g_launches.load(); }
 extern "C" int pb_device_count(void) {
     int n = 0;

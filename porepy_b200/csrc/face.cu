@@ -3,6 +3,7 @@
 // for grids of any dimension (the reference delegates its 1-D MPFA / MPSA to TPFA, numerics/fv/mpfa.py:
 // 690-712, mpsa.py:666-697); no interaction-region plan is built.
 #include "plan.hpp"
+#include "tpfa_diff.cuh"
 
 struct pb_facegrid {
     int64_t nc = 0, nf = 0;
@@ -135,6 +136,40 @@ extern "C" int pb_tpfa(pb_facegrid *g, const double *permeability, const uint8_t
     CUDA_TRY(down(bound_pressure_vector_source, o_bpvs, nnz * vdim));
     CUDA_TRY(down(bound_flux_diag, o_bf, (size_t)nf));
     CUDA_TRY(down(bound_pressure_face_diag, o_bpf, (size_t)nf));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PB_OK;
+}
+
+__global__ void tpfa_diff_kernel(int64_t nf, GeoView G, const double *__restrict__ k,
+                                 const int32_t *__restrict__ face_cells, const int32_t *__restrict__ fc_ptr,
+                                 double *__restrict__ t_hf, double *__restrict__ T, double *__restrict__ dT_dk) {
+    for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x)
+        tpfa_diff_face(f, G, k, face_cells, fc_ptr, t_hf, T, dT_dk);
+}
+
+// Differentiable TPFA (tpfa_diff.cuh): k = 9 * nc doubles, cell-major; fc_indptr as for pb_tpfa; outputs t_hf (nhf),
+// T (nf), dT_dk (nhf * 9); host pointers.
+extern "C" int pb_tpfa_diff(pb_facegrid *g, const double *k, const int32_t *fc_indptr, double *t_hf, double *T,
+                            double *dT_dk) {
+    if (!g || !k || !fc_indptr || !t_hf || !T || !dT_dk) return pb_fail_(PB_EINVAL, "null pointer");
+    cudaStream_t st = g->stream;
+    const int64_t nf = g->nf, nc = g->nc;
+    const size_t nhf = (size_t)fc_indptr[nf];
+    DevBuf dk, ip, o_t, o_T, o_d;
+    CUDA_TRY(dk.upload(k, (size_t)9 * nc, st));
+    CUDA_TRY(ip.upload(fc_indptr, (size_t)nf + 1, st));
+    CUDA_TRY(o_t.ensure(nhf * sizeof(double)));
+    CUDA_TRY(o_T.ensure((size_t)nf * sizeof(double)));
+    CUDA_TRY(o_d.ensure(nhf * 9 * sizeof(double)));
+    const int block = 256;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nf + block - 1) / block, (int64_t)kSMs * 16));
+    tpfa_diff_kernel<<<grid, block, 0, st>>>(nf, g->geo, dk.as<double>(), g->face_cells.as<int32_t>(), ip.as<int32_t>(),
+                                             o_t.as<double>(), o_T.as<double>(), o_d.as<double>());
+    pb_count_launch_();
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(t_hf, o_t.p, nhf * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(T, o_T.p, (size_t)nf * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(dT_dk, o_d.p, nhf * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return PB_OK;
 }

@@ -55,7 +55,30 @@ __global__ void kry_init_kernel(int64_t n, const double *__restrict__ b, double 
     block_add(acc, scal + KS_BB);
 }
 
-// p = r + beta (p - omega_prev v),  ph = minv p      [minv may be null]
+// Preconditioner application z = M^-1 y on one block of BS consecutive entries: BS == 1 -- minv holds the inverse
+// diagonal (Jacobi); BS > 1 -- minv holds the inverted BS x BS diagonal blocks, row-major (block Jacobi: the nd
+// displacement components of a cell in the mechanics system A = div_nd @ stress).
+template <int BS>
+__device__ __forceinline__ void apply_minv(const double *__restrict__ minv, int64_t b, const double (&y)[BS], double (&z)[BS]) {
+    if (!minv) {
+#pragma unroll
+        for (int i = 0; i < BS; ++i) z[i] = y[i];
+    } else if (BS == 1) {
+        z[0] = minv[b] * y[0];
+    } else {
+        const double *m = minv + b * (BS * BS);
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < BS; ++j) acc += m[i * BS + j] * y[j];
+            z[i] = acc;
+        }
+    }
+}
+
+// p = r + beta (p - omega_prev v),  ph = M^-1 p      [minv may be null]
+template <int BS>
 __global__ void kry_p_kernel(int64_t n, const double *__restrict__ r, double *__restrict__ p,
                              const double *__restrict__ v, const double *__restrict__ minv, double *__restrict__ ph,
                              double *__restrict__ scal, int cur) {
@@ -64,10 +87,17 @@ __global__ void kry_p_kernel(int64_t n, const double *__restrict__ r, double *__
     if (!frozen) {
         const double alpha_prev = gp[KS_RHO] / gp[KS_RHATV], omega_prev = gp[KS_TS] / gp[KS_TT];
         const double beta = (gc[KS_RHO] / gp[KS_RHO]) * (alpha_prev / omega_prev);
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-            const double pi = r[i] + beta * (p[i] - omega_prev * v[i]);
-            p[i] = pi;
-            ph[i] = minv ? minv[i] * pi : pi;
+        for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n / BS; b += (int64_t)gridDim.x * blockDim.x) {
+            double pv[BS], z[BS];
+#pragma unroll
+            for (int i = 0; i < BS; ++i) {
+                const int64_t q = b * BS + i;
+                pv[i] = r[q] + beta * (p[q] - omega_prev * v[q]);
+                p[q] = pv[i];
+            }
+            apply_minv<BS>(minv, b, pv, z);
+#pragma unroll
+            for (int i = 0; i < BS; ++i) ph[b * BS + i] = z[i];
         }
     }
     __syncthreads();
@@ -77,17 +107,25 @@ __global__ void kry_p_kernel(int64_t n, const double *__restrict__ r, double *__
     }
 }
 
-// s = r - alpha v,  sh = minv s;  zero the other parity group (its last reader was this iteration's p-update)
+// s = r - alpha v,  sh = M^-1 s;  zero the other parity group (its last reader was this iteration's p-update)
+template <int BS>
 __global__ void kry_s_kernel(int64_t n, const double *__restrict__ r, const double *__restrict__ v,
                              const double *__restrict__ minv, double *__restrict__ s, double *__restrict__ sh,
                              double *__restrict__ scal, int cur) {
     const double *gc = scal + cur * KS_GROUP;
     if (scal[KS_DONE] == 0.0) {
         const double alpha = gc[KS_RHO] / gc[KS_RHATV];
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-            const double si = r[i] - alpha * v[i];
-            s[i] = si;
-            sh[i] = minv ? minv[i] * si : si;
+        for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n / BS; b += (int64_t)gridDim.x * blockDim.x) {
+            double sv[BS], z[BS];
+#pragma unroll
+            for (int i = 0; i < BS; ++i) {
+                const int64_t q = b * BS + i;
+                sv[i] = r[q] - alpha * v[q];
+                s[q] = sv[i];
+            }
+            apply_minv<BS>(minv, b, sv, z);
+#pragma unroll
+            for (int i = 0; i < BS; ++i) sh[b * BS + i] = z[i];
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < KS_GROUP) scal[(cur ^ 1) * KS_GROUP + threadIdx.x] = 0.0;
@@ -141,16 +179,101 @@ extern "C" int pb_kry_seed(double *scal, uint64_t stream) {
     CUDA_TRY(cudaGetLastError());
     return PB_OK;
 }
+// bs: size of the diagonal blocks of the preconditioner (1 = Jacobi, 2 / 3 = block Jacobi; n must be a multiple)
 extern "C" int pb_kry_p(int64_t n, const double *r, double *p, const double *v, const double *minv, double *ph,
-                        double *scal, int cur, uint64_t stream) {
-    kry_p_kernel<<<kgrid(n), 256, 0, (cudaStream_t)stream>>>(n, r, p, v, minv, ph, scal, cur & 1);
+                        double *scal, int cur, int bs, uint64_t stream) {
+    if (bs < 1 || bs > 3 || n % bs) return pb_fail_(PB_EINVAL, "pb_kry_p: block size must be 1, 2 or 3 and divide n");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bs == 1) kry_p_kernel<1><<<kgrid(n), 256, 0, st>>>(n, r, p, v, minv, ph, scal, cur & 1);
+    else if (bs == 2) kry_p_kernel<2><<<kgrid(n / 2), 256, 0, st>>>(n, r, p, v, minv, ph, scal, cur & 1);
+    else kry_p_kernel<3><<<kgrid(n / 3), 256, 0, st>>>(n, r, p, v, minv, ph, scal, cur & 1);
     pb_count_launch_();
     CUDA_TRY(cudaGetLastError());
     return PB_OK;
 }
 extern "C" int pb_kry_s(int64_t n, const double *r, const double *v, const double *minv, double *s, double *sh,
-                        double *scal, int cur, uint64_t stream) {
-    kry_s_kernel<<<kgrid(n), 256, 0, (cudaStream_t)stream>>>(n, r, v, minv, s, sh, scal, cur & 1);
+                        double *scal, int cur, int bs, uint64_t stream) {
+    if (bs < 1 || bs > 3 || n % bs) return pb_fail_(PB_EINVAL, "pb_kry_s: block size must be 1, 2 or 3 and divide n");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bs == 1) kry_s_kernel<1><<<kgrid(n), 256, 0, st>>>(n, r, v, minv, s, sh, scal, cur & 1);
+    else if (bs == 2) kry_s_kernel<2><<<kgrid(n / 2), 256, 0, st>>>(n, r, v, minv, s, sh, scal, cur & 1);
+    else kry_s_kernel<3><<<kgrid(n / 3), 256, 0, st>>>(n, r, v, minv, s, sh, scal, cur & 1);
+    pb_count_launch_();
+    CUDA_TRY(cudaGetLastError());
+    return PB_OK;
+}
+
+// Inverses of the bs x bs diagonal blocks of a CSR matrix (rows / columns bs*b .. bs*b+bs-1), row-major, to a DEVICE
+// array of nblocks*bs*bs doubles: the block-Jacobi preconditioner of the mechanics system (one block per cell).
+// A singular block is replaced by the inverse of its diagonal (identity where that is zero, too).
+template <int BS>
+__global__ void block_diag_inv_kernel(int64_t nb, const int32_t *__restrict__ ip, const int32_t *__restrict__ ix,
+                                      const double *__restrict__ data, double *__restrict__ out) {
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
+        double D[BS][BS], E[BS][BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+#pragma unroll
+            for (int j = 0; j < BS; ++j) { D[i][j] = 0.0; E[i][j] = i == j ? 1.0 : 0.0; }
+            const int64_t row = b * BS + i;
+            for (int q = ip[row]; q < ip[row + 1]; ++q) {
+                const int64_t c = (int64_t)ix[q] - b * BS;
+                if (c >= 0 && c < BS) {
+#pragma unroll
+                    for (int j = 0; j < BS; ++j) if (c == j) D[i][j] += data[q];
+                }
+            }
+        }
+        double dg[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) dg[i] = D[i][i];
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {   // Gauss-Jordan with partial pivoting, fully unrolled (BS <= 3)
+            int piv = k;
+            double best = fabs(D[k][k]);
+#pragma unroll
+            for (int i = k + 1; i < BS; ++i) if (fabs(D[i][k]) > best) { best = fabs(D[i][k]); piv = i; }
+            if (!(best > 0.0)) { ok = false; break; }
+#pragma unroll
+            for (int i = k + 1; i < BS; ++i)
+                if (i == piv) {
+#pragma unroll
+                    for (int j = 0; j < BS; ++j) {
+                        double t = D[k][j]; D[k][j] = D[i][j]; D[i][j] = t;
+                        t = E[k][j]; E[k][j] = E[i][j]; E[i][j] = t;
+                    }
+                }
+            const double inv = 1.0 / D[k][k];
+#pragma unroll
+            for (int j = 0; j < BS; ++j) { D[k][j] *= inv; E[k][j] *= inv; }
+#pragma unroll
+            for (int i = 0; i < BS; ++i) {
+                if (i == k) continue;
+                const double f = D[i][k];
+#pragma unroll
+                for (int j = 0; j < BS; ++j) { D[i][j] -= f * D[k][j]; E[i][j] -= f * E[k][j]; }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int j = 0; j < BS; ++j)
+                out[(b * BS + i) * BS + j] = ok ? E[i][j] : (i == j ? (dg[i] != 0.0 ? 1.0 / dg[i] : 1.0) : 0.0);
+    }
+}
+
+struct CsrView { int64_t nrows, ncols, nnz; int32_t *indptr, *indices; double *data; };
+CsrView pb_csr_view_(const pb_csr *a);   // spmv.cu
+extern "C" int pb_csr_block_diag_inv_dev(const pb_csr *a, int bs, int64_t nblocks, double *out_dev, uint64_t stream) {
+    if (!a || !out_dev) return pb_fail_(PB_EINVAL, "null pointer");
+    const CsrView v = pb_csr_view_(a);
+    if (bs < 1 || bs > 3 || nblocks < 0 || nblocks * bs > v.nrows) return pb_fail_(PB_EINVAL, "pb_csr_block_diag_inv_dev: bad block size / count");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = kgrid(nblocks);
+    if (bs == 1) block_diag_inv_kernel<1><<<grid, 256, 0, st>>>(nblocks, v.indptr, v.indices, v.data, out_dev);
+    else if (bs == 2) block_diag_inv_kernel<2><<<grid, 256, 0, st>>>(nblocks, v.indptr, v.indices, v.data, out_dev);
+    else block_diag_inv_kernel<3><<<grid, 256, 0, st>>>(nblocks, v.indptr, v.indices, v.data, out_dev);
     pb_count_launch_();
     CUDA_TRY(cudaGetLastError());
     return PB_OK;

@@ -24,6 +24,7 @@
 
 int pb_fail_(int code, const std::string &msg);  // api.cu: sets pb_last_error()
 void pb_count_launch_();                         // api.cu: pb_launch_count()
+void pb_set_error_node_(int64_t node);           // api.cu: pb_last_error_node()
 #define CUDA_TRY(x)                                                                        \
     do {                                                                                   \
         cudaError_t e_ = (x);                                                              \

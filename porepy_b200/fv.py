@@ -587,6 +587,17 @@ class FaceGrid:
                                     _lib.ptr(ip, _lib._i32p), int(vdim), *[_lib.ptr(a, _lib._f64p) for a in out]))
         return out
 
+    def tpfa_diff(self, k_c, fc_indptr):
+        """Differentiable TPFA (``pb_tpfa_diff``): half-face transmissibilities, face transmissibilities and
+        dT_f/dk_c (9 values per half-face) for the cell-major 9 * nc permeability vector ``k_c``."""
+        k = np.ascontiguousarray(k_c, dtype=np.float64).reshape(-1)
+        ip = np.ascontiguousarray(fc_indptr, dtype=np.int32)
+        nhf = int(ip[-1])
+        t_hf, T, dT = np.empty(nhf), np.empty(self.nf), np.empty(nhf * 9)
+        _lib.check(self.lib.pb_tpfa_diff(self.h, _lib.ptr(k, _lib._f64p), _lib.ptr(ip, _lib._i32p),
+                                         _lib.ptr(t_hf, _lib._f64p), _lib.ptr(T, _lib._f64p), _lib.ptr(dT, _lib._f64p)))
+        return t_hf, T, dT
+
     def upwind(self, darcy_flux, bc_bits):
         """Upstream cell per face (-1: face not in the matrix) and the two boundary diagonals."""
         q = _lib.f64(darcy_flux)

@@ -59,6 +59,12 @@ class Grid:
             return sps.csr_matrix(self.cell_faces.T)
         return sps.kron(self.cell_faces.T, sps.eye(dim)).tocsr()
 
+    def compute_geometry(self):
+        """pp.Grid.compute_geometry (grids/grid.py:362): 3-D grids on the device (``porepy_b200.geometry``)."""
+        from .geometry import compute_geometry
+        compute_geometry(self, assign=True)
+        return self
+
     def set_geometry(self, face_normals, face_centers, face_areas, cell_centers, cell_volumes):
         self.face_normals = np.ascontiguousarray(face_normals, dtype=np.float64)
         self.face_centers = np.ascontiguousarray(face_centers, dtype=np.float64)

@@ -218,16 +218,26 @@ class DistributedOperator:
 
 
 def bicgstab(op: DistributedOperator, b_own, x0=None, tol: float = 1e-10, maxiter: int = 2000,
-             diag_own=None, check_every: int = 8):
-    """Right-preconditioned (Jacobi, optional) BiCGStab on the distributed operator.
+             diag_own=None, check_every: int = 8, block_inv=None):
+    """Right-preconditioned BiCGStab on the distributed operator.  Preconditioner: Jacobi (``diag_own``: the diagonal of
+    the own rows) or block Jacobi (``block_inv = (minv, bs)``: the inverted bs x bs diagonal blocks of the own rows as a
+    flat tensor, e.g. ``DeviceCsr.block_diagonal_inverse`` -- the displacement components of a cell in the mechanics
+    system), or none.
     Returns (x_own, info) with info = {"iterations", "relres", "converged", "breakdown", "spmv", "allreduce"}.
     On a CUDA operator the fused device loop runs (``_bicgstab_fused``: no host synchronisation inside the
     iteration); the eager torch recurrence below serves the CPU stand-in tests of the host logic."""
     if op.dev_csr is not None and x0 is None:
-        return _bicgstab_fused(op, b_own, tol, maxiter, diag_own, check_every)
+        return _bicgstab_fused(op, b_own, tol, maxiter, diag_own, check_every, block_inv)
     torch = op.torch
     x = torch.zeros_like(b_own) if x0 is None else x0.clone()
-    minv = None if diag_own is None else 1.0 / diag_own
+    if block_inv is not None:
+        blk = block_inv[0].reshape(-1, int(block_inv[1]), int(block_inv[1]))
+        prec = lambda vec: torch.bmm(blk, vec.reshape(-1, blk.shape[1], 1)).reshape(-1)  # noqa: E731
+    elif diag_own is not None:
+        minv = 1.0 / diag_own
+        prec = lambda vec: vec * minv  # noqa: E731
+    else:
+        prec = lambda vec: vec  # noqa: E731
     r = b_own - op.matvec(x) if x0 is not None else b_own.clone()
     rhat = r.clone()
     bnorm = float(torch.sqrt(op.dots([(b_own, b_own)])[0]))
@@ -249,7 +259,7 @@ def bicgstab(op: DistributedOperator, b_own, x0=None, tol: float = 1e-10, maxite
             return done(it - 1, True)
         beta = (rho_new / rho) * (alpha / omega)
         p = r + beta * (p - omega * v)
-        ph = p if minv is None else p * minv
+        ph = prec(p)
         v = op.matvec(ph)
         nspmv += 1
         rv = float(op.dots([(rhat, v)])[0])
@@ -258,7 +268,7 @@ def bicgstab(op: DistributedOperator, b_own, x0=None, tol: float = 1e-10, maxite
             return done(it - 1, True)
         alpha = rho_new / rv
         s = r - alpha * v
-        sh = s if minv is None else s * minv
+        sh = prec(s)
         t = op.matvec(sh)
         nspmv += 1
         d = op.dots([(t, s), (t, t), (s, s)])
@@ -279,7 +289,7 @@ def bicgstab(op: DistributedOperator, b_own, x0=None, tol: float = 1e-10, maxite
     return done(maxiter, False)
 
 
-def _bicgstab_fused(op: DistributedOperator, b_own, tol, maxiter, diag_own, check_every):
+def _bicgstab_fused(op: DistributedOperator, b_own, tol, maxiter, diag_own, check_every, block_inv=None):
     """The iteration on the device: three fused vector kernels (csrc/krylov.cu) and two SpMVs whose epilogue
     accumulates the dot products; all scalars of the recurrence stay in a 14-double device buffer, all-reduced in
     contiguous slices (NCCL on the same stream) under torch.distributed.  The preconditioned vectors are written
@@ -300,6 +310,11 @@ def _bicgstab_fused(op: DistributedOperator, b_own, tol, maxiter, diag_own, chec
     xb_p, xb_s = vec(n + ng), vec(n + ng)            # SpMV inputs [own | ghost]; ph / sh are their own parts
     ph, sh = xb_p[:n], xb_s[:n]
     minv = None if diag_own is None else (1.0 / diag_own).contiguous()
+    bs = 1
+    if block_inv is not None:
+        minv, bs = block_inv[0].contiguous(), int(block_inv[1])
+        if n % bs or minv.numel() != n * bs:
+            raise ValueError("block_inv: expected (n / bs) inverted bs x bs blocks of the own rows")
     scal = torch.zeros(14, dtype=torch.float64, device=dev)
     P = lambda a: C.c_void_p(a.data_ptr()) if a is not None else None  # noqa: E731
     S = lambda i: C.c_void_p(scal.data_ptr() + 8 * i)  # noqa: E731
@@ -333,11 +348,11 @@ def _bicgstab_fused(op: DistributedOperator, b_own, tol, maxiter, diag_own, chec
         for it in range(it0, it0 + count):
             cur = it & 1
             g = 5 * cur
-            _lib.check(lib.pb_kry_p(n, P(r), P(p), P(v), P(minv), P(ph), P(scal), cur, stream))
+            _lib.check(lib.pb_kry_p(n, P(r), P(p), P(v), P(minv), P(ph), P(scal), cur, bs, stream))
             exch(xb_p)
             _lib.check(lib.pb_csr_spmv_dots_dev(csr.h, P(xb_p), P(v), P(rhat), S(g + 0), None, None, stream))
             reduce(g + 0, g + 1)
-            _lib.check(lib.pb_kry_s(n, P(r), P(v), P(minv), P(s), P(sh), P(scal), cur, stream))
+            _lib.check(lib.pb_kry_s(n, P(r), P(v), P(minv), P(s), P(sh), P(scal), cur, bs, stream))
             exch(xb_s)
             _lib.check(lib.pb_csr_spmv_dots_dev(csr.h, P(xb_s), P(t), P(s), S(g + 1), None, S(g + 2), stream))
             reduce(g + 1, g + 3)
@@ -440,7 +455,7 @@ def solve(a, b, owner=None, tol: float = 1e-10, maxiter: int = 2000, jacobi: boo
 
 
 def solve_local(loc: LocalSystem, b_own, diag_own=None, tol: float = 1e-10, maxiter: int = 2000, device=None,
-                matvec_factory=None, group=None):
+                matvec_factory=None, group=None, block_inv=None):
     """BiCGStab on a row-distributed system given by this rank's ``LocalSystem`` (e.g. from
     ``local_system_from_shard``); ``b_own`` / ``diag_own``: NumPy arrays or torch tensors of the own rows.
     Returns (x_own, info)."""
@@ -454,6 +469,6 @@ def solve_local(loc: LocalSystem, b_own, diag_own=None, tol: float = 1e-10, maxi
     if diag_own is not None:
         dg = torch.as_tensor(np.asarray(diag_own) if not torch.is_tensor(diag_own) else diag_own,
                              dtype=torch.float64, device=device)
-    x, info = bicgstab(op, b, tol=tol, maxiter=maxiter, diag_own=dg)
+    x, info = bicgstab(op, b, tol=tol, maxiter=maxiter, diag_own=dg, block_inv=block_inv)
     info["halo_bytes_per_spmv"] = op.halo_bytes
     return x, info

@@ -52,6 +52,16 @@ class DeviceCsr:
         _lib.check(self.lib.pb_csr_diagonal(self.h, _lib.ptr(d, _lib._f64p)))
         return d
 
+    def block_diagonal_inverse(self, bs: int, nblocks: int | None = None, stream: int = 0):
+        """Inverses of the first ``nblocks`` bs x bs diagonal blocks (default: all), as a flat torch CUDA tensor of
+        nblocks*bs*bs doubles (row-major blocks): the block-Jacobi preconditioner of ``krylov.bicgstab``."""
+        import torch
+        nb = min(self.shape) // bs if nblocks is None else int(nblocks)
+        out = torch.empty(nb * bs * bs, dtype=torch.float64, device="cuda")
+        _lib.check(self.lib.pb_csr_block_diag_inv_dev(self.h, int(bs), nb, C.c_void_p(out.data_ptr()),
+                                                      stream or torch.cuda.current_stream().cuda_stream))
+        return out
+
     def checksum(self):
         """(sum, sum of squares) of the stored values: a device reduction."""
         a, b = C.c_double(), C.c_double()

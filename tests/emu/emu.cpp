@@ -13,6 +13,8 @@
 #if __has_include("../../porepy_b200/csrc/mpsa_node.cuh")
 #include "../../porepy_b200/csrc/mpsa_node.cuh"
 #include "../../porepy_b200/csrc/face_kernels.cuh"
+#include "../../porepy_b200/csrc/geometry_kernels.cuh"
+#include "../../porepy_b200/csrc/tpfa_diff.cuh"
 #define HAVE_MPSA 1
 #endif
 
@@ -109,6 +111,17 @@ int emu_tpfa(void *h, const double *fnorm, const double *fcent, const double *cc
     return 0;
 }
 
+// ---- Grid.compute_geometry (3-D): the per-face and per-cell routines of geometry.cu, (3, n) row-major arrays
+int emu_geometry_3d(int64_t nc, int64_t nf, int64_t nn, const int32_t *cf_ip, const int32_t *cf_ix, const int8_t *cf_da,
+                    const int32_t *fn_ip, const int32_t *fn_ix, const double *nodes, double *fnorm, double *fcent,
+                    double *farea, double *ccent, double *cvol) {
+    GeomOut o{fnorm, fcent, farea, ccent, cvol, nf, 1, nc, 1};
+    for (int64_t f = 0; f < nf; ++f) geom_face(f, fn_ip, fn_ix, nodes, nn, 1, o);
+    bool ok = true;
+    for (int64_t c = 0; c < nc; ++c) ok &= geom_cell(c, cf_ip, cf_ix, cf_da, fn_ip, fn_ix, nodes, nn, 1, o);
+    return ok ? 0 : 1;
+}
+
 // ---- per-face schemes on a bare face grid (any dimension): the face -> cell table is built here the way
 // face.cu builds it on the device (slot 0 = smaller cell index)
 static std::vector<int32_t> face_cells_of(int64_t nc, int64_t nf, const int32_t *cf_ip, const int32_t *cf_ix,
@@ -131,6 +144,15 @@ int emu_facegrid_tpfa(int64_t nc, int64_t nf, const int32_t *cf_ip, const int32_
     GeoView G{nullptr, fnorm, fcent, nullptr, ccent, nullptr, 0, 1, nf, 1, nc, 1};
     TpfaOut o{flux, bpc, vs, bpvs, bflux_diag, bpf_diag};
     for (int64_t f = 0; f < nf; ++f) tpfa_face(f, G, perm, nc, 1, bc, fc.data(), fc_ptr, vdim, o);
+    return 0;
+}
+
+int emu_facegrid_tpfa_diff(int64_t nc, int64_t nf, const int32_t *cf_ip, const int32_t *cf_ix, const int8_t *cf_da,
+                           const double *fnorm, const double *fcent, const double *ccent, const double *k,
+                           const int32_t *fc_ptr, double *t_hf, double *T, double *dT_dk) {
+    std::vector<int32_t> fc = face_cells_of(nc, nf, cf_ip, cf_ix, cf_da);
+    GeoView G{nullptr, fnorm, fcent, nullptr, ccent, nullptr, 0, 1, nf, 1, nc, 1};
+    for (int64_t f = 0; f < nf; ++f) tpfa_diff_face(f, G, k, fc.data(), fc_ptr, t_hf, T, dT_dk);
     return 0;
 }
 

@@ -271,6 +271,16 @@ class EmuBackedFaceGrid:
                             _p(bits, C.c_uint8), _p(ip, C.c_int32), C.c_int(vdim), *[_p(a, C.c_double) for a in out])
         return out
 
+    def tpfa_diff(self, k_c, fc_indptr):
+        L = lib()
+        ip = np.ascontiguousarray(fc_indptr, np.int32)
+        nhf = int(ip[-1])
+        k = np.ascontiguousarray(k_c, np.float64)
+        t_hf, T, dT = np.zeros(nhf), np.zeros(self.nf), np.zeros(nhf * 9)
+        L.emu_facegrid_tpfa_diff(*self._cf(), *[_p(a, C.c_double) for a in self.geo], _p(k, C.c_double),
+                                 _p(ip, C.c_int32), _p(t_hf, C.c_double), _p(T, C.c_double), _p(dT, C.c_double))
+        return t_hf, T, dT
+
     def upwind(self, darcy_flux, bc_bits):
         L = lib()
         nf = self.nf
@@ -347,3 +357,23 @@ def emu_interface_upwind_masks(interface_flux):
     s = np.sign(np.asarray(interface_flux, dtype=np.float64))
     flag = (s > 0).astype(float)
     return s, flag, 1 - flag
+
+
+def geometry_3d(g):
+    """Host build of the compute_geometry routines (porepy_b200/csrc/geometry_kernels.cuh) on a grid's topology and
+    nodes; returns (face_normals, face_centers, face_areas, cell_centers, cell_volumes)."""
+    L = lib()
+    cf = sps.csc_matrix(g.cell_faces)
+    fn = sps.csc_matrix(g.face_nodes)
+    cf.sort_indices()
+    nc, nf, nn = g.num_cells, g.num_faces, g.num_nodes
+    k = [cf.indptr.astype(np.int32), cf.indices.astype(np.int32), np.asarray(cf.data).astype(np.int8),
+         fn.indptr.astype(np.int32), fn.indices.astype(np.int32)]
+    nodes = np.ascontiguousarray(g.nodes, np.float64)
+    out = [np.zeros((3, nf)), np.zeros((3, nf)), np.zeros(nf), np.zeros((3, nc)), np.zeros(nc)]
+    rc = L.emu_geometry_3d(C.c_int64(nc), C.c_int64(nf), C.c_int64(nn), _p(k[0], C.c_int32), _p(k[1], C.c_int32),
+                           _p(k[2], C.c_int8), _p(k[3], C.c_int32), _p(k[4], C.c_int32), _p(nodes, C.c_double),
+                           *[_p(a, C.c_double) for a in out])
+    if rc:
+        raise ValueError("Some tetrahedra have negative volume")
+    return out

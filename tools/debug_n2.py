@@ -122,7 +122,7 @@ def stepper(iters, sync_mask, verify):
             p_want = r + beta * (p - omega_prev * v)
             chk("rho(cur) == (rhat, r)", it, float(h[g_ + 4]), gdot(rhat, r))
             chk("rr(cur) == (r, r)", it, float(h[g_ + 3]), gdot(r, r))
-        _lib.check(lib.pb_kry_p(n, P(r), P(p), P(v), P(minv), P(ph), P(scal), cur, st))
+        _lib.check(lib.pb_kry_p(n, P(r), P(p), P(v), P(minv), P(ph), P(scal), cur, 1, st))
         sync(1)
         if verify:
             chk("p", it, p, p_want)
@@ -145,7 +145,7 @@ def stepper(iters, sync_mask, verify):
             h = scal.cpu().numpy().copy()
             alpha = h[g_ + 4] / h[g_ + 0]
             s_want = r - alpha * v
-        _lib.check(lib.pb_kry_s(n, P(r), P(v), P(minv), P(s_), P(sh_), P(scal), cur, st))
+        _lib.check(lib.pb_kry_s(n, P(r), P(v), P(minv), P(s_), P(sh_), P(scal), cur, 1, st))
         sync(1)
         if verify:
             chk("s", it, s_, s_want)

@@ -308,6 +308,83 @@ def case_line(name, seed):
     print(name, "nc", nc, "nf", nf)
 
 
+def case_geometry(name, kind, seed, amp=0.3):
+    """``Grid.compute_geometry`` (grids/grid.py:362-778) of a 3-D grid whose nodes -- ALL of them, so the
+    faces of the hexahedra are warped -- were displaced: topology with the face-node loops in the
+    reference's own order, nodes, and the five geometry arrays the reference computes."""
+    rng = np.random.default_rng(seed)
+    if kind == "cart3d":
+        g = pp.CartGrid([5, 4, 3], [1.0, 0.8, 0.6])
+    elif kind == "tet3d":
+        g = pp.StructuredTetrahedralGrid([3, 2, 2], [1.0, 1.0, 1.0])
+    else:
+        pts = rng.random((3, 30))
+        corners = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [0, 0, 1], [1, 0, 1],
+                            [0, 1, 1], [1, 1, 1]], float).T
+        g = pp.TetrahedralGrid(np.hstack((corners, pts)))
+    g.compute_geometry()
+    if kind != "delaunay":
+        h = np.min(g.cell_volumes) ** (1.0 / 3)
+        g.nodes += amp * h * (0.5 - rng.random(g.nodes.shape))
+        g.compute_geometry()
+    fn = g.face_nodes                      # NOT re-created / sorted: the loop order is part of the input
+    cf = sps.csc_matrix(g.cell_faces)
+    cf.sort_indices()
+    d = dict(dim=np.int64(3), name=np.array(str(g.name)), nodes=g.nodes,
+             fn_indptr=fn.indptr.astype(np.int32), fn_indices=fn.indices.astype(np.int32),
+             cf_indptr=cf.indptr.astype(np.int32), cf_indices=cf.indices.astype(np.int32),
+             cf_data=cf.data.astype(np.int8), face_normals=g.face_normals, face_centers=g.face_centers,
+             face_areas=g.face_areas, cell_centers=g.cell_centers, cell_volumes=g.cell_volumes,
+             fracture_faces=np.asarray(g.tags["fracture_faces"], bool), kind=np.array("geometry"))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("wrote", name, g.num_cells, "cells")
+
+
+def case_diff_tpfa(name, kind, seed):
+    """``DifferentiableTpfa`` (numerics/fv/tpfa.py:281-760): its helper matrices on one grid, and the AD evaluation
+    of the face transmissibilities the reference builds from them (constitutive_laws.py:1544-1583) with the
+    permeability as the independent AD variable: value, Jacobian dT_f/dk_c and the half-face values."""
+    rng = np.random.default_rng(seed)
+    g = make_grid(kind, rng)
+    nc = g.num_cells
+    d = grid_arrays(g)
+    d["kind"] = np.array("diff_tpfa")
+    d["tip_faces"] = np.asarray(g.tags["tip_faces"], bool)
+    d["domain_boundary_faces"] = np.asarray(g.tags["domain_boundary_faces"], bool)
+    # a full SPD tensor per cell, 9 values per cell, cell-major (the layout of the reference's k_c vector)
+    q = rng.standard_normal((nc, 3, 3))
+    kt = np.einsum("cij,ckj->cik", q, q) + 0.5 * np.eye(3)
+    k_val = kt.reshape(-1)
+    d["k_c"] = k_val
+    dt = pp.numerics.fv.tpfa.DifferentiableTpfa()
+    sds = [g]
+    n, d_vec, dist = dt.half_face_geometry_matrices(sds)
+    put_matrix(d, "n", n)
+    put_matrix(d, "d_vec", d_vec)
+    d["dist"] = dist
+    put_matrix(d, "hf_to_f_signed", dt.half_face_map(sds, to_entity="faces", with_sign=True))
+    put_matrix(d, "c_to_hf", dt.half_face_map(sds, to_entity="half_faces", from_entity="cells"))
+    put_matrix(d, "c3_to_hf3", dt.half_face_map(sds, from_entity="cells", to_entity="half_faces", dimensions=(3, 3)))
+    put_matrix(d, "hf3_to_f", dt.half_face_map(sds, from_entity="half_faces", to_entity="faces", dimensions=(1, 3), with_sign=True))
+    put_matrix(d, "face_pairing", dt.face_pairing_from_cell_array(sds))
+    put_matrix(d, "nd_to_3d_cells_2", dt.nd_to_3d(sds, 2))
+    put_matrix(d, "nd_to_3d_faces_3", dt.nd_to_3d(sds, 3, "faces"))
+    d["boundary_sign"] = np.asarray(dt.boundary_sign(sds)._values, float)
+    d["internal_boundary_filter"] = np.asarray(dt.internal_boundary_filter(sds)._values, float)
+    d["tip_filter"] = np.asarray(dt.tip_filter(sds)._values, float)
+    # the AD chain of constitutive_laws.py:1559-1581 on AdArrays
+    d_n_by_dist = sps.diags(1 / dist) * d_vec @ n
+    k = pp.ad.AdArray(k_val, sps.identity(9 * nc, format="csr"))
+    hf_to_f = dt.half_face_map(sds, to_entity="faces", with_sign=True)
+    t_hf_inv = 1.0 / (sps.csr_matrix(d_n_by_dist) @ k)
+    T = 1.0 / (sps.csr_matrix(hf_to_f) @ t_hf_inv)
+    d["t_hf"] = 1.0 / t_hf_inv.val
+    d["T_f"] = T.val
+    put_matrix(d, "dT_dk", T.jac)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("wrote", name, nc, "cells")
+
+
 def case_mpsa(name, kind, robin, seed, biot=False, basis=False):
     rng = np.random.default_rng(seed)
     g = make_grid(kind, rng)
@@ -384,6 +461,14 @@ def main():
         (case_next_rows, ("next_cart3d", "cart3d_pert", 41), {}),
         (case_next_rows, ("next_tet3d", "tet3d", 42), {}),
         (case_next_rows, ("next_tri2d", "tri2d", 43), {}),
+        # DifferentiableTpfa (prefix "difftpfa")
+        (case_diff_tpfa, ("difftpfa_cart3d", "cart3d_pert", 81), {}),
+        (case_diff_tpfa, ("difftpfa_tet3d", "tet3d_delaunay", 82), {}),
+        (case_diff_tpfa, ("difftpfa_tri2d", "tri2d", 83), {}),
+        # Grid.compute_geometry (prefix "geom")
+        (case_geometry, ("geom_cart3d_warped", "cart3d", 71), {}),
+        (case_geometry, ("geom_tet3d_perturbed", "tet3d", 72), {}),
+        (case_geometry, ("geom_tet3d_delaunay", "delaunay", 73), {}),
         # a 1-D intersection line (prefix "line")
         (case_line, ("line1d_tilted", 44), {}),
         # the reference's in-place partial update (prefix "partial")

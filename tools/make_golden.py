@@ -385,6 +385,60 @@ def case_diff_tpfa(name, kind, seed):
     print("wrote", name, nc, "cells")
 
 
+def case_mdg(prefix, seed):
+    """A mixed-dimensional fracture network (BASELINE configs[1] / [4] in miniature): a 6 x 6 x 6 Cartesian matrix cut by
+    three grid-aligned fractures (``pp.meshing.cart_grid``) -> one 3-D grid with split faces / nodes along the
+    fractures, three 2-D fracture planes, six 1-D intersection lines and one 0-D point.  One fixture per subdomain:
+    the flux discretization (``pp.Mpfa`` with ``ambient_dimension = 3``; TPFA on the lines, mpfa.py:690-712) with
+    the fracture / tip faces as internal Neumann boundaries; the 3-D grid also gets ``pp.Mpsa``."""
+    rng = np.random.default_rng(seed)
+    f1 = np.array([[2, 2, 2, 2], [1, 5, 5, 1], [1, 1, 5, 5]], float)
+    f2 = np.array([[1, 5, 5, 1], [3, 3, 3, 3], [1, 1, 5, 5]], float)
+    f3 = np.array([[1, 5, 5, 1], [1, 1, 5, 5], [2, 2, 2, 2]], float)
+    mdg = pp.meshing.cart_grid([f1, f2, f3], nx=np.array([6, 6, 6]), physdims=np.array([6.0, 6.0, 6.0]))
+    mdg.compute_geometry()
+    for i, g in enumerate(mdg.subdomains()):
+        if g.dim == 0:
+            continue
+        nc = g.num_cells
+        k = pp.SecondOrderTensor(1 + rng.random(nc), 1 + rng.random(nc), 1 + rng.random(nc),
+                                 0.3 * rng.random(nc), 0.3 * rng.random(nc), 0.3 * rng.random(nc))
+        bf = g.get_boundary_faces()                       # domain boundary only; fracture / tip faces stay Neumann
+        x = g.face_centers[0, bf]
+        bc = pp.BoundaryCondition(g, bf[(x < 1e-10) | (x > 6 - 1e-10)], "dir")
+        data = pp.initialize_data({}, "flow", {"second_order_tensor": k, "bc": bc, "mpfa_inverter": "python",
+                                                "ambient_dimension": 3})
+        pp.Mpfa("flow").discretize(g, data)
+        M = data[pp.DISCRETIZATION_MATRICES]["flow"]
+        d = grid_arrays(g)
+        d.update(kind=np.array("mpfa"), K=k.values, bc_is_dir=bc.is_dir, bc_is_neu=bc.is_neu, bc_is_rob=bc.is_rob,
+                 bc_is_internal=bc.is_internal, bc_robin_weight=np.asarray(bc.robin_weight, float),
+                 ambient_dimension=np.int64(3), tip_faces=np.asarray(g.tags["tip_faces"], bool),
+                 domain_boundary_faces=np.asarray(g.tags["domain_boundary_faces"], bool),
+                 eta=np.float64(pp.numerics.fv._fvutils.determine_eta(g)))
+        for key in ("flux", "bound_flux", "bound_pressure_cell", "bound_pressure_face", "vector_source",
+                    "bound_pressure_vector_source"):
+            put_matrix(d, key, M[key])
+        name = f"{prefix}_flow_sd{i:02d}_dim{g.dim}"
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+        print(name, "nc", nc, "nf", g.num_faces, "fracture faces", int(g.tags["fracture_faces"].sum()))
+        if g.dim == 3:
+            C = pp.FourthOrderTensor(np.exp(0.4 * rng.standard_normal(nc)), np.exp(0.4 * rng.standard_normal(nc)))
+            vbc = pp.BoundaryConditionVectorial(g, bf[g.face_centers[2, bf] < 1e-10], "dir")
+            dm = pp.initialize_data({}, "mech", {"fourth_order_tensor": C, "bc": vbc, "mpsa_inverter": "python"})
+            pp.Mpsa("mech").discretize(g, dm)
+            Mm = dm[pp.DISCRETIZATION_MATRICES]["mech"]
+            e = grid_arrays(g)
+            e.update(kind=np.array("mpsa"), C=C.values, bc_is_dir=vbc.is_dir, bc_is_neu=vbc.is_neu, bc_is_rob=vbc.is_rob,
+                     bc_is_internal=vbc.is_internal, bc_robin_weight=np.asarray(vbc.robin_weight, float),
+                     eta=np.float64(pp.numerics.fv._fvutils.determine_eta(g)))
+            for key in ("stress", "bound_stress", "bound_displacement_cell", "bound_displacement_face"):
+                put_matrix(e, key, Mm[key])
+            name = f"{prefix}_mech_sd{i:02d}_dim3"
+            np.savez_compressed(os.path.join(OUT, name + ".npz"), **e)
+            print(name, "nc", nc)
+
+
 def case_mpsa(name, kind, robin, seed, biot=False, basis=False):
     rng = np.random.default_rng(seed)
     g = make_grid(kind, rng)
@@ -461,6 +515,8 @@ def main():
         (case_next_rows, ("next_cart3d", "cart3d_pert", 41), {}),
         (case_next_rows, ("next_tet3d", "tet3d", 42), {}),
         (case_next_rows, ("next_tri2d", "tri2d", 43), {}),
+        # mixed-dimensional fracture network, one fixture per subdomain (prefix "mdgnet")
+        (case_mdg, ("mdgnet", 91), {}),
         # DifferentiableTpfa (prefix "difftpfa")
         (case_diff_tpfa, ("difftpfa_cart3d", "cart3d_pert", 81), {}),
         (case_diff_tpfa, ("difftpfa_tet3d", "tet3d_delaunay", 82), {}),

@@ -200,9 +200,10 @@ class DevicePlan:
         cf = sps.csc_matrix(sd.cell_faces)
         fn = sps.csc_matrix(sd.face_nodes)
         self.nd, self.nc, self.nf, self.nn = int(sd.dim), sd.num_cells, sd.num_faces, sd.num_nodes
-        cfp, cfi = cf.indptr.astype(np.int32), cf.indices.astype(np.int32)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)  # noqa: E731  (no copy when scipy already holds int32)
+        cfp, cfi = i32(cf.indptr), i32(cf.indices)
         cfd = np.asarray(cf.data).astype(np.int8)
-        fnp, fni = fn.indptr.astype(np.int32), fn.indices.astype(np.int32)
+        fnp, fni = i32(fn.indptr), i32(fn.indices)
         h = C.c_void_p()
         t0 = time.perf_counter()
         _lib.check(lib.pb_plan_create(self.nd, self.nc, self.nf, self.nn,

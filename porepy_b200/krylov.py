@@ -64,13 +64,15 @@ def build_local_system(a, owner: np.ndarray, rank: int, world: int, group=None) 
     return LocalSystem(rank, world, owned, gh, a_local, recv_counts, send_index)
 
 
-def local_system_from_shard(shard, part: np.ndarray, a_rows, group=None) -> LocalSystem:
+def local_system_from_shard(shard, part: np.ndarray, a_rows, group=None, dof: int = 1) -> LocalSystem:
     """This rank's rows of the global system, straight from its shard (``shard.extract_shard`` numbers the own
     cells first): ``a_rows`` holds the rows of the own cells with columns in the shard's local cell numbering,
     i.e. already [own | ghost] -- a scipy CSR or a ``DeviceCsr`` (e.g. ``DevicePlan.mpfa_system()`` after
     ``truncate_rows(n_own)``).  No global matrix exists anywhere.  The ghost cells are regrouped by owner rank for
     the exchange through a column permutation of the ghost block, which is returned in ``extra["ghost_perm"]``
-    and applied to the receive buffer instead of to the matrix.  Collective (exchanges the ghost lists)."""
+    and applied to the receive buffer instead of to the matrix.  ``dof`` unknowns per cell (3 for the mechanics
+    system ``div_nd @ stress``: row / column ``cell * dof + component``): the cell-level halo plan is expanded.
+    Collective (exchanges the ghost lists)."""
     rank = shard.rank
     part = np.asarray(part)
     n_own = int(shard.own_cell.sum())
@@ -101,8 +103,14 @@ def local_system_from_shard(shard, part: np.ndarray, a_rows, group=None) -> Loca
     # position in the receive buffer of each ghost column: recv slot j holds ghost order[j]
     slot_of_ghost = np.empty(ghosts.size, dtype=np.int64)
     slot_of_ghost[order] = np.arange(ghosts.size)
-    return LocalSystem(rank, world, owned, ghosts[order], a_rows, recv_counts, send_index,
-                       extra={"ghost_perm": slot_of_ghost})
+    ghosts_sorted = ghosts[order]
+    if dof > 1:
+        ex = lambda ix: (np.asarray(ix, dtype=np.int64)[:, None] * dof + np.arange(dof)).ravel()  # noqa: E731
+        owned, ghosts_sorted, slot_of_ghost = ex(owned), ex(ghosts_sorted), ex(slot_of_ghost)
+        send_index = [ex(ix) for ix in send_index]
+        recv_counts = [c * dof for c in recv_counts]
+    return LocalSystem(rank, world, owned, ghosts_sorted, a_rows, recv_counts, send_index,
+                       extra={"ghost_perm": slot_of_ghost, "dof": dof})
 
 
 def _dist_initialized() -> bool:

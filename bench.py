@@ -397,6 +397,8 @@ def main():
         fetch: None | "systems" | "all" additionally downloads the two system matrices / all ten matrices."""
         d0 = sum(LazyCsr.downloads.values())
         tm = {}
+        al0 = np.zeros(4)
+        lib.pb_alloc_stats(al0.ctypes.data_as(_lib._f64p))
         t_ = time.perf_counter()
 
         def lap(name):
@@ -436,7 +438,12 @@ def main():
         if fetch:
             lap("fetch_to_host")
         d2h = b1.nbytes + b2.nbytes + 32 + 8 + sum(LazyCsr.downloads.values()) - d0
-        timing = {"stages_s": tm, "mpfa": m1.last_timing, "mpsa": m2.last_timing}
+        al1 = np.zeros(4)
+        lib.pb_alloc_stats(al1.ctypes.data_as(_lib._f64p))
+        dal = al1 - al0
+        timing = {"stages_s": tm, "mpfa": m1.last_timing, "mpsa": m2.last_timing,
+                  "device_alloc_outside_pool": {"cudaMalloc_calls": int(dal[0]), "cudaMalloc_s": float(dal[1]),
+                                                "cudaFree_calls": int(dal[2]), "cudaFree_s": float(dal[3])}}
         return (A1, b1, A2, b2, chk, sh_, lg, d1, d2), d2h, timing
 
     e2e_vals, d2h_step, timing = [], 0, {}

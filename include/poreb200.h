@@ -58,6 +58,8 @@ const char *pb_last_error(void);
 int64_t pb_last_error_node(void);
 /* number of CUDA devices visible, or -1 (no driver / no device).  Never falls back to CPU. */
 int pb_device_count(void);
+/* device allocations that missed the pooled blocks: {cudaMalloc calls, seconds, cudaFree calls, seconds} since load */
+void pb_alloc_stats(double *out4);
 /* cudaSetDevice for this process (one process per GPU). */
 int pb_set_device(int device);
 /* kernels launched by this library since load (bench.py's gpu_launches evidence). */
@@ -295,6 +297,8 @@ int pb_csr_create(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t *indp
 void pb_csr_destroy(pb_csr *a);
 /* Keep the first nrows rows (a row-partitioned system: the rows of a rank's own cells come first). */
 int pb_csr_truncate_rows(pb_csr *a, int64_t nrows);
+/* lanes per row the SpMV of this matrix runs with (autotuned at creation; POREB200_SPMV_TPR overrides) */
+int pb_csr_lanes_per_row(const pb_csr *a);
 /* diagonal (min(nrows, ncols) doubles, host) -- the Jacobi preconditioner of the Krylov solve */
 int pb_csr_diagonal(pb_csr *a, double *diag);
 /* ---- device-side sparse algebra of the AD Jacobian chain (csrc/sparse_ops.cu) ---------------------------------

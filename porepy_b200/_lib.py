@@ -29,6 +29,8 @@ _SIGNATURES = {
     "pb_set_device": (C.c_int, [C.c_int]),
     "pb_launch_count": (C.c_int64, []),
     "pb_device_pool_trim": (None, []),
+    "pb_alloc_stats": (None, [_f64p]),
+    "pb_csr_lanes_per_row": (C.c_int, [C.c_void_p]),
     "pb_fp64_peak": (C.c_int, [C.c_int, _f64p]),
     "pb_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
     "pb_host_free": (None, [C.c_void_p]),

@@ -46,6 +46,19 @@ DevPool &pb_dev_pool_() {
 extern "C" void pb_device_pool_trim(void) { pb_dev_pool_().trim(); }
 
 extern "C" const char *pb_last_error(void) { return g_err.c_str(); }
+// cudaMalloc / cudaFree calls that did not go through the block pool, and the time spent in them (diagnosis of
+// the host-side variance of a re-discretization): out = {malloc calls, malloc seconds, free calls, free seconds}
+static std::atomic<int64_t> g_alloc_calls[2];
+static std::atomic<int64_t> g_alloc_ns[2];
+void pb_alloc_stat_(int kind, double seconds) {
+    g_alloc_calls[kind & 1]++;
+    g_alloc_ns[kind & 1] += (int64_t)(seconds * 1e9);
+}
+extern "C" void pb_alloc_stats(double *out) {
+    if (!out) return;
+    out[0] = (double)g_alloc_calls[0].load(); out[1] = 1e-9 * (double)g_alloc_ns[0].load();
+    out[2] = (double)g_alloc_calls[1].load(); out[3] = 1e-9 * (double)g_alloc_ns[1].load();
+}
 extern "C" int64_t pb_last_error_node(void) { return g_err_node; }
 void pb_set_error_node_(int64_t node) { g_err_node = node; }
 extern "C" int64_t pb_launch_count(void) { return g_launches.load(); }

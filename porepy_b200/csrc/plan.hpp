@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <cstdint>
 #include <cstdlib>
@@ -74,6 +75,7 @@ struct DevPool {
     }
 };
 DevPool &pb_dev_pool_();  // api.cu
+void pb_alloc_stat_(int kind, double seconds);   // api.cu: cudaMalloc (0) / cudaFree (1) calls that missed the pool
 
 struct DevBuf {
     void *p = nullptr;
@@ -88,7 +90,11 @@ struct DevBuf {
     }
     ~DevBuf() { release(); }
     void release() {
-        if (p && !pb_dev_pool_().give(p, bytes)) cudaFree(p);
+        if (p && !pb_dev_pool_().give(p, bytes)) {
+            const auto t0_ = std::chrono::steady_clock::now();
+            cudaFree(p);
+            pb_alloc_stat_(1, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0_).count());
+        }
         p = nullptr;
         bytes = 0;
     }
@@ -98,7 +104,9 @@ struct DevBuf {
         if (n == 0) n = 8;
         size_t got = 0;
         if ((p = pb_dev_pool_().take(n, got)) != nullptr) { bytes = got; return cudaSuccess; }
+        const auto t0_ = std::chrono::steady_clock::now();
         cudaError_t e = cudaMalloc(&p, n);
+        pb_alloc_stat_(0, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0_).count());
         if (e == cudaErrorMemoryAllocation) {   // give the pooled blocks back to the driver and retry once
             (void)cudaGetLastError();
             pb_dev_pool_().trim();

@@ -148,6 +148,10 @@ static int launch_spmv(pb_csr *a, const double *x, double *y, cudaStream_t st) {
 static void autotune_tpr(pb_csr *a) {
     const double mean = a->nrows ? (double)a->nnz / (double)a->nrows : 0.0;
     a->tpr = mean <= 3 ? 2 : mean <= 6 ? 4 : mean <= 24 ? 8 : mean <= 48 ? 16 : 32;
+    if (const char *forced = getenv("POREB200_SPMV_TPR")) {   // developer knob: lanes per row (2, 4, 8, 16, 32)
+        const int t = atoi(forced);
+        if (t == 2 || t == 4 || t == 8 || t == 16 || t == 32) { a->tpr = t; return; }
+    }
     if (a->nnz <= (1 << 20) || mean > 96.0) return;   // long rows: a full warp per row
     cudaMemsetAsync(a->x, 0, (a->ncols ? a->ncols : 1) * sizeof(double), a->stream);
     float best = 1e30f;
@@ -159,7 +163,7 @@ static void autotune_tpr(pb_csr *a) {
         float ms = 1e30f;
         if (launch_spmv(a, a->x, a->y, a->stream) != PB_OK) break;
         cudaEventRecord(a->e0, a->stream);
-        for (int i = 0; i < 3; ++i) launch_spmv(a, a->x, a->y, a->stream);
+        for (int i = 0; i < 10; ++i) launch_spmv(a, a->x, a->y, a->stream);
         cudaEventRecord(a->e1, a->stream);
         if (cudaEventSynchronize(a->e1) == cudaSuccess) cudaEventElapsedTime(&ms, a->e0, a->e1);
         if (ms < best) { best = ms; best_tpr = cands[ci]; }
@@ -205,6 +209,8 @@ extern "C" int pb_csr_create(int64_t nrows, int64_t ncols, int64_t nnz, const in
     *out = a;
     return PB_OK;
 }
+
+extern "C" int pb_csr_lanes_per_row(const pb_csr *a) { return a ? a->tpr : -1; }
 
 extern "C" int pb_csr_shape(const pb_csr *a, int64_t *nrows, int64_t *ncols, int64_t *nnz) {
     if (!a) return pb_fail_(PB_EINVAL, "null matrix");

@@ -252,6 +252,11 @@ def simplex_geometry_3d(g: Grid, cn: np.ndarray) -> Grid:
     outward = np.einsum("ij,ij->j", nrm, fc - cc[:, ref_cell])
     flip = np.where(fpos >= 0, outward < 0, outward > 0)
     nrm[:, flip] *= -1.0
+    # keep the node loop of every face consistent with its normal (right-hand rule), as pp.Grid.compute_geometry
+    # derives the normal FROM the loop (grids/grid.py:590-640): swap two nodes of the flipped faces
+    ix = g.face_nodes.indices.reshape(-1, 3)
+    ix[flip, 1], ix[flip, 2] = ix[flip, 2].copy(), ix[flip, 1].copy()
+    g.face_nodes.has_sorted_indices = False
     return g.set_geometry(nrm, fc, fa, cc, cv)
 
 

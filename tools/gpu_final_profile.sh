@@ -18,7 +18,8 @@ for r in rows[1:]:
 s = sum(tot.values())
 for k, v in tot.most_common(12): print(f"{v:10.3f} ms {100*v/s:5.1f} %  x{cnt[k]:3d}  {k}")
 PY
-timeout 900 bash tools/ncu_capture.sh mpsa_tet1m_r02 "mpsa_kernel" tet1m 1 | tail -3
-timeout 900 bash tools/ncu_capture.sh mpsa_cart128_r02 "mpsa_kernel" cart128 1 | tail -3
+# ncu prints template arguments as "(int)7": the regex of the round's earlier captures
+timeout 900 bash tools/ncu_capture.sh mpsa_tet1m_r02 'mpsa_kernel.*TileGJ<.int.7,..int.2,..int.24' tet1m 1 | tail -3
+timeout 900 bash tools/ncu_capture.sh mpsa_cart128_r02 'mpsa_kernel.*TileGJ<.int.2,..int.3,..int.8' cart128 1 | tail -3
 python tools/traffic_json.py gpurun_out/r02_traffic.json tet1m=gpurun_out/mpsa_tet1m_r02_raw.csv cart128=gpurun_out/mpsa_cart128_r02_raw.csv | head -40
 rm -f gpurun_out/mpsa_tet1m_r02_source.csv gpurun_out/mpsa_cart128_r02_source.csv

@@ -98,9 +98,18 @@ __global__ void __launch_bounds__(256)
         a1 += __shfl_xor_sync(0xffffffffu, a1, o);
         a2 += __shfl_xor_sync(0xffffffffu, a2, o);
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (d1 && a1 != 0.0) atomicAdd(d1, a1);
-        if (d2 && a2 != 0.0) atomicAdd(d2, a2);
+    // one atomic per CTA and dot product (38 k same-address atomics of a one-per-warp epilogue cost 0.05-0.08 ms,
+    // a quarter of the SpMV itself: tools/krylov_micro.py)
+    __shared__ double part[2][8];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { part[0][w] = a1; part[1][w] = a2; }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double v = part[threadIdx.x >> 3][threadIdx.x & 7];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0x0000ffffu, v, o, 8);
+        if (threadIdx.x == 0 && d1 && v != 0.0) atomicAdd(d1, v);
+        if (threadIdx.x == 8 && d2 && v != 0.0) atomicAdd(d2, v);
     }
 }
 
@@ -158,7 +167,7 @@ static void autotune_tpr(pb_csr *a) {
     int best_tpr = a->tpr;
     const int cands[4] = {4, 8, 16, 32};
     for (int ci = 0; ci < 4; ++ci) {
-        if (cands[ci] * 6 < mean || cands[ci] > 8 * mean) continue;   // implausible for this row length
+        if (cands[ci] * 12 < mean || cands[ci] > 8 * mean) continue;  // implausible for this row length
         a->tpr = cands[ci];
         float ms = 1e30f;
         if (launch_spmv(a, a->x, a->y, a->stream) != PB_OK) break;

@@ -664,8 +664,12 @@ def vector_bc_basis(bc, nd: int):
     if b.ndim != 3:
         return None
     sub = b[:nd, :nd]
-    if all(np.array_equal(sub[i, j], np.full(sub.shape[2], 1.0 if i == j else 0.0)) for i in range(nd) for j in range(nd)):
-        return None   # the identity on every face (exact test: cheap, and anything else IS a rotated basis)
+    eye = np.eye(nd)[:, :, None]
+    if sub.strides[-1] == 0:        # one matrix broadcast over the faces (e.g. a restricted shard condition)
+        if np.array_equal(sub[:, :, :1], eye):
+            return None
+    elif np.array_equal(sub, np.broadcast_to(eye, sub.shape)):
+        return None   # the identity on every face (exact test, one pass; anything else IS a rotated basis)
     return np.ascontiguousarray(b[:nd, :nd])
 
 

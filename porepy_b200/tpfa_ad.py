@@ -27,9 +27,11 @@ import scipy.sparse as sps
 
 def _find(cell_faces):
     """(face, cell, sign) of the half-faces in the reference's order (``sps.find``: sorted by face, then by cell)."""
-    m = sps.coo_matrix(cell_faces)
-    order = np.lexsort((m.col, m.row))
-    return m.row[order].astype(np.int64), m.col[order].astype(np.int64), np.asarray(m.data, dtype=np.float64)[order]
+    m = sps.csr_matrix(cell_faces, copy=True)   # CSC -> CSR: a counting sort by face; ascending cells inside a face
+    m.eliminate_zeros()                          # sps.find drops explicit zeros
+    m.sort_indices()
+    fi = np.repeat(np.arange(m.shape[0], dtype=np.int64), np.diff(m.indptr))
+    return fi, m.indices.astype(np.int64), np.asarray(m.data, dtype=np.float64)
 
 
 def _expand(ind: np.ndarray, dim: int) -> np.ndarray:

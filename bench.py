@@ -501,6 +501,22 @@ def main():
         res = b_t - op_chk.matvec(x)
         rr, bbn = allsum([float(res @ res), float(b_t @ b_t)])
         true_relres = float(np.sqrt(rr / bbn))
+        # the same kernels on this rank's rows WITHOUT the collectives (ghost entries left at zero, local dot products,
+        # 64 iterations, no convergence test): what one iteration costs in compute; the rest of ms_per_iteration is NCCL
+        local_ms = None
+        if world > 1:
+            try:
+                loc_nc = kr.LocalSystem(0, 1, loc.owned, loc.ghosts, a_dev, [0], [np.zeros(0, np.int64)])
+                op_nc = kr.DistributedOperator(loc_nc, torch.device("cuda", local))
+                kr.bicgstab(op_nc, b_t, tol=0.0, maxiter=16, diag_own=diag)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                _, inc = kr.bicgstab(op_nc, b_t, tol=0.0, maxiter=64, diag_own=diag)
+                torch.cuda.synchronize()
+                local_ms = allmax([1e3 * (time.perf_counter() - t0) / 64])[0]
+                del op_nc, loc_nc
+            except Exception as e:
+                local_ms = f"{type(e).__name__}: {e}"
         krylov = {"system": "A = div @ flux of the sharded mesh (rows of each rank's own cells)", "rows": int(nc_global),
                   "inputs_finite": bool(np.isfinite(b1).all() and bool(torch.isfinite(diag).all())),
                   "halo_exchange_max_error": allmax([halo_err])[0], "true_relres": true_relres,
@@ -511,6 +527,9 @@ def main():
                   "seconds": solve_s, "spmv": info["spmv"], "allreduce": info["allreduce"],
                   "halo_bytes_per_spmv_all_ranks": int(allsum([float(info["halo_bytes_per_spmv"])])[0]),
                   "ms_per_iteration": 1e3 * solve_s / max(info["iterations"], 1),
+                  "ms_per_iteration_without_collectives": local_ms,
+                  "nccl_share_of_iteration": (None if not isinstance(local_ms, float) else
+                                              max(0.0, 1.0 - local_ms / (1e3 * solve_s / max(info["iterations"], 1)))),
                   "collectives": "ghost entries: NCCL send/recv per neighbour; dots: one all-reduce of 1-3 doubles"
                   if world > 1 else "none (single GPU)"}
         del x, loc, op_chk

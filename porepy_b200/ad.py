@@ -103,6 +103,14 @@ class DeviceAdArray:
         e = self.val.exp()
         return DeviceAdArray(e, self.jac.scaled(e))
 
+    def reciprocal(self):
+        """``1 / self`` (the ``one / x`` of the reference's harmonic means, constitutive_laws.py:1567-1581)."""
+        inv = 1.0 / self.val
+        return DeviceAdArray(inv, self.jac.scaled(-inv * inv))
+
+    def __rtruediv__(self, other):
+        return self.reciprocal() * other
+
     def host(self):
         """(val, jac) as NumPy / scipy (tests)."""
         return self.val.cpu().numpy(), self.jac.to_scipy()

@@ -251,14 +251,14 @@ __global__ void csr_diagonal_kernel(int64_t nrows, const int32_t *__restrict__ i
 extern "C" int pb_csr_diagonal(pb_csr *a, double *diag) {
     if (!a || !diag) return pb_fail_(PB_EINVAL, "null pointer");
     const int64_t n = a->nrows < a->ncols ? a->nrows : a->ncols;
-    double *d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, (n ? n : 1) * sizeof(double)));
+    DevBuf tmp;                       // pooled: no cudaMalloc / cudaFree pair (a device sync each) per call
+    CUDA_TRY(tmp.ensure((size_t)(n ? n : 1) * sizeof(double)));
+    double *d = tmp.as<double>();
     const int grid = (int)(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
     csr_diagonal_kernel<<<grid, 256, 0, a->stream>>>(n, a->indptr, a->indices, a->data, d);
     pb_count_launch_();
     cudaError_t e = cudaMemcpyAsync(diag, d, n * sizeof(double), cudaMemcpyDeviceToHost, a->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(a->stream);
-    cudaFree(d);
     if (e != cudaSuccess) return pb_fail_(PB_ECUDA, cudaGetErrorString(e));
     return PB_OK;
 }

@@ -424,7 +424,8 @@ extern "C" int pb_plan_create(int nd, int64_t nc, int64_t nf, int64_t nn, const 
             {&p->pos_cb, &H.poscb_ptr, &p->poscb_ptr, 3, &p->node_sc_ptr, &p->sc_cell, &p->nbf_ptr, &p->nbf_idx, &p->cb_indptr},
         };
         for (auto &j : jobs) {
-            if ((e = j.pos->ensure((size_t)std::max<int64_t>(1, j.ptr->back()) * sizeof(int32_t))) != cudaSuccess)
+            // + 32 bytes: a 16-byte widened bulk copy of the last node's block may read past the end (PB_EXP_TMA)
+            if ((e = j.pos->ensure((size_t)std::max<int64_t>(1, j.ptr->back()) * sizeof(int32_t) + 32)) != cudaSuccess)
                 return bail("pos map", e);
             const int block = 256;
             int64_t need = (nn * 32 + block - 1) / block;

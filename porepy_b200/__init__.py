@@ -8,6 +8,7 @@ from .fv import (Biot, DevicePlan, FaceGrid, Mpfa, Mpsa, Tpfa, Upwind, UpwindCou
                  determine_eta)
 from .geometry import compute_geometry  # noqa: F401
 from .grid import Grid, cart_grid_2d, cart_grid_3d, structured_tet_grid, tet_grid_from_cells  # noqa: F401
+from .mdflow import MdInterface, MdSubdomain, MixedDimensionalFlow  # noqa: F401
 from .params import (DISCRETIZATION_MATRICES, PARAMETERS, BoundaryCondition,  # noqa: F401
                      BoundaryConditionVectorial, FourthOrderTensor, SecondOrderTensor,
                      initialize_data)
@@ -17,4 +18,5 @@ from .tpfa_ad import DifferentiableTpfa  # noqa: F401
 __all__ = ["Mpfa", "Mpsa", "Biot", "Tpfa", "Upwind", "UpwindCoupling", "DevicePlan", "FaceGrid", "DeviceCsr", "Grid", "cart_grid_2d", "cart_grid_3d",
            "structured_tet_grid", "tet_grid_from_cells", "SecondOrderTensor", "FourthOrderTensor",
            "BoundaryCondition", "BoundaryConditionVectorial", "initialize_data", "PARAMETERS",
-           "DISCRETIZATION_MATRICES", "determine_eta", "compute_geometry", "DifferentiableTpfa"]
+           "DISCRETIZATION_MATRICES", "determine_eta", "compute_geometry", "DifferentiableTpfa",
+           "MixedDimensionalFlow", "MdSubdomain", "MdInterface"]

@@ -1,0 +1,96 @@
+"""Host stand-in for ``porepy_b200.sparse.DeviceCsr`` (scipy + CPU torch tensors) with the same interface, so that the
+AD chain of ``porepy_b200.ad`` and the equation builders on top of it (``porepy_b200.mdflow``) run in the build container.
+Test infrastructure only: the product never imports it."""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sps
+import torch
+
+
+class HostCsr:
+    def __init__(self, a):
+        self.m = sps.csr_matrix(a, dtype=np.float64)
+        self.m.sort_indices()
+        self.shape = self.m.shape
+
+    @property
+    def nnz(self):
+        return int(self.m.nnz)
+
+    def to_scipy(self):
+        return self.m.copy()
+
+    def diagonal(self):
+        return self.m.diagonal()
+
+    def matmul(self, other):
+        return HostCsr(self.m @ other.m)
+
+    def axpby(self, alpha, other, beta):
+        return HostCsr(alpha * self.m + beta * other.m)
+
+    def scaled(self, d, by_cols=False):
+        d = d.cpu().numpy() if torch.is_tensor(d) else np.asarray(d, float)
+        if d.size != self.shape[1 if by_cols else 0]:
+            raise ValueError("dimension mismatch")
+        return HostCsr(self.m @ sps.diags(d) if by_cols else sps.diags(d) @ self.m)
+
+    @staticmethod
+    def bmat(blocks):
+        return HostCsr(sps.bmat([[None if b is None else b.m for b in row] for row in blocks], format="csr"))
+
+    @staticmethod
+    def block_diag(mats):
+        return HostCsr(sps.block_diag([m.m for m in mats], format="csr"))
+
+    @staticmethod
+    def vstack(mats):
+        return HostCsr(sps.vstack([m.m for m in mats], format="csr"))
+
+    @staticmethod
+    def hstack(mats):
+        return HostCsr(sps.hstack([m.m for m in mats], format="csr"))
+
+    @staticmethod
+    def identity(n):
+        return HostCsr(sps.identity(n, format="csr"))
+
+    def __add__(self, o):
+        return self.axpby(1.0, o, 1.0)
+
+    def __sub__(self, o):
+        return self.axpby(1.0, o, -1.0)
+
+    def __neg__(self):
+        return HostCsr(-self.m)
+
+    def __mul__(self, a):
+        return HostCsr(float(a) * self.m)
+
+    __rmul__ = __mul__
+
+    def __matmul__(self, x):
+        if isinstance(x, HostCsr):
+            return self.matmul(x)
+        if type(x).__name__ == "DeviceAdArray":
+            return x.__rmatmul__(self)
+        if torch.is_tensor(x):
+            return torch.as_tensor(self.m @ x.cpu().numpy())
+        return self.m @ np.asarray(x, float)
+
+
+def install(monkeypatch):
+    """Route ``porepy_b200.ad`` to the host stand-in."""
+    from porepy_b200 import ad
+
+    def as_csr(m):
+        if isinstance(m, HostCsr):
+            return m
+        return HostCsr(sps.csr_matrix(m))
+
+    def vec(v, device=None):
+        return v.to(dtype=torch.float64) if torch.is_tensor(v) else torch.as_tensor(np.ascontiguousarray(v, dtype=np.float64))
+    monkeypatch.setattr(ad, "DeviceCsr", HostCsr)
+    monkeypatch.setattr(ad, "as_device_csr", as_csr)
+    monkeypatch.setattr(ad, "device_vector", vec)

@@ -1,0 +1,49 @@
+"""Load the mixed-dimensional flow fixtures of tools/make_mdflow_golden.py into ``porepy_b200.mdflow`` records."""
+from __future__ import annotations
+
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import scipy.sparse as sps
+
+import porepy_b200 as pb
+from porepy_b200.grid import Grid
+from porepy_b200.mdflow import MdInterface, MdSubdomain, MixedDimensionalFlow
+from golden_io import GOLDEN_DIR
+
+
+def _csr(d, key):
+    return sps.csr_matrix((d[key + "__data"], d[key + "__indices"], d[key + "__indptr"]), shape=tuple(d[key + "__shape"]))
+
+
+def load_mdflow(name: str):
+    """(MixedDimensionalFlow, reference Jacobian, reference rhs, reference solution)."""
+    d = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+    subs = []
+    for i in range(int(d["num_subdomains"])):
+        sub = {k[len(f"sd{i}__"):]: v for k, v in d.items() if k.startswith(f"sd{i}__")}
+        if int(sub["dim"]) == 0:
+            nc = sub["cell_volumes"].size
+            g = SimpleNamespace(dim=0, num_cells=nc, num_faces=0, num_nodes=sub["nodes"].shape[1], nodes=sub["nodes"],
+                                cell_centers=sub["cell_centers"], cell_volumes=sub["cell_volumes"],
+                                cell_faces=sps.csc_matrix((0, nc)), name=str(sub["name"]))
+            subs.append(MdSubdomain(g, {}, None, sub["source"]))
+            continue
+        g = Grid.from_arrays(sub)
+        g.tags["tip_faces"] = np.asarray(sub["tip_faces"], bool)
+        g.tags["domain_boundary_faces"] = np.asarray(sub["domain_boundary_faces"], bool)
+        bc = SimpleNamespace(is_dir=sub["bc_is_dir"], is_neu=sub["bc_is_neu"], is_rob=sub["bc_is_rob"],
+                             is_internal=sub["bc_is_internal"], robin_weight=sub["bc_robin_weight"], bc_type="scalar",
+                             num_faces=g.num_faces)
+        data = pb.initialize_data({}, "flow", {"second_order_tensor": pb.SecondOrderTensor.from_values(sub["K"]),
+                                               "bc": bc, "ambient_dimension": int(sub["ambient_dimension"])})
+        subs.append(MdSubdomain(g, data, sub["bc_values"], sub["source"]))
+    intfs = []
+    for j in range(int(d["num_interfaces"])):
+        p = f"if{j}__"
+        intfs.append(MdInterface(int(d[p + "primary"]), int(d[p + "secondary"]), _csr(d, p + "mortar_to_primary_int"),
+                                 _csr(d, p + "primary_to_mortar_avg"), _csr(d, p + "mortar_to_secondary_int"),
+                                 _csr(d, p + "secondary_to_mortar_avg"), d[p + "normal_permeability"],
+                                 d[p + "cell_volumes"], d[p + "secondary_aperture"]))
+    return MixedDimensionalFlow(subs, intfs, "flow"), _csr(d, "jacobian"), d["rhs"], d["solution"]

@@ -329,3 +329,45 @@ def test_install_routes_stock_models(pp, emu_plan):
     assert b.fallback_calls == {}
     assert sorted(set(seen)) == [2, 3]
     assert np.linalg.norm(ref - got) <= 1e-10 * np.linalg.norm(ref)
+
+
+def test_mixed_dimensional_flow_from_a_porepy_mdg(pp, emu_plan, monkeypatch):
+    """``porepy_b200.mdflow.MixedDimensionalFlow.from_mdg`` on the mixed-dimensional grid of a stock ``pp.SinglePhaseFlow``
+    (matrix + fracture plane + interface): every subdomain discretized by ``pb.Mpfa`` on the reference's own grids and
+    parameter dictionaries, the coupled Jacobian and right-hand side equal to ``EquationSystem.assemble`` of the model."""
+    import emu_sparse
+    import torch
+    from porepy_b200.mdflow import MixedDimensionalFlow
+    emu_sparse.install(monkeypatch)
+
+    class Model(_Geometry, _VerticalFracture, _HeterogeneousPermeability, _FlowBC, pp.SinglePhaseFlow):
+        pass
+    model = Model({"times_to_export": [], "time_manager": pp.TimeManager([0, 1.0], 1.0, constant_dt=True)})
+    model.prepare_simulation()
+    Jref, bref = model.equation_system.assemble()
+    mdg = model.mdg
+
+    def bc_values(sd):
+        bg = mdg.subdomain_to_boundary_grid(sd)
+        if bg is None or bg.num_cells == 0:
+            return np.zeros(sd.num_faces)
+        bc = mdg.subdomain_data(sd)[pp.PARAMETERS]["flow"]["bc"]
+        proj = bg.projection()
+        return np.where(bc.is_dir, proj.T @ model.bc_values_pressure(bg), proj.T @ model.bc_values_darcy_flux(bg))
+
+    def evaluated(op, n):
+        v = model.equation_system.evaluate(op)
+        return np.full(n, float(v)) if np.ndim(v) == 0 else np.asarray(v, float)
+    prob = MixedDimensionalFlow.from_mdg(
+        mdg, "flow", bc_values=bc_values,
+        normal_permeability=lambda it: evaluated(model.normal_permeability([it]), it.num_cells),
+        aperture=lambda sd: evaluated(model.aperture([sd]), sd.num_cells),
+        specific_volume=lambda it: evaluated(model.specific_volume([it]), it.num_cells))
+    for s in prob.subdomains:                       # forget the reference's own discretization
+        s.data[pp.DISCRETIZATION_MATRICES]["flow"].clear()
+    prob.discretize()
+    J, b = prob.assemble_host()
+    assert abs(J - Jref).max() <= 1e-10 * abs(Jref).max() and np.abs(b - bref).max() <= 1e-10 * np.abs(bref).max()
+    Jd, bd = prob.assemble(torch.zeros(prob.num_dofs, dtype=torch.float64))
+    assert abs(Jd.to_scipy() - Jref).max() <= 1e-10 * abs(Jref).max()
+    assert np.abs(bd.numpy() - bref).max() <= 1e-10 * np.abs(bref).max()

@@ -1,0 +1,184 @@
+"""Generate tests/golden/mdflow_*.npz: a whole mixed-dimensional single-phase flow problem of the unmodified reference
+(run in the build container; the GPU box never sees /root/reference).
+
+``pp.SinglePhaseFlow`` on a Cartesian matrix cut by three grid-aligned fractures (3-D matrix, three 2-D planes, six 1-D
+intersection lines, one 0-D point, twelve + interfaces), anisotropic heterogeneous permeability, Dirichlet pressure on
+two sides.  The fixture holds, per subdomain, the grid arrays and the parameters the reference handed to its flux
+discretization (``data[pp.PARAMETERS]["flow"]``), per interface the mortar projections and the coefficients of the
+interface law (reference models/constitutive_laws.py:1032-1076), and the reference's own global Jacobian, right-hand
+side (``EquationSystem.assemble`` at the zero state, numerics/ad/equation_system.py:1579-1713) and converged solution.
+
+    python tools/make_mdflow_golden.py
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sps
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from ref_loader import load_porepy  # noqa: E402
+from make_golden import grid_arrays  # noqa: E402
+
+pp = load_porepy()
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def put_csr(d: dict, key: str, m) -> None:
+    m = sps.csr_matrix(m)
+    m.sum_duplicates()
+    m.sort_indices()
+    d[key + "__data"], d[key + "__indices"], d[key + "__indptr"] = m.data, m.indices.astype(np.int32), m.indptr.astype(np.int32)
+    d[key + "__shape"] = np.array(m.shape, dtype=np.int64)
+
+
+def rect(axis, at, lo, hi):
+    """Corners of the axis-aligned rectangle {x_axis = at} x [lo, hi]^2."""
+    o = [a for a in range(3) if a != axis]
+    p = np.zeros((3, 4))
+    p[axis] = at
+    p[o[0]] = [lo, hi, hi, lo]
+    p[o[1]] = [lo, lo, hi, hi]
+    return p
+
+
+def make_model(n, fracs, source):
+    class Model(pp.SinglePhaseFlow):
+        def set_domain(self):
+            self._domain = pp.Domain({"xmin": 0, "xmax": 1, "ymin": 0, "ymax": 1, "zmin": 0, "zmax": 1})
+
+        def grid_type(self):
+            return "cartesian"
+
+        def meshing_arguments(self):
+            return {"cell_size": 1.0 / n}
+
+        def set_fractures(self):
+            self._fractures = [pp.PlaneFracture(f) for f in fracs]
+
+        def permeability(self, subdomains):
+            vals = []
+            for sd in subdomains:
+                rng = np.random.default_rng(1000 * sd.dim + sd.num_cells)
+                nc = sd.num_cells
+                t = np.zeros((3, 3, nc))
+                scale = 1.0 if sd.dim == 3 else 50.0          # conductive fractures
+                t[0, 0], t[1, 1], t[2, 2] = scale * (1 + rng.random((3, nc)))
+                o = 0.3 * scale * rng.random((3, nc))
+                t[0, 1] = t[1, 0] = o[0]
+                t[0, 2] = t[2, 0] = o[1]
+                t[1, 2] = t[2, 1] = o[2]
+                vals.append(t.reshape(9, nc).ravel("F"))
+            return pp.wrap_as_dense_ad_array(np.hstack(vals) if vals else np.zeros(0), name="permeability")
+
+        def normal_permeability(self, interfaces):
+            vals = [3.0 + np.cos(np.arange(i.num_cells)) for i in interfaces]
+            return pp.wrap_as_dense_ad_array(np.hstack(vals) if vals else np.zeros(0), name="normal_permeability")
+
+        def bc_type_darcy_flux(self, sd):
+            sides = self.domain_boundary_sides(sd)
+            return pp.BoundaryCondition(sd, sides.west + sides.east, "dir")
+
+        def bc_values_pressure(self, bg):
+            sides = self.domain_boundary_sides(bg)
+            v = np.zeros(bg.num_cells)
+            v[sides.west] = 1.0 + bg.cell_centers[1, sides.west]
+            return v
+
+        def bc_values_darcy_flux(self, bg):
+            sides = self.domain_boundary_sides(bg)
+            v = np.zeros(bg.num_cells)
+            v[sides.top] = -0.1 * bg.cell_volumes[sides.top]       # inflow through the top
+            return v
+
+        def extra_source(self, sd):
+            """Integrated cell sources on top of the interface inflow the reference adds itself
+            (models/fluid_mass_balance.py ``fluid_source``)."""
+            return source * sd.cell_volumes * np.sin(3 * sd.cell_centers[0]) if sd.dim == 3 else np.zeros(sd.num_cells)
+
+        def fluid_source(self, subdomains):
+            vals = [self.extra_source(sd) for sd in subdomains]
+            ext = pp.wrap_as_dense_ad_array(np.hstack(vals) if vals else np.zeros(0), name="extra_source")
+            return super().fluid_source(subdomains) + ext
+
+    return Model({"times_to_export": [], "time_manager": pp.TimeManager([0, 1.0], 1.0, constant_dt=True)})
+
+
+def full_bc_values(model, sd):
+    """Face-wise boundary data as the flux discretization consumes it: pressures on Dirichlet faces, fluxes elsewhere."""
+    mdg = model.mdg
+    v = np.zeros(sd.num_faces)
+    bg = mdg.subdomain_to_boundary_grid(sd)
+    if bg is None or bg.num_cells == 0:
+        return v
+    bc = mdg.subdomain_data(sd)[pp.PARAMETERS]["flow"]["bc"]
+    proj = bg.projection()
+    return np.where(bc.is_dir, proj.T @ model.bc_values_pressure(bg), proj.T @ model.bc_values_darcy_flux(bg))
+
+
+def scalar_field(model, op, n):
+    v = model.equation_system.evaluate(op)
+    return np.full(n, float(v)) if np.ndim(v) == 0 else np.asarray(v, float)
+
+
+def export(name, n, fracs, source=0.7):
+    model = make_model(n, fracs, source)
+    model.prepare_simulation()
+    es, mdg = model.equation_system, model.mdg
+    A0, b0 = es.assemble()
+    pp.run_time_dependent_model(model, {"prepare_simulation": False})
+    A1, b1 = es.assemble()
+    assert abs(A1 - A0).max() == 0.0 and np.linalg.norm(b1) < 1e-10 * np.linalg.norm(b0)
+    x = es.get_variable_values(iterate_index=0)
+    sds, intfs = mdg.subdomains(), mdg.interfaces()
+    d = {"num_subdomains": np.int64(len(sds)), "num_interfaces": np.int64(len(intfs)), "solution": x, "rhs": b0}
+    put_csr(d, "jacobian", A0)
+    off = 0
+    for i, sd in enumerate(sds):
+        data = mdg.subdomain_data(sd)
+        prm = data[pp.PARAMETERS]["flow"]
+        assert np.array_equal(es.dofs_of([v for v in es.variables if v.name == "pressure" and v.domain is sd]),
+                              off + np.arange(sd.num_cells))
+        off += sd.num_cells
+        g = grid_arrays(sd) if sd.dim > 0 else dict(
+            dim=np.int64(0), name=np.array(str(sd.name)), nodes=sd.nodes, cell_centers=sd.cell_centers,
+            cell_volumes=sd.cell_volumes)
+        for k, v in g.items():
+            d[f"sd{i}__{k}"] = v
+        d[f"sd{i}__source"] = np.asarray(model.extra_source(sd), float)
+        if sd.dim > 0:
+            bc = prm["bc"]
+            d[f"sd{i}__K"] = prm["second_order_tensor"].values
+            for k in ("is_dir", "is_neu", "is_rob", "is_internal"):
+                d[f"sd{i}__bc_{k}"] = getattr(bc, k)
+            d[f"sd{i}__bc_robin_weight"] = np.asarray(bc.robin_weight, float)
+            d[f"sd{i}__bc_values"] = full_bc_values(model, sd)
+            d[f"sd{i}__tip_faces"] = np.asarray(sd.tags["tip_faces"], bool)
+            d[f"sd{i}__domain_boundary_faces"] = np.asarray(sd.tags["domain_boundary_faces"], bool)
+            d[f"sd{i}__ambient_dimension"] = np.int64(prm.get("ambient_dimension", 3))
+    index = {sd: i for i, sd in enumerate(sds)}
+    for j, it in enumerate(intfs):
+        h, l = mdg.interface_to_subdomain_pair(it)
+        assert np.array_equal(es.dofs_of([v for v in es.variables if v.name == "interface_darcy_flux" and v.domain is it]),
+                              off + np.arange(it.num_cells))
+        off += it.num_cells
+        d[f"if{j}__primary"], d[f"if{j}__secondary"] = np.int64(index[h]), np.int64(index[l])
+        put_csr(d, f"if{j}__mortar_to_primary_int", it.mortar_to_primary_int())
+        put_csr(d, f"if{j}__primary_to_mortar_avg", it.primary_to_mortar_avg())
+        put_csr(d, f"if{j}__mortar_to_secondary_int", it.mortar_to_secondary_int())
+        put_csr(d, f"if{j}__secondary_to_mortar_avg", it.secondary_to_mortar_avg())
+        d[f"if{j}__normal_permeability"] = scalar_field(model, model.normal_permeability([it]), it.num_cells)
+        d[f"if{j}__cell_volumes"] = it.cell_volumes * scalar_field(model, model.specific_volume([it]), it.num_cells)
+        d[f"if{j}__secondary_aperture"] = scalar_field(model, model.aperture([l]), l.num_cells)
+    assert off == A0.shape[0]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "dofs", A0.shape[0], "nnz", A0.nnz, "subdomains", [(s.dim, s.num_cells) for s in sds],
+          "interfaces", [(i.dim, i.num_cells) for i in intfs], "|b|", np.linalg.norm(b0), "ptp(x)", np.ptp(x))
+
+
+if __name__ == "__main__":
+    export("mdflow_three_fractures", 6, [rect(0, 0.5, 1 / 6, 5 / 6), rect(1, 0.5, 1 / 6, 5 / 6), rect(2, 0.5, 1 / 6, 5 / 6)])
+    export("mdflow_one_fracture", 4, [rect(0, 0.5, 0.25, 0.75)], source=0.0)

@@ -371,3 +371,110 @@ def test_mixed_dimensional_flow_from_a_porepy_mdg(pp, emu_plan, monkeypatch):
     Jd, bd = prob.assemble(torch.zeros(prob.num_dofs, dtype=torch.float64))
     assert abs(Jd.to_scipy() - Jref).max() <= 1e-10 * abs(Jref).max()
     assert np.abs(bd.numpy() - bref).max() <= 1e-10 * np.abs(bref).max()
+
+
+def test_synthetic_fracture_network_matches_the_reference_mesher(pp, emu_plan):
+    """``porepy_b200.mdgrid.split_fractures`` (the bench's own mixed-dimensional mesh generator) against the reference's
+    mesher: the same Cartesian matrix with two disjoint fractures, coefficient fields given as functions of position,
+    ``pp.SinglePhaseFlow`` on ``create_mdg`` vs ``MixedDimensionalFlow`` on the synthetic network -- equal pressures cell
+    by cell (matched through the cell centres; the numberings differ)."""
+    import scipy.sparse.linalg as spla
+    import porepy_b200 as pb
+    from porepy_b200 import mdgrid
+    from porepy_b200.mdflow import MdInterface, MdSubdomain, MixedDimensionalFlow
+    n = 6
+
+    def kfield(x, dim):
+        return (1.0 + x[0] + 2.0 * x[1]) if dim == 3 else 50.0 * (1.0 + x[2])
+
+    def rect(at):
+        p = np.zeros((3, 4))
+        p[0] = at
+        p[1] = [1 / 6, 5 / 6, 5 / 6, 1 / 6]
+        p[2] = [1 / 6, 1 / 6, 5 / 6, 5 / 6]
+        return p
+
+    class Model(pp.SinglePhaseFlow):
+        def set_domain(self):
+            self._domain = pp.Domain({"xmin": 0, "xmax": 1, "ymin": 0, "ymax": 1, "zmin": 0, "zmax": 1})
+
+        def grid_type(self):
+            return "cartesian"
+
+        def meshing_arguments(self):
+            return {"cell_size": 1.0 / n}
+
+        def set_fractures(self):
+            self._fractures = [pp.PlaneFracture(rect(2 / 6)), pp.PlaneFracture(rect(4 / 6))]
+
+        def permeability(self, subdomains):
+            vals = []
+            for sd in subdomains:
+                t = np.zeros((3, 3, sd.num_cells))
+                t[0, 0] = t[1, 1] = t[2, 2] = kfield(sd.cell_centers, sd.dim)
+                vals.append(t.reshape(9, sd.num_cells).ravel("F"))
+            return pp.wrap_as_dense_ad_array(np.hstack(vals) if vals else np.zeros(0), name="permeability")
+
+        def bc_type_darcy_flux(self, sd):
+            sides = self.domain_boundary_sides(sd)
+            return pp.BoundaryCondition(sd, sides.west + sides.east, "dir")
+
+        def bc_values_pressure(self, bg):
+            sides = self.domain_boundary_sides(bg)
+            v = np.zeros(bg.num_cells)
+            v[sides.west] = 1.0 + bg.cell_centers[1, sides.west]
+            return v
+    model = Model({"times_to_export": [], "time_manager": pp.TimeManager([0, 1.0], 1.0, constant_dt=True)})
+    pp.run_time_dependent_model(model, {"prepare_simulation": True})
+    xref = model.equation_system.get_variable_values(iterate_index=0)
+    sds = model.mdg.subdomains()
+    assert [s.dim for s in sds] == [3, 2, 2]
+    frac = sds[1]
+    a = float(np.atleast_1d(model.equation_system.evaluate(model.aperture([frac])))[0])
+    kn = float(np.atleast_1d(model.equation_system.evaluate(model.normal_permeability(model.mdg.interfaces())))[0])
+
+    g = pb.cart_grid_3d([n, n, n])
+    sets = [mdgrid.faces_on_rectangle(g, 0, x, (1 / 6, 1 / 6), (5 / 6, 5 / 6)) for x in (2 / 6, 4 / 6)]
+    assert [s.size for s in sets] == [16, 16]
+    net = mdgrid.split_fractures(g, sets)
+    m = net.matrix
+    assert (m.num_cells, m.num_faces, m.num_nodes) == (sds[0].num_cells, sds[0].num_faces, sds[0].num_nodes)
+    assert (net.fractures[0].num_faces, net.fractures[0].num_nodes) == (frac.num_faces, frac.num_nodes)
+    assert int(net.fractures[0].tags["tip_faces"].sum()) == int(frac.tags["tip_faces"].sum()) == 16
+
+    def tensor(sd, scale):
+        return pb.SecondOrderTensor(scale * kfield(sd.cell_centers, sd.dim) * np.ones(sd.num_cells))
+    west = np.flatnonzero(m.face_centers[0] < 1e-12)
+    east = np.flatnonzero(m.face_centers[0] > 1 - 1e-12)
+    bcv = np.zeros(m.num_faces)
+    bcv[west] = 1.0 + m.face_centers[1, west]
+    subs = [MdSubdomain(m, pb.initialize_data({}, "flow", {
+        "second_order_tensor": tensor(m, 1.0), "bc": pb.BoundaryCondition(m, np.concatenate((west, east)), "dir")}), bcv)]
+    intfs = []
+    for k, fg in enumerate(net.fractures):
+        subs.append(MdSubdomain(fg, pb.initialize_data({}, "flow", {          # fracture tensor times the specific volume
+            "second_order_tensor": tensor(fg, a), "bc": pb.BoundaryCondition(fg), "ambient_dimension": 3})))
+        it = net.interfaces[k]
+        intfs.append(MdInterface(0, k + 1, it["mortar_to_primary_int"], it["primary_to_mortar_avg"],
+                                 it["mortar_to_secondary_int"], it["secondary_to_mortar_avg"],
+                                 np.full(it["cell_volumes"].size, kn), it["cell_volumes"], np.full(fg.num_cells, a)))  # specific volume of the
+        #                                             interface = that of the higher-dimensional neighbour = 1
+    prob = MixedDimensionalFlow(subs, intfs)
+    prob.discretize()
+    J, b = prob.assemble_host()
+    x = spla.spsolve(J.tocsc(), b)
+    ps, _ = prob.split(x)
+    off = 0
+    for sd in sds:
+        pref = xref[off:off + sd.num_cells]
+        off += sd.num_cells
+        cm = None
+        for cand in [m] + net.fractures:        # the reference may list the fractures in another order
+            if cand.dim == sd.dim and np.allclose(np.sort(cand.cell_centers[0]), np.sort(sd.cell_centers[0])):
+                cm, mine = cand.cell_centers, ps[([m] + net.fractures).index(cand)]
+        assert cm is not None
+        key_m = np.round(cm * 1e6).astype(np.int64)
+        key_r = np.round(sd.cell_centers * 1e6).astype(np.int64)
+        om, orr = np.lexsort(key_m), np.lexsort(key_r)
+        assert np.array_equal(key_m[:, om], key_r[:, orr])
+        assert np.abs(mine[om] - pref[orr]).max() <= 1e-9 * np.abs(xref).max()

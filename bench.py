@@ -231,6 +231,104 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+
+def md_network_problem(kind, dims, n_fractures=10, aperture=1e-3, normal_permeability=1.0, seed=0):
+    """BASELINE config[1]'s shape: a 3-D grid of the workload's kind cut by ``n_fractures`` disjoint planar fractures
+    (``porepy_b200.mdgrid``), conductive fractures, Dirichlet pressure on two sides.  Returns the
+    ``MixedDimensionalFlow`` problem and a description."""
+    import porepy_b200 as pb
+    from porepy_b200 import mdgrid
+    from porepy_b200.mdflow import MdInterface, MdSubdomain, MixedDimensionalFlow
+    g = pb.structured_tet_grid(dims) if kind == "tet" else pb.cart_grid_3d(dims)
+    n = int(dims[0])
+    h = 1.0 / n
+    lo, hi = round(0.1 * n) * h, round(0.9 * n) * h
+    planes = np.unique(np.round(np.linspace(0.08, 0.92, n_fractures) * n).astype(int))
+    planes = planes[(planes > 0) & (planes < n)]
+    sets = [mdgrid.faces_on_rectangle(g, 0, p * h, (lo, lo), (hi, hi)) for p in planes]
+    net = mdgrid.split_fractures(g, [s for s in sets if s.size])
+    m = net.matrix
+    rng = np.random.default_rng(seed)
+    west = np.flatnonzero(m.face_centers[0] < 1e-12)
+    east = np.flatnonzero(m.face_centers[0] > 1 - 1e-12)
+    bcv = np.zeros(m.num_faces)
+    bcv[west] = 1.0
+    k3 = pb.SecondOrderTensor(1 + rng.random(m.num_cells), 1 + rng.random(m.num_cells), 1 + rng.random(m.num_cells))
+    bc3 = pb.BoundaryCondition(m)
+    bc3.is_neu[west] = bc3.is_neu[east] = False
+    bc3.is_dir[west] = bc3.is_dir[east] = True
+    subs = [MdSubdomain(m, pb.initialize_data({}, "flow", {"second_order_tensor": k3, "bc": bc3}), bcv)]
+    intfs = []
+    for j, fg in enumerate(net.fractures):
+        kf = pb.SecondOrderTensor(aperture * 1e4 * (1 + rng.random(fg.num_cells)))   # tangential k x specific volume
+        subs.append(MdSubdomain(fg, pb.initialize_data({}, "flow", {"second_order_tensor": kf, "bc": pb.BoundaryCondition(fg),
+                                                                    "ambient_dimension": 3})))
+        it = net.interfaces[j]
+        intfs.append(MdInterface(0, j + 1, it["mortar_to_primary_int"], it["primary_to_mortar_avg"],
+                                 it["mortar_to_secondary_int"], it["secondary_to_mortar_avg"],
+                                 np.full(it["cell_volumes"].size, normal_permeability), it["cell_volumes"],
+                                 np.full(fg.num_cells, aperture)))
+    prob = MixedDimensionalFlow(subs, intfs)
+    desc = {"matrix_cells": int(m.num_cells), "fractures": len(net.fractures),
+            "fracture_cells": int(sum(f.num_cells for f in net.fractures)),
+            "mortar_cells": int(sum(i.num_cells for i in intfs)), "dofs": int(prob.num_dofs),
+            "aperture": aperture, "normal_permeability": normal_permeability}
+    return prob, desc
+
+
+def md_network_block(kind, dims, solve=True):
+    """Mixed-dimensional flow through the operator API and the device AD chain (row g1): every subdomain by
+    ``pb.Mpfa.discretize`` from host arrays, the coupled Jacobian by SpGEMM / block concatenation on the device, then a
+    Jacobi-BiCGStab solve.  Wall-clock seconds with device synchronisation on both sides of every stage."""
+    import torch
+    from porepy_b200 import krylov as kr
+    t0 = time.perf_counter()
+    prob, desc = md_network_problem(kind, dims)
+    desc["mesh_seconds_host"] = time.perf_counter() - t0
+    out = {"problem": desc, "calls": []}
+    J = rhs = None
+    for rep in range(3):                          # first call: plans and pools are cold
+        for s in prob.subdomains:
+            s.data.pop("discretization_matrices", None)
+        J = rhs = None
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        prob.discretize()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        J, rhs = prob.assemble()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        out["calls"].append({"discretize_s": t1 - t0, "assemble_s": t2 - t1})
+    last = out["calls"][-1]
+    cells = desc["matrix_cells"] + desc["fracture_cells"]
+    out.update(jacobian_nnz=int(J.nnz), jacobian_rows=int(J.shape[0]),
+               seconds_per_assembly=last["discretize_s"] + last["assemble_s"],
+               cells_per_s=cells / (last["discretize_s"] + last["assemble_s"]),
+               matrix_d2h_bytes=0,
+               what="host arrays -> MPFA on the 3-D grid and every fracture plane (operator API) -> coupled Jacobian and "
+                    "right-hand side resident on the device")
+    ms = J.bench(20)
+    out["spmv"] = {"ms": ms, "achieved_GBs": J.algorithmic_bytes() / (ms * 1e-3) / 1e9}
+    if solve:
+        n = J.shape[0]
+        diag = J.diagonal()
+        loc = kr.LocalSystem(0, 1, np.arange(n), np.zeros(0, np.int64), J, [0], [np.zeros(0, np.int64)])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x, info = kr.solve_local(loc, rhs, diag_own=diag, tol=1e-8, maxiter=4000)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        res = rhs - (J @ x)
+        ps, lam = prob.split(x.cpu().numpy())
+        out["solve"] = {"preconditioner": "Jacobi", "tol": 1e-8, "iterations": int(info["iterations"]),
+                        "converged": bool(info["converged"]), "breakdown": bool(info.get("breakdown", False)),
+                        "seconds": dt, "true_relres": float(torch.linalg.vector_norm(res) / torch.linalg.vector_norm(rhs)),
+                        "pressure_range_matrix": [float(ps[0].min()), float(ps[0].max())],
+                        "interface_flux_abs_sum": float(sum(np.abs(v).sum() for v in lam))}
+    return out
+
+
 def pinned_copy(a):
     """Page-locked copy of a host array (the e2e inputs are read by H2D copies at full PCIe rate)."""
     from porepy_b200 import _lib
@@ -268,6 +366,7 @@ def main():
     ap.add_argument("--no-spmv", action="store_true")
     ap.add_argument("--no-krylov", action="store_true")
     ap.add_argument("--no-mech-solve", action="store_true", help="skip the block-Jacobi solve of the mechanics system")
+    ap.add_argument("--no-md-network", action="store_true", help="skip the mixed-dimensional fracture-network extra (N = 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -660,6 +759,13 @@ def main():
             spmv[name] = {"nrows": int(dA.shape[0]), "nnz": int(dA.nnz), "ms": ms, "bound": "hbm", "achieved": gbs,
                           "peak": peak, "unit": "GB/s", "frac": gbs / peak}
         del kk
+    # ---- N = 1 extra: a 10-fracture mixed-dimensional network of the workload's size (BASELINE config[1])
+    md = None
+    if world == 1 and not args.no_md_network:
+        try:
+            md = md_network_block(kind, dims)
+        except Exception as e:     # the extra must never cost the bench line
+            md = {"error": f"{type(e).__name__}: {e}"}
     # ---- CPU baseline: the unmodified reference on a bounded sample of the same kind of mesh
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -680,7 +786,7 @@ def main():
                    "ms_mpfa": ms_mpfa / args.steps, "ms_mpsa": ms_mpsa / args.steps,
                    "wall_ms_per_step": wall_ms / args.steps},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-        "spmv": spmv, "krylov": krylov, "cpu_baseline": cpu,
+        "spmv": spmv, "krylov": krylov, "md_network": md, "cpu_baseline": cpu,
     }
     emit(json.dumps(line))
     if dist is not None:

@@ -77,8 +77,10 @@ def split_fractures(g: Grid, fracture_faces) -> FractureNetwork:
     # ---- 2. split the nodes: around a fracture node, cells connected through non-fracture faces share a copy
     fip, fix = g.face_nodes.indptr, g.face_nodes.indices
     fnode = np.zeros(nn, bool)
-    for f in all_ff:
-        fnode[fix[fip[f]:fip[f + 1]]] = True
+    if all_ff.size:
+        cnt_f = np.diff(fip)[all_ff]
+        pos = np.repeat(fip[all_ff], cnt_f) + (np.arange(cnt_f.sum()) - np.repeat(np.cumsum(cnt_f) - cnt_f, cnt_f))
+        fnode[fix[pos]] = True
     # (new face row, cell, node) triples restricted to fracture nodes
     cnt = np.diff(fip)[orig_face[rows]]
     t_face = np.repeat(rows, cnt)

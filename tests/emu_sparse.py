@@ -94,3 +94,15 @@ def install(monkeypatch):
     monkeypatch.setattr(ad, "DeviceCsr", HostCsr)
     monkeypatch.setattr(ad, "as_device_csr", as_csr)
     monkeypatch.setattr(ad, "device_vector", vec)
+
+
+def _bench(self, reps=1):
+    return 1.0
+
+
+def _algorithmic_bytes(self):
+    return 12 * self.nnz + 20 * self.shape[0]
+
+
+HostCsr.bench = _bench
+HostCsr.algorithmic_bytes = _algorithmic_bytes

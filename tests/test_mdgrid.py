@@ -125,3 +125,31 @@ def test_md_problem_on_synthetic_network_gpu(kind):
     Jh, bh = prob.assemble_host()
     assert abs(J.to_scipy() - Jh).max() <= 1e-12 * abs(Jh).max()
     assert np.abs(rhs.cpu().numpy() - bh).max() <= 1e-12 * np.abs(bh).max()
+
+
+@pytest.mark.parametrize("kind", ["tet", "cart"])
+def test_bench_md_network_block_host_build(kind, host_build, monkeypatch):
+    """The mixed-dimensional extra of bench.py on a small lattice (host build, scipy stand-in for the device algebra;
+    the Krylov leg needs the device)."""
+    import os
+    import sys
+    import torch
+    import emu_sparse
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    emu_sparse.install(monkeypatch)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    real_zeros = torch.zeros
+    monkeypatch.setattr(torch, "zeros", lambda *a, **k: real_zeros(*a, **{**k, "device": "cpu"}))
+    out = bench.md_network_block(kind, (10, 10, 10), solve=False)
+    d = out["problem"]
+    assert d["fractures"] >= 8 and d["mortar_cells"] == 2 * d["fracture_cells"]
+    assert out["jacobian_rows"] == d["dofs"] == d["matrix_cells"] + d["fracture_cells"] + d["mortar_cells"]
+    assert len(out["calls"]) == 3 and out["cells_per_s"] > 0
+    prob, _ = bench.md_network_problem(kind, (10, 10, 10))
+    prob.discretize()
+    J, b = prob.assemble_host()
+    x = spla.spsolve(J.tocsc(), b)
+    ps, lam = prob.split(x)
+    assert 0.0 <= ps[0].min() and ps[0].max() <= 1.0 + 1e-12          # discrete maximum principle (K diagonal)
+    assert sum(np.abs(v).sum() for v in lam) > 0

@@ -61,17 +61,3 @@ def test_interfaces_must_couple_adjacent_dimensions():
     it.primary, it.secondary = it.secondary, it.primary
     with pytest.raises(ValueError):
         MixedDimensionalFlow(prob.subdomains, [it])
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", CASES)
-def test_md_jacobian_gpu(name):
-    import torch
-    prob, Jref, bref, xref = load_mdflow(name)
-    prob.discretize()
-    J, rhs = prob.assemble()
-    _check(J.to_scipy(), rhs.cpu().numpy(), Jref, bref, xref)
-    Jh, bh = prob.assemble_host()
-    assert abs(J.to_scipy() - Jh).max() <= 1e-12 * abs(Jh).max()
-    _, r = prob.assemble(torch.as_tensor(xref, device="cuda"))
-    assert float(r.abs().max()) <= 1e-9 * np.abs(bref).max()

@@ -116,17 +116,6 @@ def test_pressure_linear_along_the_fractures_is_reproduced(kind, host_build):
     assert max(np.abs(v).max() for v in lam) < 1e-9
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("kind", ["hex", "tet"])
-def test_md_problem_on_synthetic_network_gpu(kind):
-    prob = problem(network(kind, n=6)[2], value=lambda x: 1.0 + x[1] - 2.0 * x[2])
-    prob.discretize()
-    J, rhs = prob.assemble()
-    Jh, bh = prob.assemble_host()
-    assert abs(J.to_scipy() - Jh).max() <= 1e-12 * abs(Jh).max()
-    assert np.abs(rhs.cpu().numpy() - bh).max() <= 1e-12 * np.abs(bh).max()
-
-
 @pytest.mark.parametrize("kind", ["tet", "cart"])
 def test_bench_md_network_block_host_build(kind, host_build, monkeypatch):
     """The mixed-dimensional extra of bench.py on a small lattice (host build, scipy stand-in for the device algebra;

@@ -170,6 +170,7 @@ struct pb_plan {
     DevBuf fn_indptr, node_sc_ptr, sc_cell, node_sf_ptr, sf_face, sf_sides, sf_bloc, slot_sf, node_nb,
         sc_ncn, posfc_ptr, posfb_ptr, poscc_ptr, poscb_ptr, pos_fc, pos_fb, pos_cc, pos_cb, fc_indptr,
         fb_indptr, cc_indptr, cb_indptr, pat_idx[4], nbf_ptr, nbf_idx, cn_ptr, cn_idx, face_cells;
+    DevBuf cf_ip, cf_ix, cf_sg;    // cell -> faces (CSC of cell_faces) kept from the device topology build: gather form of div
     int64_t pat_rows[4] = {0, 0, 0, 0}, pat_cols[4] = {0, 0, 0, 0}, pat_nnz[4] = {0, 0, 0, 0};
     // geometry
     DevBuf nodes, fnorm, fcent, farea, ccent, cvol;

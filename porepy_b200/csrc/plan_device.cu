@@ -371,5 +371,8 @@ int pb_build_device_topology_(pb_plan *p, int nd, int64_t nc, int64_t nf, int64_
     PD_TRY(cudaMemcpyAsync(hflags, flags.p, sizeof(hflags), cudaMemcpyDeviceToHost, st));
     PD_TRY(cudaStreamSynchronize(st));
     if (hflags[2]) { err = "face with more than two neighbouring cells"; return PB_EINVAL; }
+    p->cf_ip = std::move(cf_ip);
+    p->cf_ix = std::move(cf_ix);
+    p->cf_sg = std::move(cf_da);
     return PB_OK;
 }

@@ -278,10 +278,9 @@ def md_network_problem(kind, dims, n_fractures=10, aperture=1e-3, normal_permeab
 
 def md_network_block(kind, dims, solve=True):
     """Mixed-dimensional flow through the operator API and the device AD chain (row g1): every subdomain by
-    ``pb.Mpfa.discretize`` from host arrays, the coupled Jacobian by SpGEMM / block concatenation on the device, then a
-    Jacobi-BiCGStab solve.  Wall-clock seconds with device synchronisation on both sides of every stage."""
+    ``pb.Mpfa.discretize`` from host arrays, the coupled Jacobian block by block on the device (and once through the AD
+    chain), then BiCGStab on the pressure Schur complement.  Wall-clock seconds with device synchronisation on both sides of every stage."""
     import torch
-    from porepy_b200 import krylov as kr
     t0 = time.perf_counter()
     prob, desc = md_network_problem(kind, dims)
     desc["mesh_seconds_host"] = time.perf_counter() - t0
@@ -310,20 +309,26 @@ def md_network_block(kind, dims, solve=True):
                     "right-hand side resident on the device")
     ms = J.bench(20)
     out["spmv"] = {"ms": ms, "achieved_GBs": J.algorithmic_bytes() / (ms * 1e-3) / 1e9}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    Jad, _ = prob.assemble_ad()
+    torch.cuda.synchronize()
+    out["assemble_ad_s"] = time.perf_counter() - t0      # the reference's evaluation order (forward-mode AD chain)
+    out["assemble_ad_nnz"] = int(Jad.nnz)
+    del Jad
     if solve:
-        n = J.shape[0]
-        diag = J.diagonal()
-        loc = kr.LocalSystem(0, 1, np.arange(n), np.zeros(0, np.int64), J, [0], [np.zeros(0, np.int64)])
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        x, info = kr.solve_local(loc, rhs, diag_own=diag, tol=1e-8, maxiter=4000)
+        x, info = prob.solve(tol=1e-8, maxiter=4000)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         res = rhs - (J @ x)
         ps, lam = prob.split(x.cpu().numpy())
-        out["solve"] = {"preconditioner": "Jacobi", "tol": 1e-8, "iterations": int(info["iterations"]),
-                        "converged": bool(info["converged"]), "breakdown": bool(info.get("breakdown", False)),
-                        "seconds": dt, "true_relres": float(torch.linalg.vector_norm(res) / torch.linalg.vector_norm(rhs)),
+        out["solve"] = {"method": info.get("method"), "preconditioner": "Jacobi on the Schur complement's diagonal",
+                        "interface_block": f"{info.get('sweeps')} Jacobi sweeps per application of D^-1",
+                        "tol": 1e-8, "iterations": int(info["iterations"]), "converged": bool(info["converged"]),
+                        "breakdown": bool(info.get("breakdown", False)), "seconds": dt,
+                        "true_relres_full_system": float(torch.linalg.vector_norm(res) / torch.linalg.vector_norm(rhs)),
                         "pressure_range_matrix": [float(ps[0].min()), float(ps[0].max())],
                         "interface_flux_abs_sum": float(sum(np.abs(v).sum() for v in lam))}
     return out

@@ -47,11 +47,12 @@ def test_md_jacobian_host_build(name, host_build):
     prob, Jref, bref, xref = load_mdflow(name)
     prob.discretize()
     _check(*prob.assemble_host(), Jref, bref, xref)                      # block formulas
-    J, rhs = prob.assemble(torch.zeros(prob.num_dofs, dtype=torch.float64))  # the AD chain
-    _check(J.to_scipy(), rhs.numpy(), Jref, bref, xref)
-    # linear problem: the residual at the reference solution vanishes
-    _, r = prob.assemble(torch.as_tensor(xref))
-    assert np.abs(r.numpy()).max() <= 1e-9 * np.abs(bref).max()
+    for assemble in (prob.assemble_ad, prob.assemble):                   # the AD chain; the device block assembly
+        J, rhs = assemble(torch.zeros(prob.num_dofs, dtype=torch.float64))
+        _check(J.to_scipy(), rhs.numpy(), Jref, bref, xref)
+        # linear problem: the residual at the reference solution vanishes
+        _, r = assemble(torch.as_tensor(xref))
+        assert np.abs(r.numpy()).max() <= 1e-9 * np.abs(bref).max()
 
 
 def test_interfaces_must_couple_adjacent_dimensions():
@@ -61,3 +62,14 @@ def test_interfaces_must_couple_adjacent_dimensions():
     it.primary, it.secondary = it.secondary, it.primary
     with pytest.raises(ValueError):
         MixedDimensionalFlow(prob.subdomains, [it])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_schur_solve_host_build(name, host_build):
+    """``MixedDimensionalFlow.solve``: interface fluxes eliminated (Jacobi sweeps for the interface block), BiCGStab on
+    the pressure Schur complement -- against the reference's converged solution."""
+    prob, Jref, bref, xref = load_mdflow(name)
+    prob.discretize()
+    x, info = prob.solve(tol=1e-11)
+    assert info["converged"] and info["true_relres"] < 1e-9, info
+    assert np.linalg.norm(x.numpy() - xref) <= 1e-8 * np.linalg.norm(xref)

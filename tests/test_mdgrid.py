@@ -119,7 +119,7 @@ def test_pressure_linear_along_the_fractures_is_reproduced(kind, host_build):
 @pytest.mark.parametrize("kind", ["tet", "cart"])
 def test_bench_md_network_block_host_build(kind, host_build, monkeypatch):
     """The mixed-dimensional extra of bench.py on a small lattice (host build, scipy stand-in for the device algebra;
-    the Krylov leg needs the device)."""
+    BiCGStab on the Schur complement through the torch recurrence)."""
     import os
     import sys
     import torch
@@ -130,7 +130,8 @@ def test_bench_md_network_block_host_build(kind, host_build, monkeypatch):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     real_zeros = torch.zeros
     monkeypatch.setattr(torch, "zeros", lambda *a, **k: real_zeros(*a, **{**k, "device": "cpu"}))
-    out = bench.md_network_block(kind, (10, 10, 10), solve=False)
+    out = bench.md_network_block(kind, (10, 10, 10), solve=True)
+    assert out["solve"]["converged"] and out["solve"]["true_relres_full_system"] < 1e-7, out["solve"]
     d = out["problem"]
     assert d["fractures"] >= 8 and d["mortar_cells"] == 2 * d["fracture_cells"]
     assert out["jacobian_rows"] == d["dofs"] == d["matrix_cells"] + d["fracture_cells"] + d["mortar_cells"]

@@ -368,9 +368,10 @@ def test_mixed_dimensional_flow_from_a_porepy_mdg(pp, emu_plan, monkeypatch):
     prob.discretize()
     J, b = prob.assemble_host()
     assert abs(J - Jref).max() <= 1e-10 * abs(Jref).max() and np.abs(b - bref).max() <= 1e-10 * np.abs(bref).max()
-    Jd, bd = prob.assemble(torch.zeros(prob.num_dofs, dtype=torch.float64))
-    assert abs(Jd.to_scipy() - Jref).max() <= 1e-10 * abs(Jref).max()
-    assert np.abs(bd.numpy() - bref).max() <= 1e-10 * np.abs(bref).max()
+    for assemble in (prob.assemble_ad, prob.assemble):
+        Jd, bd = assemble(torch.zeros(prob.num_dofs, dtype=torch.float64))
+        assert abs(Jd.to_scipy() - Jref).max() <= 1e-10 * abs(Jref).max()
+        assert np.abs(bd.numpy() - bref).max() <= 1e-10 * np.abs(bref).max()
 
 
 def test_synthetic_fracture_network_matches_the_reference_mesher(pp, emu_plan):

@@ -15,12 +15,13 @@ def test_md_jacobian_gpu(name):
     import torch
     prob, Jref, bref, xref = load_mdflow(name)
     prob.discretize()
-    J, rhs = prob.assemble()
-    _check(J.to_scipy(), rhs.cpu().numpy(), Jref, bref, xref)
     Jh, bh = prob.assemble_host()
-    assert abs(J.to_scipy() - Jh).max() <= 1e-12 * abs(Jh).max()
-    _, r = prob.assemble(torch.as_tensor(xref, device="cuda"))
-    assert float(r.abs().max()) <= 1e-9 * np.abs(bref).max()
+    for assemble in (prob.assemble_ad, prob.assemble):
+        J, rhs = assemble()
+        _check(J.to_scipy(), rhs.cpu().numpy(), Jref, bref, xref)
+        assert abs(J.to_scipy() - Jh).max() <= 1e-12 * abs(Jh).max()
+        _, r = assemble(torch.as_tensor(xref, device="cuda"))
+        assert float(r.abs().max()) <= 1e-9 * np.abs(bref).max()
 
 
 @pytest.mark.gpu
@@ -28,24 +29,23 @@ def test_md_jacobian_gpu(name):
 def test_md_problem_on_synthetic_network_gpu(kind):
     prob = problem(network(kind, n=6)[2], value=lambda x: 1.0 + x[1] - 2.0 * x[2])
     prob.discretize()
-    J, rhs = prob.assemble()
     Jh, bh = prob.assemble_host()
-    assert abs(J.to_scipy() - Jh).max() <= 1e-12 * abs(Jh).max()
-    assert np.abs(rhs.cpu().numpy() - bh).max() <= 1e-12 * np.abs(bh).max()
+    for assemble in (prob.assemble_ad, prob.assemble):
+        J, rhs = assemble()
+        assert abs(J.to_scipy() - Jh).max() <= 1e-12 * abs(Jh).max()
+        assert np.abs(rhs.cpu().numpy() - bh).max() <= 1e-12 * np.abs(bh).max()
 
 
 @pytest.mark.gpu
-def test_md_solve_on_device():
-    """Jacobi-BiCGStab (csrc/krylov.cu) on the coupled system of the synthetic hexahedral network."""
-    import torch
+@pytest.mark.parametrize("kind", ["hex", "tet"])
+def test_md_solve_on_device(kind):
+    """``MixedDimensionalFlow.solve`` (BiCGStab on the pressure Schur complement, device SpMVs) against a direct solve
+    of the coupled system."""
     import scipy.sparse.linalg as spla
-    from porepy_b200 import krylov as kr
-    prob = problem(network("hex", n=8)[2], a=1e-2, kn=1.0, value=lambda x: 1.0 + x[0])
+    prob = problem(network(kind, n=8)[2], a=1e-3, kn=1.0, value=lambda x: 1.0 + x[0])
     prob.discretize()
+    x, info = prob.solve(tol=1e-11)
+    assert info["converged"] and info["true_relres"] < 1e-9, info
     J, rhs = prob.assemble()
-    n = J.shape[0]
-    loc = kr.LocalSystem(0, 1, np.arange(n), np.zeros(0, np.int64), J, [0], [np.zeros(0, np.int64)])
-    x, info = kr.solve_local(loc, rhs, diag_own=J.diagonal(), tol=1e-10, maxiter=3000)
-    assert info["converged"], info
     xh = spla.spsolve(J.to_scipy().tocsc(), rhs.cpu().numpy())
     assert np.linalg.norm(x.cpu().numpy() - xh) <= 1e-7 * np.linalg.norm(xh)

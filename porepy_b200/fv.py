@@ -654,9 +654,11 @@ def vector_bc_codes(bc, nd: int, nf: int):
     return codes, robw
 
 
-def vector_bc_basis(bc, nd: int):
-    """``bc.basis`` (nd, nd, nf) when it is not the identity everywhere, else None
-    (_fvutils.py:765-945: boundary conditions given in a rotated coordinate system)."""
+def vector_bc_basis(bc, nd: int, codes=None):
+    """``bc.basis`` (nd, nd, nf) when it is not the identity on some boundary face, else None
+    (_fvutils.py:765-945: boundary conditions given in a rotated coordinate system).  The basis acts on the equations
+    of boundary sub-faces only, so with the (nd, nf) condition ``codes`` of ``vector_bc_codes`` the test reads the
+    flagged faces instead of all of the (nd, nd, nf) array (40 ms at 2 * 10^6 faces, in front of every MPSA call)."""
     basis = getattr(bc, "basis", None)
     if basis is None:
         return None
@@ -668,8 +670,10 @@ def vector_bc_basis(bc, nd: int):
     if sub.strides[-1] == 0:        # one matrix broadcast over the faces (e.g. a restricted shard condition)
         if np.array_equal(sub[:, :, :1], eye):
             return None
-    elif np.array_equal(sub, np.broadcast_to(eye, sub.shape)):
-        return None   # the identity on every face (exact test, one pass; anything else IS a rotated basis)
+    else:
+        probe = sub if codes is None else sub[:, :, np.flatnonzero(np.asarray(codes).any(axis=0))]
+        if np.array_equal(probe, np.broadcast_to(eye, probe.shape)):
+            return None   # the identity on every (boundary) face: exact test; anything else IS a rotated basis
     return np.ascontiguousarray(b[:nd, :nd])
 
 
@@ -972,7 +976,7 @@ class Mpsa(_Base):
         codes, robw = vector_bc_codes(bc, sd.dim, sd.num_faces)
         t1 = time.perf_counter()
         plan.mpsa_upload(constit.values, codes, robw, float(eta), list(alphas.values()))
-        plan.mpsa_set_basis(vector_bc_basis(bc, sd.dim))
+        plan.mpsa_set_basis(vector_bc_basis(bc, sd.dim, codes))
         t2 = time.perf_counter()
         ms = plan.mpsa_assemble()
         t3 = time.perf_counter()

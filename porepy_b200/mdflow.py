@@ -193,7 +193,7 @@ class MixedDimensionalFlow:
         blocks as products of the mortar projections (a few non-zeros per row) with the device-resident boundary
         matrices, one block concatenation (``pb_csr_bmat``).  Right-hand side at the state ``x``: ``b - J x``."""
         import torch
-        blocks, rhs = self._device_blocks()
+        blocks, rhs, _ = self._device_blocks()
         J = ad.DeviceCsr.bmat(blocks)
         b = torch.cat(rhs)
         if x is not None:
@@ -201,18 +201,19 @@ class MixedDimensionalFlow:
         return J, b
 
     def _device_blocks(self):
-        """(2-D list of ``DeviceCsr`` / None, list of right-hand side pieces) of the coupled system."""
+        """(2-D list of ``DeviceCsr`` / None over the block grid [subdomains..., all interfaces], right-hand side pieces,
+        block sizes).  All interfaces form ONE block row / column (their unknowns are consecutive in the global
+        ordering), so every primary subdomain costs one set of SpGEMMs against its boundary matrices, however many
+        fractures touch it: the projections of its interfaces are stacked on the host first (a few non-zeros per row)."""
         from .params import PARAMETERS
-        nsd, n = len(self.subdomains), len(self.sizes)
+        nsd = len(self.subdomains)
         csr, dev, D = ad.as_device_csr, ad.device_vector, ad.DeviceCsr
+        nm = int(self.offsets[-1] - self.offsets[nsd])
+        lam0 = self.offsets[nsd:] - self.offsets[nsd]            # start of every interface inside the interface block
+        bsizes = self.sizes[:nsd] + [nm]
+        n = nsd + (1 if self.interfaces else 0)
         blocks = [[None] * n for _ in range(n)]
         rhs = [None] * n
-        cache = {}
-
-        def mat(i, key):                     # one device copy per subdomain matrix, shared by its interfaces
-            if (i, key) not in cache:
-                cache[(i, key)] = csr(self._matrices(i)[key])
-            return cache[(i, key)]
 
         def add(i, j, m):
             blocks[i][j] = m if blocks[i][j] is None else blocks[i][j] + m
@@ -224,23 +225,54 @@ class MixedDimensionalFlow:
                 add(i, i, csr(a))
                 r = r + dev(b)
             rhs[i] = r
-        by_primary = {}
-        for k, it in enumerate(self.interfaces):
-            by_primary.setdefault(it.primary, []).append(k)
-        for j, it in enumerate(self.interfaces):
-            jj, ih, il = nsd + j, it.primary, it.secondary
-            c = sps.diags(it.coefficient())
-            cp2m = csr(c @ sps.csr_matrix(it.primary_to_mortar_avg))
-            add(ih, jj, csr(self._div(ih)) @ (mat(ih, "bound_flux") @ csr(it.mortar_to_primary_int)))
-            add(il, jj, csr(-sps.csr_matrix(it.mortar_to_secondary_int)))
-            add(jj, ih, -(cp2m @ mat(ih, "bound_pressure_cell")))
-            add(jj, il, csr(c @ sps.csr_matrix(it.secondary_to_mortar_avg)))
-            t = cp2m @ mat(ih, "bound_pressure_face")
-            rhs[jj] = t @ dev(self._bc(ih))
-            for k in by_primary[ih]:
-                blk = -(t @ csr(self.interfaces[k].mortar_to_primary_int))
-                add(jj, nsd + k, blk + D.identity(it.num_cells) if k == j else blk)
-        return blocks, rhs
+        if not self.interfaces:
+            return blocks, rhs, bsizes
+
+        def stacked(select, shape_of, transpose_rows):
+            """Host matrix with the pieces ``select(j)`` of the interfaces placed at their offsets of the interface
+            block: side by side (columns) or on top of each other (rows); interfaces without a piece leave zeros."""
+            rows, cols, vals = [], [], []
+            n_other = shape_of
+            for j, it in enumerate(self.interfaces):
+                m = select(j, it)
+                if m is None:
+                    continue
+                m = sps.coo_matrix(m)
+                if transpose_rows:          # (interface block) x (entity): rows offset
+                    rows.append(m.row + lam0[j]); cols.append(m.col)
+                else:                       # (entity) x (interface block): columns offset
+                    rows.append(m.row); cols.append(m.col + lam0[j])
+                vals.append(m.data)
+            if not vals:
+                return None
+            shape = (nm, n_other) if transpose_rows else (n_other, nm)
+            return sps.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=shape)
+        rhs_l = None
+        d_block = D.identity(nm)
+        for i, s in enumerate(self.subdomains):
+            nf_i, nc_i = int(s.sd.num_faces), int(s.sd.num_cells)
+            m2s = stacked(lambda j, it: it.mortar_to_secondary_int if it.secondary == i else None, nc_i, False)
+            cs2m = stacked(lambda j, it: sps.diags(it.coefficient()) @ sps.csr_matrix(it.secondary_to_mortar_avg)
+                           if it.secondary == i else None, nc_i, True)
+            if m2s is not None:
+                add(i, nsd, csr(-m2s))
+                add(nsd, i, csr(cs2m))
+            m2p = stacked(lambda j, it: it.mortar_to_primary_int if it.primary == i else None, nf_i, False)
+            if m2p is None:
+                continue
+            cp2m = csr(stacked(lambda j, it: sps.diags(it.coefficient()) @ sps.csr_matrix(it.primary_to_mortar_avg)
+                               if it.primary == i else None, nf_i, True))
+            M = self._matrices(i)
+            m2p = csr(m2p)
+            add(i, nsd, csr(self._div(i)) @ (csr(M["bound_flux"]) @ m2p))
+            add(nsd, i, -(cp2m @ csr(M["bound_pressure_cell"])))
+            t = cp2m @ csr(M["bound_pressure_face"])
+            d_block = d_block - (t @ m2p)
+            r = t @ dev(self._bc(i))
+            rhs_l = r if rhs_l is None else rhs_l + r
+        add(nsd, nsd, d_block)
+        rhs[nsd] = rhs_l if rhs_l is not None else dev(np.zeros(nm))
+        return blocks, rhs, bsizes
 
     # ---- solve: interface fluxes eliminated, Krylov on the pressure Schur complement
     def solve(self, tol: float = 1e-8, maxiter: int = 4000, sweeps: int = 16):
@@ -255,18 +287,19 @@ class MixedDimensionalFlow:
         full system in ``info["true_relres"]``."""
         import torch
         from . import krylov
-        nsd, n = len(self.subdomains), len(self.sizes)
+        nsd = len(self.subdomains)
         D_ = ad.DeviceCsr
-        blocks, rhs = self._device_blocks()
+        blocks, rhs, bsizes = self._device_blocks()
+        n = len(bsizes) if self.interfaces else nsd
 
         def sub(rows, cols):
             blk = [[blocks[i][j] for j in cols] for i in rows]
             for a, i in enumerate(rows):           # pb_csr_bmat needs one matrix per block row and column
                 if all(m is None for m in blk[a]):
-                    blk[a][0] = D_(sps.csr_matrix((self.sizes[i], self.sizes[cols[0]])))
+                    blk[a][0] = D_(sps.csr_matrix((bsizes[i], bsizes[cols[0]])))
             for b_, j in enumerate(cols):
                 if all(blk[a][b_] is None for a in range(len(rows))):
-                    blk[0][b_] = D_(sps.csr_matrix((self.sizes[rows[0]], self.sizes[j])))
+                    blk[0][b_] = D_(sps.csr_matrix((bsizes[rows[0]], bsizes[j])))
             return D_.bmat(blk)
         P, L = list(range(nsd)), list(range(nsd, n))
         if not L:

@@ -81,6 +81,15 @@ def split_fractures(g: Grid, fracture_faces) -> FractureNetwork:
         cnt_f = np.diff(fip)[all_ff]
         pos = np.repeat(fip[all_ff], cnt_f) + (np.arange(cnt_f.sum()) - np.repeat(np.cumsum(cnt_f) - cnt_f, cnt_f))
         fnode[fix[pos]] = True
+    # fractures that touch would need their intersection line as a 1-D subdomain: not generated here
+    owner = np.full(nn, -1, np.int64)
+    for k, F in enumerate(fracture_faces):
+        cf_ = np.diff(fip)[F]
+        pk = np.repeat(fip[F], cf_) + (np.arange(cf_.sum()) - np.repeat(np.cumsum(cf_) - cf_, cf_))
+        nk = np.unique(fix[pk])
+        if np.any((owner[nk] >= 0) & (owner[nk] != k)):
+            raise ValueError("fractures must not share nodes (intersecting fractures are not supported by this generator)")
+        owner[nk] = k
     # (new face row, cell, node) triples restricted to fracture nodes
     cnt = np.diff(fip)[orig_face[rows]]
     t_face = np.repeat(rows, cnt)

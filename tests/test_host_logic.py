@@ -115,8 +115,14 @@ def test_bc_encoding_and_error_behaviour():
         vector_bc_codes(bc, 3, g.num_faces)
     from porepy_b200.fv import vector_bc_basis
     assert vector_bc_basis(vb, 3) is None            # identity everywhere
+    assert vector_bc_basis(vb, 3, vcodes) is None
+    interior = np.setdiff1d(np.arange(g.num_faces), bf)[0]
+    vb.basis[0, 1, interior] = 0.5                   # a basis entry on an interior face never enters an equation:
+    assert vector_bc_basis(vb, 3, vcodes) is None    # the boundary-only test (what discretize() uses) ignores it
+    vb.basis[0, 1, interior] = 0.0
     vb.basis[0, 1, bf[0]] = 0.5
     assert vector_bc_basis(vb, 3).shape == (3, 3, g.num_faces)
+    assert vector_bc_basis(vb, 3, vcodes).shape == (3, 3, g.num_faces)
 
 
 def test_determine_eta_follows_the_reference_rule():

@@ -74,6 +74,18 @@ def test_split_topology(kind):
     assert int(net.fractures[1].tags["tip_faces"].sum()) == 0
 
 
+def test_touching_fractures_are_refused():
+    g = pb.cart_grid_3d([4, 4, 4])
+    a = mdgrid.faces_on_rectangle(g, 0, 0.5, (0, 0), (1, 1))
+    b = mdgrid.faces_on_rectangle(g, 1, 0.5, (0, 0), (1, 1))
+    with pytest.raises(ValueError, match="share nodes"):
+        mdgrid.split_fractures(g, [a, b])
+    with pytest.raises(ValueError, match="share faces"):
+        mdgrid.split_fractures(g, [a, a])
+    with pytest.raises(ValueError, match="interior"):
+        mdgrid.split_fractures(g, [np.flatnonzero(g.tags["domain_boundary_faces"])[:3]])
+
+
 @pytest.fixture()
 def host_build(monkeypatch):
     from emu_binding import EmuBackedFaceGrid, EmuBackedPlan

@@ -204,6 +204,36 @@ def plugin(pp, allow_reference_fallback: bool = False) -> SimpleNamespace:
         pp.Tpfa, pp.Upwind = RefTpfa, RefUpwind
         pp.UpwindCoupling = RefUpwindCoupling
 
+    def md_flow_from_model(model, keyword=None):
+        """The mixed-dimensional Darcy problem of a prepared single-phase flow model (``pp.SinglePhaseFlow`` after
+        ``prepare_simulation``) as a ``porepy_b200.mdflow.MixedDimensionalFlow``: grids, parameter dictionaries and
+        mortar projections of ``model.mdg`` as they are, boundary data, normal permeability, apertures and specific
+        volumes evaluated from the model's own constitutive laws (models/constitutive_laws.py:203-282, 1032-1076).
+        ``.discretize()`` then runs ``porepy_b200.Mpfa`` on every subdomain and ``.assemble()`` / ``.solve()`` build and
+        solve the coupled Jacobian on the device -- with unit mobility (the model's Jacobian is then state independent)
+        it equals ``model.equation_system.assemble()``."""
+        import numpy as np
+        from .mdflow import MixedDimensionalFlow
+        mdg = model.mdg
+        kw = keyword or model.darcy_keyword
+
+        def evaluated(op, n):
+            v = model.equation_system.evaluate(op)
+            return np.full(n, float(v)) if np.ndim(v) == 0 else np.asarray(v, float)
+
+        def bc_values(sd):
+            bg = mdg.subdomain_to_boundary_grid(sd)
+            if bg is None or bg.num_cells == 0:
+                return np.zeros(sd.num_faces)
+            bc = mdg.subdomain_data(sd)[pp.PARAMETERS][kw]["bc"]
+            proj = bg.projection()
+            return np.where(bc.is_dir, proj.T @ model.bc_values_pressure(bg), proj.T @ model.bc_values_darcy_flux(bg))
+        return MixedDimensionalFlow.from_mdg(
+            mdg, kw, bc_values=bc_values,
+            normal_permeability=lambda it: evaluated(model.normal_permeability([it]), it.num_cells),
+            aperture=lambda sd: evaluated(model.aperture([sd]), sd.num_cells),
+            specific_volume=lambda it: evaluated(model.specific_volume([it]), it.num_cells))
+
     return SimpleNamespace(Mpfa=Mpfa, Mpsa=Mpsa, Biot=Biot, Tpfa=Tpfa, Upwind=Upwind, UpwindCoupling=UpwindCoupling, MpfaAd=MpfaAd, MpsaAd=MpsaAd, BiotAd=BiotAd,
-                           ModelMixin=ModelMixin, install=install, uninstall=uninstall,
+                           ModelMixin=ModelMixin, install=install, uninstall=uninstall, md_flow_from_model=md_flow_from_model,
                            fallback_calls=fallback_calls, gpu_calls=gpu_calls)

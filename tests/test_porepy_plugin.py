@@ -345,24 +345,9 @@ def test_mixed_dimensional_flow_from_a_porepy_mdg(pp, emu_plan, monkeypatch):
     model = Model({"times_to_export": [], "time_manager": pp.TimeManager([0, 1.0], 1.0, constant_dt=True)})
     model.prepare_simulation()
     Jref, bref = model.equation_system.assemble()
-    mdg = model.mdg
-
-    def bc_values(sd):
-        bg = mdg.subdomain_to_boundary_grid(sd)
-        if bg is None or bg.num_cells == 0:
-            return np.zeros(sd.num_faces)
-        bc = mdg.subdomain_data(sd)[pp.PARAMETERS]["flow"]["bc"]
-        proj = bg.projection()
-        return np.where(bc.is_dir, proj.T @ model.bc_values_pressure(bg), proj.T @ model.bc_values_darcy_flux(bg))
-
-    def evaluated(op, n):
-        v = model.equation_system.evaluate(op)
-        return np.full(n, float(v)) if np.ndim(v) == 0 else np.asarray(v, float)
-    prob = MixedDimensionalFlow.from_mdg(
-        mdg, "flow", bc_values=bc_values,
-        normal_permeability=lambda it: evaluated(model.normal_permeability([it]), it.num_cells),
-        aperture=lambda sd: evaluated(model.aperture([sd]), sd.num_cells),
-        specific_volume=lambda it: evaluated(model.specific_volume([it]), it.num_cells))
+    from porepy_b200.porepy_plugin import plugin
+    prob = plugin(pp).md_flow_from_model(model)
+    assert isinstance(prob, MixedDimensionalFlow) and prob.num_dofs == Jref.shape[0]
     for s in prob.subdomains:                       # forget the reference's own discretization
         s.data[pp.DISCRETIZATION_MATRICES]["flow"].clear()
     prob.discretize()
@@ -372,6 +357,12 @@ def test_mixed_dimensional_flow_from_a_porepy_mdg(pp, emu_plan, monkeypatch):
         Jd, bd = assemble(torch.zeros(prob.num_dofs, dtype=torch.float64))
         assert abs(Jd.to_scipy() - Jref).max() <= 1e-10 * abs(Jref).max()
         assert np.abs(bd.numpy() - bref).max() <= 1e-10 * np.abs(bref).max()
+    # ... and the solve (interface fluxes eliminated, BiCGStab on the pressure Schur complement) reproduces the model's
+    # converged state
+    x, info = prob.solve(tol=1e-12)
+    pp.run_time_dependent_model(model, {"prepare_simulation": False})
+    xref = model.equation_system.get_variable_values(iterate_index=0)
+    assert info["converged"] and np.linalg.norm(x.numpy() - xref) <= 1e-8 * np.linalg.norm(xref)
 
 
 def test_synthetic_fracture_network_matches_the_reference_mesher(pp, emu_plan):

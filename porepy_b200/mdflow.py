@@ -286,7 +286,6 @@ class MixedDimensionalFlow:
         csrc/spmv.cu).  Returns (x as a tensor in the global ordering, info) with the TRUE relative residual of the
         full system in ``info["true_relres"]``."""
         import torch
-        from . import krylov
         nsd = len(self.subdomains)
         D_ = ad.DeviceCsr
         blocks, rhs, bsizes = self._device_blocks()
@@ -305,40 +304,8 @@ class MixedDimensionalFlow:
         if not L:
             raise ValueError("no interfaces: solve the subdomain system with porepy_b200.krylov directly")
         A, B, E, Dm = sub(P, P), sub(P, L), sub(L, P), sub(L, L)
-        bp, bl = torch.cat(rhs[:nsd]), torch.cat(rhs[nsd:])
-        dl = ad.device_vector(Dm.diagonal())
-        N = Dm - D_(sps.diags(Dm.diagonal()).tocsr())      # off-diagonal part (explicit zeros on the diagonal)
-        inv_dl = 1.0 / dl
-
-        def dinv(v):
-            y = v * inv_dl
-            for _ in range(sweeps):
-                y = (v - (N @ y)) * inv_dl
-            return y
-        s_diag = ad.device_vector(A.diagonal() - (B @ E.scaled(inv_dl)).diagonal())
-
-        class Schur:
-            dev_csr = None
-
-            def __init__(self):
-                self.torch = torch
-                self.nmatvec = 0
-
-            def matvec(self, v):
-                self.nmatvec += 1
-                return (A @ v) - (B @ dinv(E @ v))
-
-            def dots(self, pairs):
-                return torch.stack([torch.dot(a, b) for a, b in pairs])
-        op = Schur()
-        p, info = krylov.bicgstab(op, bp - (B @ dinv(bl)), tol=tol, maxiter=maxiter, diag_own=s_diag)
-        lam = dinv(bl - (E @ p))
-        x = torch.cat([p, lam])
-        res = torch.cat([bp - (A @ p) - (B @ lam), bl - (E @ p) - (Dm @ lam)])
-        info = dict(info)
-        info.update(true_relres=float(torch.linalg.vector_norm(res) / torch.linalg.vector_norm(torch.cat([bp, bl]))),
-                    sweeps=sweeps, schur_matvecs=op.nmatvec, method="BiCGStab on the pressure Schur complement")
-        return x, info
+        return schur_solve(A, B, E, Dm, torch.cat(rhs[:nsd]), torch.cat(rhs[nsd:]), tol=tol, maxiter=maxiter,
+                           sweeps=sweeps)
 
     # ---- host restatement with scipy (the checker of the tests; materialises the discretization matrices)
     def assemble_host(self):
@@ -382,3 +349,43 @@ class MixedDimensionalFlow:
         x = np.asarray(x)
         parts = [x[self.offsets[k]:self.offsets[k + 1]] for k in range(len(self.sizes))]
         return parts[:len(self.subdomains)], parts[len(self.subdomains):]
+
+
+def schur_solve(A, B, E, Dm, bp, bl, tol: float = 1e-8, maxiter: int = 4000, sweeps: int = 16):
+    """Solve ``[[A, B], [E, D]] [p; lam] = [bp; bl]`` (``DeviceCsr`` blocks, CUDA tensors) by BiCGStab on the pressure
+    Schur complement ``A - B D^-1 E``; see ``MixedDimensionalFlow.solve``.  Returns (cat(p, lam), info)."""
+    import torch
+    from . import krylov
+    D_ = ad.DeviceCsr
+    dl = ad.device_vector(Dm.diagonal())
+    N = Dm - D_(sps.diags(Dm.diagonal()).tocsr())      # off-diagonal part (explicit zeros on the diagonal)
+    inv_dl = 1.0 / dl
+
+    def dinv(v):
+        y = v * inv_dl
+        for _ in range(sweeps):
+            y = (v - (N @ y)) * inv_dl
+        return y
+    s_diag = ad.device_vector(A.diagonal() - (B @ E.scaled(inv_dl)).diagonal())
+
+    class Schur:
+        dev_csr = None
+
+        def __init__(self):
+            self.torch = torch
+            self.nmatvec = 0
+
+        def matvec(self, v):
+            self.nmatvec += 1
+            return (A @ v) - (B @ dinv(E @ v))
+
+        def dots(self, pairs):
+            return torch.stack([torch.dot(a, b) for a, b in pairs])
+    op = Schur()
+    p, info = krylov.bicgstab(op, bp - (B @ dinv(bl)), tol=tol, maxiter=maxiter, diag_own=s_diag)
+    lam = dinv(bl - (E @ p))
+    res = torch.cat([bp - (A @ p) - (B @ lam), bl - (E @ p) - (Dm @ lam)])
+    info = dict(info)
+    info.update(true_relres=float(torch.linalg.vector_norm(res) / torch.linalg.vector_norm(torch.cat([bp, bl]))),
+                sweeps=sweeps, schur_matvecs=op.nmatvec, method="BiCGStab on the pressure Schur complement")
+    return torch.cat([p, lam]), info

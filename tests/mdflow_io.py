@@ -19,6 +19,10 @@ def _csr(d, key):
 
 def load_mdflow(name: str):
     """(MixedDimensionalFlow, reference Jacobian, reference rhs, reference solution)."""
+    return _load_linear_parts(name)
+
+
+def _load_linear_parts(name: str):
     d = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
     subs = []
     for i in range(int(d["num_subdomains"])):
@@ -46,4 +50,26 @@ def load_mdflow(name: str):
                                  _csr(d, p + "primary_to_mortar_avg"), _csr(d, p + "mortar_to_secondary_int"),
                                  _csr(d, p + "secondary_to_mortar_avg"), d[p + "normal_permeability"],
                                  d[p + "cell_volumes"], d[p + "secondary_aperture"]))
-    return MixedDimensionalFlow(subs, intfs, "flow"), _csr(d, "jacobian"), d["rhs"], d["solution"]
+    jac = _csr(d, "jacobian") if "jacobian__data" in d else None
+    return MixedDimensionalFlow(subs, intfs, "flow"), jac, d.get("rhs"), d["solution"]
+
+
+def load_mdflow_nonlinear(name: str):
+    """(CompressibleMixedDimensionalFlow, raw fixture) of tools/make_mdflow_golden.py ``export_nonlinear``."""
+    from porepy_b200.mdflow_nl import CompressibleMixedDimensionalFlow
+    lin, _, _, _ = _load_linear_parts(name)
+    d = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+    storage, bcs, weights = [], [], []
+    for i, s in enumerate(lin.subdomains):
+        storage.append(d[f"sd{i}__storage"])
+        if s.sd.num_faces == 0:
+            bcs.append(None)
+            weights.append(None)
+            continue
+        nf = s.sd.num_faces
+        bcs.append(SimpleNamespace(is_dir=d[f"sd{i}__ff_is_dir"], is_neu=d[f"sd{i}__ff_is_neu"], is_rob=np.zeros(nf, bool),
+                                   is_internal=np.asarray(s.sd.tags["fracture_faces"], bool), robin_weight=np.ones(nf),
+                                   bc_type="scalar", num_faces=nf))
+        weights.append(d[f"sd{i}__ff_values"])
+    fluid = {k: float(d[k]) for k in ("compressibility", "density", "viscosity", "reference_pressure")}
+    return CompressibleMixedDimensionalFlow(lin.subdomains, lin.interfaces, fluid, storage, bcs, weights), d

@@ -49,3 +49,15 @@ def test_md_solve_on_device(kind):
     J, rhs = prob.assemble()
     xh = spla.spsolve(J.to_scipy().tocsc(), rhs.cpu().numpy())
     assert np.linalg.norm(x.cpu().numpy() - xh) <= 1e-7 * np.linalg.norm(xh)
+
+
+# ---- compressible flow: the reference's Newton loop on the device AD chain (tests/test_mdflow_nonlinear.py); kept last
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["mdflownl_one_fracture", "mdflownl_three_fractures"])
+def test_compressible_md_newton_gpu(name):
+    from mdflow_io import load_mdflow_nonlinear
+    from test_mdflow_nonlinear import check_linearization, check_time_step
+    prob, d = load_mdflow_nonlinear(name)
+    prob.discretize()
+    check_linearization(prob, d, lambda t: t.cpu().numpy())
+    check_time_step(prob, d, lambda t: t.cpu().numpy())

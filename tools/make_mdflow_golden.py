@@ -45,7 +45,7 @@ def rect(axis, at, lo, hi):
     return p
 
 
-def make_model(n, fracs, source):
+def make_model(n, fracs, source, constants=None, dt=1.0):
     class Model(pp.SinglePhaseFlow):
         def set_domain(self):
             self._domain = pp.Domain({"xmin": 0, "xmax": 1, "ymin": 0, "ymax": 1, "zmin": 0, "zmax": 1})
@@ -104,7 +104,16 @@ def make_model(n, fracs, source):
             ext = pp.wrap_as_dense_ad_array(np.hstack(vals) if vals else np.zeros(0), name="extra_source")
             return super().fluid_source(subdomains) + ext
 
-    return Model({"times_to_export": [], "time_manager": pp.TimeManager([0, 1.0], 1.0, constant_dt=True)})
+        def bc_type_fluid_flux(self, sd):
+            if constants is None:               # the linear fixtures keep the model's default
+                return super().bc_type_fluid_flux(sd)
+            sides = self.domain_boundary_sides(sd)
+            return pp.BoundaryCondition(sd, sides.west + sides.east, "dir")
+
+    params = {"times_to_export": [], "time_manager": pp.TimeManager([0, 1.0], dt, constant_dt=True)}
+    if constants is not None:
+        params["material_constants"] = constants
+    return Model(params)
 
 
 def full_bc_values(model, sd):
@@ -124,18 +133,11 @@ def scalar_field(model, op, n):
     return np.full(n, float(v)) if np.ndim(v) == 0 else np.asarray(v, float)
 
 
-def export(name, n, fracs, source=0.7):
-    model = make_model(n, fracs, source)
-    model.prepare_simulation()
+def collect(model) -> dict:
+    """Grids, parameters, projections and interface coefficients of a prepared model (everything but results)."""
     es, mdg = model.equation_system, model.mdg
-    A0, b0 = es.assemble()
-    pp.run_time_dependent_model(model, {"prepare_simulation": False})
-    A1, b1 = es.assemble()
-    assert abs(A1 - A0).max() == 0.0 and np.linalg.norm(b1) < 1e-10 * np.linalg.norm(b0)
-    x = es.get_variable_values(iterate_index=0)
     sds, intfs = mdg.subdomains(), mdg.interfaces()
-    d = {"num_subdomains": np.int64(len(sds)), "num_interfaces": np.int64(len(intfs)), "solution": x, "rhs": b0}
-    put_csr(d, "jacobian", A0)
+    d = {"num_subdomains": np.int64(len(sds)), "num_interfaces": np.int64(len(intfs))}
     off = 0
     for i, sd in enumerate(sds):
         data = mdg.subdomain_data(sd)
@@ -173,12 +175,84 @@ def export(name, n, fracs, source=0.7):
         d[f"if{j}__normal_permeability"] = scalar_field(model, model.normal_permeability([it]), it.num_cells)
         d[f"if{j}__cell_volumes"] = it.cell_volumes * scalar_field(model, model.specific_volume([it]), it.num_cells)
         d[f"if{j}__secondary_aperture"] = scalar_field(model, model.aperture([l]), l.num_cells)
-    assert off == A0.shape[0]
+    assert off == es.num_dofs()
+    return d
+
+
+def export(name, n, fracs, source=0.7):
+    model = make_model(n, fracs, source)
+    model.prepare_simulation()
+    es, mdg = model.equation_system, model.mdg
+    A0, b0 = es.assemble()
+    d = collect(model)
+    pp.run_time_dependent_model(model, {"prepare_simulation": False})
+    A1, b1 = es.assemble()
+    assert abs(A1 - A0).max() == 0.0 and np.linalg.norm(b1) < 1e-10 * np.linalg.norm(b0)
+    x = es.get_variable_values(iterate_index=0)
+    sds, intfs = mdg.subdomains(), mdg.interfaces()
+    d.update(solution=x, rhs=b0)
+    put_csr(d, "jacobian", A0)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
     print(name, "dofs", A0.shape[0], "nnz", A0.nnz, "subdomains", [(s.dim, s.num_cells) for s in sds],
           "interfaces", [(i.dim, i.num_cells) for i in intfs], "|b|", np.linalg.norm(b0), "ptp(x)", np.ptp(x))
 
 
+def export_nonlinear(name, n, fracs, source=0.3):
+    """Compressible fluid (density rho0 exp(c (p - p_ref)), upwinded mobility rho / mu, storage term): one implicit time
+    step of the reference's Newton loop, driven by hand (models/solution_strategy.py: ``before_nonlinear_iteration`` ->
+    ``assemble_linear_system`` -> ``solve_linear_system`` -> ``after_nonlinear_iteration``).  Stored: the state, Jacobian
+    and right-hand side in front of the third linear solve (upwind directions from that same iterate), the converged
+    state, and what the nonlinear terms need beyond the linear fixture."""
+    fluid = pp.FluidComponent(compressibility=0.05, viscosity=1.3, density=1.7)
+    solid = pp.SolidConstants(porosity=0.2, residual_aperture=0.05)
+    model = make_model(n, fracs, source, constants={"fluid": fluid, "solid": solid}, dt=0.25)
+    model.prepare_simulation()
+    es, mdg = model.equation_system, model.mdg
+    d = collect(model)
+    model.time_manager.increase_time()
+    model.time_manager.increase_time_index()
+    model.before_nonlinear_loop()
+    x_prev = es.get_variable_values(time_step_index=0)
+    norms = []
+    for it in range(12):
+        model.before_nonlinear_iteration()
+        model.assemble_linear_system()
+        A, b = model.linear_system
+        norms.append(np.linalg.norm(b))
+        if it == 2:
+            d["iterate"] = es.get_variable_values(iterate_index=0)
+            d["iterate_rhs"] = b.copy()
+            put_csr(d, "iterate_jacobian", A)
+        if norms[-1] < 1e-13 * norms[0]:
+            break
+        model.after_nonlinear_iteration(model.solve_linear_system())
+    fl = model.fluid.reference_component
+    d.update(previous=x_prev, solution=es.get_variable_values(iterate_index=0), residual_norms=np.array(norms),
+             dt=np.float64(model.time_manager.dt), compressibility=np.float64(fl.compressibility),
+             density=np.float64(fl.density), viscosity=np.float64(fl.viscosity),
+             reference_pressure=np.float64(model.reference_variable_values.pressure))
+    for i, sd in enumerate(mdg.subdomains()):
+        sv = scalar_field(model, model.specific_volume([sd]), sd.num_cells)
+        phi = scalar_field(model, model.porosity([sd]), sd.num_cells)
+        d[f"sd{i}__storage"] = sd.cell_volumes * sv * phi
+        if sd.dim == 0:
+            continue
+        bc = model.bc_type_fluid_flux(sd)
+        d[f"sd{i}__ff_is_dir"], d[f"sd{i}__ff_is_neu"] = bc.is_dir, bc.is_neu
+        w = np.zeros(sd.num_faces)
+        bg = mdg.subdomain_to_boundary_grid(sd)
+        if bg is not None and bg.num_cells > 0:
+            proj = bg.projection()
+            pb_ = proj.T @ model.bc_values_pressure(bg)
+            rho = fl.density * np.exp(fl.compressibility * (pb_ - model.reference_variable_values.pressure))
+            w = np.where(bc.is_dir, rho / fl.viscosity, proj.T @ model.bc_values_fluid_flux(bg))
+        d[f"sd{i}__ff_values"] = w
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "dofs", es.num_dofs(), "Newton residuals", ["%.2e" % v for v in norms])
+
+
 if __name__ == "__main__":
     export("mdflow_three_fractures", 6, [rect(0, 0.5, 1 / 6, 5 / 6), rect(1, 0.5, 1 / 6, 5 / 6), rect(2, 0.5, 1 / 6, 5 / 6)])
     export("mdflow_one_fracture", 4, [rect(0, 0.5, 0.25, 0.75)], source=0.0)
+    export_nonlinear("mdflownl_three_fractures", 6, [rect(0, 0.5, 1 / 6, 5 / 6), rect(1, 0.5, 1 / 6, 5 / 6), rect(2, 0.5, 1 / 6, 5 / 6)])
+    export_nonlinear("mdflownl_one_fracture", 4, [rect(0, 0.5, 0.25, 0.75)])

@@ -269,6 +269,7 @@ def md_network_problem(kind, dims, n_fractures=10, aperture=1e-3, normal_permeab
                                  np.full(it["cell_volumes"].size, normal_permeability), it["cell_volumes"],
                                  np.full(fg.num_cells, aperture)))
     prob = MixedDimensionalFlow(subs, intfs)
+    prob.bench_extras = {"west": west, "east": east, "porosity": 0.2, "aperture": aperture}
     desc = {"matrix_cells": int(m.num_cells), "fractures": len(net.fractures),
             "fracture_cells": int(sum(f.num_cells for f in net.fractures)),
             "mortar_cells": int(sum(i.num_cells for i in intfs)), "dofs": int(prob.num_dofs),
@@ -276,7 +277,42 @@ def md_network_problem(kind, dims, n_fractures=10, aperture=1e-3, normal_permeab
     return prob, desc
 
 
-def md_network_block(kind, dims, solve=True):
+def md_newton_block(prob, dt=0.05, max_iterations=4):
+    """One implicit time step of COMPRESSIBLE flow on the same network (``porepy_b200.mdflow_nl``: the reference's Newton
+    loop, every linearization through the device AD chain, every step solved on the pressure Schur complement)."""
+    import torch
+    import porepy_b200 as pb
+    from porepy_b200.mdflow_nl import CompressibleMixedDimensionalFlow
+    ex = prob.bench_extras
+    fluid = {"compressibility": 0.05, "density": 1.0, "viscosity": 1.0, "reference_pressure": 0.0}
+    storage, bcs, weights = [], [], []
+    for i, s in enumerate(prob.subdomains):
+        g = s.sd
+        sv = 1.0 if g.dim == 3 else ex["aperture"]
+        storage.append(g.cell_volumes * sv * ex["porosity"])
+        bc = pb.BoundaryCondition(g)
+        w = np.zeros(g.num_faces)
+        if g.dim == 3:
+            for f in (ex["west"], ex["east"]):
+                bc.is_neu[f] = False
+                bc.is_dir[f] = True
+            w[ex["west"]] = fluid["density"] * np.exp(fluid["compressibility"] * 1.0) / fluid["viscosity"]   # p_b = 1
+            w[ex["east"]] = fluid["density"] / fluid["viscosity"]                                             # p_b = 0
+        bcs.append(bc)
+        weights.append(w)
+    nl = CompressibleMixedDimensionalFlow(prob.subdomains, prob.interfaces, fluid, storage, bcs, weights)
+    x0 = torch.zeros(nl.num_dofs, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    x, hist = nl.time_step(x0, dt, tol=1e-8, max_iterations=max_iterations, linear_tol=1e-8)
+    torch.cuda.synchronize()
+    ps, lam = nl.split(x.cpu().numpy())
+    return {"what": "compressible fluid (c = 0.05), storage term, upwinded mobility; Newton from p = 0, one time step",
+            "dt": dt, "seconds": time.perf_counter() - t0, "history": hist,
+            "pressure_range_matrix": [float(ps[0].min()), float(ps[0].max())]}
+
+
+def md_network_block(kind, dims, solve=True, newton=True):
     """Mixed-dimensional flow through the operator API and the device AD chain (row g1): every subdomain by
     ``pb.Mpfa.discretize`` from host arrays, the coupled Jacobian block by block on the device (and once through the AD
     chain), then BiCGStab on the pressure Schur complement.  Wall-clock seconds with device synchronisation on both sides of every stage."""
@@ -331,6 +367,12 @@ def md_network_block(kind, dims, solve=True):
                         "true_relres_full_system": float(torch.linalg.vector_norm(res) / torch.linalg.vector_norm(rhs)),
                         "pressure_range_matrix": [float(ps[0].min()), float(ps[0].max())],
                         "interface_flux_abs_sum": float(sum(np.abs(v).sum() for v in lam))}
+    if newton and out["assemble_ad_s"] < 5.0:
+        try:
+            del J, rhs
+            out["newton"] = md_newton_block(prob)
+        except Exception as e:     # an extra of the extra
+            out["newton"] = {"error": f"{type(e).__name__}: {e}"}
     return out
 
 

@@ -88,10 +88,11 @@ def test_touching_fractures_are_refused():
 
 @pytest.fixture()
 def host_build(monkeypatch):
-    from emu_binding import EmuBackedFaceGrid, EmuBackedPlan
+    from emu_binding import EmuBackedFaceGrid, EmuBackedPlan, emu_interface_upwind_masks
     from porepy_b200 import fv
     monkeypatch.setattr(fv, "DevicePlan", EmuBackedPlan)
     monkeypatch.setattr(fv, "FaceGrid", EmuBackedFaceGrid)
+    monkeypatch.setattr(fv, "interface_upwind_masks", emu_interface_upwind_masks)
 
 
 def _solve_and_check(prob, value, tol):
@@ -148,6 +149,10 @@ def test_bench_md_network_block_host_build(kind, host_build, monkeypatch):
     assert d["fractures"] >= 8 and d["mortar_cells"] == 2 * d["fracture_cells"]
     assert out["jacobian_rows"] == d["dofs"] == d["matrix_cells"] + d["fracture_cells"] + d["mortar_cells"]
     assert len(out["calls"]) == 3 and out["cells_per_s"] > 0
+    nw = out["newton"]
+    assert "error" not in nw, nw
+    assert nw["history"][-1]["residual"] <= 1e-6 * nw["history"][0]["residual"], nw
+    assert all(h.get("linear_converged", True) for h in nw["history"]), nw
     prob, _ = bench.md_network_problem(kind, (10, 10, 10))
     prob.discretize()
     J, b = prob.assemble_host()

@@ -61,3 +61,13 @@ def test_compressible_md_newton_gpu(name):
     prob.discretize()
     check_linearization(prob, d, lambda t: t.cpu().numpy())
     check_time_step(prob, d, lambda t: t.cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_poromechanics_model_gpu():
+    """``pp.Poromechanics`` on the device AD chain, Newton updates by the fused Jacobi-BiCGStab (tests/test_poromech_model.py)."""
+    from test_poromech_model import check, load_problem
+    prob, d = load_problem()
+    prob.discretize()
+    hist = check(prob, d, lambda t: t.cpu().numpy())
+    assert all(h.get("linear_converged", True) for h in hist), hist

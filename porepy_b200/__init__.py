@@ -15,10 +15,11 @@ from .params import (DISCRETIZATION_MATRICES, PARAMETERS, BoundaryCondition,  # 
                      BoundaryConditionVectorial, FourthOrderTensor, SecondOrderTensor,
                      initialize_data)
 from .sparse import DeviceCsr  # noqa: F401
+from .thermoporomech import Thermoporomechanics  # noqa: F401
 from .tpfa_ad import DifferentiableTpfa  # noqa: F401
 
 __all__ = ["Mpfa", "Mpsa", "Biot", "Tpfa", "Upwind", "UpwindCoupling", "DevicePlan", "FaceGrid", "DeviceCsr", "Grid", "cart_grid_2d", "cart_grid_3d",
            "structured_tet_grid", "tet_grid_from_cells", "SecondOrderTensor", "FourthOrderTensor",
            "BoundaryCondition", "BoundaryConditionVectorial", "initialize_data", "PARAMETERS",
            "DISCRETIZATION_MATRICES", "determine_eta", "compute_geometry", "DifferentiableTpfa",
-           "MixedDimensionalFlow", "MdSubdomain", "MdInterface", "CompressibleMixedDimensionalFlow", "Poromechanics"]
+           "MixedDimensionalFlow", "MdSubdomain", "MdInterface", "CompressibleMixedDimensionalFlow", "Poromechanics", "Thermoporomechanics"]

@@ -71,3 +71,13 @@ def test_poromechanics_model_gpu():
     prob.discretize()
     hist = check(prob, d, lambda t: t.cpu().numpy())
     assert all(h.get("linear_converged", True) for h in hist), hist
+
+
+@pytest.mark.gpu
+def test_thermoporomechanics_model_gpu():
+    """``pp.Thermoporomechanics`` on the device AD chain, Newton updates by the fused Jacobi-BiCGStab (tests/test_thm_model.py)."""
+    from test_thm_model import check, load_problem
+    prob, d = load_problem()
+    prob.discretize()
+    hist = check(prob, d, lambda t: t.cpu().numpy())
+    assert all(h.get("linear_converged", True) for h in hist), hist

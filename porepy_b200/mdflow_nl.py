@@ -106,7 +106,6 @@ class CompressibleMixedDimensionalFlow(MixedDimensionalFlow):
 
     # ---- value and Jacobian of every equation at x (previous time step: x_prev)
     def equations(self, x, x_prev=None, dt: float = 1.0) -> list:
-        import torch
         if x_prev is None:
             raise ValueError("the compressible problem needs the previous time step")
         nsd = len(self.subdomains)
@@ -153,7 +152,6 @@ class CompressibleMixedDimensionalFlow(MixedDimensionalFlow):
             tr = (csr(M["bound_pressure_cell"]) @ p[it.primary]) + (csr(M["bound_pressure_face"]) @ boundary[it.primary])
             jump = (k.p2m[j] @ tr) - (k.s2m[j] @ p[it.secondary])
             eqs.append(lam[j] - jump * k.coef[j])
-        del torch
         return eqs
 
     def linearize(self, x, x_prev, dt: float):

@@ -10,6 +10,7 @@ from .geometry import compute_geometry  # noqa: F401
 from .grid import Grid, cart_grid_2d, cart_grid_3d, structured_tet_grid, tet_grid_from_cells  # noqa: F401
 from .mdflow import MdInterface, MdSubdomain, MixedDimensionalFlow  # noqa: F401
 from .mdflow_nl import CompressibleMixedDimensionalFlow  # noqa: F401
+from .mdthermal import MixedDimensionalMassEnergy  # noqa: F401
 from .poromech import Poromechanics  # noqa: F401
 from .params import (DISCRETIZATION_MATRICES, PARAMETERS, BoundaryCondition,  # noqa: F401
                      BoundaryConditionVectorial, FourthOrderTensor, SecondOrderTensor,
@@ -22,4 +23,4 @@ __all__ = ["Mpfa", "Mpsa", "Biot", "Tpfa", "Upwind", "UpwindCoupling", "DevicePl
            "structured_tet_grid", "tet_grid_from_cells", "SecondOrderTensor", "FourthOrderTensor",
            "BoundaryCondition", "BoundaryConditionVectorial", "initialize_data", "PARAMETERS",
            "DISCRETIZATION_MATRICES", "determine_eta", "compute_geometry", "DifferentiableTpfa",
-           "MixedDimensionalFlow", "MdSubdomain", "MdInterface", "CompressibleMixedDimensionalFlow", "Poromechanics", "Thermoporomechanics"]
+           "MixedDimensionalFlow", "MdSubdomain", "MdInterface", "CompressibleMixedDimensionalFlow", "Poromechanics", "Thermoporomechanics", "MixedDimensionalMassEnergy"]

@@ -162,34 +162,45 @@ class CompressibleMixedDimensionalFlow(MixedDimensionalFlow):
     def time_step(self, x_prev, dt: float, tol: float = 1e-10, max_iterations: int = 15, linear_tol: float = 1e-10,
                   verbose: bool = False):
         """One implicit time step by Newton's method from the state ``x_prev``.  Returns (x as a tensor, history)."""
-        import torch
         nsd = len(self.subdomains)
-        npd = int(self.offsets[nsd])
         x_prev = ad.device_vector(x_prev)
-        x = x_prev.clone()
-        hist, r0 = [], None
-        for it in range(max_iterations + 1):
+
+        def equations(x):
             self.update_upwind(x)
-            eqs = self.equations(x, x_prev, dt)
-            rn = float(torch.sqrt(sum((e.val * e.val).sum() for e in eqs)))
-            r0 = rn if r0 is None else r0
-            rec = {"iteration": it, "residual": rn}
-            hist.append(rec)
-            if verbose:
-                print(rec, flush=True)
-            if rn <= tol * max(r0, 1e-300) or it == max_iterations:
-                break
-            # rows by equation group, columns by selection: the four blocks of the Schur solve
-            D_ = ad.DeviceCsr
-            Jp = eqs[0].jac if nsd == 1 else D_.vstack([e.jac for e in eqs[:nsd]])
-            Jl = eqs[nsd].jac if len(eqs) == nsd + 1 else D_.vstack([e.jac for e in eqs[nsd:]])
-            n = self.num_dofs
-            sel_p = D_(sps.csr_matrix((np.ones(npd), (np.arange(npd), np.arange(npd))), shape=(n, npd)))
-            sel_l = D_(sps.csr_matrix((np.ones(n - npd), (np.arange(npd, n), np.arange(n - npd))), shape=(n, n - npd)))
-            bp = -torch.cat([e.val for e in eqs[:nsd]])
-            bl = -torch.cat([e.val for e in eqs[nsd:]])
-            dx, info = schur_solve(Jp @ sel_p, Jp @ sel_l, Jl @ sel_p, Jl @ sel_l, bp, bl, tol=linear_tol)
-            rec.update(linear_iterations=int(info["iterations"]), linear_converged=bool(info["converged"]),
-                       linear_true_relres=info["true_relres"])
-            x = x + dx
-        return x, hist
+            return self.equations(x, x_prev, dt)
+        return newton_schur(equations, x_prev, nsd, int(self.offsets[nsd]), self.num_dofs, tol, max_iterations,
+                            linear_tol, verbose)
+
+
+def newton_schur(equations, x0, n_primary_equations: int, n_primary_unknowns: int, n: int, tol: float = 1e-10,
+                 max_iterations: int = 15, linear_tol: float = 1e-10, verbose: bool = False):
+    """Newton's method on ``equations(x) -> [DeviceAdArray, ...]`` whose first ``n_primary_equations`` entries are the
+    subdomain balances and whose unknown vector starts with the ``n_primary_unknowns`` subdomain unknowns; the interface
+    unknowns behind them are eliminated in every step (``mdflow.schur_solve``).  Rows are split by equation group, columns
+    by two selection matrices (SpGEMM).  Returns (x, history)."""
+    import torch
+    D_ = ad.DeviceCsr
+    npd, nq = int(n_primary_unknowns), int(n_primary_equations)
+    sel_p = D_(sps.csr_matrix((np.ones(npd), (np.arange(npd), np.arange(npd))), shape=(n, npd)))
+    sel_l = D_(sps.csr_matrix((np.ones(n - npd), (np.arange(npd, n), np.arange(n - npd))), shape=(n, n - npd)))
+    x = ad.device_vector(x0).clone()
+    hist, r0 = [], None
+    for it in range(max_iterations + 1):
+        eqs = equations(x)
+        rn = float(torch.sqrt(sum((e.val * e.val).sum() for e in eqs)))
+        r0 = rn if r0 is None else r0
+        rec = {"iteration": it, "residual": rn}
+        hist.append(rec)
+        if verbose:
+            print(rec, flush=True)
+        if rn <= tol * max(r0, 1e-300) or it == max_iterations:
+            break
+        Jp = eqs[0].jac if nq == 1 else D_.vstack([e.jac for e in eqs[:nq]])
+        Jl = eqs[nq].jac if len(eqs) == nq + 1 else D_.vstack([e.jac for e in eqs[nq:]])
+        bp = -torch.cat([e.val for e in eqs[:nq]])
+        bl = -torch.cat([e.val for e in eqs[nq:]])
+        dx, info = schur_solve(Jp @ sel_p, Jp @ sel_l, Jl @ sel_p, Jl @ sel_l, bp, bl, tol=linear_tol)
+        rec.update(linear_iterations=int(info["iterations"]), linear_converged=bool(info["converged"]),
+                   linear_true_relres=info["true_relres"])
+        x = x + dx
+    return x, hist

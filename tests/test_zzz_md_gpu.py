@@ -81,3 +81,14 @@ def test_thermoporomechanics_model_gpu():
     prob.discretize()
     hist = check(prob, d, lambda t: t.cpu().numpy())
     assert all(h.get("linear_converged", True) for h in hist), hist
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["mdthermal_one_fracture", "mdthermal_three_fractures"])
+def test_mass_and_energy_balance_on_a_network_gpu(name):
+    """``pp.MassAndEnergyBalance`` on a fracture network (tests/test_mdthermal.py) with the device sparse algebra."""
+    from mdflow_io import load_mdthermal
+    from test_mdthermal import check
+    prob, d = load_mdthermal(name)
+    prob.discretize()
+    check(prob, d, lambda t: t.cpu().numpy())

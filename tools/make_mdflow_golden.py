@@ -45,8 +45,10 @@ def rect(axis, at, lo, hi):
     return p
 
 
-def make_model(n, fracs, source, constants=None, dt=1.0):
-    class Model(pp.SinglePhaseFlow):
+def make_model(n, fracs, source, constants=None, dt=1.0, base=None, mixin=None):
+    bases = ((mixin,) if mixin is not None else ()) + (base or pp.SinglePhaseFlow,)
+
+    class Model(*bases):
         def set_domain(self):
             self._domain = pp.Domain({"xmin": 0, "xmax": 1, "ymin": 0, "ymax": 1, "zmin": 0, "zmax": 1})
 
@@ -251,8 +253,137 @@ def export_nonlinear(name, n, fracs, source=0.3):
     print(name, "dofs", es.num_dofs(), "Newton residuals", ["%.2e" % v for v in norms])
 
 
+def export_thermal(name, n, fracs, source=0.3):
+    """``pp.MassAndEnergyBalance`` on the network (compressible, thermally expanding fluid; Fourier and upwinded enthalpy
+    fluxes on subdomains and interfaces): the fixture of ``export_nonlinear`` plus the thermal parameters, and the index
+    arrays that map the reference's dof / equation numbering (interleaved per grid) to [p | T | lambda | eta | eps] and
+    [mass | energy | Darcy law | Fourier law | enthalpy law]."""
+    fluid = pp.FluidComponent(compressibility=0.05, viscosity=1.3, density=1.7, thermal_expansion=0.03,
+                              specific_heat_capacity=2.0, thermal_conductivity=0.7)
+    solid = pp.SolidConstants(porosity=0.2, residual_aperture=0.05, thermal_expansion=0.02, specific_heat_capacity=1.5,
+                              thermal_conductivity=1.1, density=2.5, normal_permeability=2.0)
+
+    class Thermal:
+        def bc_type_fourier_flux(self, sd):
+            s = self.domain_boundary_sides(sd)
+            return pp.BoundaryCondition(sd, s.west + s.east, "dir")
+
+        def bc_type_enthalpy_flux(self, sd):
+            s = self.domain_boundary_sides(sd)
+            return pp.BoundaryCondition(sd, s.west + s.east, "dir")
+
+        def bc_values_temperature(self, bg):
+            s = self.domain_boundary_sides(bg)
+            v = np.zeros(bg.num_cells)
+            v[s.west] = 0.5 + 0.2 * bg.cell_centers[2, s.west]
+            return v
+    model = make_model(n, fracs, source, constants={"fluid": fluid, "solid": solid}, dt=0.25,
+                       base=pp.MassAndEnergyBalance, mixin=Thermal)
+    model.prepare_simulation()
+    es, mdg = model.equation_system, model.mdg
+    sds, intfs = mdg.subdomains(), mdg.interfaces()
+    # grids, flow parameters, projections: as for the flow fixtures (``collect`` asserts the flow model's dof layout)
+    d = {"num_subdomains": np.int64(len(sds)), "num_interfaces": np.int64(len(intfs))}
+    index = {sd: i for i, sd in enumerate(sds)}
+    fl = model.fluid.reference_component
+    p_ref, t_ref = model.reference_variable_values.pressure, model.reference_variable_values.temperature
+
+    def dofs(name, g):
+        return es.dofs_of([v for v in es.variables if v.name == name and v.domain is g])
+    cols, rows, r0 = [], {}, 0
+    for eq in es.equations:
+        for g in (sds if eq in ("mass_balance_equation", "energy_balance_equation") else
+                  intfs if eq.startswith("interface") else []):
+            rows[(eq, g)] = np.arange(r0, r0 + g.num_cells)
+            r0 += g.num_cells
+    for var, grids in (("pressure", sds), ("temperature", sds), ("interface_darcy_flux", intfs),
+                       ("interface_fourier_flux", intfs), ("interface_enthalpy_flux", intfs)):
+        cols += [dofs(var, g) for g in grids]
+    order = [("mass_balance_equation", sds), ("energy_balance_equation", sds), ("interface_darcy_flux_equation", intfs),
+             ("interface_fourier_flux_equation", intfs), ("interface_enthalpy_flux_equation", intfs)]
+    d["column_map"] = np.concatenate(cols)          # my unknown k is the reference's dof column_map[k]
+    d["row_map"] = np.concatenate([rows[(eq, g)] for eq, grids in order for g in grids])
+    for i, sd in enumerate(sds):
+        data = mdg.subdomain_data(sd)
+        prm = data[pp.PARAMETERS]
+        g = grid_arrays(sd) if sd.dim > 0 else dict(dim=np.int64(0), name=np.array(str(sd.name)), nodes=sd.nodes,
+                                                     cell_centers=sd.cell_centers, cell_volumes=sd.cell_volumes)
+        for k, v in g.items():
+            d[f"sd{i}__{k}"] = v
+        d[f"sd{i}__source"] = np.asarray(model.extra_source(sd), float)
+        d[f"sd{i}__volume"] = sd.cell_volumes * scalar_field(model, model.specific_volume([sd]), sd.num_cells)
+        d[f"sd{i}__porosity"] = scalar_field(model, model.porosity([sd]), sd.num_cells)
+        if sd.dim == 0:
+            continue
+        bg = mdg.subdomain_to_boundary_grid(sd)
+        has = bg is not None and bg.num_cells > 0
+        proj = bg.projection() if has else None
+        pb_ = proj.T @ model.bc_values_pressure(bg) if has else np.zeros(sd.num_faces)
+        tb = proj.T @ model.bc_values_temperature(bg) if has else np.zeros(sd.num_faces)
+        rho_b = fl.density * np.exp(fl.compressibility * (pb_ - p_ref) - fl.thermal_expansion * (tb - t_ref))
+
+        def comb(bc, dirv, neu):
+            return np.where(bc.is_dir, dirv, proj.T @ neu(bg)) if has else np.zeros(sd.num_faces)
+        for key, kw in (("flow", "flow"), ("fourier", "fourier_discretization")):
+            bc = prm[kw]["bc"]
+            d[f"sd{i}__{key}_K"] = prm[kw]["second_order_tensor"].values
+            for f in ("is_dir", "is_neu", "is_rob", "is_internal"):
+                d[f"sd{i}__{key}_bc_{f}"] = getattr(bc, f)
+            d[f"sd{i}__{key}_bc_robin_weight"] = np.asarray(bc.robin_weight, float)
+        d[f"sd{i}__flow_bc_values"] = comb(prm["flow"]["bc"], pb_, model.bc_values_darcy_flux)
+        d[f"sd{i}__fourier_bc_values"] = comb(prm["fourier_discretization"]["bc"], tb, model.bc_values_fourier_flux)
+        for key, bc, dirv, neu in (("ff", model.bc_type_fluid_flux(sd), rho_b / fl.viscosity, model.bc_values_fluid_flux),
+                                   ("ef", model.bc_type_enthalpy_flux(sd),
+                                    fl.specific_heat_capacity * (tb - t_ref) * rho_b / fl.viscosity,
+                                    model.bc_values_enthalpy_flux)):
+            d[f"sd{i}__{key}_is_dir"], d[f"sd{i}__{key}_is_neu"] = bc.is_dir, bc.is_neu
+            d[f"sd{i}__{key}_values"] = comb(bc, dirv, neu)
+        d[f"sd{i}__tip_faces"] = np.asarray(sd.tags["tip_faces"], bool)
+        d[f"sd{i}__domain_boundary_faces"] = np.asarray(sd.tags["domain_boundary_faces"], bool)
+        d[f"sd{i}__ambient_dimension"] = np.int64(prm["flow"].get("ambient_dimension", 3))
+    for j, it in enumerate(intfs):
+        h, l = mdg.interface_to_subdomain_pair(it)
+        d[f"if{j}__primary"], d[f"if{j}__secondary"] = np.int64(index[h]), np.int64(index[l])
+        put_csr(d, f"if{j}__mortar_to_primary_int", it.mortar_to_primary_int())
+        put_csr(d, f"if{j}__primary_to_mortar_avg", it.primary_to_mortar_avg())
+        put_csr(d, f"if{j}__mortar_to_secondary_int", it.mortar_to_secondary_int())
+        put_csr(d, f"if{j}__secondary_to_mortar_avg", it.secondary_to_mortar_avg())
+        d[f"if{j}__normal_permeability"] = scalar_field(model, model.normal_permeability([it]), it.num_cells)
+        d[f"if{j}__normal_thermal_conductivity"] = scalar_field(model, model.normal_thermal_conductivity([it]), it.num_cells)
+        d[f"if{j}__cell_volumes"] = it.cell_volumes * scalar_field(model, model.specific_volume([it]), it.num_cells)
+        d[f"if{j}__secondary_aperture"] = scalar_field(model, model.aperture([l]), l.num_cells)
+    model.time_manager.increase_time()
+    model.time_manager.increase_time_index()
+    model.before_nonlinear_loop()
+    x_prev = es.get_variable_values(time_step_index=0)
+    norms = []
+    for it in range(15):
+        model.before_nonlinear_iteration()
+        model.assemble_linear_system()
+        A, b = model.linear_system
+        norms.append(np.linalg.norm(b))
+        if it == 2:
+            d["iterate"] = es.get_variable_values(iterate_index=0)
+            d["iterate_rhs"] = b.copy()
+            put_csr(d, "iterate_jacobian", A)
+        if norms[-1] < 1e-12 * norms[0]:
+            break
+        model.after_nonlinear_iteration(model.solve_linear_system())
+    so = model.solid
+    d.update(previous=x_prev, solution=es.get_variable_values(iterate_index=0), residual_norms=np.array(norms),
+             dt=np.float64(model.time_manager.dt), compressibility=np.float64(fl.compressibility),
+             density=np.float64(fl.density), viscosity=np.float64(fl.viscosity),
+             fluid_thermal_expansion=np.float64(fl.thermal_expansion), fluid_heat_capacity=np.float64(fl.specific_heat_capacity),
+             reference_pressure=np.float64(p_ref), reference_temperature=np.float64(t_ref),
+             solid_heat_capacity=np.float64(so.specific_heat_capacity), solid_density=np.float64(so.density))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "dofs", es.num_dofs(), "Newton residuals", ["%.2e" % v for v in norms])
+
+
 if __name__ == "__main__":
     export("mdflow_three_fractures", 6, [rect(0, 0.5, 1 / 6, 5 / 6), rect(1, 0.5, 1 / 6, 5 / 6), rect(2, 0.5, 1 / 6, 5 / 6)])
     export("mdflow_one_fracture", 4, [rect(0, 0.5, 0.25, 0.75)], source=0.0)
     export_nonlinear("mdflownl_three_fractures", 6, [rect(0, 0.5, 1 / 6, 5 / 6), rect(1, 0.5, 1 / 6, 5 / 6), rect(2, 0.5, 1 / 6, 5 / 6)])
     export_nonlinear("mdflownl_one_fracture", 4, [rect(0, 0.5, 0.25, 0.75)])
+    export_thermal("mdthermal_three_fractures", 6, [rect(0, 0.5, 1 / 6, 5 / 6), rect(1, 0.5, 1 / 6, 5 / 6), rect(2, 0.5, 1 / 6, 5 / 6)])
+    export_thermal("mdthermal_one_fracture", 4, [rect(0, 0.5, 0.25, 0.75)])

@@ -1,0 +1,229 @@
+"""From a prepared PorePy model to the device problems of this package: the glue a PorePy user needs to hand a live
+``pp.SinglePhaseFlow`` / ``pp.MassAndEnergyBalance`` (on a fracture network) or ``pp.Poromechanics`` /
+``pp.Thermoporomechanics`` (3-D subdomain) over to ``porepy_b200`` -- grids, parameter dictionaries and mortar projections
+of ``model.mdg`` as they are; boundary data, coefficients and constants evaluated from the model's own methods
+(``bc_values_*``, ``bc_type_*``, ``normal_permeability``, ``aperture``, ``specific_volume``, ``porosity``, the fluid and
+solid constants).  Reached through ``porepy_plugin.plugin(pp)``: ``b200.compressible_flow_from_model(model)`` etc.
+
+The model's data dictionaries are not modified: every problem gets its own dictionaries (the parameter entries are shared,
+the discretization matrices and the upwind parameters are the problem's own).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sps
+
+from .params import DISCRETIZATION_MATRICES, PARAMETERS
+
+
+def _evaluated(model, op, n):
+    v = model.equation_system.evaluate(op)
+    v = getattr(v, "val", v)
+    return np.full(n, float(v)) if np.ndim(v) == 0 else np.asarray(v, float)
+
+
+def _own_data(data: dict, keywords) -> dict:
+    return {PARAMETERS: {kw: dict(data[PARAMETERS][kw]) for kw in keywords if kw in data.get(PARAMETERS, {})},
+            DISCRETIZATION_MATRICES: {}}
+
+
+def _face_values(model, sd, bc, dirichlet, neumann):
+    """Boundary operator of a flux law on ``sd``: ``dirichlet(bg)`` on the Dirichlet faces of ``bc``, ``neumann(bg)``
+    elsewhere (``_combine_boundary_operators`` of the models), as a face array."""
+    bg = model.mdg.subdomain_to_boundary_grid(sd)
+    if bg is None or bg.num_cells == 0:
+        return np.zeros(sd.num_faces)
+    proj = bg.projection()
+    return np.where(bc.is_dir, proj.T @ dirichlet(bg), proj.T @ neumann(bg))
+
+
+def _fluid(model, thermal: bool) -> dict:
+    fl = model.fluid.reference_component
+    out = dict(compressibility=fl.compressibility, density=fl.density, viscosity=fl.viscosity,
+               reference_pressure=model.reference_variable_values.pressure)
+    if thermal:
+        out.update(thermal_expansion=fl.thermal_expansion, heat_capacity=fl.specific_heat_capacity,
+                   conductivity=fl.thermal_conductivity, reference_temperature=model.reference_variable_values.temperature)
+    return out
+
+
+def _boundary_weights(model, sd, fluid: dict, thermal: bool):
+    """(rho / mu, c_f (T - T0) rho / mu) of the boundary pressure / temperature, as functions of a boundary grid."""
+    def rho(bg):
+        e = fluid["compressibility"] * (model.bc_values_pressure(bg) - fluid["reference_pressure"])
+        if thermal:
+            e = e - fluid["thermal_expansion"] * (model.bc_values_temperature(bg) - fluid["reference_temperature"])
+        return fluid["density"] * np.exp(e)
+
+    def w(bg):
+        return rho(bg) / fluid["viscosity"]
+
+    def we(bg):
+        return fluid["heat_capacity"] * (model.bc_values_temperature(bg) - fluid["reference_temperature"]) * w(bg)
+    return w, we
+
+
+def _interfaces(model, thermal: bool):
+    from .mdflow import MdInterface
+    mdg = model.mdg
+    index = {id(sd): i for i, sd in enumerate(mdg.subdomains())}
+    out, kappa_t = [], []
+    for it in mdg.interfaces():
+        if getattr(it, "codim", 1) != 1:
+            continue
+        h, l = mdg.interface_to_subdomain_pair(it)
+        out.append(MdInterface(index[id(h)], index[id(l)], it.mortar_to_primary_int(), it.primary_to_mortar_avg(),
+                               it.mortar_to_secondary_int(), it.secondary_to_mortar_avg(),
+                               _evaluated(model, model.normal_permeability([it]), it.num_cells),
+                               np.asarray(it.cell_volumes, float) * _evaluated(model, model.specific_volume([it]), it.num_cells),
+                               _evaluated(model, model.aperture([l]), l.num_cells)))
+        if thermal:
+            kappa_t.append(_evaluated(model, model.normal_thermal_conductivity([it]), it.num_cells))
+    return out, kappa_t
+
+
+def compressible_flow_from_model(model):
+    """``pp.SinglePhaseFlow`` (compressible fluid) on ``model.mdg`` -> ``CompressibleMixedDimensionalFlow``; unknowns and
+    equations in the model's own order."""
+    from .mdflow import MdSubdomain
+    from .mdflow_nl import CompressibleMixedDimensionalFlow
+    mdg, kw = model.mdg, model.darcy_keyword
+    fluid = _fluid(model, False)
+    subs, storage, bcs, weights = [], [], [], []
+    for sd in mdg.subdomains():
+        data = _own_data(mdg.subdomain_data(sd), [kw])
+        n = sd.num_cells
+        storage.append(np.asarray(sd.cell_volumes, float) * _evaluated(model, model.specific_volume([sd]), n)
+                       * _evaluated(model, model.porosity([sd]), n))
+        if sd.num_faces == 0:
+            subs.append(MdSubdomain(sd, data))
+            bcs.append(None)
+            weights.append(None)
+            continue
+        w, _ = _boundary_weights(model, sd, fluid, False)
+        bc_ff = model.bc_type_fluid_flux(sd)
+        subs.append(MdSubdomain(sd, data, _face_values(model, sd, data[PARAMETERS][kw]["bc"], model.bc_values_pressure,
+                                                       model.bc_values_darcy_flux)))
+        bcs.append(bc_ff)
+        weights.append(_face_values(model, sd, bc_ff, w, model.bc_values_fluid_flux))
+    intfs, _ = _interfaces(model, False)
+    prob = CompressibleMixedDimensionalFlow(subs, intfs, fluid, storage, bcs, weights, keyword=kw)
+    prob.mobility_keyword = "b200_mobility"
+    return prob
+
+
+def mass_energy_from_model(model):
+    """``pp.MassAndEnergyBalance`` on ``model.mdg`` -> (``MixedDimensionalMassEnergy``, column_map, row_map): unknown k
+    of the problem is dof ``column_map[k]`` of the model's ``EquationSystem``, equation k its row ``row_map[k]``."""
+    from .mdflow import MdSubdomain
+    from .mdthermal import MixedDimensionalMassEnergy
+    mdg, es = model.mdg, model.equation_system
+    fk, tk = model.darcy_keyword, model.fourier_keyword
+    fluid = _fluid(model, True)
+    solid = dict(density=model.solid.density, heat_capacity=model.solid.specific_heat_capacity)
+    sds = list(mdg.subdomains())
+    subs, volume, porosity, bcv, bct = [], [], [], [], []
+    for sd in sds:
+        data = _own_data(mdg.subdomain_data(sd), [fk, tk])
+        n = sd.num_cells
+        volume.append(np.asarray(sd.cell_volumes, float) * _evaluated(model, model.specific_volume([sd]), n))
+        porosity.append(_evaluated(model, model.porosity([sd]), n))
+        subs.append(MdSubdomain(sd, data))
+        if sd.num_faces == 0:
+            bcv.append(None)
+            bct.append(None)
+            continue
+        w, we = _boundary_weights(model, sd, fluid, True)
+        ff, ef = model.bc_type_fluid_flux(sd), model.bc_type_enthalpy_flux(sd)
+        prm = data[PARAMETERS]
+        bcv.append(dict(flow=_face_values(model, sd, prm[fk]["bc"], model.bc_values_pressure, model.bc_values_darcy_flux),
+                        fourier=_face_values(model, sd, prm[tk]["bc"], model.bc_values_temperature, model.bc_values_fourier_flux),
+                        fluid_flux=_face_values(model, sd, ff, w, model.bc_values_fluid_flux),
+                        enthalpy_flux=_face_values(model, sd, ef, we, model.bc_values_enthalpy_flux)))
+        bct.append(dict(fluid_flux=ff, enthalpy_flux=ef))
+    intfs, kappa_t = _interfaces(model, True)
+    prob = MixedDimensionalMassEnergy(subs, intfs, fluid, solid, volume, porosity, bcv, bct, kappa_t, flow_keyword=fk,
+                                      fourier_keyword=tk)
+    prob.mobility_keyword, prob.enthalpy_upwind_keyword = "b200_mobility", "b200_enthalpy_upwind"
+    its = [it for it in mdg.interfaces() if getattr(it, "codim", 1) == 1]
+
+    def dofs(name, g):
+        return es.dofs_of([v for v in es.variables if v.name == name and v.domain is g])
+    cols = [dofs(name, g) for name, grids in ((model.pressure_variable, sds), (model.temperature_variable, sds),
+                                               (model.interface_darcy_flux_variable, its),
+                                               (model.interface_fourier_flux_variable, its),
+                                               (model.interface_enthalpy_flux_variable, its)) for g in grids]
+    rows, r0 = {}, 0
+    for eq in es.equations:
+        grids = sds if eq in ("mass_balance_equation", "energy_balance_equation") else its if eq.startswith("interface") else []
+        for g in grids:
+            rows[(eq, id(g))] = np.arange(r0, r0 + g.num_cells)
+            r0 += g.num_cells
+    order = [("mass_balance_equation", sds), ("energy_balance_equation", sds), ("interface_darcy_flux_equation", its),
+             ("interface_fourier_flux_equation", its), ("interface_enthalpy_flux_equation", its)]
+    return prob, np.concatenate(cols), np.concatenate([rows[(eq, id(g))] for eq, grids in order for g in grids])
+
+
+def _mechanics_boundary(model, sd, data, mk):
+    bg = model.mdg.subdomain_to_boundary_grid(sd)
+    proj3 = sps.kron(bg.projection(), sps.identity(3)).tocsr()
+    bc = data[PARAMETERS][mk]["bc"]
+    return np.where(np.asarray(bc.is_dir).ravel("F"), proj3.T @ model.bc_values_displacement(bg),
+                    proj3.T @ model.bc_values_stress(bg))
+
+
+def _n_inv(model):
+    so = model.solid
+    bulk = so.lame_lambda + 2.0 * so.shear_modulus / 3.0          # ``bulk_modulus`` of the solid constants
+    return (so.biot_coefficient - so.porosity) * (1.0 - so.biot_coefficient) / bulk
+
+
+def poromechanics_from_model(model):
+    """``pp.Poromechanics`` on a 3-D subdomain without fractures -> ``Poromechanics`` (unknowns [p | u], the model's
+    own order)."""
+    from .poromech import Poromechanics
+    sds = list(model.mdg.subdomains())
+    if len(sds) != 1 or sds[0].dim != 3:
+        raise NotImplementedError("one 3-D subdomain without fractures is expected")
+    sd = sds[0]
+    fk, mk = model.darcy_keyword, model.stress_keyword
+    data = _own_data(model.mdg.subdomain_data(sd), [fk, mk])
+    fluid = _fluid(model, False)
+    w, _ = _boundary_weights(model, sd, fluid, False)
+    bc_ff = model.bc_type_fluid_flux(sd)
+    prob = Poromechanics(sd, data, fluid, dict(reference_porosity=model.solid.porosity, n_inv=_n_inv(model)),
+                         _face_values(model, sd, data[PARAMETERS][fk]["bc"], model.bc_values_pressure, model.bc_values_darcy_flux),
+                         _mechanics_boundary(model, sd, data, mk), bc_ff,
+                         _face_values(model, sd, bc_ff, w, model.bc_values_fluid_flux), flow_keyword=fk, mechanics_keyword=mk)
+    prob.mobility_keyword = "b200_mobility"
+    return prob
+
+
+def thermoporomechanics_from_model(model):
+    """``pp.Thermoporomechanics`` on a 3-D subdomain without fractures -> ``Thermoporomechanics`` (unknowns [u | p | T],
+    the model's own order)."""
+    from .thermoporomech import Thermoporomechanics
+    sds = list(model.mdg.subdomains())
+    if len(sds) != 1 or sds[0].dim != 3:
+        raise NotImplementedError("one 3-D subdomain without fractures is expected")
+    sd = sds[0]
+    fk, tk, mk, ck = model.darcy_keyword, model.fourier_keyword, model.stress_keyword, model.enthalpy_keyword
+    data = _own_data(model.mdg.subdomain_data(sd), [fk, tk, mk])
+    fluid = _fluid(model, True)
+    so = model.solid
+    solid = dict(reference_porosity=so.porosity, n_inv=_n_inv(model), biot_coefficient=so.biot_coefficient,
+                 thermal_expansion=so.thermal_expansion, heat_capacity=so.specific_heat_capacity,
+                 conductivity=so.thermal_conductivity, density=so.density)
+    w, we = _boundary_weights(model, sd, fluid, True)
+    ff, ef = model.bc_type_fluid_flux(sd), model.bc_type_enthalpy_flux(sd)
+    prm = data[PARAMETERS]
+    bc = dict(flow=_face_values(model, sd, prm[fk]["bc"], model.bc_values_pressure, model.bc_values_darcy_flux),
+              fourier=_face_values(model, sd, prm[tk]["bc"], model.bc_values_temperature, model.bc_values_fourier_flux),
+              mechanics=_mechanics_boundary(model, sd, data, mk),
+              fluid_flux=_face_values(model, sd, ff, w, model.bc_values_fluid_flux),
+              enthalpy_flux=_face_values(model, sd, ef, we, model.bc_values_enthalpy_flux),
+              fluid_flux_type=ff, enthalpy_flux_type=ef)
+    prob = Thermoporomechanics(sd, data, fluid, solid, bc, flow_keyword=fk, fourier_keyword=tk, mechanics_keyword=mk,
+                               thermal_keyword=ck)
+    prob.mobility_keyword, prob.enthalpy_upwind_keyword = "b200_mobility", "b200_enthalpy_upwind"
+    return prob

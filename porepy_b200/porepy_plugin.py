@@ -234,6 +234,12 @@ def plugin(pp, allow_reference_fallback: bool = False) -> SimpleNamespace:
             aperture=lambda sd: evaluated(model.aperture([sd]), sd.num_cells),
             specific_volume=lambda it: evaluated(model.specific_volume([it]), it.num_cells))
 
+    from . import model_bridge as bridge
     return SimpleNamespace(Mpfa=Mpfa, Mpsa=Mpsa, Biot=Biot, Tpfa=Tpfa, Upwind=Upwind, UpwindCoupling=UpwindCoupling, MpfaAd=MpfaAd, MpsaAd=MpsaAd, BiotAd=BiotAd,
                            ModelMixin=ModelMixin, install=install, uninstall=uninstall, md_flow_from_model=md_flow_from_model,
+                           # nonlinear model problems on the device AD chain (porepy_b200/model_bridge.py)
+                           compressible_flow_from_model=bridge.compressible_flow_from_model,
+                           mass_energy_from_model=bridge.mass_energy_from_model,
+                           poromechanics_from_model=bridge.poromechanics_from_model,
+                           thermoporomechanics_from_model=bridge.thermoporomechanics_from_model,
                            fallback_calls=fallback_calls, gpu_calls=gpu_calls)

@@ -470,3 +470,102 @@ def test_synthetic_fracture_network_matches_the_reference_mesher(pp, emu_plan):
         om, orr = np.lexsort(key_m), np.lexsort(key_r)
         assert np.array_equal(key_m[:, om], key_r[:, orr])
         assert np.abs(mine[om] - pref[orr]).max() <= 1e-9 * np.abs(xref).max()
+
+
+# ---- live models handed to the device problems (porepy_b200/model_bridge.py) ------------------------------------
+
+
+def _newton_iterates(pp, model, n_before=2):
+    """Drive the reference's Newton loop by hand (solution_strategy.py): returns (previous state, iterate, J, rhs) in
+    front of linear solve number ``n_before`` of the first time step."""
+    model.prepare_simulation()
+    es = model.equation_system
+    model.time_manager.increase_time()
+    model.time_manager.increase_time_index()
+    model.before_nonlinear_loop()
+    for _ in range(n_before):
+        model.before_nonlinear_iteration()
+        model.assemble_linear_system()
+        model.after_nonlinear_iteration(model.solve_linear_system())
+    model.before_nonlinear_iteration()
+    model.assemble_linear_system()
+    A, b = model.linear_system
+    return es.get_variable_values(time_step_index=0), es.get_variable_values(iterate_index=0), A, b
+
+
+@pytest.fixture()
+def emu_device(emu_plan, monkeypatch):
+    import emu_sparse
+    emu_sparse.install(monkeypatch)
+
+
+def test_live_poromechanics_and_thermoporomechanics_models(pp, emu_device):
+    """``plugin(pp).poromechanics_from_model`` / ``thermoporomechanics_from_model``: the device problem built from a live
+    model linearizes to the model's own Jacobian and right-hand side at the model's own iterate."""
+    import make_poromech_golden as gp
+    import make_thm_golden as gt
+    from porepy_b200.porepy_plugin import plugin
+    b = plugin(pp)
+    fluid = pp.FluidComponent(compressibility=0.05, viscosity=1.3, density=1.7, thermal_expansion=0.03,
+                              specific_heat_capacity=2.0, thermal_conductivity=0.7)
+    solid = pp.SolidConstants(porosity=0.2, biot_coefficient=0.8, lame_lambda=2.0, shear_modulus=1.5, permeability=1.0,
+                              thermal_expansion=0.02, specific_heat_capacity=1.5, thermal_conductivity=1.1, density=2.5)
+    for cls, build in ((gp.Model, b.poromechanics_from_model), (gt.Model, b.thermoporomechanics_from_model)):
+        model = cls({"times_to_export": [], "time_manager": pp.TimeManager([0, 1.0], 0.25, constant_dt=True),
+                     "material_constants": {"fluid": fluid, "solid": solid}})
+        x_prev, x_it, A, rhs = _newton_iterates(pp, model)
+        prob = build(model)
+        prob.discretize()
+        J, r = prob.linearize(x_it, x_prev, model.time_manager.dt)
+        assert abs(J.to_scipy() - A).max() <= 1e-10 * abs(A).max(), cls
+        assert np.abs(r.numpy() - rhs).max() <= 1e-10 * max(np.abs(rhs).max(), 1e-3 * abs(A).max())
+        sd = model.mdg.subdomains()[0]
+        assert "b200_mobility" not in model.mdg.subdomain_data(sd)[pp.PARAMETERS]      # the model's data stay untouched
+
+
+def test_live_fracture_network_flow_and_energy_models(pp, emu_device):
+    """``compressible_flow_from_model`` (``pp.SinglePhaseFlow``) and ``mass_energy_from_model`` (``pp.MassAndEnergyBalance``)
+    on a live three-fracture network."""
+    import make_mdflow_golden as g
+    from porepy_b200.porepy_plugin import plugin
+    b = plugin(pp)
+    fracs = [g.rect(0, 0.5, 0.25, 0.75), g.rect(1, 0.5, 0.25, 0.75)]
+    fluid = pp.FluidComponent(compressibility=0.05, viscosity=1.3, density=1.7, thermal_expansion=0.03,
+                              specific_heat_capacity=2.0, thermal_conductivity=0.7)
+    solid = pp.SolidConstants(porosity=0.2, residual_aperture=0.05, thermal_expansion=0.02, specific_heat_capacity=1.5,
+                              thermal_conductivity=1.1, density=2.5, normal_permeability=2.0)
+
+    class Thermal:
+        def bc_type_fourier_flux(self, sd):
+            s = self.domain_boundary_sides(sd)
+            return pp.BoundaryCondition(sd, s.west + s.east, "dir")
+
+        def bc_type_enthalpy_flux(self, sd):
+            s = self.domain_boundary_sides(sd)
+            return pp.BoundaryCondition(sd, s.west + s.east, "dir")
+
+        def bc_values_temperature(self, bg):
+            s = self.domain_boundary_sides(bg)
+            v = np.zeros(bg.num_cells)
+            v[s.west] = 0.5 + 0.2 * bg.cell_centers[2, s.west]
+            return v
+    consts = {"fluid": fluid, "solid": solid}
+    # flow: the extra source of the fixture model is passed by hand (the bridge knows the model's laws, not its overrides)
+    model = g.make_model(4, fracs, 0.3, constants=consts, dt=0.25)
+    x_prev, x_it, A, rhs = _newton_iterates(pp, model)
+    prob = b.compressible_flow_from_model(model)
+    for s in prob.subdomains:
+        s.source = model.extra_source(s.sd)
+    prob.discretize()
+    J, r = prob.linearize(x_it, x_prev, model.time_manager.dt)
+    assert abs(J.to_scipy() - A).max() <= 1e-10 * abs(A).max()
+    assert np.abs(r.numpy() - rhs).max() <= 1e-10 * max(np.abs(rhs).max(), 1e-3 * abs(A).max())
+    # mass + energy: the reference interleaves unknowns and equations per grid
+    model = g.make_model(4, fracs, 0.0, constants=consts, dt=0.25, base=pp.MassAndEnergyBalance, mixin=Thermal)
+    x_prev, x_it, A, rhs = _newton_iterates(pp, model)
+    prob, cm, rm = b.mass_energy_from_model(model)
+    prob.discretize()
+    J, r = prob.linearize(x_it[cm], x_prev[cm], model.time_manager.dt)
+    Aref = A.tocsr()[rm][:, cm]
+    assert abs(J.to_scipy() - Aref).max() <= 1e-10 * abs(Aref).max()
+    assert np.abs(r.numpy() - rhs[rm]).max() <= 1e-10 * max(np.abs(rhs).max(), 1e-3 * abs(A).max())

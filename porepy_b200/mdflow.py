@@ -275,13 +275,13 @@ class MixedDimensionalFlow:
         return blocks, rhs, bsizes
 
     # ---- solve: interface fluxes eliminated, Krylov on the pressure Schur complement
-    def solve(self, tol: float = 1e-8, maxiter: int = 4000, sweeps: int = 16):
+    def solve(self, tol: float = 1e-8, maxiter: int = 4000, sweeps: int | None = None):
         """Solve the coupled system on the device.  Jacobi-BiCGStab on the full matrix breaks down (the interface rows
         make it indefinite-like: 4000 iterations without convergence at 10^6 cells, breakdown at 2 * 10^4), while the
         pressure Schur complement ``S = A - B D^-1 E`` (interface fluxes eliminated: a Robin-type coupling between the
         two sides) behaves like the flow matrix itself.  ``D`` (interface x interface: identity plus the MPFA pressure
-        trace of neighbouring fracture faces) is strongly diagonally dominant, so ``D^-1`` is applied by a fixed number
-        of Jacobi sweeps (error factor ~0.2 per sweep) inside a matrix-free operator; BiCGStab runs on ``S`` with the
+        trace of neighbouring fracture faces) is strongly diagonally dominant, so ``D^-1`` is applied by Jacobi sweeps
+        (their number from the measured contraction factor, ~0.2 per sweep here) inside a matrix-free operator; BiCGStab runs on ``S`` with the
         diagonal of ``A - B diag(D)^-1 E`` as preconditioner (torch recurrence of ``krylov.bicgstab``; the SpMVs are
         csrc/spmv.cu).  Returns (x as a tensor in the global ordering, info) with the TRUE relative residual of the
         full system in ``info["true_relres"]``."""
@@ -351,14 +351,44 @@ class MixedDimensionalFlow:
         return parts[:len(self.subdomains)], parts[len(self.subdomains):]
 
 
-def schur_solve(A, B, E, Dm, bp, bl, tol: float = 1e-8, maxiter: int = 4000, sweeps: int = 16):
+def schur_solve(A, B, E, Dm, bp, bl, tol: float = 1e-8, maxiter: int = 4000, sweeps: int | None = None):
     """Solve ``[[A, B], [E, D]] [p; lam] = [bp; bl]`` (``DeviceCsr`` blocks, CUDA tensors) by BiCGStab on the pressure
-    Schur complement ``A - B D^-1 E``; see ``MixedDimensionalFlow.solve``.  Returns (cat(p, lam), info)."""
+    Schur complement ``A - B D^-1 E``; see ``MixedDimensionalFlow.solve``.  ``D^-1`` is applied by Jacobi sweeps; their
+    number is measured on the host copy of the small interface block (sweeps until two probe vectors are solved to 1e-12;
+    ``ValueError`` if 80 do not suffice: the elimination would not converge); ``sweeps`` overrides it.
+    Returns (cat(p, lam), info); ``info["converged"]`` also requires the TRUE residual of the full system to have
+    reached 100 x ``tol``."""
     import torch
     from . import krylov
     D_ = ad.DeviceCsr
-    dl = ad.device_vector(Dm.diagonal())
-    N = Dm - D_(sps.diags(Dm.diagonal()).tocsr())      # off-diagonal part (explicit zeros on the diagonal)
+    dh = Dm.to_scipy()                                   # interface x interface: a few non-zeros per mortar cell
+    diag = dh.diagonal()
+    if np.any(diag == 0.0):
+        raise ValueError("the interface block has a zero on its diagonal")
+    off = (dh - sps.diags(diag)).tocsr()
+    rho = None
+    if sweeps is None:
+        # how many sweeps bring the Jacobi iteration on D to 1e-12?  Measured on the host copy with two probe vectors
+        # (the row-sum bound is useless here: the enthalpy law couples eps to lambda with a weight > 1, yet that part is
+        # nilpotent -- what counts is the spectral radius of the iteration matrix)
+        rng = np.random.default_rng(0)
+        sweeps = 0
+        for v in (np.ones(dh.shape[0]), rng.standard_normal(dh.shape[0])):
+            y, k, err = v / diag, 0, 1.0
+            while k < 80:
+                err = float(np.linalg.norm(dh @ y - v) / max(np.linalg.norm(v), 1e-300))
+                if err <= 1e-12:
+                    break
+                y = (v - off @ y) / diag
+                k += 1
+            if err > 1e-12:
+                raise ValueError("Jacobi sweeps do not converge on the interface block (residual "
+                                 f"{err:.2e} after {k} sweeps): the elimination of the interface unknowns does not apply")
+            sweeps = max(sweeps, k)
+        sweeps = max(sweeps, 2)
+        rho = float(np.exp(np.log(1e-12) / sweeps))           # observed mean contraction per sweep
+    dl = ad.device_vector(diag)
+    N = Dm - D_(sps.diags(diag).tocsr())                 # off-diagonal part (explicit zeros on the diagonal)
     inv_dl = 1.0 / dl
 
     def dinv(v):
@@ -386,6 +416,8 @@ def schur_solve(A, B, E, Dm, bp, bl, tol: float = 1e-8, maxiter: int = 4000, swe
     lam = dinv(bl - (E @ p))
     res = torch.cat([bp - (A @ p) - (B @ lam), bl - (E @ p) - (Dm @ lam)])
     info = dict(info)
-    info.update(true_relres=float(torch.linalg.vector_norm(res) / torch.linalg.vector_norm(torch.cat([bp, bl]))),
-                sweeps=sweeps, schur_matvecs=op.nmatvec, method="BiCGStab on the pressure Schur complement")
+    true_relres = float(torch.linalg.vector_norm(res) / torch.linalg.vector_norm(torch.cat([bp, bl])))
+    info.update(true_relres=true_relres, sweeps=int(sweeps), contraction=rho, schur_matvecs=op.nmatvec,
+                converged=bool(info["converged"]) and true_relres <= 100.0 * tol,
+                method="BiCGStab on the pressure Schur complement")
     return torch.cat([p, lam]), info

@@ -96,14 +96,23 @@ class MixedDimensionalFlow:
 
     @classmethod
     def from_mdg(cls, mdg, keyword: str = "flow", bc_values=None, sources=None, normal_permeability=None,
-                 aperture=None, specific_volume=None):
+                 aperture=None, specific_volume=None, own_data: bool = True):
         """From a PorePy ``MixedDimensionalGrid`` (grids/md_grid.py; duck-typed: ``subdomains``, ``interfaces``,
         ``subdomain_data``, ``interface_to_subdomain_pair`` and the ``MortarGrid`` projections).  The callables map a
         grid to an array: ``bc_values(sd)`` faces, ``sources(sd)`` cells, ``normal_permeability(intf)`` mortar cells,
-        ``aperture(sd)`` cells, ``specific_volume(intf)`` mortar cells (defaults 0 / 0 / 1 / 1 / 1)."""
+        ``aperture(sd)`` cells, ``specific_volume(intf)`` mortar cells (defaults 0 / 0 / 1 / 1 / 1).  ``own_data``: work on
+        copies of the grids' data dictionaries (shared parameter entries, own ``bc_values`` and discretization matrices)
+        so that the grid's own dictionaries -- a live model's -- stay untouched."""
+        from .params import PARAMETERS
         sds = list(mdg.subdomains())
         index = {id(sd): i for i, sd in enumerate(sds)}
-        subs = [MdSubdomain(sd, mdg.subdomain_data(sd),
+
+        def data_of(sd):
+            d = mdg.subdomain_data(sd)
+            if not own_data:
+                return d
+            return {PARAMETERS: {keyword: dict(d.get(PARAMETERS, {}).get(keyword, {}))}, DISCRETIZATION_MATRICES: {}}
+        subs = [MdSubdomain(sd, data_of(sd),
                             None if bc_values is None else np.asarray(bc_values(sd), float),
                             None if sources is None else np.asarray(sources(sd), float)) for sd in sds]
         intfs = []

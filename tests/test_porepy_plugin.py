@@ -348,9 +348,11 @@ def test_mixed_dimensional_flow_from_a_porepy_mdg(pp, emu_plan, monkeypatch):
     from porepy_b200.porepy_plugin import plugin
     prob = plugin(pp).md_flow_from_model(model)
     assert isinstance(prob, MixedDimensionalFlow) and prob.num_dofs == Jref.shape[0]
-    for s in prob.subdomains:                       # forget the reference's own discretization
-        s.data[pp.DISCRETIZATION_MATRICES]["flow"].clear()
+    for s in prob.subdomains:                       # own dictionaries: nothing of the reference's discretization in them
+        assert not s.data[pp.DISCRETIZATION_MATRICES]
     prob.discretize()
+    sd0 = model.mdg.subdomains()[0]
+    assert "bc_values" not in model.mdg.subdomain_data(sd0)[pp.PARAMETERS]["flow"]      # the live model's data stay untouched
     J, b = prob.assemble_host()
     assert abs(J - Jref).max() <= 1e-10 * abs(Jref).max() and np.abs(b - bref).max() <= 1e-10 * np.abs(bref).max()
     for assemble in (prob.assemble_ad, prob.assemble):

@@ -113,3 +113,14 @@ def test_ad_functions_gpu():
             return g.val.cpu().numpy(), g.jac.to_scipy()
         return g.cpu().numpy(), None
     run_checks(make, ad_functions, to_host, load_porepy())
+
+
+@pytest.mark.gpu
+def test_frictional_contact_gpu():
+    """``pp.MomentumBalance`` with a sliding fracture on the device AD chain (tests/test_contact_model.py); the Newton
+    updates of this saddle-point system are solved on the host in the test."""
+    import torch
+    from test_contact_model import check, load_problem
+    prob, d = load_problem()
+    prob.discretize()
+    check(prob, d, lambda t: t.cpu().numpy(), lambda a: torch.as_tensor(np.asarray(a, float), device="cuda"))

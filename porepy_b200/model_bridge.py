@@ -227,3 +227,41 @@ def thermoporomechanics_from_model(model):
                                thermal_keyword=ck)
     prob.mobility_keyword, prob.enthalpy_upwind_keyword = "b200_mobility", "b200_enthalpy_upwind"
     return prob
+
+
+def fractured_momentum_from_model(model):
+    """``pp.MomentumBalance`` with fractures in frictional contact -> (``FracturedMomentumBalance``, column_map): one 3-D
+    matrix subdomain, any number of 2-D fractures (each with its two-sided interface); unknown k of the problem is dof
+    ``column_map[k]`` of the model ([u | contact tractions | interface displacements])."""
+    from .contact import FractureContact, FracturedMomentumBalance
+    mdg, es = model.mdg, model.equation_system
+    mats = list(mdg.subdomains(dim=3))
+    fracs = list(mdg.subdomains(dim=2))
+    if len(mats) != 1 or any(sd.dim < 2 for sd in mdg.subdomains()):
+        raise NotImplementedError("one 3-D matrix subdomain and 2-D fractures without intersections are expected")
+    mat = mats[0]
+    mk = model.stress_keyword
+    data = _own_data(mdg.subdomain_data(mat), [mk])
+
+    def scalar(op):
+        return float(np.atleast_1d(_evaluated(model, op, 1))[0])
+    contacts, intfs = [], []
+    for frac in fracs:
+        intf = [it for it in mdg.interfaces() if mdg.interface_to_subdomain_pair(it)[1] is frac][0]
+        rot = mdg.subdomain_data(frac)["tangential_normal_projection"].project_tangential_normal(frac.num_cells)
+        contacts.append(FractureContact(intf.mortar_to_primary_avg(), intf.primary_to_mortar_int(),
+                                        intf.mortar_to_secondary_avg(), intf.secondary_to_mortar_int(),
+                                        sps.csr_matrix(intf.sign_of_mortar_sides(1)).diagonal(), intf.cell_volumes, rot))
+        intfs.append(intf)
+    constants = dict(numerical_constant=scalar(model.contact_mechanics_numerical_constant(fracs)),
+                     characteristic_traction=scalar(model.characteristic_contact_traction(fracs)),
+                     friction_coefficient=scalar(model.friction_coefficient(fracs)),
+                     dilation_angle=model.solid.dilation_angle, reference_gap=model.solid.fracture_gap,
+                     open_state_tolerance=model.numerical.open_state_tolerance)
+    prob = FracturedMomentumBalance(mat, data, _mechanics_boundary(model, mat, data, mk), contacts, constants, keyword=mk)
+
+    def dofs(name, g):
+        return es.dofs_of([v for v in es.variables if v.name == name and v.domain is g])
+    cols = [dofs(model.displacement_variable, mat)] + [dofs(model.contact_traction_variable, f) for f in fracs] \
+        + [dofs(model.interface_displacement_variable, it) for it in intfs]
+    return prob, np.concatenate(cols)

@@ -242,4 +242,5 @@ def plugin(pp, allow_reference_fallback: bool = False) -> SimpleNamespace:
                            mass_energy_from_model=bridge.mass_energy_from_model,
                            poromechanics_from_model=bridge.poromechanics_from_model,
                            thermoporomechanics_from_model=bridge.thermoporomechanics_from_model,
+                           fractured_momentum_from_model=bridge.fractured_momentum_from_model,
                            fallback_calls=fallback_calls, gpu_calls=gpu_calls)

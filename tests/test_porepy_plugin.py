@@ -571,3 +571,20 @@ def test_live_fracture_network_flow_and_energy_models(pp, emu_device):
     Aref = A.tocsr()[rm][:, cm]
     assert abs(J.to_scipy() - Aref).max() <= 1e-10 * abs(Aref).max()
     assert np.abs(r.numpy() - rhs[rm]).max() <= 1e-10 * max(np.abs(rhs).max(), 1e-3 * abs(A).max())
+
+
+def test_live_contact_mechanics_model(pp, emu_device):
+    """``plugin(pp).fractured_momentum_from_model``: a live ``pp.MomentumBalance`` with a compressed, sheared fracture."""
+    import make_contact_golden as gc
+    from porepy_b200.porepy_plugin import plugin
+    solid = pp.SolidConstants(lame_lambda=2.0, shear_modulus=1.5, friction_coefficient=0.4, fracture_gap=1e-4,
+                              dilation_angle=0.1)
+    model = gc.Model({"times_to_export": [], "time_manager": pp.TimeManager([0, 1.0], 1.0, constant_dt=True),
+                      "material_constants": {"solid": solid}})
+    x_prev, x_it, A, rhs = _newton_iterates(pp, model, n_before=1)
+    prob, cm = plugin(pp).fractured_momentum_from_model(model)
+    prob.discretize()
+    J, r = prob.linearize(x_it[cm], x_prev[cm])
+    Aref = A.tocsr()[:, cm]                       # equations in the model's own order
+    assert abs(J.to_scipy() - Aref).max() <= 1e-10 * abs(Aref).max()
+    assert np.abs(r.numpy() - rhs).max() <= 1e-10 * np.abs(rhs).max()

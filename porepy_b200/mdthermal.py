@@ -1,6 +1,6 @@
 """Mass and energy balance in a fracture network, the reference's ``pp.MassAndEnergyBalance`` on the device AD chain --
 the thermal half of BASELINE config[4] on a mixed-dimensional grid (the mechanical half on a 3-D subdomain:
-``porepy_b200.thermoporomech``; frictional contact is not restated).
+``porepy_b200.thermoporomech``; frictional contact on a fracture: ``porepy_b200.contact``).
 
 Per subdomain: pressure and temperature; per interface: Darcy flux ``lambda``, Fourier flux ``eta``, enthalpy flux ``eps``.
 

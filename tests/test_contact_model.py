@@ -8,6 +8,7 @@ import os
 from types import SimpleNamespace
 
 import numpy as np
+import pytest
 import scipy.sparse as sps
 import scipy.sparse.linalg as spla
 
@@ -21,8 +22,11 @@ def _csr(d, key):
     return sps.csr_matrix((d[key + "__data"], d[key + "__indices"], d[key + "__indptr"]), shape=tuple(d[key + "__shape"]))
 
 
-def load_problem():
-    d = dict(np.load(os.path.join(GOLDEN_DIR, "contact_model.npz"), allow_pickle=False))
+CASES = ["contact_model", "contact_sticking", "contact_open", "contact_mixed"]   # sliding / sticking / open / open + sliding
+
+
+def load_problem(name="contact_model"):
+    d = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
     g = Grid.from_arrays({k[len("matrix__"):]: v for k, v in d.items() if k.startswith("matrix__")})
     nf = g.num_faces
     vbc = SimpleNamespace(is_dir=d["mech_is_dir"], is_neu=d["mech_is_neu"], is_rob=d["mech_is_rob"],
@@ -43,7 +47,8 @@ def check(prob, d, to_host, make_tensor):
     J, rhs = prob.linearize(d["iterate"], d["previous"])
     Jref, bref = _csr(d, "iterate_jacobian"), d["iterate_rhs"]
     assert abs(J.to_scipy() - Jref).max() <= 1e-10 * abs(Jref).max()
-    assert np.abs(to_host(rhs) - bref).max() <= 1e-10 * np.abs(bref).max()
+    # (in the sticking and open cases the stored iterate is already converged: compare on the Jacobian's scale then)
+    assert np.abs(to_host(rhs) - bref).max() <= 1e-10 * max(np.abs(bref).max(), 1e-3 * abs(Jref).max())
 
     def direct(Jd, r):                                             # zeros on the diagonal of the complementarity rows
         return make_tensor(spla.spsolve(Jd.to_scipy().tocsc(), to_host(r)))
@@ -51,21 +56,35 @@ def check(prob, d, to_host, make_tensor):
     ref = d["residual_norms"]
     assert hist[-1]["residual"] <= 1e-10 * hist[0]["residual"] and len(hist) <= len(ref) + 1, hist
     for mine, theirs in zip(hist[:4], ref[:4]):                    # the semismooth loop's own (non-monotone) history
-        assert abs(mine["residual"] - theirs) <= 0.05 * theirs, (hist, ref)
+        if theirs > 1e-9 * ref[0]:
+            assert abs(mine["residual"] - theirs) <= 0.05 * theirs, (hist, ref)
     xh = to_host(x)
     assert np.linalg.norm(xh - d["solution"]) <= 1e-8 * np.linalg.norm(d["solution"])
-    t = xh[prob.offsets[1]:prob.offsets[2]].reshape(-1, 3)         # sliding: |t_t| = mu |t_n| in every fracture cell
-    assert np.allclose(np.linalg.norm(t[:, :2], axis=1), float(d["friction_coefficient"]) * np.abs(t[:, 2]), rtol=1e-8)
-    assert np.all(t[:, 2] < 0)
+    # the contact conditions at the converged state: open cells carry no traction, closed ones a compressive normal
+    # traction and a tangential one inside (sticking) or on (sliding) the friction cone
+    t = xh[prob.offsets[1]:prob.offsets[2]].reshape(-1, 3)
+    mu = float(d["friction_coefficient"])
+    is_open = np.abs(t[:, 2]) < 1e-12
+    assert np.all(np.abs(t[is_open]) < 1e-12) and np.all(t[~is_open, 2] < 0)
+    assert np.all(np.linalg.norm(t[~is_open, :2], axis=1) <= mu * np.abs(t[~is_open, 2]) * (1 + 1e-8))
+    return t
 
 
-def test_frictional_contact_host_build(monkeypatch):
+@pytest.mark.parametrize("name", CASES)
+def test_frictional_contact_host_build(name, monkeypatch):
     import torch
     from emu_binding import EmuBackedPlan
     from porepy_b200 import fv
     import emu_sparse
     monkeypatch.setattr(fv, "DevicePlan", EmuBackedPlan)
     emu_sparse.install(monkeypatch)
-    prob, d = load_problem()
+    prob, d = load_problem(name)
     prob.discretize()
-    check(prob, d, lambda t: t.numpy(), lambda a: torch.as_tensor(np.asarray(a, float)))
+    t = check(prob, d, lambda t: t.numpy(), lambda a: torch.as_tensor(np.asarray(a, float)))
+    mu = float(d["friction_coefficient"])
+    ratio = np.linalg.norm(t[:, :2], axis=1) / np.maximum(mu * np.abs(t[:, 2]), 1e-300)
+    expect = {"contact_model": lambda: np.allclose(ratio, 1.0, rtol=1e-8),            # sliding everywhere
+              "contact_sticking": lambda: np.all(ratio < 0.2),
+              "contact_open": lambda: np.all(t == 0.0),
+              "contact_mixed": lambda: np.sum(np.abs(t[:, 2]) < 1e-12) == 2 and np.allclose(ratio[np.abs(t[:, 2]) > 1e-12], 1.0)}
+    assert expect[name](), (name, t)

@@ -116,11 +116,12 @@ def test_ad_functions_gpu():
 
 
 @pytest.mark.gpu
-def test_frictional_contact_gpu():
+@pytest.mark.parametrize("name", ["contact_model", "contact_sticking", "contact_open", "contact_mixed"])
+def test_frictional_contact_gpu(name):
     """``pp.MomentumBalance`` with a sliding fracture on the device AD chain (tests/test_contact_model.py); the Newton
     updates of this saddle-point system are solved on the host in the test."""
     import torch
     from test_contact_model import check, load_problem
-    prob, d = load_problem()
+    prob, d = load_problem(name)
     prob.discretize()
     check(prob, d, lambda t: t.cpu().numpy(), lambda a: torch.as_tensor(np.asarray(a, float), device="cuda"))

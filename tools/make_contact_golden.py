@@ -47,20 +47,33 @@ class Model(pp.MomentumBalance):
         bc.internal_to_dirichlet(sd)
         return bc
 
+    scenario = "sliding"
+
     def bc_values_displacement(self, bg):
         s = self.domain_boundary_sides(bg)
         v = np.zeros((3, bg.num_cells))
-        v[0, s.east] = -0.01 * (1 + 0.3 * bg.cell_centers[2, s.east])     # compress across the fracture, unevenly
-        v[1, s.east] = 0.02                                                # and shear it
-        v[2, s.east] = 0.005 * bg.cell_centers[1, s.east]
+        if self.scenario == "sliding":
+            v[0, s.east] = -0.01 * (1 + 0.3 * bg.cell_centers[2, s.east])     # compress across the fracture, unevenly
+            v[1, s.east] = 0.02                                                # and shear it
+            v[2, s.east] = 0.005 * bg.cell_centers[1, s.east]
+        elif self.scenario == "sticking":                                      # strong compression, little shear
+            v[0, s.east] = -0.02
+            v[1, s.east] = 0.002 * bg.cell_centers[2, s.east]
+        elif self.scenario == "open":                                          # pull the fracture open (+ some shear)
+            v[0, s.east] = 0.01 * (1 + 0.5 * bg.cell_centers[1, s.east])
+            v[2, s.east] = 0.004
+        elif self.scenario == "mixed":                                         # a rotation-like load: part closes, part opens
+            v[0, s.east] = 0.03 * (bg.cell_centers[2, s.east] - 0.5)
+            v[1, s.east] = 0.01
         return v.ravel("F")
 
 
-def main():
+def main(scenario="sliding", name="contact_model"):
     solid = pp.SolidConstants(lame_lambda=2.0, shear_modulus=1.5, friction_coefficient=0.4, fracture_gap=1e-4,
                               dilation_angle=0.1)
     m = Model({"times_to_export": [], "time_manager": pp.TimeManager([0, 1.0], 1.0, constant_dt=True),
                "material_constants": {"solid": solid}})
+    m.scenario = scenario
     m.prepare_simulation()
     es, mdg = m.equation_system, m.mdg
     mat, frac, intf = mdg.subdomains(dim=3)[0], mdg.subdomains(dim=2)[0], mdg.interfaces()[0]
@@ -113,12 +126,15 @@ def main():
     put_csr(d, "local_coordinates", rot)
     for key in ("mortar_to_primary_avg", "primary_to_mortar_int", "mortar_to_secondary_avg", "secondary_to_mortar_int"):
         put_csr(d, key, getattr(intf, key)())
-    np.savez_compressed(os.path.join(OUT, "contact_model.npz"), **d)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
     t = d["solution"][dofs("contact_traction")].reshape(-1, 3)
-    print("contact_model dofs", es.num_dofs(), "Newton residuals", ["%.2e" % v for v in norms])
+    print(name, "dofs", es.num_dofs(), "Newton residuals", ["%.2e" % v for v in norms])
     print("   contact traction (t1, t2, n) per fracture cell:\\n", t, "\\n   |t_t| / (mu |t_n|):",
           np.linalg.norm(t[:, :2], axis=1) / (0.4 * np.abs(t[:, 2])))
 
 
 if __name__ == "__main__":
-    main()
+    main("sliding", "contact_model")
+    main("sticking", "contact_sticking")
+    main("open", "contact_open")
+    main("mixed", "contact_mixed")

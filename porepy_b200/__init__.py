@@ -5,6 +5,7 @@ The CUDA library (``libporeb200.so``, built in-tree by ``porepy_b200.build``) is
 first use; there is no CPU fallback.
 """
 from .contact import FractureContact, FracturedMomentumBalance  # noqa: F401
+from .fractured_poromech import FractureCoupling, FracturedPoromechanics  # noqa: F401
 from .fv import (Biot, DevicePlan, FaceGrid, Mpfa, Mpsa, Tpfa, Upwind, UpwindCoupling,  # noqa: F401
                  determine_eta)
 from .geometry import compute_geometry  # noqa: F401
@@ -24,4 +25,4 @@ __all__ = ["Mpfa", "Mpsa", "Biot", "Tpfa", "Upwind", "UpwindCoupling", "DevicePl
            "structured_tet_grid", "tet_grid_from_cells", "SecondOrderTensor", "FourthOrderTensor",
            "BoundaryCondition", "BoundaryConditionVectorial", "initialize_data", "PARAMETERS",
            "DISCRETIZATION_MATRICES", "determine_eta", "compute_geometry", "DifferentiableTpfa",
-           "MixedDimensionalFlow", "MdSubdomain", "MdInterface", "CompressibleMixedDimensionalFlow", "Poromechanics", "Thermoporomechanics", "MixedDimensionalMassEnergy", "FracturedMomentumBalance", "FractureContact"]
+           "MixedDimensionalFlow", "MdSubdomain", "MdInterface", "CompressibleMixedDimensionalFlow", "Poromechanics", "Thermoporomechanics", "MixedDimensionalMassEnergy", "FracturedMomentumBalance", "FractureContact", "FracturedPoromechanics", "FractureCoupling"]

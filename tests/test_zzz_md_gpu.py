@@ -125,3 +125,15 @@ def test_frictional_contact_gpu(name):
     prob, d = load_problem(name)
     prob.discretize()
     check(prob, d, lambda t: t.cpu().numpy(), lambda a: torch.as_tensor(np.asarray(a, float), device="cuda"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["contact_poromech", "contact_poromech_mixed"])
+def test_fractured_poromechanics_with_contact_gpu(name):
+    """``pp.Poromechanics`` on a fractured medium with frictional contact (tests/test_contact_poromech.py) on the device AD
+    chain; the Newton updates of the saddle-point system are solved on the host in the test."""
+    import torch
+    from test_contact_poromech import check, load_problem
+    prob, d = load_problem(name)
+    prob.discretize()
+    check(prob, d, lambda t: t.cpu().numpy(), lambda a: torch.as_tensor(np.asarray(a, float), device="cuda"))

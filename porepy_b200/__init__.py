@@ -6,6 +6,7 @@ first use; there is no CPU fallback.
 """
 from .contact import FractureContact, FracturedMomentumBalance  # noqa: F401
 from .fractured_poromech import FractureCoupling, FracturedPoromechanics  # noqa: F401
+from .fractured_thm import FracturedThermoporomechanics  # noqa: F401
 from .fv import (Biot, DevicePlan, FaceGrid, Mpfa, Mpsa, Tpfa, Upwind, UpwindCoupling,  # noqa: F401
                  determine_eta)
 from .geometry import compute_geometry  # noqa: F401
@@ -25,4 +26,4 @@ __all__ = ["Mpfa", "Mpsa", "Biot", "Tpfa", "Upwind", "UpwindCoupling", "DevicePl
            "structured_tet_grid", "tet_grid_from_cells", "SecondOrderTensor", "FourthOrderTensor",
            "BoundaryCondition", "BoundaryConditionVectorial", "initialize_data", "PARAMETERS",
            "DISCRETIZATION_MATRICES", "determine_eta", "compute_geometry", "DifferentiableTpfa",
-           "MixedDimensionalFlow", "MdSubdomain", "MdInterface", "CompressibleMixedDimensionalFlow", "Poromechanics", "Thermoporomechanics", "MixedDimensionalMassEnergy", "FracturedMomentumBalance", "FractureContact", "FracturedPoromechanics", "FractureCoupling"]
+           "MixedDimensionalFlow", "MdSubdomain", "MdInterface", "CompressibleMixedDimensionalFlow", "Poromechanics", "Thermoporomechanics", "MixedDimensionalMassEnergy", "FracturedMomentumBalance", "FractureContact", "FracturedPoromechanics", "FractureCoupling", "FracturedThermoporomechanics"]

@@ -137,3 +137,15 @@ def test_fractured_poromechanics_with_contact_gpu(name):
     prob, d = load_problem(name)
     prob.discretize()
     check(prob, d, lambda t: t.cpu().numpy(), lambda a: torch.as_tensor(np.asarray(a, float), device="cuda"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["contact_thm", "contact_thm_mixed"])
+def test_fractured_thermoporomechanics_with_contact_gpu(name):
+    """BASELINE config[4] as the reference states it: ``pp.Thermoporomechanics`` on a fractured medium with frictional
+    contact (tests/test_contact_thm.py) on the device AD chain; Newton updates solved on the host in the test."""
+    import torch
+    from test_contact_thm import check, load_problem
+    prob, d = load_problem(name)
+    prob.discretize()
+    check(prob, d, lambda t: t.cpu().numpy(), lambda a: torch.as_tensor(np.asarray(a, float), device="cuda"))

@@ -280,7 +280,173 @@ def main_poromechanics(scenario="sliding", name="contact_poromech"):
     print("   contact traction:", np.array2string(t, precision=4).replace("\n", ";"))
 
 
+def main_thm(scenario="sliding", name="contact_thm"):
+    """``pp.Thermoporomechanics`` on the fractured domain: BASELINE config[4] (thermo-poromechanics + frictional contact, full
+    Newton loop) on one fracture."""
+    class ThmModel(pp.Thermoporomechanics):
+        set_domain, grid_type, meshing_arguments = Model.set_domain, Model.grid_type, Model.meshing_arguments
+        set_fractures, stiffness_tensor = Model.set_fractures, Model.stiffness_tensor
+        bc_type_mechanics, bc_values_displacement = Model.bc_type_mechanics, Model.bc_values_displacement
+
+        def permeability(self, subdomains):
+            vals = []
+            for sd in subdomains:
+                rng = np.random.default_rng(5 + sd.num_cells)
+                nc = sd.num_cells
+                t = np.zeros((3, 3, nc))
+                scale = 1.0 if sd.dim == 3 else 20.0
+                t[0, 0], t[1, 1], t[2, 2] = scale * (1 + rng.random((3, nc)))
+                o = 0.3 * scale * rng.random((3, nc))
+                t[0, 1] = t[1, 0] = o[0]
+                t[0, 2] = t[2, 0] = o[1]
+                t[1, 2] = t[2, 1] = o[2]
+                vals.append(t.reshape(9, nc).ravel("F"))
+            return pp.wrap_as_dense_ad_array(np.hstack(vals) if vals else np.zeros(0), name="permeability")
+
+        def bc_type_darcy_flux(self, sd):
+            s = self.domain_boundary_sides(sd)
+            return pp.BoundaryCondition(sd, s.south + s.north, "dir")
+        bc_type_fluid_flux = bc_type_fourier_flux = bc_type_enthalpy_flux = bc_type_darcy_flux
+
+        def bc_values_pressure(self, bg):
+            s = self.domain_boundary_sides(bg)
+            v = np.zeros(bg.num_cells)
+            v[s.south] = 0.02 * (1 + bg.cell_centers[0, s.south])
+            return v
+
+        def bc_values_temperature(self, bg):
+            s = self.domain_boundary_sides(bg)
+            v = np.zeros(bg.num_cells)
+            v[s.south] = 0.3 + 0.1 * bg.cell_centers[2, s.south]
+            return v
+    fluid = pp.FluidComponent(compressibility=0.05, viscosity=1.3, density=1.7, thermal_expansion=0.03,
+                              specific_heat_capacity=2.0, thermal_conductivity=0.7)
+    solid = pp.SolidConstants(porosity=0.2, biot_coefficient=0.8, lame_lambda=2.0, shear_modulus=1.5, permeability=1.0,
+                              normal_permeability=2.0, residual_aperture=0.05, friction_coefficient=0.4, fracture_gap=1e-4,
+                              dilation_angle=0.1, thermal_expansion=0.02, specific_heat_capacity=1.5,
+                              thermal_conductivity=1.1, density=2.5)
+    m = ThmModel({"times_to_export": [], "time_manager": pp.TimeManager([0, 1.0], 0.25, constant_dt=True),
+                  "material_constants": {"fluid": fluid, "solid": solid}})
+    m.scenario = scenario
+    m.prepare_simulation()
+    es, mdg = m.equation_system, m.mdg
+    mat, frac, intf = mdg.subdomains(dim=3)[0], mdg.subdomains(dim=2)[0], mdg.interfaces()[0]
+
+    def dofs(name, g=None):
+        return es.dofs_of([v for v in es.variables if v.name == name and (g is None or v.domain is g)])
+    d = {f"matrix__{k}": v for k, v in grid_arrays(mat).items()}
+    d.update({f"fracture__{k}": v for k, v in grid_arrays(frac).items()})
+    d["fracture__tip_faces"] = np.asarray(frac.tags["tip_faces"], bool)
+    d["fracture__domain_boundary_faces"] = np.asarray(frac.tags["domain_boundary_faces"], bool)
+    d["matrix__domain_boundary_faces"] = np.asarray(mat.tags["domain_boundary_faces"], bool)
+    for key, sd in (("matrix", mat), ("fracture", frac)):
+        for short, kw in (("flow", "flow"), ("fourier", "fourier_discretization")):
+            prm = mdg.subdomain_data(sd)[pp.PARAMETERS][kw]
+            d[f"{key}__{short}_K"] = prm["second_order_tensor"].values.copy()       # at the initial state
+            for f in ("is_dir", "is_neu", "is_rob", "is_internal"):
+                d[f"{key}__{short}_{f}"] = getattr(prm["bc"], f)
+    svm = mdg.subdomain_data(mat)[pp.PARAMETERS]["mechanics"]["scalar_vector_mappings"]
+    d["alpha_flow"], d["alpha_thermal"] = svm["flow"].values, svm[m.enthalpy_keyword].values
+    layout = {"normal_fracture_deformation_equation": [(frac, 1)], "tangential_fracture_deformation_equation": [(frac, 2)],
+              "momentum_balance_equation": [(mat, 3)], "interface_force_balance_equation": [(intf, 3)],
+              "mass_balance_equation": [(mat, 1), (frac, 1)], "interface_darcy_flux_equation": [(intf, 1)],
+              "energy_balance_equation": [(mat, 1), (frac, 1)], "interface_fourier_flux_equation": [(intf, 1)],
+              "interface_enthalpy_flux_equation": [(intf, 1)]}
+    rows, r0 = {}, 0
+    for eq in es.equations:
+        for g, k in layout.get(eq, []):
+            rows[(eq, id(g))] = np.arange(r0, r0 + k * g.num_cells)
+            r0 += k * g.num_cells
+    m.time_manager.increase_time()
+    m.time_manager.increase_time_index()
+    m.before_nonlinear_loop()
+    x_prev = es.get_variable_values(time_step_index=0)
+    norms = []
+    for it in range(25):
+        m.before_nonlinear_iteration()
+        m.assemble_linear_system()
+        A, b = m.linear_system
+        norms.append(np.linalg.norm(b))
+        if it == 0:
+            d["initial_rhs"] = b.copy()
+            put_csr(d, "initial_jacobian", A)
+        if it == 3:                       # aperture off its residual value here: the re-discretized fracture fluxes matter
+            d["iterate"] = es.get_variable_values(iterate_index=0)
+            d["iterate_rhs"] = b.copy()
+            put_csr(d, "iterate_jacobian", A)
+        if norms[-1] < 1e-11 * norms[0]:
+            break
+        m.after_nonlinear_iteration(m.solve_linear_system())
+    bg = mdg.subdomain_to_boundary_grid(mat)
+    proj = bg.projection()
+    proj3 = sps.kron(proj, sps.eye(3)).tocsr()
+    prm = mdg.subdomain_data(mat)[pp.PARAMETERS]
+    bcm, bcf, bct = prm["mechanics"]["bc"], prm["flow"]["bc"], prm["fourier_discretization"]["bc"]
+    bff, bfe = m.bc_type_fluid_flux(mat), m.bc_type_enthalpy_flux(mat)
+    fl, so = m.fluid.reference_component, m.solid
+    p_ref, t_ref = m.reference_variable_values.pressure, m.reference_variable_values.temperature
+    pb_, tb = proj.T @ m.bc_values_pressure(bg), proj.T @ m.bc_values_temperature(bg)
+    rho_b = fl.density * np.exp(fl.compressibility * (pb_ - p_ref) - fl.thermal_expansion * (tb - t_ref))
+
+    def scalar(op):
+        v = es.evaluate(op)
+        return float(np.atleast_1d(getattr(v, "val", v))[0])
+
+    def field(op, n):
+        v = es.evaluate(op)
+        v = getattr(v, "val", v)
+        return np.full(n, float(v)) if np.ndim(v) == 0 else np.asarray(v, float)
+    kb = so.lame_lambda + 2 * so.shear_modulus / 3
+    rot = mdg.subdomain_data(frac)["tangential_normal_projection"].project_tangential_normal(frac.num_cells)
+    order_c = [dofs("pressure", mat), dofs("pressure", frac), dofs("temperature", mat), dofs("temperature", frac), dofs("u"),
+               dofs("contact_traction"), dofs("interface_darcy_flux"), dofs("interface_fourier_flux"),
+               dofs("interface_enthalpy_flux"), dofs("u_interface")]
+    order_r = [("mass_balance_equation", mat), ("mass_balance_equation", frac), ("energy_balance_equation", mat),
+               ("energy_balance_equation", frac), ("momentum_balance_equation", mat), ("interface_darcy_flux_equation", intf),
+               ("interface_fourier_flux_equation", intf), ("interface_enthalpy_flux_equation", intf),
+               ("interface_force_balance_equation", intf), ("normal_fracture_deformation_equation", frac),
+               ("tangential_fracture_deformation_equation", frac)]
+    d.update(previous=x_prev, solution=es.get_variable_values(iterate_index=0), residual_norms=np.array(norms),
+             column_map=np.concatenate(order_c), row_map=np.concatenate([rows[(eq, id(g))] for eq, g in order_r]),
+             dt=np.float64(m.time_manager.dt),
+             C=prm["mechanics"]["fourth_order_tensor"].values,
+             biot_coefficient=np.float64(so.biot_coefficient), reference_porosity=np.float64(so.porosity),
+             n_inv=np.float64((so.biot_coefficient - so.porosity) * (1 - so.biot_coefficient) / kb),
+             compressibility=np.float64(fl.compressibility), density=np.float64(fl.density), viscosity=np.float64(fl.viscosity),
+             fluid_thermal_expansion=np.float64(fl.thermal_expansion), fluid_heat_capacity=np.float64(fl.specific_heat_capacity),
+             fluid_conductivity=np.float64(fl.thermal_conductivity), solid_thermal_expansion=np.float64(so.thermal_expansion),
+             solid_heat_capacity=np.float64(so.specific_heat_capacity), solid_conductivity=np.float64(so.thermal_conductivity),
+             solid_density=np.float64(so.density), reference_pressure=np.float64(p_ref), reference_temperature=np.float64(t_ref),
+             residual_aperture=np.float64(so.residual_aperture),
+             normal_permeability=field(m.normal_permeability([intf]), intf.num_cells),
+             normal_thermal_conductivity=field(m.normal_thermal_conductivity([intf]), intf.num_cells),
+             mech_is_dir=bcm.is_dir, mech_is_neu=bcm.is_neu, mech_is_rob=bcm.is_rob, mech_is_internal=bcm.is_internal,
+             mech_bc_values=np.where(bcm.is_dir.ravel("F"), proj3.T @ m.bc_values_displacement(bg),
+                                     proj3.T @ m.bc_values_stress(bg)),
+             flow_bc_values=np.where(bcf.is_dir, pb_, proj.T @ m.bc_values_darcy_flux(bg)),
+             fourier_bc_values=np.where(bct.is_dir, tb, proj.T @ m.bc_values_fourier_flux(bg)),
+             ff_is_dir=bff.is_dir, ff_is_neu=bff.is_neu,
+             ff_values=np.where(bff.is_dir, rho_b / fl.viscosity, proj.T @ m.bc_values_fluid_flux(bg)),
+             ef_is_dir=bfe.is_dir, ef_is_neu=bfe.is_neu,
+             ef_values=np.where(bfe.is_dir, fl.specific_heat_capacity * (tb - t_ref) * rho_b / fl.viscosity,
+                                proj.T @ m.bc_values_enthalpy_flux(bg)),
+             mortar_sign=sps.csr_matrix(intf.sign_of_mortar_sides(1)).diagonal(), mortar_volumes=intf.cell_volumes,
+             numerical_constant=np.float64(scalar(m.contact_mechanics_numerical_constant([frac]))),
+             characteristic_traction=np.float64(scalar(m.characteristic_contact_traction([frac]))),
+             friction_coefficient=np.float64(scalar(m.friction_coefficient([frac]))),
+             dilation_angle=np.float64(so.dilation_angle), reference_gap=np.float64(so.fracture_gap),
+             open_state_tolerance=np.float64(m.numerical.open_state_tolerance))
+    put_csr(d, "local_coordinates", rot)
+    for key in ("mortar_to_primary_avg", "primary_to_mortar_int", "mortar_to_secondary_avg", "secondary_to_mortar_int",
+                "mortar_to_primary_int", "primary_to_mortar_avg", "mortar_to_secondary_int", "secondary_to_mortar_avg"):
+        put_csr(d, key, getattr(intf, key)())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "dofs", es.num_dofs(), "Newton residuals", ["%.2e" % v for v in norms])
+
+
 if __name__ == "__main__":
+    main_thm("sliding", "contact_thm")
+    main_thm("mixed", "contact_thm_mixed")
     main_poromechanics("sliding", "contact_poromech")
     main_poromechanics("mixed", "contact_poromech_mixed")
     main("sliding", "contact_model")

@@ -265,3 +265,125 @@ def fractured_momentum_from_model(model):
     cols = [dofs(model.displacement_variable, mat)] + [dofs(model.contact_traction_variable, f) for f in fracs] \
         + [dofs(model.interface_displacement_variable, it) for it in intfs]
     return prob, np.concatenate(cols)
+
+
+def _contact_constants(model, fracs):
+    def scalar(op):
+        return float(np.atleast_1d(_evaluated(model, op, 1))[0])
+    return dict(numerical_constant=scalar(model.contact_mechanics_numerical_constant(fracs)),
+                characteristic_traction=scalar(model.characteristic_contact_traction(fracs)),
+                friction_coefficient=scalar(model.friction_coefficient(fracs)),
+                dilation_angle=model.solid.dilation_angle, reference_gap=model.solid.fracture_gap,
+                open_state_tolerance=model.numerical.open_state_tolerance)
+
+
+def _fractured_problem(model, thermal: bool):
+    """Shared part of the two fractured (thermo-)poromechanics bridges."""
+    from .fractured_poromech import FractureCoupling
+    mdg, es = model.mdg, model.equation_system
+    mats, fracs = list(mdg.subdomains(dim=3)), list(mdg.subdomains(dim=2))
+    if len(mats) != 1 or any(sd.dim < 2 for sd in mdg.subdomains()):
+        raise NotImplementedError("one 3-D matrix subdomain and 2-D fractures without intersections are expected")
+    mat = mats[0]
+    fk, mk = model.darcy_keyword, model.stress_keyword
+    kws = [fk, mk] + ([model.fourier_keyword] if thermal else [])
+    data = _own_data(mdg.subdomain_data(mat), kws)
+    a_res = model.solid.residual_aperture
+    couplings, intfs, kappa_t = [], [], []
+    for frac in fracs:
+        intf = [it for it in mdg.interfaces() if mdg.interface_to_subdomain_pair(it)[1] is frac][0]
+        fdata = _own_data(mdg.subdomain_data(frac), [fk] + ([model.fourier_keyword] if thermal else []))
+        k_now = np.asarray(fdata[PARAMETERS][fk]["second_order_tensor"].values, float)
+        a_now = _evaluated(model, model.specific_volume([frac]), frac.num_cells)       # the tensor holds k x specific volume
+        proj = {name: getattr(intf, name)() for name in (
+            "mortar_to_primary_avg", "primary_to_mortar_int", "mortar_to_secondary_avg", "secondary_to_mortar_int",
+            "mortar_to_primary_int", "primary_to_mortar_avg", "mortar_to_secondary_int", "secondary_to_mortar_avg")}
+        rot = mdg.subdomain_data(frac)["tangential_normal_projection"].project_tangential_normal(frac.num_cells)
+        couplings.append(FractureCoupling(frac, fdata, proj, sps.csr_matrix(intf.sign_of_mortar_sides(1)).diagonal(),
+                                          intf.cell_volumes, rot, _evaluated(model, model.normal_permeability([intf]), intf.num_cells),
+                                          k_now / a_now[None, None, :]))
+        intfs.append(intf)
+        if thermal:
+            kappa_t.append(_evaluated(model, model.normal_thermal_conductivity([intf]), intf.num_cells))
+    fluid = _fluid(model, thermal)
+    so = model.solid
+    solid = dict(reference_porosity=so.porosity, n_inv=_n_inv(model), residual_aperture=a_res)
+    w, we = _boundary_weights(model, mat, fluid, thermal)
+    ff = model.bc_type_fluid_flux(mat)
+    prm = data[PARAMETERS]
+    bc = dict(flow=_face_values(model, mat, prm[fk]["bc"], model.bc_values_pressure, model.bc_values_darcy_flux),
+              mechanics=_mechanics_boundary(model, mat, data, mk),
+              fluid_flux=_face_values(model, mat, ff, w, model.bc_values_fluid_flux), fluid_flux_type=ff)
+
+    def dofs(name, g):
+        return es.dofs_of([v for v in es.variables if v.name == name and v.domain is g])
+    return mat, fracs, intfs, data, couplings, fluid, solid, bc, kappa_t, (w, we), dofs
+
+
+def _row_map(model, layout_order):
+    es = model.equation_system
+    rows, r0 = {}, 0
+    sizes = {}
+    for eq, groups in layout_order:
+        for g, mult in groups:
+            sizes[(eq, id(g))] = mult * g.num_cells
+    for eq in es.equations:
+        for (name, gid), n in sizes.items():
+            if name == eq:
+                rows[(name, gid)] = np.arange(r0, r0 + n)
+                r0 += n
+    return np.concatenate([rows[(eq, id(g))] for eq, groups in layout_order for g, _ in groups])
+
+
+def fractured_poromechanics_from_model(model):
+    """``pp.Poromechanics`` on a fractured medium with frictional contact -> (``FracturedPoromechanics``, column_map,
+    row_map)."""
+    from .fractured_poromech import FracturedPoromechanics
+    mat, fracs, intfs, data, couplings, fluid, solid, bc, _, _, dofs = _fractured_problem(model, False)
+    prob = FracturedPoromechanics(mat, data, couplings, fluid, solid, _contact_constants(model, fracs), bc,
+                                  flow_keyword=model.darcy_keyword, mechanics_keyword=model.stress_keyword)
+    prob.mobility_keyword = "b200_mobility"
+    cols = [dofs(model.pressure_variable, mat)] + [dofs(model.pressure_variable, f) for f in fracs] \
+        + [dofs(model.displacement_variable, mat)] + [dofs(model.contact_traction_variable, f) for f in fracs] \
+        + [dofs(model.interface_darcy_flux_variable, it) for it in intfs] \
+        + [dofs(model.interface_displacement_variable, it) for it in intfs]
+    order = [("mass_balance_equation", [(mat, 1)] + [(f, 1) for f in fracs]), ("momentum_balance_equation", [(mat, 3)]),
+             ("interface_darcy_flux_equation", [(it, 1) for it in intfs]),
+             ("interface_force_balance_equation", [(it, 3) for it in intfs]),
+             ("normal_fracture_deformation_equation", [(f, 1) for f in fracs]),
+             ("tangential_fracture_deformation_equation", [(f, 2) for f in fracs])]
+    return prob, np.concatenate(cols), _row_map(model, order)
+
+
+def fractured_thermoporomechanics_from_model(model):
+    """``pp.Thermoporomechanics`` on a fractured medium with frictional contact (BASELINE config[4]) ->
+    (``FracturedThermoporomechanics``, column_map, row_map)."""
+    from .fractured_thm import FracturedThermoporomechanics
+    mat, fracs, intfs, data, couplings, fluid, solid, bc, kappa_t, (w, we), dofs = _fractured_problem(model, True)
+    so = model.solid
+    solid.update(biot_coefficient=so.biot_coefficient, thermal_expansion=so.thermal_expansion,
+                 heat_capacity=so.specific_heat_capacity, conductivity=so.thermal_conductivity, density=so.density)
+    tk = model.fourier_keyword
+    ef = model.bc_type_enthalpy_flux(mat)
+    bc.update(fourier=_face_values(model, mat, data[PARAMETERS][tk]["bc"], model.bc_values_temperature, model.bc_values_fourier_flux),
+              enthalpy_flux=_face_values(model, mat, ef, we, model.bc_values_enthalpy_flux), enthalpy_flux_type=ef)
+    prob = FracturedThermoporomechanics(mat, data, couplings, fluid, solid, _contact_constants(model, fracs), bc, kappa_t,
+                                        flow_keyword=model.darcy_keyword, fourier_keyword=tk,
+                                        mechanics_keyword=model.stress_keyword, thermal_keyword=model.enthalpy_keyword)
+    prob.mobility_keyword, prob.enthalpy_upwind_keyword = "b200_mobility", "b200_enthalpy_upwind"
+    pv, tv = model.pressure_variable, model.temperature_variable
+    cols = [dofs(pv, mat)] + [dofs(pv, f) for f in fracs] + [dofs(tv, mat)] + [dofs(tv, f) for f in fracs] \
+        + [dofs(model.displacement_variable, mat)] + [dofs(model.contact_traction_variable, f) for f in fracs] \
+        + [dofs(model.interface_darcy_flux_variable, it) for it in intfs] \
+        + [dofs(model.interface_fourier_flux_variable, it) for it in intfs] \
+        + [dofs(model.interface_enthalpy_flux_variable, it) for it in intfs] \
+        + [dofs(model.interface_displacement_variable, it) for it in intfs]
+    order = [("mass_balance_equation", [(mat, 1)] + [(f, 1) for f in fracs]),
+             ("energy_balance_equation", [(mat, 1)] + [(f, 1) for f in fracs]), ("momentum_balance_equation", [(mat, 3)]),
+             ("interface_darcy_flux_equation", [(it, 1) for it in intfs]),
+             ("interface_fourier_flux_equation", [(it, 1) for it in intfs]),
+             ("interface_enthalpy_flux_equation", [(it, 1) for it in intfs]),
+             ("interface_force_balance_equation", [(it, 3) for it in intfs]),
+             ("normal_fracture_deformation_equation", [(f, 1) for f in fracs]),
+             ("tangential_fracture_deformation_equation", [(f, 2) for f in fracs])]
+    return prob, np.concatenate(cols), _row_map(model, order)

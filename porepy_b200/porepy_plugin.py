@@ -243,4 +243,6 @@ def plugin(pp, allow_reference_fallback: bool = False) -> SimpleNamespace:
                            poromechanics_from_model=bridge.poromechanics_from_model,
                            thermoporomechanics_from_model=bridge.thermoporomechanics_from_model,
                            fractured_momentum_from_model=bridge.fractured_momentum_from_model,
+                           fractured_poromechanics_from_model=bridge.fractured_poromechanics_from_model,
+                           fractured_thermoporomechanics_from_model=bridge.fractured_thermoporomechanics_from_model,
                            fallback_calls=fallback_calls, gpu_calls=gpu_calls)

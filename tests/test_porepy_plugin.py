@@ -588,3 +588,52 @@ def test_live_contact_mechanics_model(pp, emu_device):
     Aref = A.tocsr()[:, cm]                       # equations in the model's own order
     assert abs(J.to_scipy() - Aref).max() <= 1e-10 * abs(Aref).max()
     assert np.abs(r.numpy() - rhs).max() <= 1e-10 * np.abs(rhs).max()
+
+
+def test_live_fractured_thermoporomechanics_with_contact(pp, emu_device):
+    """BASELINE config[4] from a live model: ``plugin(pp).fractured_thermoporomechanics_from_model`` (and the
+    poromechanics variant) linearize to the model's own Jacobian at the model's own fourth iterate."""
+    import make_contact_golden as gc
+    from porepy_b200.porepy_plugin import plugin
+    b = plugin(pp)
+
+    class Base:
+        set_domain, grid_type, meshing_arguments = gc.Model.set_domain, gc.Model.grid_type, gc.Model.meshing_arguments
+        set_fractures, stiffness_tensor = gc.Model.set_fractures, gc.Model.stiffness_tensor
+        bc_type_mechanics, bc_values_displacement = gc.Model.bc_type_mechanics, gc.Model.bc_values_displacement
+        scenario = "mixed"
+
+        def bc_type_darcy_flux(self, sd):
+            s = self.domain_boundary_sides(sd)
+            return pp.BoundaryCondition(sd, s.south + s.north, "dir")
+        bc_type_fluid_flux = bc_type_fourier_flux = bc_type_enthalpy_flux = bc_type_darcy_flux
+
+        def bc_values_pressure(self, bg):
+            s = self.domain_boundary_sides(bg)
+            v = np.zeros(bg.num_cells)
+            v[s.south] = 0.02 * (1 + bg.cell_centers[0, s.south])
+            return v
+
+        def bc_values_temperature(self, bg):
+            s = self.domain_boundary_sides(bg)
+            v = np.zeros(bg.num_cells)
+            v[s.south] = 0.3 + 0.1 * bg.cell_centers[2, s.south]
+            return v
+    fluid = pp.FluidComponent(compressibility=0.05, viscosity=1.3, density=1.7, thermal_expansion=0.03,
+                              specific_heat_capacity=2.0, thermal_conductivity=0.7)
+    solid = pp.SolidConstants(porosity=0.2, biot_coefficient=0.8, lame_lambda=2.0, shear_modulus=1.5, permeability=1.0,
+                              normal_permeability=2.0, residual_aperture=0.05, friction_coefficient=0.4, fracture_gap=1e-4,
+                              dilation_angle=0.1, thermal_expansion=0.02, specific_heat_capacity=1.5,
+                              thermal_conductivity=1.1, density=2.5)
+    for ref_cls, build in ((pp.Poromechanics, b.fractured_poromechanics_from_model),
+                           (pp.Thermoporomechanics, b.fractured_thermoporomechanics_from_model)):
+        model = type("Live", (Base, ref_cls), {})({
+            "times_to_export": [], "time_manager": pp.TimeManager([0, 1.0], 0.25, constant_dt=True),
+            "material_constants": {"fluid": fluid, "solid": solid}})
+        x_prev, x_it, A, rhs = _newton_iterates(pp, model, n_before=3)
+        prob, cm, rm = build(model)
+        prob.discretize()
+        J, r = prob.linearize(x_it[cm], x_prev[cm], model.time_manager.dt)
+        Aref = A.tocsr()[rm][:, cm]
+        assert abs(J.to_scipy() - Aref).max() <= 1e-10 * abs(Aref).max(), ref_cls
+        assert np.abs(r.numpy() - rhs[rm]).max() <= 1e-10 * max(np.abs(rhs).max(), 1e-3 * abs(A).max())

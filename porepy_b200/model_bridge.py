@@ -291,6 +291,9 @@ def _fractured_problem(model, thermal: bool):
     a_res = model.solid.residual_aperture
     couplings, intfs, kappa_t = [], [], []
     for frac in fracs:
+        if np.any(np.asarray(frac.tags["domain_boundary_faces"], bool)):
+            raise NotImplementedError("fractures reaching the domain boundary (boundary data on the fracture) are not "
+                                      "handled by FracturedPoromechanics / FracturedThermoporomechanics yet")
         intf = [it for it in mdg.interfaces() if mdg.interface_to_subdomain_pair(it)[1] is frac][0]
         fdata = _own_data(mdg.subdomain_data(frac), [fk] + ([model.fourier_keyword] if thermal else []))
         k_now = np.asarray(fdata[PARAMETERS][fk]["second_order_tensor"].values, float)

@@ -637,3 +637,68 @@ def test_live_fractured_thermoporomechanics_with_contact(pp, emu_device):
         Aref = A.tocsr()[rm][:, cm]
         assert abs(J.to_scipy() - Aref).max() <= 1e-10 * abs(Aref).max(), ref_cls
         assert np.abs(r.numpy() - rhs[rm]).max() <= 1e-10 * max(np.abs(rhs).max(), 1e-3 * abs(A).max())
+
+
+def test_live_two_fractures_thermoporomechanics_and_contact(pp, emu_device):
+    """Two parallel fractures (two fracture subdomains, two interfaces): the multi-fracture ordering of the contact, the
+    fractured poromechanics and the fractured thermo-poromechanics problems against live models."""
+    import make_contact_golden as gc
+    from make_mdflow_golden import rect
+    from porepy_b200.porepy_plugin import plugin
+    b = plugin(pp)
+
+    class Geometry:
+        set_domain, grid_type, stiffness_tensor = gc.Model.set_domain, gc.Model.grid_type, gc.Model.stiffness_tensor
+        bc_type_mechanics = gc.Model.bc_type_mechanics
+
+        def meshing_arguments(self):
+            return {"cell_size": 0.25}
+
+        def set_fractures(self):
+            self._fractures = [pp.PlaneFracture(rect(0, 0.25, 0.25, 0.75)), pp.PlaneFracture(rect(0, 0.75, 0.25, 0.75))]
+
+        def bc_values_displacement(self, bg):
+            s = self.domain_boundary_sides(bg)
+            v = np.zeros((3, bg.num_cells))
+            v[0, s.east] = 0.02 * (bg.cell_centers[2, s.east] - 0.4)       # part of each fracture closes, part opens
+            v[1, s.east] = 0.01
+            return v.ravel("F")
+
+        def bc_type_darcy_flux(self, sd):
+            s = self.domain_boundary_sides(sd)
+            return pp.BoundaryCondition(sd, s.south + s.north, "dir")
+        bc_type_fluid_flux = bc_type_fourier_flux = bc_type_enthalpy_flux = bc_type_darcy_flux
+
+        def bc_values_pressure(self, bg):
+            s = self.domain_boundary_sides(bg)
+            v = np.zeros(bg.num_cells)
+            v[s.south] = 0.02 * (1 + bg.cell_centers[0, s.south])
+            return v
+
+        def bc_values_temperature(self, bg):
+            s = self.domain_boundary_sides(bg)
+            v = np.zeros(bg.num_cells)
+            v[s.south] = 0.3 + 0.1 * bg.cell_centers[2, s.south]
+            return v
+    fluid = pp.FluidComponent(compressibility=0.05, viscosity=1.3, density=1.7, thermal_expansion=0.03,
+                              specific_heat_capacity=2.0, thermal_conductivity=0.7)
+    solid = pp.SolidConstants(porosity=0.2, biot_coefficient=0.8, lame_lambda=2.0, shear_modulus=1.5, permeability=1.0,
+                              normal_permeability=2.0, residual_aperture=0.05, friction_coefficient=0.4, fracture_gap=1e-4,
+                              dilation_angle=0.1, thermal_expansion=0.02, specific_heat_capacity=1.5,
+                              thermal_conductivity=1.1, density=2.5)
+    params = {"times_to_export": [], "material_constants": {"fluid": fluid, "solid": solid}}
+    for ref_cls, build, dt in ((pp.MomentumBalance, b.fractured_momentum_from_model, None),
+                               (pp.Poromechanics, b.fractured_poromechanics_from_model, 0.25),
+                               (pp.Thermoporomechanics, b.fractured_thermoporomechanics_from_model, 0.25)):
+        model = type("Live2", (Geometry, ref_cls), {})(dict(
+            params, time_manager=pp.TimeManager([0, 1.0], dt or 1.0, constant_dt=True)))
+        x_prev, x_it, A, rhs = _newton_iterates(pp, model, n_before=3)
+        assert len(model.mdg.subdomains(dim=2)) == 2
+        out = build(model)
+        prob, cm = out[0], out[1]
+        rm = out[2] if len(out) > 2 else np.arange(A.shape[0])
+        prob.discretize()
+        J, r = prob.linearize(x_it[cm], x_prev[cm]) if dt is None else prob.linearize(x_it[cm], x_prev[cm], dt)
+        Aref = A.tocsr()[rm][:, cm]
+        assert abs(J.to_scipy() - Aref).max() <= 1e-10 * abs(Aref).max(), ref_cls
+        assert np.abs(r.numpy() - rhs[rm]).max() <= 1e-10 * max(np.abs(rhs).max(), 1e-3 * abs(A).max()), ref_cls

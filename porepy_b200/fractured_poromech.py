@@ -40,11 +40,14 @@ class FractureCoupling:
     ``second_order_tensor`` entry is written at every linearization: ``intrinsic_permeability`` (3, 3, nfc) times the
     aperture), the eight scalar mortar projections of its two-sided interface (``*_int`` / ``*_avg`` of the
     reference's ``MortarGrid``), ``mortar_sign``, ``mortar_volumes``, ``local_coordinates`` (3 nfc x 3 nfc) and the normal
-    permeability per mortar cell."""
+    permeability per mortar cell; ``bc``: boundary data of a fracture that reaches the domain boundary."""
 
     def __init__(self, sd, data, projections: dict, mortar_sign, mortar_volumes, local_coordinates, normal_permeability,
-                 intrinsic_permeability):
+                 intrinsic_permeability, bc: dict | None = None):
         self.sd, self.data = sd, data
+        # boundary data of a fracture that reaches the domain boundary: face arrays ``flow``, ``fluid_flux`` (and
+        # ``fourier``, ``enthalpy_flux``) plus the objects ``fluid_flux_type`` (``enthalpy_flux_type``); None: closed tips
+        self.bc = bc
         self.k_intrinsic = np.asarray(intrinsic_permeability, float)
         self.p = {k: sps.csr_matrix(v) for k, v in projections.items()}
         self.sign = np.asarray(mortar_sign, float)
@@ -142,7 +145,8 @@ class FracturedPoromechanics:
                     p2m3=csr(sps.kron(p["primary_to_mortar_int"], i3).tocsr()),
                     jump=csr(jump), traction=csr(trac), pressure_load=csr(pressure_load),
                     sel_n=csr(sel_n), sel_t=csr(sel_t), s2t=csr(s2t), coef=dev(fc.volumes * fc.kappa * 2.0),
-                    div=csr(sps.csr_matrix(fc.sd.cell_faces.T)), vol=dev(np.asarray(fc.sd.cell_volumes, float))))
+                    div=csr(sps.csr_matrix(fc.sd.cell_faces.T)), vol=dev(np.asarray(fc.sd.cell_volumes, float)),
+                    bc=None if fc.bc is None else {key: dev(v) for key, v in fc.bc.items() if not key.endswith("_type")}))
             self._const = k
         return self._const
 
@@ -155,6 +159,22 @@ class FracturedPoromechanics:
         for j in range(len(self.fractures)):
             b = (k.fr[j].m2p3 @ uj[j]) + b
         return ((k.div_u @ u) + (k.div_u_b @ b) + (k.cons @ dp)) * k.inv_vol + dp * self.so.n_inv + self.so.reference_porosity
+
+    def _fracture_flux(self, fc, q, p):
+        """Darcy flux of a fracture: flux p (+ bound_flux p_b when the fracture carries boundary data)."""
+        F = fc.data[DISCRETIZATION_MATRICES][self.fk]
+        flux = ad.as_device_csr(F["flux"]) @ p
+        if q.bc is not None:
+            flux = flux + (ad.as_device_csr(F["bound_flux"]) @ q.bc["flow"])
+        return flux
+
+    def _advective(self, T, flux, weight, q, key):
+        """Upwinded advective flux of a fracture (constitutive_laws.py:2555-2560) with its own boundary data, if any."""
+        csr = ad.as_device_csr
+        out = flux * (csr(T["transport"]) @ weight)
+        if q.bc is not None:
+            out = out + (csr(T["rhs_dir"]) @ (flux * q.bc[key])) + (csr(T["rhs_neu"]) @ q.bc[key])
+        return out
 
     def _aperture(self, uj_j, q):
         return fn.maximum((q.sel_n @ (q.jump @ uj_j)) + self.so.residual_aperture, self.so.residual_aperture)
@@ -183,8 +203,8 @@ class FracturedPoromechanics:
         Upwind(mk).discretize(self.sd, self.data)
         for j, fc in enumerate(self.fractures):
             prm = fc.data.setdefault(PARAMETERS, {}).setdefault(mk, {})
-            prm["darcy_flux"] = (ad.as_device_csr(fc.data[DISCRETIZATION_MATRICES][self.fk]["flux"]) @ pf[j]).cpu().numpy()
-            prm["bc"] = fc.data[PARAMETERS][self.fk]["bc"]
+            prm["darcy_flux"] = self._fracture_flux(fc, k.fr[j], pf[j]).cpu().numpy()
+            prm["bc"] = fc.data[PARAMETERS][self.fk]["bc"] if fc.bc is None else fc.bc["fluid_flux_type"]
             Upwind(mk).discretize(fc.sd, fc.data)
             d = self._intf_data[j]
             d.setdefault(PARAMETERS, {}).setdefault(mk, {})["darcy_flux"] = lam[j].cpu().numpy()
@@ -226,11 +246,11 @@ class FracturedPoromechanics:
         for j, fc in enumerate(self.fractures):
             q = k.fr[j]
             a, a_n = self._aperture(uj[j], q), self._aperture(ujn[j], q)
-            # ---- fracture: mass balance (tips closed or with the boundary data of the fracture's own bc: zero here)
+            # ---- fracture: mass balance
             Tf = fc.data[DISCRETIZATION_MATRICES][mk]
-            qf = csr(fc.data[DISCRETIZATION_MATRICES][self.fk]["flux"]) @ pf[j]
+            qf = self._fracture_flux(fc, q, pf[j])
             mass_f.append((a * self._density(pf[j]) - a_n * self._density(pfn[j])) * (q.vol * (1.0 / dt))
-                          + (q.div @ (qf * (csr(Tf["transport"]) @ wf[j]))) - (q.m2s @ ifl[j]))
+                          + (q.div @ self._advective(Tf, qf, wf[j], q, "fluid_flux")) - (q.m2s @ ifl[j]))
             # ---- interface: Darcy law with the current aperture; force balance with the fluid pressure on the walls
             darcy.append(lam[j] - ((q.p2m @ trace_p) - (q.s2m @ pf[j])) * (q.s2m @ a.reciprocal()) * q.coef)
             force.append((q.p2m3 @ (stress * k.outward)) + (q.traction @ t[j]) + (q.pressure_load @ pf[j]))

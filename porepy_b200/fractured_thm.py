@@ -121,10 +121,12 @@ class FracturedThermoporomechanics(FracturedPoromechanics):
             prm["darcy_flux"], prm["bc"] = q3, bc
             Upwind(kw).discretize(self.sd, self.data)
         for j, fc in enumerate(self.fractures):
-            qf = (ad.as_device_csr(fc.data[DISCRETIZATION_MATRICES][self.fk]["flux"]) @ pf[j]).cpu().numpy()
-            prm = fc.data.setdefault(PARAMETERS, {}).setdefault(self.mobility_keyword, {})
-            prm["darcy_flux"], prm["bc"] = qf, fc.data[PARAMETERS][self.fk]["bc"]
-            Upwind(self.mobility_keyword).discretize(fc.sd, fc.data)        # shared by the mass and the enthalpy flux
+            qf = self._fracture_flux(fc, k.fr[j], pf[j]).cpu().numpy()
+            for kw, key in ((self.mobility_keyword, "fluid_flux_type"), (self.enthalpy_upwind_keyword, "enthalpy_flux_type")):
+                prm = fc.data.setdefault(PARAMETERS, {}).setdefault(kw, {})
+                prm["darcy_flux"] = qf
+                prm["bc"] = fc.data[PARAMETERS][self.fk]["bc"] if fc.bc is None else fc.bc[key]
+                Upwind(kw).discretize(fc.sd, fc.data)
             d = self._intf_data[j]
             d.setdefault(PARAMETERS, {}).setdefault(self.mobility_keyword, {})["darcy_flux"] = lam[j].cpu().numpy()
             UpwindCoupling(self.mobility_keyword).discretize(self.sd, fc.sd, SimpleNamespace(num_cells=fc.num_mortar),
@@ -185,16 +187,20 @@ class FracturedThermoporomechanics(FracturedPoromechanics):
         for j, fc in enumerate(self.fractures):
             q = k.fr[j]
             a, a_n = self._aperture(uj[j], q), self._aperture(ujn[j], q)
-            Tf = fc.data[DISCRETIZATION_MATRICES][mk]
-            qf = csr(fc.data[DISCRETIZATION_MATRICES][self.fk]["flux"]) @ pf[j]
-            fof = csr(fc.data[DISCRETIZATION_MATRICES][self.tk]["flux"]) @ tf[j]
+            Tf, Tef = fc.data[DISCRETIZATION_MATRICES][mk], fc.data[DISCRETIZATION_MATRICES][ek]
+            qf = self._fracture_flux(fc, q, pf[j])
+            Fof = fc.data[DISCRETIZATION_MATRICES][self.tk]
+            fof = csr(Fof["flux"]) @ tf[j]
+            if q.bc is not None:
+                fof = fof + (csr(Fof["bound_flux"]) @ q.bc["fourier"])
             rhof, rhofn = self._density(pf[j], tf[j]), self._density(pfn[j], tfn[j])
-            mass_f.append((a * rhof - a_n * rhofn) * (q.vol * (1.0 / dt)) + (q.div @ (qf * (csr(Tf["transport"]) @ wf[j])))
-                          - (q.m2s @ ifl[j]))
+            mass_f.append((a * rhof - a_n * rhofn) * (q.vol * (1.0 / dt))
+                          + (q.div @ self._advective(Tf, qf, wf[j], q, "fluid_flux")) - (q.m2s @ ifl[j]))
             ef = rhof * (tf[j] - t0) * fl.heat_capacity - pf[j]                  # porosity 1: no solid part
             efn = rhofn * (tfn[j] - t0) * fl.heat_capacity - pfn[j]
             energy_f.append((a * ef - a_n * efn) * (q.vol * (1.0 / dt))
-                            + (q.div @ (qf * (csr(Tf["transport"]) @ wef[j]) + fof)) - (q.m2s @ (eta[j] + eps[j])))
+                            + (q.div @ (self._advective(Tef, qf, wef[j], q, "enthalpy_flux") + fof))
+                            - (q.m2s @ (eta[j] + eps[j])))
             inv_a = q.s2m @ a.reciprocal()
             darcy.append(lam[j] - ((q.p2m @ trace_p) - (q.s2m @ pf[j])) * inv_a * q.coef)
             fourier.append(eta[j] - ((q.p2m @ trace_t) - (q.s2m @ tf[j])) * inv_a * q.coef_t)

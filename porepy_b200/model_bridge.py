@@ -291,9 +291,6 @@ def _fractured_problem(model, thermal: bool):
     a_res = model.solid.residual_aperture
     couplings, intfs, kappa_t = [], [], []
     for frac in fracs:
-        if np.any(np.asarray(frac.tags["domain_boundary_faces"], bool)):
-            raise NotImplementedError("fractures reaching the domain boundary (boundary data on the fracture) are not "
-                                      "handled by FracturedPoromechanics / FracturedThermoporomechanics yet")
         intf = [it for it in mdg.interfaces() if mdg.interface_to_subdomain_pair(it)[1] is frac][0]
         fdata = _own_data(mdg.subdomain_data(frac), [fk] + ([model.fourier_keyword] if thermal else []))
         k_now = np.asarray(fdata[PARAMETERS][fk]["second_order_tensor"].values, float)
@@ -302,9 +299,22 @@ def _fractured_problem(model, thermal: bool):
             "mortar_to_primary_avg", "primary_to_mortar_int", "mortar_to_secondary_avg", "secondary_to_mortar_int",
             "mortar_to_primary_int", "primary_to_mortar_avg", "mortar_to_secondary_int", "secondary_to_mortar_avg")}
         rot = mdg.subdomain_data(frac)["tangential_normal_projection"].project_tangential_normal(frac.num_cells)
+        fbc = None
+        if np.any(np.asarray(frac.tags["domain_boundary_faces"], bool)):      # the fracture reaches the domain boundary
+            fl_ = _fluid(model, thermal)
+            wf_, wef_ = _boundary_weights(model, frac, fl_, thermal)
+            fft = model.bc_type_fluid_flux(frac)
+            fbc = dict(flow=_face_values(model, frac, fdata[PARAMETERS][fk]["bc"], model.bc_values_pressure, model.bc_values_darcy_flux),
+                       fluid_flux=_face_values(model, frac, fft, wf_, model.bc_values_fluid_flux), fluid_flux_type=fft)
+            if thermal:
+                eft = model.bc_type_enthalpy_flux(frac)
+                fbc.update(fourier=_face_values(model, frac, fdata[PARAMETERS][model.fourier_keyword]["bc"],
+                                                model.bc_values_temperature, model.bc_values_fourier_flux),
+                           enthalpy_flux=_face_values(model, frac, eft, wef_, model.bc_values_enthalpy_flux),
+                           enthalpy_flux_type=eft)
         couplings.append(FractureCoupling(frac, fdata, proj, sps.csr_matrix(intf.sign_of_mortar_sides(1)).diagonal(),
                                           intf.cell_volumes, rot, _evaluated(model, model.normal_permeability([intf]), intf.num_cells),
-                                          k_now / a_now[None, None, :]))
+                                          k_now / a_now[None, None, :], bc=fbc))
         intfs.append(intf)
         if thermal:
             kappa_t.append(_evaluated(model, model.normal_thermal_conductivity([intf]), intf.num_cells))

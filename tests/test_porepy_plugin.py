@@ -655,7 +655,7 @@ def test_live_two_fractures_thermoporomechanics_and_contact(pp, emu_device):
             return {"cell_size": 0.25}
 
         def set_fractures(self):
-            self._fractures = [pp.PlaneFracture(rect(0, 0.25, 0.25, 0.75)), pp.PlaneFracture(rect(0, 0.75, 0.25, 0.75))]
+            self._fractures = [pp.PlaneFracture(rect(0, 0.25, 0.25, 0.75)), pp.PlaneFracture(rect(0, 0.75, 0.0, 0.5))]   # the second one reaches the domain boundary: pressure / temperature data on its south edge
 
         def bc_values_displacement(self, bg):
             s = self.domain_boundary_sides(bg)
